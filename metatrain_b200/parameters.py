@@ -1,0 +1,139 @@
+"""Parameter containers of the B200 PET backend.
+
+The drop-in contract (level B1) requires the ``state_dict`` of our backend
+to have exactly the reference's keys, shapes and *order* (``species_to_species_index``
+first — ``src/metatrain/pet/modules/backend.py:63-71`` — because
+``PET.load_checkpoint`` probes the dtype from the first float entry,
+``src/metatrain/pet/model.py:978-981``), and the seed-0 initial values must equal the
+reference's so that its known-answer test (``pet/tests/test_regression.py:66-74``)
+transfers.  Both follow from creating the same leaf modules in the same order; the leaf
+modules here are *only* parameter holders — their ``forward`` is never called, all
+arithmetic happens in the CUDA engine (``metatrain_b200/csrc``).
+
+Creation order mirrored (no code shared): ``backend.py:73-136`` (GNN layers, combination
+norms/MLPs, embedders, empty head dicts), ``transformer.py:181-196`` (attention, norms,
+MLP, centre contraction/expansion/MLP), ``transformer.py:446-461`` (geometry embedder,
+compress, neighbour embedder), ``backend.py:171-217`` (heads + last layers per target).
+"""
+from math import prod
+from typing import Dict, List
+
+import torch
+from torch import nn
+
+
+class _Holder(nn.Module):
+    """A module that only owns sub-modules/parameters; calling it is a bug."""
+
+    def forward(self, *args, **kwargs):  # pragma: no cover
+        raise RuntimeError("parameter holder: arithmetic lives in the CUDA engine")
+
+
+def _swiglu_holder(d_model: int, d_ff: int) -> _Holder:
+    h = _Holder()
+    h.w_in = nn.Linear(d_model, 2 * d_ff)
+    h.w_out = nn.Linear(d_ff, d_model)
+    return h
+
+
+def _transformer_layer_holder(d_pet: int, d_node: int, d_ff: int) -> _Holder:
+    layer = _Holder()
+    layer.attention = _Holder()
+    layer.attention.input_linear = nn.Linear(d_pet, 3 * d_pet)
+    layer.attention.output_linear = nn.Linear(d_pet, d_pet)
+    layer.norm_attention = nn.RMSNorm(d_pet)
+    layer.norm_mlp = nn.RMSNorm(d_pet)
+    layer.mlp = _swiglu_holder(d_pet, d_ff)
+    layer.center_contraction = nn.Linear(d_node, d_pet)
+    layer.center_expansion = nn.Linear(d_pet, d_node)
+    layer.norm_center_features = nn.RMSNorm(d_node)
+    layer.center_mlp = _swiglu_holder(d_node, 2 * d_node)
+    return layer
+
+
+def _gnn_layer_holder(d_pet, d_node, d_ff, n_attention, n_species, is_first) -> _Holder:
+    g = _Holder()
+    g.trans = _Holder()
+    g.trans.layers = nn.ModuleList(
+        [_transformer_layer_holder(d_pet, d_node, d_ff) for _ in range(n_attention)]
+    )
+    g.edge_embedder = nn.Linear(4, d_pet)
+    n_merge = 2 if is_first else 3
+    g.compress = nn.Sequential(
+        nn.Linear(n_merge * d_pet, d_pet), nn.SiLU(), nn.Linear(d_pet, d_pet)
+    )
+    if not is_first:
+        g.neighbor_embedder = nn.Embedding(n_species, d_pet)
+    return g
+
+
+def _head_holder(d_in: int, d_head: int) -> nn.Sequential:
+    return nn.Sequential(
+        nn.Linear(d_in, d_head), nn.SiLU(), nn.Linear(d_head, d_head), nn.SiLU()
+    )
+
+
+class PETParameters(nn.Module):
+    """Owns every learnable tensor of the PET backend under the reference's names."""
+
+    def __init__(self, hypers: dict, atomic_types: List[int]) -> None:
+        super().__init__()
+        self.d_pet = int(hypers["d_pet"])
+        self.d_node = int(hypers["d_node"])
+        self.d_head = int(hypers["d_head"])
+        self.d_feedforward = int(hypers["d_feedforward"])
+        self.num_gnn_layers = int(hypers["num_gnn_layers"])
+        self.num_attention_layers = int(hypers["num_attention_layers"])
+        n_species = len(atomic_types)
+
+        self.register_buffer(
+            "species_to_species_index", torch.full((max(atomic_types) + 1,), -1)
+        )
+        for i, z in enumerate(atomic_types):
+            self.species_to_species_index[z] = i
+
+        self.gnn_layers = nn.ModuleList(
+            [
+                _gnn_layer_holder(self.d_pet, self.d_node, self.d_feedforward,
+                                  self.num_attention_layers, n_species, l == 0)
+                for l in range(self.num_gnn_layers)
+            ]
+        )
+        self.num_readout_layers = 1  # feedforward featurizer (backend.py:93-94)
+        self.combination_norms = nn.ModuleList(
+            [nn.LayerNorm(2 * self.d_pet) for _ in range(self.num_gnn_layers)]
+        )
+        self.combination_mlps = nn.ModuleList(
+            [
+                nn.Sequential(nn.Linear(2 * self.d_pet, 2 * self.d_pet), nn.SiLU(),
+                              nn.Linear(2 * self.d_pet, self.d_pet))
+                for _ in range(self.num_gnn_layers)
+            ]
+        )
+        self.node_embedders = nn.ModuleList(
+            [nn.Embedding(n_species, self.d_node) for _ in range(self.num_readout_layers)]
+        )
+        self.edge_embedder = nn.Embedding(n_species, self.d_pet)
+        self.node_heads = nn.ModuleDict()
+        self.edge_heads = nn.ModuleDict()
+        self.node_last_layers = nn.ModuleDict()
+        self.edge_last_layers = nn.ModuleDict()
+
+    def add_output(self, target_name: str, output_shapes: Dict[str, List[int]]) -> None:
+        r = range(self.num_readout_layers)
+        self.node_heads[target_name] = nn.ModuleList(
+            [_head_holder(self.d_node, self.d_head) for _ in r])
+        self.edge_heads[target_name] = nn.ModuleList(
+            [_head_holder(self.d_pet, self.d_head) for _ in r])
+        self.node_last_layers[target_name] = nn.ModuleList(
+            [nn.ModuleDict({k: nn.Linear(self.d_head, prod(s)) for k, s in output_shapes.items()})
+             for _ in r])
+        self.edge_last_layers[target_name] = nn.ModuleList(
+            [nn.ModuleDict({k: nn.Linear(self.d_head, prod(s)) for k, s in output_shapes.items()})
+             for _ in r])
+
+    def remove_output(self, target_name: str) -> None:
+        for table in (self.node_heads, self.edge_heads, self.node_last_layers,
+                      self.edge_last_layers):
+            if target_name in table:
+                del table[target_name]

@@ -1,0 +1,166 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference backend.
+
+Run in the build container only (needs ``/root/reference``):
+
+    python tests/golden/make_golden.py
+
+For every case it stores the inputs (species, fp32 positions, cell, the neighbor list fed
+to both sides) and the outputs of the reference's ``PETBackend.preprocess ->
+calculate_features -> predict -> torch.autograd.grad`` (energies, per-atom energies,
++dE/dr, strain gradient, feature check-sums), fp32 and (for the accuracy floor) fp64,
+plus a fingerprint of the seed-0 weights so the tests can prove that the product module
+initialises identically to the reference.
+
+Reference entry points exercised: ``src/metatrain/pet/modules/backend.py:238,344,420``;
+the golden energies of case ``qm9_5`` are additionally hard-coded in the reference at
+``src/metatrain/pet/tests/test_regression.py:66-74``.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_loader  # noqa: E402
+from oracle.structures import (  # noqa: E402
+    neighbor_list,
+    read_lammps_atomic,
+    read_xyz_frames,
+    silicon_box,
+)
+
+RES = os.path.join(ref_loader.REFERENCE_ROOT, "tests", "resources")
+
+
+def weight_fingerprint(state_dict):
+    """[n_tensors, 2] (sum, sum of squares) in float64, in state-dict order."""
+    rows = []
+    for v in state_dict.values():
+        v64 = v.detach().to(torch.float64)
+        rows.append([float(v64.sum()), float((v64 * v64).sum())])
+    return np.array(rows, dtype=np.float64)
+
+
+def batch_frames(frames, cutoff):
+    pos, cen, nei, sh, Z, sysi, cells = [], [], [], [], [], [], []
+    off = 0
+    for k, f in enumerate(frames):
+        i, j, S = neighbor_list(f["positions"], f["cell"], f["pbc"], cutoff)
+        pos.append(f["positions"])
+        cen.append(i + off)
+        nei.append(j + off)
+        sh.append(S)
+        Z.append(f["Z"])
+        sysi.append(np.full(len(f["Z"]), k, dtype=np.int64))
+        cells.append(f["cell"])
+        off += len(f["Z"])
+    return dict(
+        positions=np.concatenate(pos).astype(np.float32),
+        centers=np.concatenate(cen).astype(np.int64),
+        neighbors=np.concatenate(nei).astype(np.int64),
+        cell_shifts=np.concatenate(sh).astype(np.int64).reshape(-1, 3),
+        species=np.concatenate(Z).astype(np.int64),
+        system_indices=np.concatenate(sysi).astype(np.int64),
+        cells=np.stack(cells).astype(np.float32),
+    )
+
+
+def run_reference(backend, inp, target, dtype, with_strain):
+    t = lambda a, dt=None: torch.tensor(a) if dt is None else torch.tensor(a).to(dt)  # noqa: E731
+    pos = t(inp["positions"], dtype).requires_grad_(True)
+    cells = t(inp["cells"], dtype)
+    strain = torch.eye(3, dtype=dtype, requires_grad=True)
+    pos_in, cells_in = (pos @ strain, cells @ strain) if with_strain else (pos, cells)
+    sysi = t(inp["system_indices"])
+    bd = backend.preprocess(pos_in, t(inp["centers"]), t(inp["neighbors"]), t(inp["species"]),
+                            cells_in, t(inp["cell_shifts"]), sysi, 1.0)
+    nodes, edges = backend.calculate_features(bd)
+    pred, _, _ = backend.predict(nodes, edges, bd, cells_in, sysi, [target])
+    atomic = pred[target][0]
+    energies = torch.zeros(cells.shape[0], atomic.shape[1], dtype=dtype).index_add_(0, sysi, atomic)
+    wrt = [pos] + ([strain] if with_strain else [])
+    grads = torch.autograd.grad(energies.sum(), wrt)
+    out = dict(
+        energies=energies.detach().numpy(),
+        atomic=atomic.detach().numpy(),
+        dE_dpos=grads[0].numpy(),
+        node_features_sum=np.array([float(nodes[0].double().sum()), float(nodes[0].double().abs().sum())]),
+        edge_features_sum=np.array([float((edges[0] * bd["padding_mask"][..., None]).double().sum()),
+                                    float((edges[0] * bd["padding_mask"][..., None]).double().abs().sum())]),
+        n_edges_kept=np.array(int(bd["padding_mask"].sum())),
+    )
+    if with_strain:
+        out["dE_dstrain"] = grads[1].numpy()
+    return out
+
+
+def make_case(name, frames, atomic_types, target="energy", hypers=None, nl_cutoff=4.5,
+              with_strain=False, fp64=True):
+    inp = batch_frames(frames, nl_cutoff)
+    be32 = ref_loader.build_reference_backend(atomic_types, target, hypers).eval()
+    fp = weight_fingerprint(be32.state_dict())
+    ref32 = run_reference(be32, inp, target, torch.float32, with_strain)
+    payload = dict(inp)
+    payload["atomic_types"] = np.array(atomic_types, dtype=np.int64)
+    payload["target"] = np.array(target)
+    payload["hypers_override"] = np.array(repr(hypers or {}))
+    payload["weight_fingerprint"] = fp
+    for k, v in ref32.items():
+        payload["ref32_" + k] = v
+    if fp64:
+        be64 = ref_loader.build_reference_backend(atomic_types, target, hypers, dtype=torch.float64).eval()
+        ref64 = run_reference(be64, inp, target, torch.float64, with_strain)
+        for k in ("energies", "atomic", "dE_dpos", "dE_dstrain"):
+            if k in ref64:
+                payload["ref64_" + k] = ref64[k]
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **payload)
+    n_e = int(ref32["n_edges_kept"])
+    print(f"{name}: N={len(inp['species'])} E_in={len(inp['centers'])} E_kept={n_e} "
+          f"E={ref32['energies'].ravel()[:5]} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    return payload
+
+
+def main():
+    torch.set_num_threads(8)
+    qm9 = read_xyz_frames(os.path.join(RES, "qm9_reduced_100.xyz"), 5)
+    p = make_case("qm9_5", qm9, [1, 6, 7, 8], target="mtt::U0")
+    hard_coded = np.array([1.146098375320, 0.171331465244, 0.539504408836,
+                           0.861489117146, 0.177449733019])  # test_regression.py:66-74
+    err = np.abs(p["ref32_energies"].ravel() - hard_coded).max()
+    print("qm9_5 vs reference's hard-coded goldens: max abs diff", err)
+    assert err < 1e-5
+
+    water = read_lammps_atomic(os.path.join(RES, "periodic_water.data"), {1: 1, 2: 8})
+    make_case("water_384", [water], [1, 8])
+    # non-strict neighbor list: pairs out to 5.5 A are handed in and must be dropped
+    make_case("water_384_nonstrict", [water], [1, 8], nl_cutoff=5.5, fp64=False)
+
+    carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
+    make_case("carbon_5", carbon, [6], with_strain=False)
+
+    si = silicon_box()
+    make_case("si_64", [si], [14], with_strain=True)
+    make_case("si_64_cosine", [si], [14], hypers=dict(cutoff_function="Cosine"), fp64=False)
+
+    # the periodic 2-atom system of pet/tests/test_backend.py:68-80 (strain gradient)
+    co = dict(Z=np.array([6, 8]), positions=np.array([[0.0, 0.0, 0.0], [1.5, 1.5, 1.5]]),
+              cell=3.5 * np.eye(3), pbc=True)
+    make_case("co_periodic", [co], [1, 6, 7, 8], with_strain=True)
+
+    # H2O of test_backend.py:57-65 + isolated C (test_functionality.py:106-159) + a
+    # dissociated pair, batched -> ragged rows, rows with zero neighbours
+    h2o = dict(Z=np.array([8, 1, 1]),
+               positions=np.array([[0.0, 0.0, 0.119], [0.0, 0.757, -0.477], [0.0, -0.757, -0.477]]),
+               cell=np.zeros((3, 3)), pbc=False)
+    lone = dict(Z=np.array([6]), positions=np.zeros((1, 3)), cell=np.zeros((3, 3)), pbc=False)
+    pair = dict(Z=np.array([6, 6]), positions=np.array([[0.0, 0, 0], [0, 0, 100.0]]),
+                cell=np.zeros((3, 3)), pbc=False)
+    make_case("ragged_mix", [h2o, lone, pair, qm9[0]], [1, 6, 7, 8])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""Shared helpers for the parity tests."""
+import ast
+import os
+import random
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64",
+                "si_64_cosine", "co_periodic", "ragged_mix"]
+
+# pet/documentation.py:159-259 defaults
+DEFAULT_HYPERS = dict(
+    cutoff=4.5, num_neighbors_adaptive=None, adaptive_cutoff_method="solver",
+    cutoff_function="Bump", cutoff_width=0.5, cutoff_width_adaptive=1.0, d_pet=128,
+    d_head=128, d_node=256, d_feedforward=256, num_heads=8, num_attention_layers=2,
+    num_gnn_layers=2, normalization="RMSNorm", activation="SwiGLU",
+    attention_temperature=1.0, transformer_type="PreLN", featurizer_type="feedforward",
+    zbl=False, long_range=dict(enable=False), system_conditioning=False, max_charge=10,
+    max_spin_multiplicity=10,
+)
+
+
+def load_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    g["target"] = str(g["target"])
+    g["hypers"] = dict(DEFAULT_HYPERS)
+    g["hypers"].update(ast.literal_eval(str(g["hypers_override"])))
+    g["atomic_types"] = [int(z) for z in g["atomic_types"]]
+    return g
+
+
+def seed_all(seed=0):
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def golden_inputs(g, device="cpu", dtype=torch.float32):
+    t = lambda k: torch.tensor(g[k]).to(device)  # noqa: E731
+    return dict(
+        positions=t("positions").to(dtype), centers=t("centers"), neighbors=t("neighbors"),
+        species=t("species"), cells=t("cells").to(dtype), cell_shifts=t("cell_shifts"),
+        system_indices=t("system_indices"),
+    )
+
+
+def weight_fingerprint(state_dict):
+    rows = []
+    for v in state_dict.values():
+        v64 = v.detach().to(torch.float64).cpu()
+        rows.append([float(v64.sum()), float((v64 * v64).sum())])
+    return np.array(rows, dtype=np.float64)
