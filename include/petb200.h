@@ -1,0 +1,235 @@
+/*
+ * libpetb200 — C ABI of the B200-native PET forward/backward engine.
+ *
+ * Drop-in boundary: these entry points are what a binding of the
+ * reference's tensor backend `PETBackend` (metatensor/metatrain @ e2af0672,
+ * src/metatrain/pet/modules/backend.py:12) would call instead of the torch ops it
+ * executes today.  Every function
+ *   - takes plain device pointers + sizes (no torch types), row-major, 16-byte aligned
+ *     rows, fp32 features and int32 indices;
+ *   - is asynchronous on the given CUDA stream, never synchronises, allocates, frees
+ *     or retains a pointer past the call (the caller owns every buffer and workspace);
+ *   - returns PETB200_OK (0) or a negative error code; the message is available from
+ *     petb200_last_error() (thread local).  The Python host turns it into RuntimeError,
+ *     which `mtt` wraps as ArchitectureError (src/metatrain/utils/errors.py:1-19).
+ *
+ * Edge layout: CSR over centre atoms, unpadded.  Edge e = (i -> j, S) lives at
+ * row_ptr[i] <= e < row_ptr[i+1] in neighbor-list order (the stable order the
+ * reference's NEF grid uses, src/metatrain/pet/modules/nef.py:34-85); col[e] = j,
+ * ctr[e] = i, rev[e] = index of (j -> i, -S) (nef.py:88-166).
+ *
+ * Token layout inside a GNN layer: one [E + N, d_pet] matrix; rows [0, E) are the edge
+ * tokens in CSR order, row E + i is the centre token of atom i
+ * (transformer.py:214 concatenates [centre; edges] per atom).
+ */
+#ifndef PETB200_H
+#define PETB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* petb200_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define PETB200_API __attribute__((visibility("default")))
+#else
+#define PETB200_API
+#endif
+
+enum {
+  PETB200_OK = 0,
+  PETB200_ERR_INVALID_ARGUMENT = -1,
+  PETB200_ERR_CUDA = -2,
+  PETB200_ERR_WORKSPACE = -3,
+  PETB200_ERR_UNSUPPORTED = -4
+};
+
+/* GEMM epilogues */
+enum {
+  PETB200_EPI_NONE = 0,       /* C = rs*acc + bias (+ residual)                         */
+  PETB200_EPI_SILU = 1,       /* pre = rs*acc + bias -> aux_out ; C = silu(pre) (+res)  */
+  PETB200_EPI_SWIGLU = 2,     /* [u|g] = rs*acc + bias -> aux_out ; C = u * sigmoid(g)  */
+  PETB200_EPI_MUL_DSILU = 3,  /* C = acc * silu'(aux_in)          (dgrad through SiLU)  */
+  PETB200_EPI_SWIGLU_BWD = 4  /* C = [acc*sig(g) | acc*u*sig'(g)] (dgrad through SwiGLU)*/
+};
+
+/* GEMM arithmetic */
+enum {
+  PETB200_PREC_FP32 = 0,   /* FFMA, exact fp32 (parity reference)                       */
+  PETB200_PREC_BF16X3 = 1, /* tcgen05 kind::f16, 2-term bf16 split, 3 MMAs, fp32 accum  */
+  PETB200_PREC_BF16 = 2    /* tcgen05 kind::f16, single bf16 pass (fast, ~1e-2 eV/A)    */
+};
+
+/* cutoff functions, src/metatrain/pet/modules/utilities.py:4-39 */
+enum { PETB200_CUTOFF_BUMP = 0, PETB200_CUTOFF_COSINE = 1 };
+
+PETB200_API const char* petb200_last_error(void);
+PETB200_API int petb200_version(void);
+
+/* ------------------------------------------------------------------ topology (a4-a6)
+ * Replaces the integer half of compute_batch_tensors (structures.py:265-363):
+ * drop pairs beyond the cutoff (non-strict list), count neighbours per centre, order
+ * edges by centre (stable), find the reversed edge of every edge.                     */
+
+/* Step 1: keep[e] = |r_j - r_i + S.cell| + 1e-15 <= cutoff (structures.py:220-221,267);
+ * counts[i] += keep.  counts must be zeroed by the caller (N+1 entries, last unused). */
+PETB200_API int petb200_nl_filter_count(const float* positions, const float* cells,
+                            const int32_t* system_of_atom, const int32_t* centers,
+                            const int32_t* neighbors, const int32_t* shifts,
+                            int64_t n_pairs, int64_t n_atoms, float cutoff,
+                            int32_t* keep, int32_t* counts, petb200_stream_t stream);
+
+/* Bytes of scratch needed by petb200_csr_build for n_pairs / n_atoms. */
+PETB200_API size_t petb200_csr_build_workspace(int64_t n_pairs, int64_t n_atoms);
+
+/* Step 2: row_ptr = exclusive scan(counts) (N+1 entries; row_ptr[N] = E_kept),
+ * stats[0] = E_kept, stats[1] = max_i counts[i]; perm[k] = index in the input list of
+ * CSR edge k (stable by centre; only the first E_kept entries are meaningful).         */
+PETB200_API int petb200_csr_build(const int32_t* centers, const int32_t* keep, const int32_t* counts,
+                      int64_t n_pairs, int64_t n_atoms, int32_t* row_ptr, int32_t* perm,
+                      int32_t* stats, void* workspace, size_t workspace_bytes,
+                      petb200_stream_t stream);
+
+/* Step 3: gather the kept pairs into CSR order.                                        */
+PETB200_API int petb200_csr_gather(const int32_t* perm, const int32_t* centers,
+                       const int32_t* neighbors, const int32_t* shifts, int64_t n_edges,
+                       int32_t* ctr, int32_t* col, int32_t* shift_csr,
+                       petb200_stream_t stream);
+
+/* Step 4: rev[e] = index of (col[e] -> ctr[e], -S_e) (nef.py:88-166).  *n_missing is
+ * incremented for every edge whose reverse does not exist (non-symmetric list).        */
+PETB200_API int petb200_reverse_map(const int32_t* row_ptr, const int32_t* ctr, const int32_t* col,
+                        const int32_t* shift_csr, int64_t n_edges, int32_t* rev,
+                        int32_t* n_missing, petb200_stream_t stream);
+
+/* CSR <-> padded NEF ([N, M, D], zero padded; nef.py:169-218).                         */
+PETB200_API int petb200_csr_to_nef(const float* x_csr, const int32_t* row_ptr, int64_t n_atoms,
+                       int64_t n_edges, int width_m, int d, float* x_nef,
+                       petb200_stream_t stream);
+PETB200_API int petb200_nef_to_csr(const float* x_nef, const int32_t* row_ptr, const int32_t* ctr,
+                       int64_t n_atoms, int64_t n_edges, int width_m, int d, float* x_csr,
+                       petb200_stream_t stream);
+
+/* ------------------------------------------------------------------ geometry (a4, a7)
+ * r_e = x_j - x_i + S.cell (structures.py:212-220); d_e = sqrt(r.r + 1e-15) (:330);
+ * f_e = cutoff_function(|r_e| + 1e-15) (:221,306-316; utilities.py:4-39).              */
+PETB200_API int petb200_edges_fwd(const float* positions, const float* cells,
+                      const int32_t* system_of_atom, const int32_t* ctr, const int32_t* col,
+                      const int32_t* shift_csr, int64_t n_edges, float cutoff, float width,
+                      int cutoff_function, float* edge_vec, float* edge_dist,
+                      float* cutoff_factor, petb200_stream_t stream);
+
+/* Backward of petb200_edges_fwd + the force scatter: G_e = d_vec + d_dist*r/d +
+ * d_fc*f'(|r|)*r/|r|;  d_pos[i] = sum_{e in row i} (G_rev(e) - G_e) (segmented reduce, no
+ * atomics);  d_cells[b] += sum_e S_e^T G_e.  edge_grad is [E,3] scratch.               */
+PETB200_API int petb200_edges_bwd(const float* d_vec, const float* d_dist, const float* d_fc,
+                      const float* edge_vec, const float* edge_dist,
+                      const int32_t* row_ptr, const int32_t* ctr, const int32_t* rev,
+                      const int32_t* shift_csr, const int32_t* system_of_atom,
+                      int64_t n_atoms, int64_t n_edges, float cutoff, float width,
+                      int cutoff_function, float* edge_grad, float* d_pos, float* d_cells,
+                      petb200_stream_t stream);
+
+/* --------------------------------------------------------------- dense contractions
+ * C[M,N] = epilogue(row_scale * (A[M,K] . W[N,K]^T) + bias) (+ residual) — every
+ * torch.nn.Linear of transformer.py / backend.py, and its dgrad with W^T.             */
+PETB200_API int petb200_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C,
+                 int64_t ldc, int64_t M, int N, int K, const float* bias,
+                 const float* row_scale, const float* residual, int64_t ldr,
+                 const float* aux_in, float* aux_out, int64_t ld_aux, int epilogue,
+                 int accumulate, int precision, petb200_stream_t stream);
+
+/* out[m,:] = table[idx[m],:] (torch.nn.Embedding, backend.py:515-516).                 */
+PETB200_API int petb200_embedding(const float* table, const int32_t* idx, int64_t n_rows, int d,
+                      float* out, int64_t ld_out, petb200_stream_t stream);
+
+/* out[k][n] = in[n][k] * (col_scale ? col_scale[k] : 1): weight preparation
+ * (dgrad operand W^T; RMSNorm weight folded into the following Linear).                */
+PETB200_API int petb200_transpose_scale(const float* in, int rows, int cols, const float* col_scale,
+                            float* out_transposed, float* out_scaled,
+                            petb200_stream_t stream);
+
+/* GNN-layer input (transformer.py:500-519): cat[e] = [W_geo.(r_e,d_e)+b | NbrEmb[z_j] |
+ * m_e]; the neighbour-embedding block is absent when nbr_table is null (first layer).  */
+PETB200_API int petb200_compress_input(const float* edge_vec, const float* edge_dist,
+                           const float* w_geo, const float* b_geo, const float* nbr_table,
+                           const int32_t* z_neighbor, const float* messages,
+                           int64_t n_edges, int d, float* cat, petb200_stream_t stream);
+
+/* d_(r,d)[e] (+)= W_geo^T . d_geo[e]  (backward of the 4 -> d geometry embedder).      */
+PETB200_API int petb200_geom_embed_bwd(const float* d_geo, int64_t ld, const float* w_geo,
+                           int64_t n_edges, int d, int accumulate, float* d_vec,
+                           float* d_dist, petb200_stream_t stream);
+
+/* ------------------------------------------------------------------------ RMSNorm
+ * rstd[m] = rsqrt(mean(x[m,:]^2) + eps), eps = FLT_EPSILON (torch.nn.RMSNorm default;
+ * transformer.py:184-186,193).  The norm weight is folded into the next Linear.        */
+PETB200_API int petb200_rms_rstd(const float* x, int64_t n_rows, int d, float* rstd,
+                     petb200_stream_t stream);
+/* out = base + rstd*(d_xhat - xhat*mean(d_xhat*xhat)), xhat = x*rstd.                  */
+PETB200_API int petb200_rms_bwd(const float* d_xhat, const float* x, const float* rstd,
+                    const float* base, int64_t n_rows, int d, float* out,
+                    petb200_stream_t stream);
+
+/* ---------------------------------------------------------------------- attention
+ * Per-atom multi-head attention over tokens {centre i} U {edges of row i} with the
+ * key-only additive bias log(max(w_q, 1e-15)), w = 1 for the centre token and f_e for
+ * edge tokens (transformer.py:86-152, 524-540).  qkv is [E+N, 3*d] = [q | k | v], each
+ * split into num_heads heads of 16; out is [E+N, d]; lse is [E+N, num_heads].           */
+PETB200_API int petb200_attention_fwd(const float* qkv, const int32_t* row_ptr,
+                          const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
+                          int num_heads, int head_dim, float scale, int max_row,
+                          float* out, float* lse, petb200_stream_t stream);
+/* d_qkv from d_out; d_fc[e] += (sum_{heads,queries} dS[.,e]) / f_e  (f_e > 1e-15).     */
+PETB200_API int petb200_attention_bwd(const float* qkv, const float* out, const float* lse,
+                          const float* d_out, const int32_t* row_ptr,
+                          const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
+                          int num_heads, int head_dim, float scale, int max_row,
+                          float* d_qkv, float* d_fc, petb200_stream_t stream);
+
+/* ------------------------------------------------ message reversal + combine (a8)
+ * backend.py:559-575: cc[e] = LayerNorm_{2d}(cat[t_e, t_rev(e)]) (eps 1e-5, affine).
+ * This is the HBM-bound "edge scatter" kernel: 2 KB of algorithmic traffic per edge.   */
+PETB200_API int petb200_combine_ln_fwd(const float* t, const int32_t* rev, const float* gamma,
+                           const float* beta, int64_t n_edges, int d, float* cc,
+                           float* mean, float* rstd, petb200_stream_t stream);
+PETB200_API int petb200_combine_ln_bwd(const float* d_cc, const float* t, const int32_t* rev,
+                           const float* gamma, const float* mean, const float* rstd,
+                           int64_t n_edges, int d, float* d_cat, petb200_stream_t stream);
+/* out[e] = base[e] + d_cat[e, :d] + d_cat[rev[e], d:]  (rev is an involution, so the
+ * scatter of the reversed half is a gather: no atomics).                               */
+PETB200_API int petb200_combine_scatter_bwd(const float* d_cat, const float* base, const int32_t* rev,
+                                int64_t n_edges, int d, float* out,
+                                petb200_stream_t stream);
+
+/* ------------------------------------------------------------------- readout (a12)
+ * backend.py:195-217, 762-772: atomic[i,p] = w_n[p].n2[i] + b_n[p] +
+ * sum_{e in row i} f_e * (w_e[p].e2[e] + b_e[p]);  edge_pred[e,p] is kept for backward. */
+PETB200_API int petb200_readout_fwd(const float* node_feat, const float* edge_feat, const float* w_node,
+                        const float* b_node, const float* w_edge, const float* b_edge,
+                        const float* cutoff_factor, const int32_t* row_ptr, int64_t n_atoms,
+                        int64_t n_edges, int d, int n_out, float* atomic, float* edge_pred,
+                        petb200_stream_t stream);
+/* node_pre / edge_pre (nullable): pre-activations of the SiLU that produced node_feat /
+ * edge_feat; when given, the returned gradients are w.r.t. those pre-activations.
+ * d_fc[e] += sum_p edge_pred[e,p] * d_atomic[ctr[e],p].                                 */
+PETB200_API int petb200_readout_bwd(const float* d_atomic, const float* edge_pred, const float* w_node,
+                        const float* w_edge, const float* cutoff_factor, const int32_t* ctr,
+                        const float* node_pre, const float* edge_pre,
+                        int64_t n_atoms, int64_t n_edges, int d, int n_out, float* d_node_feat,
+                        float* d_edge_feat, float* d_fc, petb200_stream_t stream);
+
+/* per-structure sums, src/metatrain/utils/sum_over_atoms.py:31 (deterministic: atoms of a
+ * structure are contiguous; one warp per structure).                                    */
+PETB200_API int petb200_sum_over_atoms(const float* atomic, const int32_t* struct_ptr,
+                           int64_t n_structures, int n_out, float* energies,
+                           petb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETB200_H */

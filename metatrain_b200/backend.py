@@ -1,0 +1,366 @@
+"""``B200PETBackend`` — drop-in replacement of the reference's tensor backend.
+
+Mirrors ``metatrain.pet.modules.backend.PETBackend``
+(``src/metatrain/pet/modules/backend.py:12``): same constructor, ``add_output`` /
+``remove_output``, and the three plain-tensor stages ``preprocess`` (``:238``),
+``calculate_features`` (``:344``) and ``predict`` (``:420``) that ``PET.forward`` calls
+(``src/metatrain/pet/model.py:417,500,530``); same ``state_dict`` keys/order/initial values
+(see ``parameters.py``), same exception types for invalid hyper-parameters.
+
+Internally nothing is padded: edges live in a CSR layout and every stage is one
+``torch.autograd.Function`` whose forward/backward are hand-scheduled sequences of CUDA
+kernels from ``libpetb200.so`` (``engine.py``).  The padded NEF tensors that ``PET.forward``
+may read from ``batch_data`` (``padding_mask``, ``cutoff_factors``, ``edge_distances``, ...,
+``model.py:436-459,512-513``) are still produced, from the CSR data, so that the wrapper
+keeps working unchanged.
+
+Not built yet (raise ``NotImplementedError``): adaptive cutoff, residual featurizer,
+PostLN / LayerNorm / SiLU variants, system conditioning, weight gradients (training).
+"""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import engine
+from .lib import CUTOFF_BUMP, CUTOFF_COSINE, PREC_BF16, PREC_BF16X3, PREC_FP32, call, ptr
+from .parameters import PETParameters
+
+Tensor = torch.Tensor
+
+_AVAILABLE_NORMALIZATIONS = ["LayerNorm", "RMSNorm"]
+_AVAILABLE_TRANSFORMER_TYPES = ["PostLN", "PreLN"]
+_AVAILABLE_ACTIVATIONS = ["SiLU", "SwiGLU"]
+_PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+
+
+def _require_cuda(t: Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"B200PETBackend.{what}: expected CUDA tensors; this backend has no CPU path")
+
+
+# ------------------------------------------------------------------ autograd stages
+class _EdgeGeometry(torch.autograd.Function):
+    """positions, cells -> (edge vectors, embedder distances, cutoff factors), CSR order."""
+
+    @staticmethod
+    def forward(ctx, positions, cells, topo, cutoff, width, func):
+        pos = positions.detach().to(torch.float32).contiguous()
+        cel = cells.detach().to(torch.float32).contiguous()
+        vec, dist, fc = engine.edges_forward(topo, pos, cel, cutoff, width, func)
+        ctx.topo, ctx.params = topo, (cutoff, width, func)
+        ctx.in_dtypes = (positions.dtype, cells.dtype)
+        ctx.save_for_backward(vec, dist)
+        return vec, dist, fc
+
+    @staticmethod
+    def backward(ctx, d_vec, d_dist, d_fc):
+        vec, dist = ctx.saved_tensors
+        cutoff, width, func = ctx.params
+        need_cells = ctx.needs_input_grad[1]
+        c = lambda g: None if g is None else g.contiguous()  # noqa: E731
+        d_pos, d_cells = engine.edges_backward(
+            ctx.topo, vec, dist, c(d_vec), c(d_dist), c(d_fc), cutoff, width, func, need_cells)
+        d_pos = d_pos.to(ctx.in_dtypes[0])
+        if d_cells is not None:
+            d_cells = d_cells.to(ctx.in_dtypes[1])
+        return d_pos, d_cells, None, None, None, None
+
+
+class _Features(torch.autograd.Function):
+    """(edge vectors, distances, cutoff factors) -> (node features, edge messages)."""
+
+    @staticmethod
+    def forward(ctx, vec, dist, fc, backend, topo):
+        pw = backend._packed()
+        prec = backend._precision
+        h, m, saved = engine.features_forward(pw, backend.hypers, topo, vec.contiguous(),
+                                              dist.contiguous(), fc.contiguous(), prec)
+        ctx.backend, ctx.topo, ctx.pw, ctx.saved, ctx.fc, ctx.prec = backend, topo, pw, saved, fc, prec
+        return h, m
+
+    @staticmethod
+    def backward(ctx, d_h, d_m):
+        topo = ctx.topo
+        if d_h is None:
+            d_h = torch.zeros((topo.n_atoms, ctx.backend.d_node), device=ctx.fc.device)
+        if d_m is None:
+            d_m = torch.zeros((topo.n_edges, ctx.backend.d_pet), device=ctx.fc.device)
+        d_vec, d_dist, d_fc = engine.features_backward(
+            ctx.pw, ctx.backend.hypers, topo, ctx.fc.contiguous(), ctx.saved, d_h, d_m, ctx.prec)
+        ctx.saved = None
+        return d_vec, d_dist, d_fc, None, None
+
+
+class _Predict(torch.autograd.Function):
+    """(node features, edge messages, cutoff factors) -> per-atom predictions [N, P]."""
+
+    @staticmethod
+    def forward(ctx, h, m, fc, backend, topo, name):
+        pw = backend._packed()
+        prec = backend._precision
+        atomic, saved = engine.predict_forward(pw, topo, name, h.contiguous(), m.contiguous(),
+                                               fc.contiguous(), prec)
+        ctx.topo, ctx.pw, ctx.saved, ctx.fc, ctx.name, ctx.prec = topo, pw, saved, fc, name, prec
+        return atomic
+
+    @staticmethod
+    def backward(ctx, d_atomic):
+        d_h, d_m, d_fc = engine.predict_backward(ctx.pw, ctx.topo, ctx.name, ctx.fc.contiguous(),
+                                                 ctx.saved, d_atomic, ctx.prec)
+        ctx.saved = None
+        return d_h, d_m, d_fc, None, None, None
+
+
+class _CsrToNef(torch.autograd.Function):
+    """[E, ...] CSR edge array -> zero-padded [N, M, ...] NEF array (nef.py:169-201)."""
+
+    @staticmethod
+    def forward(ctx, x, topo):
+        d = 1
+        for s in x.shape[1:]:
+            d *= s
+        out = torch.empty((topo.n_atoms, topo.max_row) + tuple(x.shape[1:]), device=x.device)
+        call("csr_to_nef", ptr(x.contiguous()), ptr(topo.row_ptr), topo.n_atoms, topo.n_edges,
+             topo.max_row, d, ptr(out))
+        ctx.topo, ctx.d, ctx.tail = topo, d, tuple(x.shape[1:])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        topo = ctx.topo
+        out = torch.empty((topo.n_edges,) + ctx.tail, device=g.device)
+        call("nef_to_csr", ptr(g.contiguous()), ptr(topo.row_ptr), ptr(topo.ctr), topo.n_atoms,
+             topo.n_edges, topo.max_row, ctx.d, ptr(out))
+        return out, None
+
+
+class _NefToCsr(torch.autograd.Function):
+    """padded NEF array -> CSR edge array (nef.py:204-218)."""
+
+    @staticmethod
+    def forward(ctx, x, topo):
+        tail = tuple(x.shape[2:])
+        d = 1
+        for s in tail:
+            d *= s
+        out = torch.empty((topo.n_edges,) + tail, device=x.device)
+        call("nef_to_csr", ptr(x.contiguous()), ptr(topo.row_ptr), ptr(topo.ctr), topo.n_atoms,
+             topo.n_edges, topo.max_row, d, ptr(out))
+        ctx.topo, ctx.d, ctx.tail = topo, d, tail
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        topo = ctx.topo
+        out = torch.empty((topo.n_atoms, topo.max_row) + ctx.tail, device=g.device)
+        call("csr_to_nef", ptr(g.contiguous()), ptr(topo.row_ptr), topo.n_atoms, topo.n_edges,
+             topo.max_row, ctx.d, ptr(out))
+        return out, None
+
+
+# ------------------------------------------------------------------------ the module
+class B200PETBackend(PETParameters):
+    """CUDA (sm_100a) implementation of the PET tensor backend.
+
+    :param hypers: PET ``ModelHypers`` (``src/metatrain/pet/documentation.py:156-259``).
+    :param atomic_types: sorted list of supported atomic numbers.
+    :param precision: GEMM arithmetic — ``"fp32"`` (FFMA, parity reference),
+        ``"bf16x3"`` (tcgen05, 2-term bf16 split, fp32 accumulate; meets 1e-4 eV/A) or
+        ``"bf16"`` (single-pass tcgen05; fast, ~1e-2 eV/A).
+    """
+
+    NUM_FEATURE_TYPES: int = 2
+
+    def __init__(self, hypers: dict, atomic_types: List[int], precision: str = "fp32") -> None:
+        # same validation and exception types as the reference
+        if hypers["normalization"] not in _AVAILABLE_NORMALIZATIONS:  # transformer.py:329-333
+            raise ValueError(f"Unknown normalization flag: {hypers['normalization']}. "
+                             f"Please choose from: {_AVAILABLE_NORMALIZATIONS}")
+        if hypers["transformer_type"] not in _AVAILABLE_TRANSFORMER_TYPES:  # :335-339
+            raise ValueError(f"Unknown transformer flag: {hypers['transformer_type']}. "
+                             f"Please choose from: {_AVAILABLE_TRANSFORMER_TYPES}")
+        if hypers["activation"] not in _AVAILABLE_ACTIVATIONS:  # :342-346
+            raise ValueError(f"Unknown activation flag: {hypers['activation']}. "
+                             f"Please choose from: {_AVAILABLE_ACTIVATIONS}")
+        if hypers["d_pet"] % hypers["num_heads"] != 0:  # transformer.py:80-81
+            raise ValueError("total dimension is not divisible by the number of heads")
+        if hypers["cutoff_function"].lower() not in ("bump", "cosine"):  # structures.py:312-316
+            raise ValueError(f"Unknown cutoff function type: {hypers['cutoff_function']}. "
+                             f"Supported types are 'Cosine' and 'Bump'.")
+        unsupported = []
+        if hypers["normalization"] != "RMSNorm":
+            unsupported.append("normalization=" + hypers["normalization"])
+        if hypers["transformer_type"] != "PreLN":
+            unsupported.append("transformer_type=" + hypers["transformer_type"])
+        if hypers["activation"] != "SwiGLU":
+            unsupported.append("activation=" + hypers["activation"])
+        if hypers["featurizer_type"] != "feedforward":
+            unsupported.append("featurizer_type=" + str(hypers["featurizer_type"]))
+        if hypers.get("num_neighbors_adaptive") is not None:
+            unsupported.append("num_neighbors_adaptive (adaptive cutoff)")
+        if hypers.get("system_conditioning"):
+            unsupported.append("system_conditioning")
+        if (hypers["d_pet"], hypers["d_node"], hypers["d_head"], hypers["num_heads"]) != (128, 256, 128, 8):
+            unsupported.append("d_pet/d_node/d_head/num_heads other than 128/256/128/8")
+        if hypers["d_feedforward"] % 64 != 0:
+            unsupported.append("d_feedforward not a multiple of 64")
+        if unsupported:
+            raise NotImplementedError(
+                "B200PETBackend: not built yet (SURVEY.md 8(f).4): " + ", ".join(unsupported))
+        if precision not in _PRECISIONS:
+            raise ValueError(f"unknown precision {precision!r}; choose from {list(_PRECISIONS)}")
+        super().__init__(hypers, atomic_types)
+        self.hypers = dict(hypers)
+        self.nl_is_strict = bool(hypers["long_range"]["enable"])
+        self.cutoff = float(hypers["cutoff"])
+        self.cutoff_function = hypers["cutoff_function"]
+        self.cutoff_width = float(hypers["cutoff_width"])
+        self.num_heads = int(hypers["num_heads"])
+        self.system_conditioning = None
+        self._precision = _PRECISIONS[precision]
+        self._cutoff_id = CUTOFF_BUMP if self.cutoff_function.lower() == "bump" else CUTOFF_COSINE
+        self._pw: Optional[engine.PackedWeights] = None
+        #: also emit the reference's padded NEF tensors from preprocess()/calculate_features()
+        #: (needed by the PET wrapper for feature / diagnostic outputs; energies+forces
+        #: only need the CSR handles)
+        self.emit_nef = True
+
+    # ------------------------------------------------------------------ internals
+    def set_precision(self, precision: str) -> None:
+        self._precision = _PRECISIONS[precision]
+
+    def _packed(self) -> engine.PackedWeights:
+        if self._pw is None or not self._pw.is_current(self):
+            self._pw = engine.PackedWeights(self)
+        return self._pw
+
+    def _check_inference(self) -> None:
+        if self.training and torch.is_grad_enabled() and any(
+                p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "B200PETBackend: weight gradients / double backward (training) are not built "
+                "yet (SURVEY.md 8(f).3); call .eval() or freeze the parameters")
+
+    # ------------------------------------------------------------------ stage 1
+    def preprocess(
+        self,
+        positions: Tensor,
+        centers: Tensor,
+        neighbors: Tensor,
+        species: Tensor,
+        cells: Tensor,
+        cell_shifts: Tensor,
+        system_indices: Tensor,
+        cutoff_width_adaptive: float = 1.0,
+    ) -> Dict[str, Tensor]:
+        """Same signature and returned keys as ``PETBackend.preprocess`` (backend.py:238)."""
+        _require_cuda(positions, "preprocess")
+        z_nodes = self.species_to_species_index[species.long()]
+        topo = engine.build_topology(positions, centers, neighbors, cell_shifts, cells,
+                                     system_indices, z_nodes, self.cutoff)
+        vec, dist, fc = _EdgeGeometry.apply(positions, cells, topo, self.cutoff,
+                                            self.cutoff_width, self._cutoff_id)
+        if not self.emit_nef:
+            batch_data = {"element_indices_nodes": z_nodes}
+        else:
+            batch_data = self._nef_batch_data(topo, positions, z_nodes, vec, dist, fc)
+        # CSR handles consumed by calculate_features / predict (not part of the reference's
+        # dictionary; plain tensors + one opaque python attribute)
+        vec._petb200_topology = topo
+        batch_data["_petb200_vec"] = vec
+        batch_data["_petb200_dist"] = dist
+        batch_data["_petb200_fc"] = fc
+        return batch_data
+
+    def _nef_batch_data(self, topo, positions, z_nodes, vec, dist, fc) -> Dict[str, Tensor]:
+        """The padded NEF view of the batch that ``PET.forward`` may read
+        (model.py:436-459,512-513,545,560); derived from the CSR data."""
+        n, m = topo.n_atoms, topo.max_row
+        counts = (topo.row_ptr[1:] - topo.row_ptr[:-1]).long()
+        mask = torch.arange(m, device=positions.device)[None, :] < counts[:, None]
+        slot = torch.arange(topo.n_edges, device=positions.device) - topo.row_ptr[:-1].long()[topo.ctr.long()]
+        z_nbr_nef = torch.zeros((n, m), device=positions.device, dtype=torch.long)
+        rev_flat = torch.arange(n * m, device=positions.device).reshape(n, m).clone()
+        if topo.n_edges > 0:
+            ctr_l, rev_l = topo.ctr.long(), topo.rev.long()
+            z_nbr_nef[ctr_l, slot] = topo.z_neighbors.long()
+            rev_flat[ctr_l, slot] = ctr_l[rev_l] * m + slot[rev_l]
+        vec_nef = _CsrToNef.apply(vec, topo)
+        dist_nef = _CsrToNef.apply(dist, topo)
+        # the reference's padded distances are sqrt(0 + 1e-15) (structures.py:330)
+        dist_nef = torch.where(mask, dist_nef, torch.full_like(dist_nef, 1e-15 ** 0.5))
+        batch_data: Dict[str, Tensor] = {
+            "element_indices_nodes": z_nodes,
+            "element_indices_neighbors": z_nbr_nef,
+            "edge_vectors": vec_nef,
+            "edge_distances": dist_nef,
+            "padding_mask": mask,
+            "reverse_neighbor_index": rev_flat,
+            "cutoff_factors": _CsrToNef.apply(fc, topo),
+            "atomic_cutoffs_stats": torch.full((n,), self.cutoff, device=positions.device,
+                                               dtype=positions.dtype),
+            "centers": topo.ctr.long(),
+            "neighbors": topo.col.long(),
+            "nef_to_edges_neighbor": slot,
+            "cell_shifts": topo.shift,
+        }
+        return batch_data
+
+    @staticmethod
+    def _topology_of(batch_data: Dict[str, Tensor]) -> engine.Topology:
+        try:
+            return batch_data["_petb200_vec"]._petb200_topology
+        except (KeyError, AttributeError):
+            raise RuntimeError(
+                "B200PETBackend: batch_data was not produced by this backend's preprocess() "
+                "(CSR handles missing)") from None
+
+    # ------------------------------------------------------------------ stage 2
+    def calculate_features(
+        self, batch_data: Dict[str, Tensor], capture_diagnostics: bool = False
+    ) -> Tuple[List[Tensor], List[Tensor]]:
+        """Same contract as ``PETBackend.calculate_features`` (backend.py:344): returns
+        ``([node features [N, d_node]], [edge features [N, M, d_pet]])``."""
+        if capture_diagnostics:
+            raise NotImplementedError("B200PETBackend: diagnostic feature capture is not built")
+        self._check_inference()
+        topo = self._topology_of(batch_data)
+        h, m = _Features.apply(batch_data["_petb200_vec"], batch_data["_petb200_dist"],
+                               batch_data["_petb200_fc"], self, topo)
+        if not self.emit_nef:
+            return [h], [m]  # CSR [E, d_pet]; predict() recognises it by its rank
+        m_nef = _CsrToNef.apply(m, topo)
+        m_nef._petb200_csr = m  # lets predict() skip the NEF round trip
+        return [h], [m_nef]
+
+    # ------------------------------------------------------------------ stage 3
+    def predict(
+        self,
+        node_features_list: List[Tensor],
+        edge_features_list: List[Tensor],
+        batch_data: Dict[str, Tensor],
+        cells: Tensor,
+        system_indices: Tensor,
+        requested_output_names: List[str],
+    ) -> Tuple[Dict[str, List[Tensor]], Dict[str, List[Tensor]], Dict[str, List[Tensor]]]:
+        """Same contract as ``PETBackend.predict`` (backend.py:420).  The last-layer
+        feature dictionaries are returned empty (only needed for ``mtt::aux`` outputs)."""
+        self._check_inference()
+        topo = self._topology_of(batch_data)
+        fc = batch_data["_petb200_fc"]
+        h = node_features_list[0]
+        m_in = edge_features_list[0]
+        m = getattr(m_in, "_petb200_csr", None)
+        if m is None:
+            m = m_in if m_in.dim() == 2 else _NefToCsr.apply(m_in, topo)
+        atomic_predictions: Dict[str, List[Tensor]] = {}
+        for name in self.node_last_layers.keys():
+            if name not in requested_output_names:
+                continue
+            if name == "non_conservative_stress":
+                raise NotImplementedError("B200PETBackend: non_conservative_stress is not built")
+            atomic = _Predict.apply(h, m, fc, self, topo, name)
+            sizes = self._packed().heads[name]["block_sizes"]
+            atomic_predictions[name] = list(torch.split(atomic, sizes, dim=1))
+        return atomic_predictions, {}, {}

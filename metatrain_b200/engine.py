@@ -1,0 +1,456 @@
+"""Host-side sequencing of the PET forward/backward engine over the C ABI.
+
+Everything numerical happens in ``libpetb200.so``; this file only allocates buffers
+(``torch.empty`` — PyTorch is the device-memory and stream plumbing) and calls the entry
+points of ``include/petb200.h`` in order.  The backward pass is hand-scheduled (no autograd
+inside a stage); ``metatrain_b200/backend.py`` wraps the three stages of the reference's
+tensor backend (``PETBackend.preprocess / calculate_features / predict``,
+``src/metatrain/pet/modules/backend.py:238,344,420``) as ``torch.autograd.Function``s so
+that ``torch.autograd.grad(E, positions)`` (``src/metatrain/utils/output_gradient.py:34-40``)
+keeps working unchanged.
+
+Equations: SURVEY.md Appendix A (derived from the cited reference lines).
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib
+from .lib import (EPI_MUL_DSILU, EPI_NONE, EPI_SILU, EPI_SWIGLU, EPI_SWIGLU_BWD, PREC_FP32,
+                  call, ptr)
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------- helpers
+def _empty(shape, like: Tensor, dtype=torch.float32) -> Tensor:
+    return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+def gemm(a: Tensor, w: Tensor, out: Tensor, *, bias=None, row_scale=None, residual=None,
+         aux_in=None, aux_out=None, epilogue=EPI_NONE, accumulate=False,
+         precision=PREC_FP32) -> Tensor:
+    """out = epilogue(row_scale * (a @ w.T) + bias) (+ residual).  2-D views with unit
+    inner stride are allowed for every operand (leading dimension = stride(0))."""
+    m, k = a.shape
+    n = w.shape[0]
+    assert w.shape[1] == k and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    aux = aux_in if aux_in is not None else aux_out
+    call(
+        "gemm", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), m, n, k,
+        ptr(bias), ptr(row_scale), ptr(residual),
+        residual.stride(0) if residual is not None else 0,
+        ptr(aux_in), ptr(aux_out), aux.stride(0) if aux is not None else 0,
+        epilogue, int(accumulate), precision,
+    )
+    return out
+
+
+# ---------------------------------------------------------------------------- topology
+@dataclass
+class Topology:
+    """CSR edge topology of one batch (all index tensors int32, on the device)."""
+    n_atoms: int
+    n_edges: int
+    n_structures: int
+    max_row: int              # largest neighbour count of any atom (= NEF width M)
+    row_ptr: Tensor           # [N+1]
+    ctr: Tensor               # [E] centre atom of each edge
+    col: Tensor               # [E] neighbour atom
+    rev: Tensor               # [E] index of the reversed edge
+    shift: Tensor             # [E,3] cell shifts
+    system_of_atom: Tensor    # [N]
+    z_nodes: Tensor           # [N] species index of each atom
+    z_neighbors: Tensor       # [E] species index of each edge's neighbour
+    perm: Tensor              # [E] index of each CSR edge in the caller's neighbor list
+
+
+def build_topology(positions: Tensor, centers: Tensor, neighbors: Tensor, cell_shifts: Tensor,
+                   cells: Tensor, system_indices: Tensor, z_nodes: Tensor, cutoff: float,
+                   check_symmetric: bool = True) -> Topology:
+    """a4-a6 of SURVEY.md 8(a): filter pairs beyond the cutoff, CSR by centre (stable),
+    reverse-edge map.  One device->host read of (E, max neighbours, missing reverses) —
+    the reference syncs at the same place (structures.py:292-294)."""
+    dev = positions.device
+    n_atoms = positions.shape[0]
+    n_pairs = centers.shape[0]
+    i32 = torch.int32
+    centers = centers.to(i32).contiguous()
+    neighbors = neighbors.to(i32).contiguous()
+    cell_shifts = cell_shifts.to(i32).contiguous()
+    sys_atom = system_indices.to(i32).contiguous()
+    pos = positions.detach().to(torch.float32).contiguous()
+    cells32 = cells.detach().to(torch.float32).contiguous()
+
+    keep = torch.empty(max(n_pairs, 1), device=dev, dtype=i32)
+    counts = torch.zeros(n_atoms + 1, device=dev, dtype=i32)
+    call("nl_filter_count", ptr(pos), ptr(cells32), ptr(sys_atom), ptr(centers), ptr(neighbors),
+         ptr(cell_shifts), n_pairs, n_atoms, float(cutoff), ptr(keep), ptr(counts))
+    ws_bytes = lib.load().petb200_csr_build_workspace(n_pairs, n_atoms)
+    workspace = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    row_ptr = torch.empty(n_atoms + 1, device=dev, dtype=i32)
+    perm = torch.empty(max(n_pairs, 1), device=dev, dtype=i32)
+    stats = torch.zeros(3, device=dev, dtype=i32)  # E_kept, max row, missing reverses
+    call("csr_build", ptr(centers), ptr(keep), ptr(counts), n_pairs, n_atoms, ptr(row_ptr),
+         ptr(perm), ptr(stats), ptr(workspace), ws_bytes)
+    # the edge count sizes every later buffer: one small D2H read
+    n_edges, max_row = (int(v) for v in stats[:2].tolist())
+    ctr = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
+    col = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
+    shift = torch.empty((max(n_edges, 1), 3), device=dev, dtype=i32)[:n_edges]
+    rev = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
+    call("csr_gather", ptr(perm), ptr(centers), ptr(neighbors), ptr(cell_shifts), n_edges,
+         ptr(ctr), ptr(col), ptr(shift))
+    call("reverse_map", ptr(row_ptr), ptr(ctr), ptr(col), ptr(shift), n_edges, ptr(rev),
+         ptr(stats[2:]))
+    if check_symmetric and n_edges > 0:
+        missing = int(stats[2].item())
+        if missing:
+            raise ValueError(
+                f"neighbor list is not symmetric: {missing} edges have no reversed edge "
+                "(PET needs a full list, src/metatrain/pet/model.py:99-104)")
+    z_nodes = z_nodes.to(i32).contiguous()
+    z_neighbors = z_nodes[col.long()] if n_edges > 0 else torch.empty(0, device=dev, dtype=i32)
+    n_structures = cells.shape[0]
+    return Topology(n_atoms, n_edges, n_structures, max_row, row_ptr, ctr, col, rev, shift,
+                    sys_atom, z_nodes, z_neighbors.contiguous(), perm[:n_edges])
+
+
+# ---------------------------------------------------------------------- weight packing
+def _t_and_scaled(weight: Tensor, col_scale: Optional[Tensor] = None, want_scaled=False):
+    """(W * diag(col_scale))^T and optionally the scaled copy, via petb200_transpose_scale."""
+    rows, cols = weight.shape
+    w = weight.detach().contiguous()
+    out_t = torch.empty((cols, rows), device=w.device, dtype=torch.float32)
+    out_s = torch.empty_like(w) if want_scaled else None
+    call("transpose_scale", ptr(w), rows, cols,
+         ptr(col_scale.detach().contiguous()) if col_scale is not None else None,
+         ptr(out_t), ptr(out_s))
+    return out_t, out_s
+
+
+class PackedWeights:
+    """Device-side views/derivatives of the module parameters the kernels consume:
+    RMSNorm weights folded into the following Linear (W.diag(gamma)), and W^T for every
+    dgrad contraction.  Rebuilt whenever a parameter's storage or version changes."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.signature = self._signature(module)
+        g = lambda t: t.detach()  # noqa: E731
+        self.gnn: List[dict] = []
+        for layer in module.gnn_layers:
+            L: dict = {}
+            L["w_geo"] = g(layer.edge_embedder.weight).contiguous()
+            L["b_geo"] = g(layer.edge_embedder.bias)
+            L["w1"] = g(layer.compress[0].weight)
+            L["b1"] = g(layer.compress[0].bias)
+            L["w1_t"], _ = _t_and_scaled(layer.compress[0].weight)
+            L["w2"] = g(layer.compress[2].weight)
+            L["b2"] = g(layer.compress[2].bias)
+            L["w2_t"], _ = _t_and_scaled(layer.compress[2].weight)
+            L["nbr"] = (g(layer.neighbor_embedder.weight).contiguous()
+                        if hasattr(layer, "neighbor_embedder") else None)
+            L["tl"] = []
+            for tl in layer.trans.layers:
+                T: dict = {}
+                T["w_qkv_t"], T["w_qkv"] = _t_and_scaled(
+                    tl.attention.input_linear.weight, tl.norm_attention.weight, True)
+                T["b_qkv"] = g(tl.attention.input_linear.bias)
+                T["w_o"] = g(tl.attention.output_linear.weight)
+                T["b_o"] = g(tl.attention.output_linear.bias)
+                T["w_o_t"], _ = _t_and_scaled(tl.attention.output_linear.weight)
+                T["w_in_t"], T["w_in"] = _t_and_scaled(tl.mlp.w_in.weight, tl.norm_mlp.weight, True)
+                T["b_in"] = g(tl.mlp.w_in.bias)
+                T["w_out"] = g(tl.mlp.w_out.weight)
+                T["b_out"] = g(tl.mlp.w_out.bias)
+                T["w_out_t"], _ = _t_and_scaled(tl.mlp.w_out.weight)
+                T["w_con"] = g(tl.center_contraction.weight)
+                T["b_con"] = g(tl.center_contraction.bias)
+                T["w_con_t"], _ = _t_and_scaled(tl.center_contraction.weight)
+                T["w_exp"] = g(tl.center_expansion.weight)
+                T["b_exp"] = g(tl.center_expansion.bias)
+                T["w_exp_t"], _ = _t_and_scaled(tl.center_expansion.weight)
+                T["wc_in_t"], T["wc_in"] = _t_and_scaled(
+                    tl.center_mlp.w_in.weight, tl.norm_center_features.weight, True)
+                T["bc_in"] = g(tl.center_mlp.w_in.bias)
+                T["wc_out"] = g(tl.center_mlp.w_out.weight)
+                T["bc_out"] = g(tl.center_mlp.w_out.bias)
+                T["wc_out_t"], _ = _t_and_scaled(tl.center_mlp.w_out.weight)
+                L["tl"].append(T)
+            self.gnn.append(L)
+        self.combine: List[dict] = []
+        for norm, mlp in zip(module.combination_norms, module.combination_mlps):
+            C: dict = {}
+            C["gamma"], C["beta"] = g(norm.weight), g(norm.bias)
+            C["w_a"], C["b_a"] = g(mlp[0].weight), g(mlp[0].bias)
+            C["w_b"], C["b_b"] = g(mlp[2].weight), g(mlp[2].bias)
+            C["w_a_t"], _ = _t_and_scaled(mlp[0].weight)
+            C["w_b_t"], _ = _t_and_scaled(mlp[2].weight)
+            self.combine.append(C)
+        self.node_emb = g(module.node_embedders[0].weight).contiguous()
+        self.edge_emb = g(module.edge_embedder.weight).contiguous()
+        self.heads: Dict[str, dict] = {}
+        for name in module.node_heads.keys():
+            H: dict = {}
+            nh, eh = module.node_heads[name][0], module.edge_heads[name][0]
+            for tag, head in (("n", nh), ("e", eh)):
+                H[tag + "1"], H[tag + "1_b"] = g(head[0].weight), g(head[0].bias)
+                H[tag + "2"], H[tag + "2_b"] = g(head[2].weight), g(head[2].bias)
+                H[tag + "1_t"], _ = _t_and_scaled(head[0].weight)
+                H[tag + "2_t"], _ = _t_and_scaled(head[2].weight)
+            keys = list(module.node_last_layers[name][0].keys())
+            H["block_keys"] = keys
+            H["block_sizes"] = [module.node_last_layers[name][0][k].weight.shape[0] for k in keys]
+            H["wn"] = torch.cat([g(module.node_last_layers[name][0][k].weight) for k in keys]).contiguous()
+            H["bn"] = torch.cat([g(module.node_last_layers[name][0][k].bias) for k in keys]).contiguous()
+            H["we"] = torch.cat([g(module.edge_last_layers[name][0][k].weight) for k in keys]).contiguous()
+            H["be"] = torch.cat([g(module.edge_last_layers[name][0][k].bias) for k in keys]).contiguous()
+            self.heads[name] = H
+
+    @staticmethod
+    def _signature(module):
+        return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+    def is_current(self, module) -> bool:
+        return self.signature == self._signature(module)
+
+
+# ---------------------------------------------------------------------------- geometry
+def edges_forward(topo: Topology, positions: Tensor, cells: Tensor, cutoff, width, func):
+    E = topo.n_edges
+    vec = _empty((E, 3), positions)
+    dist = _empty((E,), positions)
+    fc = _empty((E,), positions)
+    call("edges_fwd", ptr(positions), ptr(cells), ptr(topo.system_of_atom), ptr(topo.ctr),
+         ptr(topo.col), ptr(topo.shift), E, float(cutoff), float(width), func,
+         ptr(vec), ptr(dist), ptr(fc))
+    return vec, dist, fc
+
+
+def edges_backward(topo: Topology, vec, dist, d_vec, d_dist, d_fc, cutoff, width, func,
+                   need_cells: bool):
+    E, N = topo.n_edges, topo.n_atoms
+    scratch = _empty((max(E, 1), 3), vec)
+    d_pos = _empty((N, 3), vec)
+    d_cells = torch.zeros((topo.n_structures, 3, 3), device=vec.device) if need_cells else None
+    call("edges_bwd", ptr(d_vec), ptr(d_dist), ptr(d_fc), ptr(vec), ptr(dist), ptr(topo.row_ptr),
+         ptr(topo.ctr), ptr(topo.rev), ptr(topo.shift), ptr(topo.system_of_atom), N, E,
+         float(cutoff), float(width), func, ptr(scratch), ptr(d_pos), ptr(d_cells))
+    return d_pos, d_cells
+
+
+# ---------------------------------------------------------------------------- features
+def _rstd(x: Tensor) -> Tensor:
+    out = _empty((x.shape[0],), x)
+    call("rms_rstd", ptr(x), x.shape[0], x.shape[1], ptr(out))
+    return out
+
+
+def _rms_bwd(d_xhat, x, rstd, base, out):
+    call("rms_bwd", ptr(d_xhat), ptr(x), ptr(rstd), ptr(base), x.shape[0], x.shape[1], ptr(out))
+    return out
+
+
+def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32):
+    """backend.py:496-587 + transformer.py:463-562,203-234 on the CSR layout.
+    Returns (node features [N,d_node], edge messages [E,d_pet], saved-for-backward)."""
+    N, E = topo.n_atoms, topo.n_edges
+    d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
+    scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    h = _empty((N, dn), vec)
+    call("embedding", ptr(pw.node_emb), ptr(topo.z_nodes), N, dn, ptr(h), dn)
+    m = _empty((E, d), vec)
+    call("embedding", ptr(pw.edge_emb), ptr(topo.z_neighbors), E, d, ptr(m), d)
+    saved = []
+    for l, (L, C) in enumerate(zip(pw.gnn, pw.combine)):
+        S: dict = {"tl": []}
+        width = 3 * d if L["nbr"] is not None else 2 * d
+        cat = _empty((E, width), vec)
+        call("compress_input", ptr(vec), ptr(dist), ptr(L["w_geo"]), ptr(L["b_geo"]),
+             ptr(L["nbr"]), ptr(topo.z_neighbors), ptr(m), E, d, ptr(cat))
+        c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
+        gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec)
+        del cat
+        X = _empty((E + N, d), vec)
+        gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec)
+        del a1
+        S["c1"] = c1
+        for T in L["tl"]:
+            K: dict = {}
+            gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec)
+            rstd1 = _rstd(X)
+            qkv = _empty((E + N, 3 * d), vec)
+            gemm(X, T["w_qkv"], qkv, bias=T["b_qkv"], row_scale=rstd1, precision=prec)
+            o = _empty((E + N, d), vec)
+            lse = _empty((E + N, nh), vec)
+            call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,
+                 scale, topo.max_row, ptr(o), ptr(lse))
+            Xn = _empty((E + N, d), vec)  # rows [:E] = t' ; rows [E:] = next centre token
+            gemm(o[:E], T["w_o"], Xn[:E], bias=T["b_o"], residual=X[:E], precision=prec)
+            yc = _empty((N, d), vec)
+            gemm(o[E:], T["w_o"], yc, bias=T["b_o"], precision=prec)
+            h1 = _empty((N, dn), vec)
+            gemm(yc, T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec)
+            # centre MLP (d_node -> 4 d_node -> d_node, SwiGLU)
+            rstd3 = _rstd(h1)
+            ugc = _empty((N, 4 * dn), vec)
+            sc = _empty((N, 2 * dn), vec)
+            gemm(h1, T["wc_in"], sc, bias=T["bc_in"], row_scale=rstd3, epilogue=EPI_SWIGLU,
+                 aux_out=ugc, precision=prec)
+            h2 = _empty((N, dn), vec)
+            gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec)
+            # edge MLP (d_pet -> 2 d_ff -> d_pet, SwiGLU)
+            tp = Xn[:E]
+            rstd2 = _rstd(tp)
+            dff = T["w_out"].shape[1]
+            ug = _empty((E, 2 * dff), vec)
+            s = _empty((E, dff), vec)
+            gemm(tp, T["w_in"], s, bias=T["b_in"], row_scale=rstd2, epilogue=EPI_SWIGLU,
+                 aux_out=ug, precision=prec)
+            Xnn = _empty((E + N, d), vec)
+            gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec)
+            del s, sc
+            K.update(X=X, rstd1=rstd1, qkv=qkv, o=o, lse=lse, tp=tp, rstd2=rstd2, ug=ug,
+                     h1=h1, rstd3=rstd3, ugc=ugc)
+            S["tl"].append(K)
+            X, h = Xnn, h2
+        t = X[:E]
+        cc = _empty((E, 2 * d), vec)
+        mean, rstd = _empty((E,), vec), _empty((E,), vec)
+        call("combine_ln_fwd", ptr(t), ptr(topo.rev), ptr(C["gamma"]), ptr(C["beta"]), E, d,
+             ptr(cc), ptr(mean), ptr(rstd))
+        p1, q1 = _empty((E, 2 * d), vec), _empty((E, 2 * d), vec)
+        gemm(cc, C["w_a"], q1, bias=C["b_a"], epilogue=EPI_SILU, aux_out=p1, precision=prec)
+        del cc
+        # m <- m + t + W_b q1 + b_b   (in place on our own message buffer)
+        gemm(q1, C["w_b"], m, bias=C["b_b"], residual=t, accumulate=True, precision=prec)
+        del q1
+        S.update(t=t, mean=mean, rstd=rstd, p1=p1)
+        saved.append(S)
+    return h, m, saved
+
+
+def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_m,
+                      prec=PREC_FP32):
+    """Hand-scheduled dgrad of :func:`features_forward`.  Consumes d_h
+    [N,d_node] and d_m [E,d_pet]; returns (d_vec [E,3], d_dist [E], d_fc [E])."""
+    N, E = topo.n_atoms, topo.n_edges
+    d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
+    scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    ref = fc
+    d_vec = torch.zeros((E, 3), device=ref.device)
+    d_dist = torch.zeros((E,), device=ref.device)
+    d_fc = torch.zeros((E,), device=ref.device)
+    d_m = d_m.contiguous().clone()  # accumulated in place below
+    d_h = d_h.contiguous()
+    n_layers = len(pw.gnn)
+    for l in range(n_layers - 1, -1, -1):
+        L, C, S = pw.gnn[l], pw.combine[l], saved[l]
+        # ---- message update:  m_out = m_in + t + W_b silu(W_a LN(cat[t, t_rev]) + b_a) + b_b
+        d_p1 = _empty((E, 2 * d), ref)
+        gemm(d_m, C["w_b_t"], d_p1, epilogue=EPI_MUL_DSILU, aux_in=S["p1"], precision=prec)
+        d_cc = _empty((E, 2 * d), ref)
+        gemm(d_p1, C["w_a_t"], d_cc, precision=prec)
+        d_cat = d_p1  # reuse
+        call("combine_ln_bwd", ptr(d_cc), ptr(S["t"]), ptr(topo.rev), ptr(C["gamma"]),
+             ptr(S["mean"]), ptr(S["rstd"]), E, d, ptr(d_cat))
+        d_t = _empty((E, d), ref)
+        call("combine_scatter_bwd", ptr(d_cat), ptr(d_m), ptr(topo.rev), E, d, ptr(d_t))
+        del d_cc, d_cat, d_p1
+        for k in range(len(L["tl"]) - 1, -1, -1):
+            T, K = L["tl"][k], S["tl"][k]
+            dff = T["w_out"].shape[1]
+            # ---- edge MLP: t'' = t' + W_out swiglu(W_in rms(t'))
+            d_ug = _empty((E, 2 * dff), ref)
+            gemm(d_t, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec)
+            d_xh = _empty((E, d), ref)
+            gemm(d_ug, T["w_in_t"], d_xh, precision=prec)
+            del d_ug
+            d_tp = _empty((E, d), ref)
+            _rms_bwd(d_xh, K["tp"], K["rstd2"], d_t, d_tp)
+            # ---- centre MLP: h2 = h1 + Wc_out swiglu(Wc_in rms(h1))
+            d_ugc = _empty((N, 4 * dn), ref)
+            gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec)
+            d_xhc = _empty((N, dn), ref)
+            gemm(d_ugc, T["wc_in_t"], d_xhc, precision=prec)
+            d_h1 = _empty((N, dn), ref)
+            _rms_bwd(d_xhc, K["h1"], K["rstd3"], d_h, d_h1)
+            # ---- h1 = h + W_exp y_c ;  t' = t + y_e ;  y = W_o o
+            d_yc = _empty((N, d), ref)
+            gemm(d_h1, T["w_exp_t"], d_yc, precision=prec)
+            d_o = _empty((E + N, d), ref)
+            gemm(d_tp, T["w_o_t"], d_o[:E], precision=prec)
+            gemm(d_yc, T["w_o_t"], d_o[E:], precision=prec)
+            d_qkv = _empty((E + N, 3 * d), ref)
+            call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o),
+                 ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row,
+                 ptr(d_qkv), ptr(d_fc))
+            d_xh1 = d_o  # reuse
+            gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec)
+            del d_qkv
+            d_t_new = d_xh  # reuse
+            _rms_bwd(d_xh1[:E], K["X"][:E], K["rstd1"][:E], d_tp, d_t_new)
+            d_c = d_yc  # reuse
+            _rms_bwd(d_xh1[E:], K["X"][E:], K["rstd1"][E:], None, d_c)
+            if l > 0 or k > 0:
+                d_h_new = _empty((N, dn), ref)
+                gemm(d_c, T["w_con_t"], d_h_new, residual=d_h1, precision=prec)
+                d_h = d_h_new
+            d_t = d_t_new
+        # ---- token builder: t = W_2 silu(W_1 cat[geo, nbr, m] + b_1) + b_2
+        d_c1 = _empty((E, d), ref)
+        gemm(d_t, L["w2_t"], d_c1, epilogue=EPI_MUL_DSILU, aux_in=S["c1"], precision=prec)
+        d_geo = _empty((E, d), ref)
+        gemm(d_c1, L["w1_t"][:d], d_geo, precision=prec)
+        call("geom_embed_bwd", ptr(d_geo), d, ptr(L["w_geo"]), E, d, 1, ptr(d_vec), ptr(d_dist))
+        if l > 0:
+            width = L["w1_t"].shape[0]
+            gemm(d_c1, L["w1_t"][width - d:], d_m, accumulate=True, precision=prec)
+    return d_vec, d_dist, d_fc
+
+
+# ----------------------------------------------------------------------------- readout
+def predict_forward(pw: PackedWeights, topo: Topology, name: str, h, m, fc, prec=PREC_FP32):
+    """backend.py:651-777 for one target: heads, last layers, sum_j f_ij e_ij."""
+    H = pw.heads[name]
+    N, E = topo.n_atoms, topo.n_edges
+    dh = H["n2"].shape[0]
+    n1, n1p = _empty((N, dh), h), _empty((N, dh), h)
+    gemm(h, H["n1"], n1, bias=H["n1_b"], epilogue=EPI_SILU, aux_out=n1p, precision=prec)
+    n2, n2p = _empty((N, dh), h), _empty((N, dh), h)
+    gemm(n1, H["n2"], n2, bias=H["n2_b"], epilogue=EPI_SILU, aux_out=n2p, precision=prec)
+    e1, e1p = _empty((E, dh), h), _empty((E, dh), h)
+    gemm(m, H["e1"], e1, bias=H["e1_b"], epilogue=EPI_SILU, aux_out=e1p, precision=prec)
+    e2, e2p = _empty((E, dh), h), _empty((E, dh), h)
+    gemm(e1, H["e2"], e2, bias=H["e2_b"], epilogue=EPI_SILU, aux_out=e2p, precision=prec)
+    n_out = H["wn"].shape[0]
+    atomic = _empty((N, n_out), h)
+    pe = _empty((E, n_out), h)
+    call("readout_fwd", ptr(n2), ptr(e2), ptr(H["wn"]), ptr(H["bn"]), ptr(H["we"]), ptr(H["be"]),
+         ptr(fc), ptr(topo.row_ptr), N, E, dh, n_out, ptr(atomic), ptr(pe))
+    saved = dict(n1p=n1p, n2p=n2p, e1p=e1p, e2p=e2p, pe=pe, n2=n2, e2=e2)
+    return atomic, saved
+
+
+def predict_backward(pw: PackedWeights, topo: Topology, name: str, fc, saved, d_atomic,
+                     prec=PREC_FP32):
+    H = pw.heads[name]
+    N, E = topo.n_atoms, topo.n_edges
+    dh = H["n2"].shape[0]
+    n_out = H["wn"].shape[0]
+    d_atomic = d_atomic.contiguous()
+    d_n2p, d_e2p = _empty((N, dh), fc), _empty((E, dh), fc)
+    d_fc = torch.zeros((E,), device=fc.device)
+    call("readout_bwd", ptr(d_atomic), ptr(saved["pe"]), ptr(H["wn"]), ptr(H["we"]), ptr(fc),
+         ptr(topo.ctr), ptr(saved["n2p"]), ptr(saved["e2p"]), N, E, dh, n_out, ptr(d_n2p),
+         ptr(d_e2p), ptr(d_fc))
+    d_n1p = _empty((N, dh), fc)
+    gemm(d_n2p, H["n2_t"], d_n1p, epilogue=EPI_MUL_DSILU, aux_in=saved["n1p"], precision=prec)
+    d_h = _empty((N, H["n1"].shape[1]), fc)
+    gemm(d_n1p, H["n1_t"], d_h, precision=prec)
+    d_e1p = _empty((E, dh), fc)
+    gemm(d_e2p, H["e2_t"], d_e1p, epilogue=EPI_MUL_DSILU, aux_in=saved["e1p"], precision=prec)
+    d_m = _empty((E, H["e1"].shape[1]), fc)
+    gemm(d_e1p, H["e1_t"], d_m, precision=prec)
+    return d_h, d_m, d_fc

@@ -1,0 +1,85 @@
+"""Energy + force evaluation through the backend: the plain-tensor mirror of
+``metatrain.utils.evaluate_model.evaluate_model`` (``src/metatrain/utils/evaluate_model.py:21-160``).
+
+Same recipe as the reference: re-leaf the positions (``_prepare_system``, ``:294-348``;
+optionally the strain trick ``:310-321``), run the three backend stages, sum per structure
+(``src/metatrain/utils/sum_over_atoms.py:31``), then ``torch.autograd.grad`` of the summed
+energies w.r.t. positions/strain (``src/metatrain/utils/output_gradient.py:34-40``).  The
+returned position gradient is **+dE/dr** like the reference's ``"positions"`` gradient
+block (``evaluate_model.py:128-141``); forces are its negative.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from .lib import call, ptr
+
+Tensor = torch.Tensor
+
+
+class _SumOverAtoms(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, atomic, struct_ptr, system_indices):
+        n_struct = struct_ptr.shape[0] - 1
+        out = torch.empty((n_struct, atomic.shape[1]), device=atomic.device)
+        call("sum_over_atoms", ptr(atomic.contiguous()), ptr(struct_ptr), n_struct,
+             atomic.shape[1], ptr(out))
+        ctx.save_for_backward(system_indices)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (system_indices,) = ctx.saved_tensors
+        return g[system_indices], None, None
+
+
+def sum_over_atoms(atomic: Tensor, system_indices: Tensor, n_structures: int) -> Tensor:
+    """Per-structure sums of per-atom predictions; atoms of a structure are contiguous
+    (they are, after ``concatenate_structures``, structures.py:17-112)."""
+    idx = system_indices.long()
+    counts = torch.bincount(idx, minlength=n_structures)
+    struct_ptr = torch.zeros(n_structures + 1, device=atomic.device, dtype=torch.int32)
+    struct_ptr[1:] = torch.cumsum(counts, 0)
+    return _SumOverAtoms.apply(atomic, struct_ptr, idx)
+
+
+def evaluate(
+    backend,
+    positions: Tensor,
+    centers: Tensor,
+    neighbors: Tensor,
+    species: Tensor,
+    cells: Tensor,
+    cell_shifts: Tensor,
+    system_indices: Tensor,
+    target: str = "energy",
+    gradients: bool = True,
+    strain: bool = False,
+) -> Dict[str, Tensor]:
+    """One energy(+forces, +strain gradient) evaluation of a batch of structures.
+
+    Returns ``energies [B, P]``, ``atomic [N, P]`` and, if requested, ``dE_dpos [N, 3]``
+    and ``dE_dstrain [3, 3]`` (a single strain shared by the batch).
+    """
+    pos = positions.detach().clone().requires_grad_(gradients)
+    pos_in, cells_in = pos, cells
+    eps: Optional[Tensor] = None
+    if strain:
+        eps = torch.eye(3, device=pos.device, dtype=pos.dtype, requires_grad=True)
+        pos_in = pos @ eps
+        cells_in = cells @ eps
+    batch = backend.preprocess(pos_in, centers, neighbors, species, cells_in, cell_shifts,
+                               system_indices, 1.0)
+    nodes, edges = backend.calculate_features(batch)
+    pred, _, _ = backend.predict(nodes, edges, batch, cells_in, system_indices, [target])
+    atomic = torch.cat(pred[target], dim=1) if len(pred[target]) > 1 else pred[target][0]
+    energies = sum_over_atoms(atomic, system_indices, cells.shape[0])
+    out = {"energies": energies.detach(), "atomic": atomic.detach()}
+    if gradients:
+        wrt = [pos] + ([eps] if strain else [])
+        grads = torch.autograd.grad(
+            [energies], wrt, grad_outputs=[torch.ones_like(energies)])
+        out["dE_dpos"] = grads[0]
+        if strain:
+            out["dE_dstrain"] = grads[1]
+    return out

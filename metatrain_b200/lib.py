@@ -1,0 +1,114 @@
+"""ctypes binding of ``libpetb200.so`` (the C ABI declared in ``include/petb200.h``).
+
+There is deliberately no CPU or PyTorch fallback: if the shared library is missing or a
+call fails, a ``RuntimeError`` is raised (the reference's CLI wraps such errors as
+``ArchitectureError``, ``src/metatrain/utils/errors.py:1-19``).
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+import torch
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+_LIB_PATH = os.path.join(_CSRC, "libpetb200.so")
+_lock = threading.Lock()
+_lib = None
+
+# enums of include/petb200.h
+EPI_NONE, EPI_SILU, EPI_SWIGLU, EPI_MUL_DSILU, EPI_SWIGLU_BWD = range(5)
+PREC_FP32, PREC_BF16X3, PREC_BF16 = range(3)
+CUTOFF_BUMP, CUTOFF_COSINE = range(2)
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I = ctypes.c_int
+_F = ctypes.c_float
+_SZ = ctypes.c_size_t
+
+# name -> argument ctypes (return type is int unless listed in _RESTYPE)
+_SIGNATURES = {
+    "petb200_nl_filter_count": [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _P, _P, _P],
+    "petb200_csr_build_workspace": [_I64, _I64],
+    "petb200_csr_build": [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, _SZ, _P],
+    "petb200_csr_gather": [_P, _P, _P, _P, _I64, _P, _P, _P, _P],
+    "petb200_reverse_map": [_P, _P, _P, _P, _I64, _P, _P, _P],
+    "petb200_csr_to_nef": [_P, _P, _I64, _I64, _I, _I, _P, _P],
+    "petb200_nef_to_csr": [_P, _P, _P, _I64, _I64, _I, _I, _P, _P],
+    "petb200_edges_fwd": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _I, _P, _P, _P, _P],
+    "petb200_edges_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _I,
+                          _P, _P, _P, _P],
+    "petb200_gemm": [_P, _I64, _P, _I64, _P, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P,
+                     _I64, _I, _I, _I, _P],
+    "petb200_embedding": [_P, _P, _I64, _I, _P, _I64, _P],
+    "petb200_transpose_scale": [_P, _I, _I, _P, _P, _P, _P],
+    "petb200_compress_input": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
+    "petb200_geom_embed_bwd": [_P, _I64, _P, _I64, _I, _I, _P, _P, _P],
+    "petb200_rms_rstd": [_P, _I64, _I, _P, _P],
+    "petb200_rms_bwd": [_P, _P, _P, _P, _I64, _I, _P, _P],
+    "petb200_attention_fwd": [_P, _P, _P, _I64, _I64, _I, _I, _F, _I, _P, _P, _P],
+    "petb200_attention_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _I, _P, _P, _P],
+    "petb200_combine_ln_fwd": [_P, _P, _P, _P, _I64, _I, _P, _P, _P, _P],
+    "petb200_combine_ln_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
+    "petb200_combine_scatter_bwd": [_P, _P, _P, _I64, _I, _P, _P],
+    "petb200_readout_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P],
+    "petb200_readout_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P, _P],
+    "petb200_sum_over_atoms": [_P, _P, _I64, _I, _P, _P],
+    "petb200_last_error": [],
+    "petb200_version": [],
+}
+_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_last_error": ctypes.c_char_p}
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def build(verbose: bool = False) -> str:
+    """Compile ``libpetb200.so`` in-tree for sm_100a (``make`` in ``csrc/``)."""
+    proc = subprocess.run(["make", "-C", _CSRC, "-j8"], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("building libpetb200.so failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stdout)
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (once).  Raises ``RuntimeError`` if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(_LIB_PATH):
+                raise RuntimeError(
+                    f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                    "g.build()'` (or `make -C metatrain_b200/csrc`). There is no fallback path."
+                )
+            lib = ctypes.CDLL(_LIB_PATH)
+            for name, argtypes in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.argtypes = argtypes
+                fn.restype = _RESTYPE.get(name, ctypes.c_int)
+            _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (``None`` -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    """Invoke ``petb200_<name>`` on torch's current stream; raise on a non-zero status."""
+    lib = load()
+    status = getattr(lib, "petb200_" + name)(*args, stream_ptr())
+    if status != 0:
+        msg = lib.petb200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"petb200_{name} failed ({status}): {msg}")

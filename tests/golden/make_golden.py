@@ -136,6 +136,10 @@ def main():
 
     water = read_lammps_atomic(os.path.join(RES, "periodic_water.data"), {1: 1, 2: 8})
     make_case("water_384", [water], [1, 8])
+    # seed box of the 10k / 100k water benchmarks (positions only)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(HERE)), "metatrain_b200",
+                                     "data", "water_384.npz"),
+                        Z=water["Z"], positions=water["positions"], cell=water["cell"])
     # non-strict neighbor list: pairs out to 5.5 A are handed in and must be dropped
     make_case("water_384_nonstrict", [water], [1, 8], nl_cutoff=5.5, fp64=False)
 

@@ -1,0 +1,295 @@
+"""GPU unit tests: every C-ABI op of libpetb200 against a plain PyTorch fp32/fp64 reference
+of the same op (called through the C ABI via ctypes, on ``cuda:0``)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from metatrain_b200 import engine, lib  # noqa: E402
+from metatrain_b200.lib import (EPI_MUL_DSILU, EPI_NONE, EPI_SILU, EPI_SWIGLU, EPI_SWIGLU_BWD,  # noqa: E402
+                                call, ptr)
+
+DEV = "cuda:0"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def ragged_rows(n_atoms, max_count, seed=0, with_empty=True):
+    g = torch.Generator().manual_seed(seed)
+    counts = torch.randint(0 if with_empty else 1, max_count + 1, (n_atoms,), generator=g)
+    if with_empty and n_atoms > 2:
+        counts[1] = 0
+        counts[2] = max_count
+    row_ptr = torch.zeros(n_atoms + 1, dtype=torch.int32)
+    row_ptr[1:] = torch.cumsum(counts, 0)
+    return row_ptr.to(DEV), int(row_ptr[-1]), int(counts.max())
+
+
+def assert_close(a, b, atol, rtol, what=""):
+    a, b = a.double().cpu(), b.double().cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), f"{what}: max err {err.max():.3e} (|ref| max {b.abs().max():.3e}), {int(bad.sum())} bad"
+
+
+# ---------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(1000, 128, 128), (77, 384, 128), (513, 128, 384),
+                                   (300, 256, 256), (129, 1024, 256), (40, 256, 512), (0, 128, 128)])
+def test_gemm_plain_bias_rowscale_residual(M, N, K):
+    a, w, b = rnd(M, K), rnd(N, K, scale=0.1), rnd(N)
+    rs, res = rnd(M).abs() + 0.5, rnd(M, N)
+    out = torch.empty(M, N, device=DEV)
+    engine.gemm(a, w, out, bias=b, row_scale=rs, residual=res)
+    ref = rs[:, None].double() * (a.double() @ w.double().T) + b.double() + res.double()
+    assert_close(out, ref, 1e-4, 1e-5, "gemm")
+    # accumulate
+    out2 = out.clone()
+    engine.gemm(a, w, out2, accumulate=True)
+    assert_close(out2, ref + a.double() @ w.double().T, 2e-4, 1e-5, "gemm accumulate")
+
+
+def test_gemm_strided_views():
+    M, N, K = 333, 128, 128
+    big_a, big_w = rnd(M, 3 * K), rnd(2 * N, 2 * K, scale=0.1)
+    big_out = torch.zeros(M + 50, N, device=DEV)
+    a, w = big_a[:, K:2 * K], big_w[N:, K:]
+    engine.gemm(a, w, big_out[50:])
+    assert_close(big_out[50:], a.double() @ w.double().T, 1e-4, 1e-5, "gemm views")
+    assert float(big_out[:50].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(700, 128, 256), (65, 256, 128)])
+def test_gemm_silu_and_dsilu(M, N, K):
+    a, w, b = rnd(M, K), rnd(N, K, scale=0.1), rnd(N)
+    out, pre = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    engine.gemm(a, w, out, bias=b, epilogue=EPI_SILU, aux_out=pre)
+    ref_pre = a.double() @ w.double().T + b.double()
+    assert_close(pre, ref_pre, 1e-4, 1e-5, "silu pre")
+    assert_close(out, F.silu(ref_pre), 1e-4, 1e-5, "silu out")
+    # dgrad through the SiLU: d_pre = (g @ W2) * silu'(pre)
+    g, w2 = rnd(M, K, seed=3), rnd(N, K, seed=4, scale=0.1)
+    d = torch.empty(M, N, device=DEV)
+    engine.gemm(g, w2, d, epilogue=EPI_MUL_DSILU, aux_in=pre)
+    p = pre.double().clone().requires_grad_(True)
+    (F.silu(p) * (g.double() @ w2.double().T)).sum().backward()
+    assert_close(d, p.grad, 1e-4, 1e-5, "mul_dsilu")
+
+
+@pytest.mark.parametrize("M,Fdim,K", [(500, 256, 128), (90, 512, 256)])
+def test_gemm_swiglu_fwd_bwd(M, Fdim, K):
+    a, w, b = rnd(M, K), rnd(2 * Fdim, K, scale=0.1), rnd(2 * Fdim)
+    rs = rnd(M).abs() + 0.5
+    out, ug = torch.empty(M, Fdim, device=DEV), torch.empty(M, 2 * Fdim, device=DEV)
+    engine.gemm(a, w, out, bias=b, row_scale=rs, epilogue=EPI_SWIGLU, aux_out=ug)
+    ref_ug = rs[:, None].double() * (a.double() @ w.double().T) + b.double()
+    u, g = ref_ug.chunk(2, dim=-1)
+    assert_close(ug, ref_ug, 1e-4, 1e-5, "swiglu preact")
+    assert_close(out, u * torch.sigmoid(g), 1e-4, 1e-5, "swiglu out")
+    # backward: d_ug from d_s = go @ Wout   (Wout^T passed as the [F, d] operand)
+    go, wout_t = rnd(M, 128, seed=5), rnd(Fdim, 128, seed=6, scale=0.1)
+    d_ug = torch.empty(M, 2 * Fdim, device=DEV)
+    engine.gemm(go, wout_t, d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=ug)
+    x = ug.double().clone().requires_grad_(True)
+    uu, gg = x.chunk(2, dim=-1)
+    ((uu * torch.sigmoid(gg)) * (go.double() @ wout_t.double().T)).sum().backward()
+    assert_close(d_ug, x.grad, 1e-4, 1e-5, "swiglu bwd")
+
+
+def test_gemm_rejects_bad_shapes():
+    a, w, out = rnd(16, 128), rnd(100, 128), torch.empty(16, 100, device=DEV)
+    with pytest.raises(RuntimeError, match="multiple of 128"):
+        engine.gemm(a, w, out)
+
+
+# ----------------------------------------------------------------------- attention
+def _attention_reference(qkv, row_ptr, fc, n_atoms, n_edges, nh, scale):
+    """Dense per-atom attention in fp64 with autograd (transformer.py:86-152 semantics)."""
+    d = qkv.shape[1] // 3
+    hd = d // nh
+    out = torch.zeros(n_edges + n_atoms, d, dtype=torch.float64)
+    rp = row_ptr.cpu().tolist()
+    for i in range(n_atoms):
+        rows = [n_edges + i] + list(range(rp[i], rp[i + 1]))
+        x = qkv[rows]
+        q, k, v = (x[:, j * d:(j + 1) * d].reshape(len(rows), nh, hd).transpose(0, 1) for j in range(3))
+        w = torch.cat([torch.ones(1, dtype=torch.float64), fc[rp[i]:rp[i + 1]]])
+        bias = torch.log(w.clamp_min(1e-15))
+        a = torch.softmax(q @ k.transpose(-1, -2) * scale + bias[None, None, :], dim=-1)
+        out[rows] = (a @ v).transpose(0, 1).reshape(len(rows), d)
+    return out
+
+
+@pytest.mark.parametrize("n_atoms,max_count", [(37, 48), (5, 70), (3, 1)])
+def test_attention_fwd_bwd(n_atoms, max_count):
+    nh, hd = 8, 16
+    d = nh * hd
+    row_ptr, E, mx = ragged_rows(n_atoms, max_count, seed=n_atoms)
+    qkv = rnd(E + n_atoms, 3 * d)
+    g = torch.Generator().manual_seed(1)
+    fc = torch.rand(E, generator=g).to(DEV)
+    if E > 3:
+        fc[0] = 0.0       # clamped key
+        fc[1] = 1e-20
+        fc[2] = 1.0
+    scale = 0.25
+    out = torch.empty(E + n_atoms, d, device=DEV)
+    lse = torch.empty(E + n_atoms, nh, device=DEV)
+    call("attention_fwd", ptr(qkv), ptr(row_ptr), ptr(fc), n_atoms, E, nh, hd, scale, mx, ptr(out), ptr(lse))
+    x = qkv.double().cpu().requires_grad_(True)
+    f = fc.double().cpu().requires_grad_(True)
+    ref = _attention_reference(x, row_ptr, f, n_atoms, E, nh, scale)
+    assert_close(out, ref.detach(), 2e-5, 1e-5, "attention out")
+    go = rnd(E + n_atoms, d, seed=9)
+    ref.backward(go.double().cpu())
+    d_qkv = torch.empty_like(qkv)
+    d_fc = torch.zeros(E, device=DEV)
+    call("attention_bwd", ptr(qkv), ptr(out), ptr(lse), ptr(go), ptr(row_ptr), ptr(fc), n_atoms, E,
+         nh, hd, scale, mx, ptr(d_qkv), ptr(d_fc))
+    assert_close(d_qkv, x.grad, 5e-5, 1e-4, "attention d_qkv")
+    ref_dfc = f.grad.clone()
+    assert_close(d_fc, ref_dfc, 5e-4, 1e-4, "attention d_fc")
+
+
+# ------------------------------------------------------------------------ row-wise
+@pytest.mark.parametrize("d", [128, 256])
+def test_rms_rstd_and_bwd(d):
+    M = 1001
+    x, gamma = rnd(M, d), rnd(d).abs() + 0.5
+    rstd = torch.empty(M, device=DEV)
+    call("rms_rstd", ptr(x), M, d, ptr(rstd))
+    ref_rstd = torch.rsqrt((x.double() ** 2).mean(-1) + torch.finfo(torch.float32).eps)
+    assert_close(rstd, ref_rstd, 1e-6, 1e-5, "rstd")
+    # y = rms_norm(x) * gamma ; dy given ; d_xhat = dy * gamma
+    dy, base = rnd(M, d, seed=1), rnd(M, d, seed=2)
+    xx = x.double().clone().requires_grad_(True)
+    y = F.rms_norm(xx, (d,), gamma.double(), torch.finfo(torch.float32).eps)
+    y.backward(dy.double())
+    out = torch.empty(M, d, device=DEV)
+    d_xhat = (dy * gamma).contiguous()
+    call("rms_bwd", ptr(d_xhat), ptr(x), ptr(rstd), ptr(base), M, d, ptr(out))
+    assert_close(out, xx.grad + base.double(), 2e-5, 1e-5, "rms_bwd")
+    call("rms_bwd", ptr(d_xhat), ptr(x), ptr(rstd), None, M, d, ptr(out))
+    assert_close(out, xx.grad, 2e-5, 1e-5, "rms_bwd no base")
+
+
+def _random_involution(E, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    perm = torch.randperm(E, generator=g)
+    rev = torch.arange(E)
+    for k in range(0, E - 1, 2):
+        a, b = int(perm[k]), int(perm[k + 1])
+        rev[a], rev[b] = b, a
+    return rev.to(torch.int32).to(DEV)
+
+
+def test_combine_ln_fwd_bwd_scatter():
+    E, d = 999, 128
+    t, gamma, beta = rnd(E, d), rnd(2 * d).abs() + 0.5, rnd(2 * d)
+    rev = _random_involution(E)
+    cc, mean, rstd = torch.empty(E, 2 * d, device=DEV), torch.empty(E, device=DEV), torch.empty(E, device=DEV)
+    call("combine_ln_fwd", ptr(t), ptr(rev), ptr(gamma), ptr(beta), E, d, ptr(cc), ptr(mean), ptr(rstd))
+    tt = t.double().clone().requires_grad_(True)
+    cat = torch.cat([tt, tt[rev.long()]], dim=-1)
+    ref = F.layer_norm(cat, (2 * d,), gamma.double(), beta.double(), 1e-5)
+    assert_close(cc, ref.detach(), 2e-5, 1e-5, "combine_ln_fwd")
+    g, base = rnd(E, 2 * d, seed=3), rnd(E, d, seed=4)
+    ref.backward(g.double())
+    d_cat = torch.empty(E, 2 * d, device=DEV)
+    call("combine_ln_bwd", ptr(g), ptr(t), ptr(rev), ptr(gamma), ptr(mean), ptr(rstd), E, d, ptr(d_cat))
+    out = torch.empty(E, d, device=DEV)
+    call("combine_scatter_bwd", ptr(d_cat), ptr(base), ptr(rev), E, d, ptr(out))
+    assert_close(out, tt.grad + base.double(), 5e-5, 1e-5, "combine bwd")
+
+
+def test_embedding_transpose_compress_geom():
+    E, d = 777, 128
+    table = rnd(5, d)
+    idx = torch.randint(0, 5, (E,), generator=torch.Generator().manual_seed(0)).to(torch.int32).to(DEV)
+    out = torch.empty(E, d, device=DEV)
+    call("embedding", ptr(table), ptr(idx), E, d, ptr(out), d)
+    assert torch.equal(out, table[idx.long()])
+    # transpose + column scale
+    w, cs = rnd(384, 128), rnd(128)
+    wt, ws = torch.empty(128, 384, device=DEV), torch.empty(384, 128, device=DEV)
+    call("transpose_scale", ptr(w), 384, 128, ptr(cs), ptr(wt), ptr(ws))
+    assert torch.equal(ws, w * cs[None, :]) and torch.equal(wt, (w * cs[None, :]).T.contiguous())
+    w2 = rnd(100, 36)
+    w2t = torch.empty(36, 100, device=DEV)
+    call("transpose_scale", ptr(w2), 100, 36, None, ptr(w2t), None)
+    assert torch.equal(w2t, w2.T.contiguous())
+    # compress_input
+    vec, dist, wg, bg, msg = rnd(E, 3), rnd(E).abs(), rnd(d, 4), rnd(d), rnd(E, d, seed=2)
+    for nbr in (None, table):
+        width = 3 * d if nbr is not None else 2 * d
+        cat = torch.empty(E, width, device=DEV)
+        call("compress_input", ptr(vec), ptr(dist), ptr(wg), ptr(bg), ptr(nbr), ptr(idx), ptr(msg), E, d, ptr(cat))
+        geo = torch.cat([vec, dist[:, None]], 1).double() @ wg.double().T + bg.double()
+        parts = [geo] + ([table[idx.long()].double()] if nbr is not None else []) + [msg.double()]
+        assert_close(cat, torch.cat(parts, 1), 1e-5, 1e-5, "compress_input")
+    # geometry embedder backward on a strided view
+    big = rnd(E, 3 * d, seed=7)
+    d_vec, d_dist = torch.ones(E, 3, device=DEV), torch.ones(E, device=DEV)
+    call("geom_embed_bwd", ptr(big[:, d:2 * d]), 3 * d, ptr(wg), E, d, 1, ptr(d_vec), ptr(d_dist))
+    r4 = big[:, d:2 * d].double() @ wg.double()
+    assert_close(d_vec, r4[:, :3] + 1, 1e-4, 1e-5, "geom bwd vec")
+    assert_close(d_dist, r4[:, 3] + 1, 1e-4, 1e-5, "geom bwd dist")
+
+
+def test_readout_and_sum():
+    n_atoms, d, P = 41, 128, 3
+    row_ptr, E, _ = ragged_rows(n_atoms, 30, seed=5)
+    ctr = torch.repeat_interleave(torch.arange(n_atoms), (row_ptr[1:] - row_ptr[:-1]).long().cpu()).to(torch.int32).to(DEV)
+    nf, ef = rnd(n_atoms, d), rnd(E, d)
+    wn, bn, we, be = rnd(P, d, scale=0.1), rnd(P), rnd(P, d, seed=1, scale=0.1), rnd(P, seed=1)
+    fc = torch.rand(E, generator=torch.Generator().manual_seed(2)).to(DEV)
+    atomic, pe = torch.empty(n_atoms, P, device=DEV), torch.empty(E, P, device=DEV)
+    call("readout_fwd", ptr(nf), ptr(ef), ptr(wn), ptr(bn), ptr(we), ptr(be), ptr(fc), ptr(row_ptr),
+         n_atoms, E, d, P, ptr(atomic), ptr(pe))
+    nfd, efd, fcd = (t.double().clone().requires_grad_(True) for t in (nf, ef, fc))
+    ref_pe = efd @ we.double().T + be.double()
+    ref = (nfd @ wn.double().T + bn.double()).index_add(0, ctr.long(), ref_pe * fcd[:, None])
+    assert_close(pe, ref_pe.detach(), 1e-5, 1e-5, "edge pred")
+    assert_close(atomic, ref.detach(), 1e-4, 1e-5, "atomic")
+    g = rnd(n_atoms, P, seed=8)
+    ref.backward(g.double())
+    dn, de, dfc = torch.empty(n_atoms, d, device=DEV), torch.empty(E, d, device=DEV), torch.zeros(E, device=DEV)
+    call("readout_bwd", ptr(g), ptr(pe), ptr(wn), ptr(we), ptr(fc), ptr(ctr), None, None, n_atoms, E, d, P,
+         ptr(dn), ptr(de), ptr(dfc))
+    assert_close(dn, nfd.grad, 1e-5, 1e-5, "d node feat")
+    assert_close(de, efd.grad, 1e-5, 1e-5, "d edge feat")
+    assert_close(dfc, fcd.grad, 1e-4, 1e-5, "d fc")
+    # with the SiLU pre-activation fused
+    npre, epre = rnd(n_atoms, d, seed=11), rnd(E, d, seed=12)
+    call("readout_bwd", ptr(g), ptr(pe), ptr(wn), ptr(we), ptr(fc), ptr(ctr), ptr(npre), ptr(epre),
+         n_atoms, E, d, P, ptr(dn), ptr(de), None)
+    ds = lambda x: torch.sigmoid(x) * (1 + x * (1 - torch.sigmoid(x)))  # noqa: E731
+    assert_close(dn, nfd.grad * ds(npre.double()), 1e-5, 1e-5, "d node pre")
+    assert_close(de, efd.grad * ds(epre.double()), 1e-5, 1e-5, "d edge pre")
+    # per-structure sums
+    struct_ptr = torch.tensor([0, 10, 10, 41], dtype=torch.int32, device=DEV)
+    energies = torch.empty(3, P, device=DEV)
+    call("sum_over_atoms", ptr(atomic), ptr(struct_ptr), 3, P, ptr(energies))
+    ref_e = torch.stack([atomic[:10].double().sum(0), torch.zeros(P, dtype=torch.float64, device=DEV),
+                         atomic[10:].double().sum(0)])
+    assert_close(energies, ref_e, 1e-4, 1e-5, "sum over atoms")
+
+
+def test_csr_nef_roundtrip():
+    n_atoms = 23
+    row_ptr, E, mx = ragged_rows(n_atoms, 9, seed=3)
+    counts = (row_ptr[1:] - row_ptr[:-1]).long()
+    ctr = torch.repeat_interleave(torch.arange(n_atoms, device=DEV), counts).to(torch.int32)
+    x = rnd(E, 3)
+    nef = torch.empty(n_atoms, mx, 3, device=DEV)
+    call("csr_to_nef", ptr(x), ptr(row_ptr), n_atoms, E, mx, 3, ptr(nef))
+    mask = torch.arange(mx, device=DEV)[None, :] < counts[:, None]
+    assert torch.equal(nef[mask], x) and float(nef[~mask].abs().sum()) == 0.0
+    back = torch.empty(E, 3, device=DEV)
+    call("nef_to_csr", ptr(nef), ptr(row_ptr), ptr(ctr), n_atoms, E, mx, 3, ptr(back))
+    assert torch.equal(back, x)

@@ -1,0 +1,194 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the committed golden
+vectors of the unmodified reference, against the oracle on the same seeded inputs, and —
+at BASELINE.json's full size — through size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import GOLDEN_CASES, golden_inputs, load_golden, seed_all  # noqa: E402
+from metatrain_b200 import B200PETBackend, evaluate  # noqa: E402
+from metatrain_b200.systems import make_batch, replicate, water_384  # noqa: E402
+from oracle import pet_oracle  # noqa: E402
+
+DEV = "cuda:0"
+FORCE_TOL = 1e-4  # eV/A, BASELINE.json north_star ("forces within 1e-4 eV/A of reference")
+
+
+def make_backend(g, precision="fp32"):
+    seed_all(0)
+    be = B200PETBackend(g["hypers"], g["atomic_types"], precision=precision)
+    be.add_output(g["target"], {g["target"] + "___0": [1]})
+    return be.to(DEV).eval()
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_matches_reference_golden(case):
+    g = load_golden(case)
+    be = make_backend(g)
+    strain = "ref32_dE_dstrain" in g
+    out = evaluate(be, **golden_inputs(g, DEV), target=g["target"], strain=strain)
+    e = out["energies"].cpu().numpy()
+    scale = max(1.0, float(np.abs(g["ref32_energies"]).max()))
+    assert np.abs(e - g["ref32_energies"]).max() <= 1e-5 * scale
+    assert np.abs(out["atomic"].cpu().numpy() - g["ref32_atomic"]).max() <= 2e-5
+    f_err = np.abs(out["dE_dpos"].cpu().numpy() - g["ref32_dE_dpos"]).max()
+    assert f_err <= FORCE_TOL, f"force max-abs-err {f_err:.2e}"
+    assert f_err <= 2e-5, f"fp32 path should sit at the fp32 noise floor, got {f_err:.2e}"
+    if strain:
+        assert np.abs(out["dE_dstrain"].cpu().numpy() - g["ref32_dE_dstrain"]).max() <= 1e-4
+    if "ref64_dE_dpos" in g:
+        assert np.abs(out["dE_dpos"].cpu().numpy() - g["ref64_dE_dpos"]).max() <= FORCE_TOL
+
+
+def test_reference_hard_coded_energies():
+    """src/metatrain/pet/tests/test_regression.py:66-74, same assert_close tolerance."""
+    g = load_golden("qm9_5")
+    out = evaluate(make_backend(g), **golden_inputs(g, DEV), target=g["target"], gradients=False)
+    expected = torch.tensor([1.146098375320, 0.171331465244, 0.539504408836, 0.861489117146,
+                             0.177449733019])
+    torch.testing.assert_close(out["energies"].cpu().ravel(), expected)
+
+
+@pytest.mark.parametrize("case", ["si_64", "ragged_mix", "carbon_5"])
+def test_stages_match_oracle(case):
+    """Stage-by-stage comparison with the oracle on identical weights and inputs."""
+    g = load_golden(case)
+    be = make_backend(g)
+    sd = {k: v.detach().cpu() for k, v in be.state_dict().items()}
+    ref = pet_oracle.energy_and_gradients(sd, g["hypers"], **golden_inputs(g), target=g["target"])
+    inp = golden_inputs(g, DEV)
+    pos = inp["positions"].clone().requires_grad_(True)
+    bd = be.preprocess(pos, inp["centers"], inp["neighbors"], inp["species"], inp["cells"],
+                       inp["cell_shifts"], inp["system_indices"], 1.0)
+    rb = ref["batch"]
+    # integer work is bit exact
+    assert torch.equal(bd["padding_mask"].cpu(), rb["mask"])
+    assert torch.equal(bd["element_indices_nodes"].cpu(), rb["z_nodes"])
+    assert torch.equal(bd["element_indices_neighbors"].cpu()[rb["mask"]], rb["z_neighbors"][rb["mask"]])
+    assert torch.equal(bd["reverse_neighbor_index"].cpu()[rb["mask"]], rb["reverse_flat"][rb["mask"]])
+    torch.testing.assert_close(bd["edge_vectors"].detach().cpu(), rb["edge_vectors"].detach(), atol=1e-6, rtol=1e-6)
+    torch.testing.assert_close(bd["edge_distances"].detach().cpu()[rb["mask"]],
+                               rb["edge_distances"].detach()[rb["mask"]], atol=1e-6, rtol=1e-6)
+    torch.testing.assert_close(bd["cutoff_factors"].detach().cpu(), rb["cutoff_factors"].detach(),
+                               atol=2e-6, rtol=1e-5)
+    nodes, edges = be.calculate_features(bd)
+    assert nodes[0].shape == ref["node_features"].shape and edges[0].shape == ref["edge_features"].shape
+    torch.testing.assert_close(nodes[0].detach().cpu(), ref["node_features"], atol=2e-4, rtol=1e-4)
+    m = rb["mask"][..., None]
+    torch.testing.assert_close(edges[0].detach().cpu() * m, ref["edge_features"] * m, atol=2e-4, rtol=1e-4)
+    pred, _, _ = be.predict(nodes, edges, bd, inp["cells"], inp["system_indices"], [g["target"]])
+    torch.testing.assert_close(pred[g["target"]][0].detach().cpu(), ref["atomic"], atol=2e-5, rtol=1e-5)
+    (grad,) = torch.autograd.grad(pred[g["target"]][0].sum(), pos)
+    assert (grad.cpu() - ref["dE_dpos"]).abs().max() <= 2e-5
+
+
+def test_predict_accepts_plain_nef_tensor():
+    """The B1 contract: predict() consumes an [N, M, d] edge tensor (e.g. one modified by
+    the caller); gradients flow through the NEF<->CSR conversion."""
+    g = load_golden("si_64")
+    be = make_backend(g)
+    inp = golden_inputs(g, DEV)
+    pos = inp["positions"].clone().requires_grad_(True)
+    bd = be.preprocess(pos, inp["centers"], inp["neighbors"], inp["species"], inp["cells"],
+                       inp["cell_shifts"], inp["system_indices"], 1.0)
+    nodes, edges = be.calculate_features(bd)
+    plain = edges[0] * 1.0  # a new tensor without the CSR shortcut attribute
+    a, _, _ = be.predict(nodes, [plain], bd, inp["cells"], inp["system_indices"], [g["target"]])
+    b, _, _ = be.predict(nodes, edges, bd, inp["cells"], inp["system_indices"], [g["target"]])
+    torch.testing.assert_close(a[g["target"]][0], b[g["target"]][0], atol=0, rtol=0)
+    (ga,) = torch.autograd.grad(a[g["target"]][0].sum(), pos, retain_graph=True)
+    (gb,) = torch.autograd.grad(b[g["target"]][0].sum(), pos)
+    torch.testing.assert_close(ga, gb, atol=1e-6, rtol=1e-6)
+
+
+def test_csr_only_mode_equals_default():
+    g = load_golden("water_384")
+    be = make_backend(g)
+    a = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    be.emit_nef = False
+    b = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    assert torch.equal(a["energies"], b["energies"]) and torch.equal(a["dE_dpos"], b["dE_dpos"])
+
+
+def test_deterministic():
+    g = load_golden("water_384")
+    be = make_backend(g)
+    a = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    b = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    assert torch.equal(a["dE_dpos"], b["dE_dpos"]) and torch.equal(a["atomic"], b["atomic"])
+
+
+def test_empty_and_errors():
+    g = load_golden("qm9_5")
+    be = make_backend(g)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=DEV)  # noqa: E731
+    # empty system, src/metatrain/pet/tests/test_functionality.py:79-103
+    out = evaluate(be, z(0, 3), z(0, dt=torch.int32), z(0, dt=torch.int32), z(0, dt=torch.int32),
+                   z(1, 3, 3), z(0, 3, dt=torch.int32), z(0, dt=torch.int64), target=g["target"],
+                   gradients=False)
+    assert out["atomic"].numel() == 0 and float(out["energies"].abs().sum()) == 0.0
+    # a one-directional neighbor list must be rejected loudly (the reference silently
+    # produces garbage)
+    inp = golden_inputs(g, DEV)
+    half = inp["centers"] < inp["neighbors"]
+    with pytest.raises(ValueError, match="not symmetric"):
+        be.preprocess(inp["positions"], inp["centers"][half], inp["neighbors"][half], inp["species"],
+                      inp["cells"], inp["cell_shifts"][half], inp["system_indices"], 1.0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        be.preprocess(*(t.cpu() for t in (inp["positions"], inp["centers"], inp["neighbors"],
+                                          inp["species"], inp["cells"], inp["cell_shifts"],
+                                          inp["system_indices"])), 1.0)
+    be.train()
+    with pytest.raises(NotImplementedError, match="training"):
+        evaluate(be, **inp, target=g["target"])
+
+
+def test_neighbor_order_invariance():
+    """Shuffling the neighbor list changes nothing but fp summation order."""
+    g = load_golden("si_64")
+    be = make_backend(g)
+    inp = golden_inputs(g, DEV)
+    a = evaluate(be, **inp, target=g["target"])
+    perm = torch.randperm(inp["centers"].shape[0], generator=torch.Generator().manual_seed(0)).to(DEV)
+    inp2 = dict(inp, centers=inp["centers"][perm], neighbors=inp["neighbors"][perm],
+                cell_shifts=inp["cell_shifts"][perm])
+    b = evaluate(be, **inp2, target=g["target"])
+    torch.testing.assert_close(a["energies"], b["energies"], atol=1e-4, rtol=1e-6)
+    assert (a["dE_dpos"] - b["dE_dpos"]).abs().max() <= 2e-5
+
+
+# ------------------------------------------------ BASELINE.json config 2: 10k-atom water
+@pytest.fixture(scope="module")
+def water_10k():
+    g = load_golden("water_384")
+    be = make_backend(g)
+    be.emit_nef = False
+    box = replicate(water_384(), (3, 3, 3))
+    batch = {k: v.to(DEV) for k, v in make_batch([box], 4.5).items()}
+    return g, be, batch, evaluate(be, **batch, target=g["target"])
+
+
+def test_10k_replication_property(water_10k):
+    """A 3x3x3 tiling of the 384-atom box has 27x its energy and tiled forces: pins the
+    full-size configuration to the reference's golden for the seed box."""
+    g, be, batch, out = water_10k
+    n = 384
+    assert batch["positions"].shape[0] == 27 * n and batch["centers"].shape[0] == 392040
+    e_ref = float(g["ref64_energies"].ravel()[0])
+    assert abs(float(out["energies"]) / 27.0 - e_ref) <= 2e-5 * abs(e_ref)
+    f = out["dE_dpos"].cpu().numpy().reshape(27, n, 3)
+    assert np.abs(f - g["ref64_dE_dpos"][None]).max() <= FORCE_TOL
+    assert np.abs(out["atomic"].cpu().numpy().reshape(27, n) - g["ref64_atomic"].reshape(1, n)).max() <= 5e-5
+
+
+def test_10k_physical_invariants(water_10k):
+    g, be, batch, out = water_10k
+    # Newton's third law: the net force vanishes
+    assert out["dE_dpos"].sum(0).abs().max() <= 5e-3
+    # rigid translation (atoms leave the home cell; shifts stay valid) leaves E unchanged
+    moved = dict(batch, positions=batch["positions"] + torch.tensor([3.3, -1.7, 0.9], device=DEV))
+    out2 = evaluate(be, **moved, target=g["target"])
+    assert abs(float(out2["energies"]) - float(out["energies"])) <= 2e-6 * abs(float(out["energies"]))
+    assert (out2["dE_dpos"] - out["dE_dpos"]).abs().max() <= FORCE_TOL

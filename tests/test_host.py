@@ -1,0 +1,104 @@
+"""CPU tests of the host-side logic: C-ABI surface, parameter/state-dict contract,
+neighbor list, hyper-parameter validation (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import DEFAULT_HYPERS, load_golden, seed_all, weight_fingerprint
+from metatrain_b200 import B200PETBackend, lib
+from metatrain_b200.neighbors import neighbor_list
+from metatrain_b200.systems import make_batch, replicate, silicon_box, water_384
+from oracle.structures import neighbor_list as oracle_neighbor_list
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "petb200.h")).read()
+    return sorted(set(re.findall(r"PETB200_API\s+[\w\s\*]+?\b(petb200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.isfile(lib.library_path()):
+        lib.build()
+    handle = ctypes.CDLL(lib.library_path())
+    names = declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/petb200.h but not exported"
+    assert set(names) == set(lib._SIGNATURES), "ctypes table out of sync with the header"
+    assert handle.petb200_version() >= 1
+
+
+def test_state_dict_contract():
+    g = load_golden("qm9_5")
+    seed_all(0)
+    be = B200PETBackend(g["hypers"], g["atomic_types"])
+    be.add_output(g["target"], {g["target"] + "___0": [1]})
+    sd = be.state_dict()
+    first = next(iter(sd))
+    assert first == "species_to_species_index" and not sd[first].is_floating_point()
+    np.testing.assert_array_equal(weight_fingerprint(sd), g["weight_fingerprint"])
+    assert sum(p.numel() for p in be.parameters()) == 2903298  # 4 species + 1 head
+    be.remove_output(g["target"])
+    assert not any("heads" in k or "last_layers" in k for k in be.state_dict())
+
+
+def test_hyper_validation_matches_reference_error_types():
+    bad = dict(DEFAULT_HYPERS, normalization="BatchNorm")
+    with pytest.raises(ValueError, match="Unknown normalization flag"):
+        B200PETBackend(bad, [1])
+    with pytest.raises(ValueError, match="Unknown transformer flag"):
+        B200PETBackend(dict(DEFAULT_HYPERS, transformer_type="x"), [1])
+    with pytest.raises(ValueError, match="Unknown activation flag"):
+        B200PETBackend(dict(DEFAULT_HYPERS, activation="relu"), [1])
+    with pytest.raises(ValueError, match="not divisible"):
+        B200PETBackend(dict(DEFAULT_HYPERS, num_heads=7), [1])
+    with pytest.raises(ValueError, match="Unknown cutoff function"):
+        B200PETBackend(dict(DEFAULT_HYPERS, cutoff_function="step"), [1])
+    with pytest.raises(NotImplementedError):
+        B200PETBackend(dict(DEFAULT_HYPERS, featurizer_type="residual"), [1])
+    with pytest.raises(NotImplementedError):
+        B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16), [1])
+
+
+def test_no_cpu_fallback():
+    be = B200PETBackend(DEFAULT_HYPERS, [1, 8])
+    be.add_output("energy", {"energy___0": [1]})
+    b = make_batch([water_384()], 4.5)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        be.preprocess(b["positions"], b["centers"], b["neighbors"], b["species"], b["cells"],
+                      b["cell_shifts"], b["system_indices"], 1.0)
+
+
+@pytest.mark.parametrize("case", ["water_384", "carbon_5", "si_64", "ragged_mix", "co_periodic"])
+def test_host_neighbor_list_reproduces_golden_lists(case):
+    g = load_golden(case)
+    for b in range(g["cells"].shape[0]):
+        sel = g["system_indices"] == b
+        pos, cell = g["positions"][sel].astype(np.float64), g["cells"][b].astype(np.float64)
+        periodic = bool(np.abs(cell).sum() > 0)
+        i, j, s = neighbor_list(pos, cell, periodic, 4.5)
+        off = int(np.nonzero(sel)[0][0]) if sel.any() else 0
+        e = np.isin(g["centers"], np.nonzero(sel)[0])
+        ref = set(zip((g["centers"][e] - off).tolist(), (g["neighbors"][e] - off).tolist(),
+                      map(tuple, g["cell_shifts"][e].tolist())))
+        assert set(zip(i.tolist(), j.tolist(), map(tuple, s.tolist()))) == ref
+
+
+def test_host_neighbor_list_wrapped_positions_and_big_box():
+    box = silicon_box()
+    a = neighbor_list(box["positions"], box["cell"], True, 4.5)
+    b = oracle_neighbor_list(box["positions"], box["cell"], True, 4.5)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    moved = box["positions"] + np.array([31.0, -17.0, 5.5])  # far outside the home cell
+    i, j, s = neighbor_list(moved, box["cell"], True, 4.5)
+    r = moved[j] - moved[i] + s @ box["cell"]
+    assert len(i) == len(a[0]) and np.linalg.norm(r, axis=1).max() <= 4.5
+    big = replicate(water_384(), (2, 2, 2))
+    i, j, s = neighbor_list(big["positions"], big["cell"], True, 4.5)
+    assert len(i) == 8 * 14520
