@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the PET energy+forces hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl petb200|reference]
+
+One "step" = one energy+forces evaluation (preprocess -> features -> predict ->
+autograd.grad to positions) of the 10 368-atom periodic water box (BASELINE.json
+configs[1]; the reference's 384-atom water fixture tiled 3x3x3).  Metric: atom-steps/s.
+
+* ``value``       inputs (positions + neighbor list) resident in HBM, CUDA-event timing.
+* ``e2e``         the same metric through the public API (`metatrain_b200.evaluate`) with
+                  pinned HOST buffers: H2D of positions + neighbor list and D2H of
+                  energies + forces inside the timed region of every step.
+* ``roofline``    dominant kernel (the GEMM), timed per launch with CUDA events on the
+                  launching stream in extra instrumented steps; algorithmic FLOPs =
+                  sum 2*M*N*K of the launches.  ``edge_scatter`` = the HBM-bound message
+                  reversal + LayerNorm kernel (2060 B of algorithmic traffic per edge).
+* ``cpu_baseline``/``--impl reference``  the oracle port (oracle/pet_oracle.py: the
+                  reference's algorithm with the reference's torch CPU primitives) on the
+                  host cores, bounded sample of the same workload.
+
+N > 1: one process per GPU (torchrun), each rank evaluates its own independent box (the
+batched evaluator loop of src/metatrain/cli/eval.py:148-310 shards by structures with no
+data-path collective) -> weak scaling; value = atoms of all ranks / max-over-ranks time.
+"""
+import argparse
+import contextlib
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CUTOFF = 4.5
+REPS = (3, 3, 3)
+TARGET = "energy"
+METRIC = "atom-steps/sec (energy+forces), PET 10k-atom water box"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="petb200", choices=["petb200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PETB200_PRECISION", "fp32"))
+    ap.add_argument("--reps", type=int, nargs=3, default=list(REPS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def hypers():
+    from helpers import DEFAULT_HYPERS
+    return dict(DEFAULT_HYPERS)
+
+
+def seeded_state_dict():
+    from helpers import seed_all
+    from metatrain_b200.parameters import PETParameters
+    seed_all(0)
+    p = PETParameters(hypers(), [1, 8])
+    p.add_output(TARGET, {TARGET + "___0": [1]})
+    return p.state_dict()
+
+
+# ------------------------------------------------------------------ CPU reference arm
+def oracle_step(sd, hyp, batch):
+    from oracle import pet_oracle
+    return pet_oracle.energy_and_gradients(sd, hyp, **batch, target=TARGET)
+
+
+def time_oracle(reps, steps, warmup):
+    """atom-steps/s of the oracle port on the host cores for a `reps` tiling."""
+    from metatrain_b200.systems import make_batch, replicate, water_384
+    torch.set_num_threads(os.cpu_count())
+    sd, hyp = seeded_state_dict(), hypers()
+    batch = make_batch([replicate(water_384(), reps)], CUTOFF)
+    batch = {k: (v.long() if not v.is_floating_point() else v) for k, v in batch.items()}
+    n_atoms = batch["positions"].shape[0]
+    for _ in range(warmup):
+        oracle_step(sd, hyp, batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(sd, hyp, batch)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return n_atoms / dt, dt, n_atoms
+
+
+def pick_reference_sample(steps, warmup, budget_s=150.0):
+    """Largest tiling of the workload whose (steps + warmup) CPU passes fit the budget."""
+    _, t1, _ = time_oracle((1, 1, 1), 1, 1)
+    for reps, n in (((3, 3, 3), 27), ((2, 2, 2), 8)):
+        if (steps + warmup) * n * 1.4 * t1 <= budget_s:
+            return reps
+    return (1, 1, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = pick_reference_sample(args.steps, args.warmup)
+    value, dt, n_atoms = time_oracle(reps, args.steps, max(args.warmup, 1))
+    sample = (f"water {reps[0]}x{reps[1]}x{reps[2]} tiling ({n_atoms} atoms) of the 10 368-atom "
+              f"workload, {args.steps} steps after {max(args.warmup, 1)} warm-up")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "atom-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PET default hypers, periodic water box tiled from the 384-atom "
+                               "fixture, cutoff 4.5 A, energy + forces", "atoms": n_atoms},
+        "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": os.cpu_count(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in out.strip().splitlines():
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class KernelTimer:
+    """CUDA-event timing of individual C-ABI calls on the launching stream."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.records = []
+
+    @contextlib.contextmanager
+    def __call__(self, name, args):
+        if name not in self.names:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        work = 0.0
+        if name == "gemm":
+            work = 2.0 * args[6] * args[7] * args[8]  # M, N, K
+        elif name in ("combine_ln_fwd",):
+            work = float(args[4])  # edges
+        self.records.append((name, a, b, work))
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b, work in self.records:
+            t, w, n = out.get(name, (0.0, 0.0, 0))
+            out[name] = (t + a.elapsed_time(b) * 1e-3, w + work, n + 1)
+        return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return p["hbm_gbs"], p["bf16_tflops"], p["bf16_tflops_sustained"], "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def run_petb200(args):
+    import torch.distributed as dist
+
+    from helpers import seed_all
+    from metatrain_b200 import B200PETBackend, evaluate, lib
+    from metatrain_b200.systems import make_batch, replicate, water_384
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    seed_all(0)
+    be = B200PETBackend(hypers(), [1, 8], precision=args.precision)
+    be.add_output(TARGET, {TARGET + "___0": [1]})
+    be = be.to(dev).eval()
+    be.emit_nef = False  # energies + forces only need the CSR handles
+
+    box = replicate(water_384(), tuple(args.reps))
+    host = make_batch([box], CUTOFF, pin_memory=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    n_atoms = host["positions"].shape[0]
+    n_edges = host["centers"].shape[0]
+
+    def step_resident():
+        return evaluate(be, **resident, target=TARGET)
+
+    e_host = torch.empty((1, 1), dtype=torch.float32).pin_memory()
+    f_host = torch.empty((n_atoms, 3), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        dev_in = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out = evaluate(be, **dev_in, target=TARGET)
+        e_host.copy_(out["energies"], non_blocking=True)
+        f_host.copy_(out["dE_dpos"], non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_resident()
+    # accuracy next to the throughput: tiled forces vs the reference's golden for the seed box
+    from helpers import load_golden
+    g = load_golden("water_384")
+    tiles = n_atoms // 384
+    f = out["dE_dpos"].cpu().numpy().reshape(tiles, 384, 3)
+    force_err = float(np.abs(f - g["ref32_dE_dpos"][None]).max())
+    energy_err = float(abs(float(out["energies"]) / tiles - float(g["ref32_energies"].ravel()[0])) / 384)
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    lib.launch_count = 0
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        step_resident()
+    t_end.record()
+    barrier()
+    launches = lib.launch_count
+    clocks = sampler.stop() if rank == 0 else None
+    sec = t_start.elapsed_time(t_end) * 1e-3
+    if world > 1:
+        t = torch.tensor([sec], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t)
+    value = world * n_atoms * args.steps / sec
+
+    # end to end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_sec], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t)
+    e2e_value = world * n_atoms * args.steps / e2e_sec
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = e_host.numel() * 4 + f_host.numel() * 4
+
+    # per-kernel roofline: instrumented extra steps (not part of the timed regions above)
+    timer = KernelTimer(["gemm", "combine_ln_fwd", "attention_fwd", "attention_bwd"])
+    lib.profile_hook = timer
+    for _ in range(3):
+        step_resident()
+    lib.profile_hook = None
+    tot = timer.totals()
+    hbm, tf_burst, tf_sust, which = peaks()
+    g_t, g_flops, g_n = tot["gemm"]
+    c_t, c_edges, c_n = tot["combine_ln_fwd"]
+    gemm_tflops = g_flops / g_t * 1e-12
+    scatter_bytes = 2060.0 * c_edges  # 2x512 B read + 4 B rev + 1024 B write + 8 B stats per edge
+    scatter_gbs = scatter_bytes / c_t * 1e-9
+    step_ms = sec / args.steps * 1e3
+    roofline = {
+        "kernel": "gemm (all dense contractions of the step)", "bound": "tensor",
+        "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
+        "frac": gemm_tflops / tf_sust, "traffic": None, "peak_source": which + " (sustained bf16)",
+        "launches_per_step": g_n // 3, "ms_per_step": g_t / 3 * 1e3,
+        "share_of_step": (g_t / 3 * 1e3) / step_ms, "precision": args.precision,
+    }
+    edge_scatter = {
+        "kernel": "combine_ln_fwd (message reversal + LayerNorm)", "bound": "hbm",
+        "achieved": scatter_gbs, "peak": hbm, "unit": "GB/s", "frac": scatter_gbs / hbm,
+        "traffic": None, "peak_source": which, "avg_launch_us": c_t / c_n * 1e6,
+    }
+    attn = {k: {"ms_per_step": tot[k][0] / 3 * 1e3} for k in ("attention_fwd", "attention_bwd")}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (2-term split, fp32 accumulate)",
+                  "bf16": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"PET default hypers, periodic water box {args.reps[0]}x{args.reps[1]}x"
+                               f"{args.reps[2]} tiling of the 384-atom fixture, cutoff 4.5 A, "
+                               "energy + forces (BASELINE.json configs[1])",
+                   "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges,
+                   "parallelism": f"{world} independent boxes (1 per GPU)" if world > 1 else "1 GPU",
+                   "cache": "per-step working set (~8 GB of activations) >> 126 MB L2; no explicit flush"},
+        "force_max_abs_err_eV_per_A": force_err, "energy_abs_err_eV_per_atom": energy_err,
+        "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec / args.steps * 1e3},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "edge_scatter": edge_scatter, "attention": attn,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, dt, n = time_oracle((2, 2, 2), 1, 1)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "atom-steps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"water 2x2x2 tiling ({n} atoms) of the workload, 1 step after 1 warm-up "
+                      f"({dt:.2f} s/step)"}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_petb200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,7 +88,6 @@ class _Features(torch.autograd.Function):
             d_m = torch.zeros((topo.n_edges, ctx.backend.d_pet), device=ctx.fc.device)
         d_vec, d_dist, d_fc = engine.features_backward(
             ctx.pw, ctx.backend.hypers, topo, ctx.fc.contiguous(), ctx.saved, d_h, d_m, ctx.prec)
-        ctx.saved = None
         return d_vec, d_dist, d_fc, None, None
 
 
@@ -108,7 +107,6 @@ class _Predict(torch.autograd.Function):
     def backward(ctx, d_atomic):
         d_h, d_m, d_fc = engine.predict_backward(ctx.pw, ctx.topo, ctx.name, ctx.fc.contiguous(),
                                                  ctx.saved, d_atomic, ctx.prec)
-        ctx.saved = None
         return d_h, d_m, d_fc, None, None, None
 
 

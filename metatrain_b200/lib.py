@@ -105,10 +105,23 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched by each entry point (for bench.py's ``gpu_launches`` claim)
+_KERNELS_PER_CALL = {"edges_bwd": 3, "csr_build": 6, "readout_bwd": 2}
+launch_count = 0
+#: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
+profile_hook = None
+
+
 def call(name: str, *args) -> None:
     """Invoke ``petb200_<name>`` on torch's current stream; raise on a non-zero status."""
+    global launch_count
     lib = load()
-    status = getattr(lib, "petb200_" + name)(*args, stream_ptr())
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
+    if profile_hook is not None:
+        with profile_hook(name, args):
+            status = getattr(lib, "petb200_" + name)(*args, stream_ptr())
+    else:
+        status = getattr(lib, "petb200_" + name)(*args, stream_ptr())
     if status != 0:
         msg = lib.petb200_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"petb200_{name} failed ({status}): {msg}")

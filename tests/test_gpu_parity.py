@@ -68,7 +68,9 @@ def test_stages_match_oracle(case):
     assert torch.equal(bd["element_indices_nodes"].cpu(), rb["z_nodes"])
     assert torch.equal(bd["element_indices_neighbors"].cpu()[rb["mask"]], rb["z_neighbors"][rb["mask"]])
     assert torch.equal(bd["reverse_neighbor_index"].cpu()[rb["mask"]], rb["reverse_flat"][rb["mask"]])
-    torch.testing.assert_close(bd["edge_vectors"].detach().cpu(), rb["edge_vectors"].detach(), atol=1e-6, rtol=1e-6)
+    # padded slots differ by construction (the reference aliases edge 0 there, we write zeros)
+    torch.testing.assert_close(bd["edge_vectors"].detach().cpu()[rb["mask"]],
+                               rb["edge_vectors"].detach()[rb["mask"]], atol=1e-6, rtol=1e-6)
     torch.testing.assert_close(bd["edge_distances"].detach().cpu()[rb["mask"]],
                                rb["edge_distances"].detach()[rb["mask"]], atol=1e-6, rtol=1e-6)
     torch.testing.assert_close(bd["cutoff_factors"].detach().cpu(), rb["cutoff_factors"].detach(),
