@@ -143,6 +143,12 @@ PETB200_API int petb200_gemm(const float* A, int64_t lda, const float* W, int64_
                  const float* aux_in, float* aux_out, int64_t ld_aux, int epilogue,
                  int accumulate, int precision, petb200_stream_t stream);
 
+/* Weight preparation for PETB200_PREC_BF16X3 / BF16: row r of `out` (same byte size as
+ * the fp32 row) = [cols bf16 "hi" | cols bf16 "lo"], w = hi + lo + O(2^-17 w).  With those
+ * precisions petb200_gemm expects its W argument in this format.                        */
+PETB200_API int petb200_split_bf16(const float* w, int64_t rows, int cols, float* out,
+                       petb200_stream_t stream);
+
 /* out[m,:] = table[idx[m],:] (torch.nn.Embedding, backend.py:515-516).                 */
 PETB200_API int petb200_embedding(const float* table, const int32_t* idx, int64_t n_rows, int d,
                       float* out, int64_t ld_out, petb200_stream_t stream);

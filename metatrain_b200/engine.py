@@ -28,14 +28,35 @@ def _empty(shape, like: Tensor, dtype=torch.float32) -> Tensor:
     return torch.empty(shape, device=like.device, dtype=dtype)
 
 
+def split_weight(w: Tensor, pack=None) -> Tensor:
+    """bf16 hi/lo form of a weight (petb200_split_bf16), cached on ``pack`` (which keeps the
+    source tensors alive, so storage addresses cannot be recycled under the cache).
+    Row-slice views of a cached base map onto the same rows of the split buffer."""
+    cache = pack.split_cache if pack is not None else {}
+    key = (w.untyped_storage().data_ptr(), w._version)
+    base = cache.get(key)
+    if base is None:
+        n_el = w.untyped_storage().nbytes() // 4
+        cols = w.shape[1]
+        assert w.stride(0) == cols and n_el % cols == 0, "split_weight: need a dense [rows, K] base"
+        full = torch.as_strided(w, (n_el // cols, cols), (cols, 1), 0)
+        base = torch.empty_like(full)
+        call("split_bf16", ptr(full), full.shape[0], cols, ptr(base))
+        cache[key] = base
+    return torch.as_strided(base, w.shape, w.stride(), w.storage_offset())
+
+
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, bias=None, row_scale=None, residual=None,
          aux_in=None, aux_out=None, epilogue=EPI_NONE, accumulate=False,
-         precision=PREC_FP32) -> Tensor:
+         precision=PREC_FP32, pack=None) -> Tensor:
     """out = epilogue(row_scale * (a @ w.T) + bias) (+ residual).  2-D views with unit
-    inner stride are allowed for every operand (leading dimension = stride(0))."""
+    inner stride are allowed for every operand (leading dimension = stride(0)).  With a
+    tensor-core precision the weight is swapped for its cached bf16 hi/lo split."""
     m, k = a.shape
     n = w.shape[0]
     assert w.shape[1] == k and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    if precision != PREC_FP32:
+        w = split_weight(w, pack)
     aux = aux_in if aux_in is not None else aux_out
     call(
         "gemm", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), m, n, k,
@@ -137,6 +158,7 @@ class PackedWeights:
 
     def __init__(self, module: torch.nn.Module):
         self.signature = self._signature(module)
+        self.split_cache: Dict[tuple, Tensor] = {}
         g = lambda t: t.detach()  # noqa: E731
         self.gnn: List[dict] = []
         for layer in module.gnn_layers:
@@ -270,36 +292,36 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
         call("compress_input", ptr(vec), ptr(dist), ptr(L["w_geo"]), ptr(L["b_geo"]),
              ptr(L["nbr"]), ptr(topo.z_neighbors), ptr(m), E, d, ptr(cat))
         c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
-        gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec)
+        gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec, pack=pw)
         del cat
         X = _empty((E + N, d), vec)
-        gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec)
+        gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec, pack=pw)
         del a1
         S["c1"] = c1
         for T in L["tl"]:
             K: dict = {}
-            gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec)
+            gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec, pack=pw)
             rstd1 = _rstd(X)
             qkv = _empty((E + N, 3 * d), vec)
-            gemm(X, T["w_qkv"], qkv, bias=T["b_qkv"], row_scale=rstd1, precision=prec)
+            gemm(X, T["w_qkv"], qkv, bias=T["b_qkv"], row_scale=rstd1, precision=prec, pack=pw)
             o = _empty((E + N, d), vec)
             lse = _empty((E + N, nh), vec)
             call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,
                  scale, topo.max_row, ptr(o), ptr(lse))
             Xn = _empty((E + N, d), vec)  # rows [:E] = t' ; rows [E:] = next centre token
-            gemm(o[:E], T["w_o"], Xn[:E], bias=T["b_o"], residual=X[:E], precision=prec)
+            gemm(o[:E], T["w_o"], Xn[:E], bias=T["b_o"], residual=X[:E], precision=prec, pack=pw)
             yc = _empty((N, d), vec)
-            gemm(o[E:], T["w_o"], yc, bias=T["b_o"], precision=prec)
+            gemm(o[E:], T["w_o"], yc, bias=T["b_o"], precision=prec, pack=pw)
             h1 = _empty((N, dn), vec)
-            gemm(yc, T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec)
+            gemm(yc, T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec, pack=pw)
             # centre MLP (d_node -> 4 d_node -> d_node, SwiGLU)
             rstd3 = _rstd(h1)
             ugc = _empty((N, 4 * dn), vec)
             sc = _empty((N, 2 * dn), vec)
             gemm(h1, T["wc_in"], sc, bias=T["bc_in"], row_scale=rstd3, epilogue=EPI_SWIGLU,
-                 aux_out=ugc, precision=prec)
+                 aux_out=ugc, precision=prec, pack=pw)
             h2 = _empty((N, dn), vec)
-            gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec)
+            gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec, pack=pw)
             # edge MLP (d_pet -> 2 d_ff -> d_pet, SwiGLU)
             tp = Xn[:E]
             rstd2 = _rstd(tp)
@@ -307,9 +329,9 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
             ug = _empty((E, 2 * dff), vec)
             s = _empty((E, dff), vec)
             gemm(tp, T["w_in"], s, bias=T["b_in"], row_scale=rstd2, epilogue=EPI_SWIGLU,
-                 aux_out=ug, precision=prec)
+                 aux_out=ug, precision=prec, pack=pw)
             Xnn = _empty((E + N, d), vec)
-            gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec)
+            gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec, pack=pw)
             del s, sc
             K.update(X=X, rstd1=rstd1, qkv=qkv, o=o, lse=lse, tp=tp, rstd2=rstd2, ug=ug,
                      h1=h1, rstd3=rstd3, ugc=ugc)
@@ -321,10 +343,10 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
         call("combine_ln_fwd", ptr(t), ptr(topo.rev), ptr(C["gamma"]), ptr(C["beta"]), E, d,
              ptr(cc), ptr(mean), ptr(rstd))
         p1, q1 = _empty((E, 2 * d), vec), _empty((E, 2 * d), vec)
-        gemm(cc, C["w_a"], q1, bias=C["b_a"], epilogue=EPI_SILU, aux_out=p1, precision=prec)
+        gemm(cc, C["w_a"], q1, bias=C["b_a"], epilogue=EPI_SILU, aux_out=p1, precision=prec, pack=pw)
         del cc
         # m <- m + t + W_b q1 + b_b   (in place on our own message buffer)
-        gemm(q1, C["w_b"], m, bias=C["b_b"], residual=t, accumulate=True, precision=prec)
+        gemm(q1, C["w_b"], m, bias=C["b_b"], residual=t, accumulate=True, precision=prec, pack=pw)
         del q1
         S.update(t=t, mean=mean, rstd=rstd, p1=p1)
         saved.append(S)
@@ -349,9 +371,9 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
         L, C, S = pw.gnn[l], pw.combine[l], saved[l]
         # ---- message update:  m_out = m_in + t + W_b silu(W_a LN(cat[t, t_rev]) + b_a) + b_b
         d_p1 = _empty((E, 2 * d), ref)
-        gemm(d_m, C["w_b_t"], d_p1, epilogue=EPI_MUL_DSILU, aux_in=S["p1"], precision=prec)
+        gemm(d_m, C["w_b_t"], d_p1, epilogue=EPI_MUL_DSILU, aux_in=S["p1"], precision=prec, pack=pw)
         d_cc = _empty((E, 2 * d), ref)
-        gemm(d_p1, C["w_a_t"], d_cc, precision=prec)
+        gemm(d_p1, C["w_a_t"], d_cc, precision=prec, pack=pw)
         d_cat = d_p1  # reuse
         call("combine_ln_bwd", ptr(d_cc), ptr(S["t"]), ptr(topo.rev), ptr(C["gamma"]),
              ptr(S["mean"]), ptr(S["rstd"]), E, d, ptr(d_cat))
@@ -363,31 +385,31 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
             dff = T["w_out"].shape[1]
             # ---- edge MLP: t'' = t' + W_out swiglu(W_in rms(t'))
             d_ug = _empty((E, 2 * dff), ref)
-            gemm(d_t, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec)
+            gemm(d_t, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec, pack=pw)
             d_xh = _empty((E, d), ref)
-            gemm(d_ug, T["w_in_t"], d_xh, precision=prec)
+            gemm(d_ug, T["w_in_t"], d_xh, precision=prec, pack=pw)
             del d_ug
             d_tp = _empty((E, d), ref)
             _rms_bwd(d_xh, K["tp"], K["rstd2"], d_t, d_tp)
             # ---- centre MLP: h2 = h1 + Wc_out swiglu(Wc_in rms(h1))
             d_ugc = _empty((N, 4 * dn), ref)
-            gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec)
+            gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec, pack=pw)
             d_xhc = _empty((N, dn), ref)
-            gemm(d_ugc, T["wc_in_t"], d_xhc, precision=prec)
+            gemm(d_ugc, T["wc_in_t"], d_xhc, precision=prec, pack=pw)
             d_h1 = _empty((N, dn), ref)
             _rms_bwd(d_xhc, K["h1"], K["rstd3"], d_h, d_h1)
             # ---- h1 = h + W_exp y_c ;  t' = t + y_e ;  y = W_o o
             d_yc = _empty((N, d), ref)
-            gemm(d_h1, T["w_exp_t"], d_yc, precision=prec)
+            gemm(d_h1, T["w_exp_t"], d_yc, precision=prec, pack=pw)
             d_o = _empty((E + N, d), ref)
-            gemm(d_tp, T["w_o_t"], d_o[:E], precision=prec)
-            gemm(d_yc, T["w_o_t"], d_o[E:], precision=prec)
+            gemm(d_tp, T["w_o_t"], d_o[:E], precision=prec, pack=pw)
+            gemm(d_yc, T["w_o_t"], d_o[E:], precision=prec, pack=pw)
             d_qkv = _empty((E + N, 3 * d), ref)
             call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o),
                  ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row,
                  ptr(d_qkv), ptr(d_fc))
             d_xh1 = d_o  # reuse
-            gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec)
+            gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec, pack=pw)
             del d_qkv
             d_t_new = d_xh  # reuse
             _rms_bwd(d_xh1[:E], K["X"][:E], K["rstd1"][:E], d_tp, d_t_new)
@@ -395,18 +417,18 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
             _rms_bwd(d_xh1[E:], K["X"][E:], K["rstd1"][E:], None, d_c)
             if l > 0 or k > 0:
                 d_h_new = _empty((N, dn), ref)
-                gemm(d_c, T["w_con_t"], d_h_new, residual=d_h1, precision=prec)
+                gemm(d_c, T["w_con_t"], d_h_new, residual=d_h1, precision=prec, pack=pw)
                 d_h = d_h_new
             d_t = d_t_new
         # ---- token builder: t = W_2 silu(W_1 cat[geo, nbr, m] + b_1) + b_2
         d_c1 = _empty((E, d), ref)
-        gemm(d_t, L["w2_t"], d_c1, epilogue=EPI_MUL_DSILU, aux_in=S["c1"], precision=prec)
+        gemm(d_t, L["w2_t"], d_c1, epilogue=EPI_MUL_DSILU, aux_in=S["c1"], precision=prec, pack=pw)
         d_geo = _empty((E, d), ref)
-        gemm(d_c1, L["w1_t"][:d], d_geo, precision=prec)
+        gemm(d_c1, L["w1_t"][:d], d_geo, precision=prec, pack=pw)
         call("geom_embed_bwd", ptr(d_geo), d, ptr(L["w_geo"]), E, d, 1, ptr(d_vec), ptr(d_dist))
         if l > 0:
             width = L["w1_t"].shape[0]
-            gemm(d_c1, L["w1_t"][width - d:], d_m, accumulate=True, precision=prec)
+            gemm(d_c1, L["w1_t"][width - d:], d_m, accumulate=True, precision=prec, pack=pw)
     return d_vec, d_dist, d_fc
 
 
@@ -417,13 +439,13 @@ def predict_forward(pw: PackedWeights, topo: Topology, name: str, h, m, fc, prec
     N, E = topo.n_atoms, topo.n_edges
     dh = H["n2"].shape[0]
     n1, n1p = _empty((N, dh), h), _empty((N, dh), h)
-    gemm(h, H["n1"], n1, bias=H["n1_b"], epilogue=EPI_SILU, aux_out=n1p, precision=prec)
+    gemm(h, H["n1"], n1, bias=H["n1_b"], epilogue=EPI_SILU, aux_out=n1p, precision=prec, pack=pw)
     n2, n2p = _empty((N, dh), h), _empty((N, dh), h)
-    gemm(n1, H["n2"], n2, bias=H["n2_b"], epilogue=EPI_SILU, aux_out=n2p, precision=prec)
+    gemm(n1, H["n2"], n2, bias=H["n2_b"], epilogue=EPI_SILU, aux_out=n2p, precision=prec, pack=pw)
     e1, e1p = _empty((E, dh), h), _empty((E, dh), h)
-    gemm(m, H["e1"], e1, bias=H["e1_b"], epilogue=EPI_SILU, aux_out=e1p, precision=prec)
+    gemm(m, H["e1"], e1, bias=H["e1_b"], epilogue=EPI_SILU, aux_out=e1p, precision=prec, pack=pw)
     e2, e2p = _empty((E, dh), h), _empty((E, dh), h)
-    gemm(e1, H["e2"], e2, bias=H["e2_b"], epilogue=EPI_SILU, aux_out=e2p, precision=prec)
+    gemm(e1, H["e2"], e2, bias=H["e2_b"], epilogue=EPI_SILU, aux_out=e2p, precision=prec, pack=pw)
     n_out = H["wn"].shape[0]
     atomic = _empty((N, n_out), h)
     pe = _empty((E, n_out), h)
@@ -446,11 +468,11 @@ def predict_backward(pw: PackedWeights, topo: Topology, name: str, fc, saved, d_
          ptr(topo.ctr), ptr(saved["n2p"]), ptr(saved["e2p"]), N, E, dh, n_out, ptr(d_n2p),
          ptr(d_e2p), ptr(d_fc))
     d_n1p = _empty((N, dh), fc)
-    gemm(d_n2p, H["n2_t"], d_n1p, epilogue=EPI_MUL_DSILU, aux_in=saved["n1p"], precision=prec)
+    gemm(d_n2p, H["n2_t"], d_n1p, epilogue=EPI_MUL_DSILU, aux_in=saved["n1p"], precision=prec, pack=pw)
     d_h = _empty((N, H["n1"].shape[1]), fc)
-    gemm(d_n1p, H["n1_t"], d_h, precision=prec)
+    gemm(d_n1p, H["n1_t"], d_h, precision=prec, pack=pw)
     d_e1p = _empty((E, dh), fc)
-    gemm(d_e2p, H["e2_t"], d_e1p, epilogue=EPI_MUL_DSILU, aux_in=saved["e1p"], precision=prec)
+    gemm(d_e2p, H["e2_t"], d_e1p, epilogue=EPI_MUL_DSILU, aux_in=saved["e1p"], precision=prec, pack=pw)
     d_m = _empty((E, H["e1"].shape[1]), fc)
-    gemm(d_e1p, H["e1_t"], d_m, precision=prec)
+    gemm(d_e1p, H["e1_t"], d_m, precision=prec, pack=pw)
     return d_h, d_m, d_fc

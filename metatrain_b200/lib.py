@@ -41,6 +41,7 @@ _SIGNATURES = {
                           _P, _P, _P, _P],
     "petb200_gemm": [_P, _I64, _P, _I64, _P, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P,
                      _I64, _I, _I, _I, _P],
+    "petb200_split_bf16": [_P, _I64, _I, _P, _P],
     "petb200_embedding": [_P, _P, _I64, _I, _P, _I64, _P],
     "petb200_transpose_scale": [_P, _I, _I, _P, _P, _P, _P],
     "petb200_compress_input": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],

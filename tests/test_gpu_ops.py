@@ -9,9 +9,12 @@ pytestmark = pytest.mark.gpu
 
 from metatrain_b200 import engine, lib  # noqa: E402
 from metatrain_b200.lib import (EPI_MUL_DSILU, EPI_NONE, EPI_SILU, EPI_SWIGLU, EPI_SWIGLU_BWD,  # noqa: E402
-                                call, ptr)
+                                PREC_BF16, PREC_BF16X3, PREC_FP32, call, ptr)
 
 DEV = "cuda:0"
+# (precision id, absolute tolerance scale relative to fp32) for the GEMM tests
+PRECISIONS = [pytest.param(PREC_FP32, 1.0, id="fp32"), pytest.param(PREC_BF16X3, 3.0, id="bf16x3"),
+              pytest.param(PREC_BF16, 1500.0, id="bf16")]
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -39,19 +42,35 @@ def assert_close(a, b, atol, rtol, what=""):
 
 
 # ---------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("prec,tol", PRECISIONS)
 @pytest.mark.parametrize("M,N,K", [(1000, 128, 128), (77, 384, 128), (513, 128, 384),
-                                   (300, 256, 256), (129, 1024, 256), (40, 256, 512), (0, 128, 128)])
-def test_gemm_plain_bias_rowscale_residual(M, N, K):
+                                   (300, 256, 256), (129, 1024, 256), (40, 256, 512), (0, 128, 128),
+                                   (40000, 128, 128), (19000, 512, 1024)])
+def test_gemm_plain_bias_rowscale_residual(M, N, K, prec, tol):
     a, w, b = rnd(M, K), rnd(N, K, scale=0.1), rnd(N)
     rs, res = rnd(M).abs() + 0.5, rnd(M, N)
     out = torch.empty(M, N, device=DEV)
-    engine.gemm(a, w, out, bias=b, row_scale=rs, residual=res)
+    engine.gemm(a, w, out, bias=b, row_scale=rs, residual=res, precision=prec)
     ref = rs[:, None].double() * (a.double() @ w.double().T) + b.double() + res.double()
-    assert_close(out, ref, 1e-4, 1e-5, "gemm")
+    assert_close(out, ref, 1e-4 * tol, 1e-5 * tol, "gemm")
     # accumulate
     out2 = out.clone()
-    engine.gemm(a, w, out2, accumulate=True)
-    assert_close(out2, ref + a.double() @ w.double().T, 2e-4, 1e-5, "gemm accumulate")
+    engine.gemm(a, w, out2, accumulate=True, precision=prec)
+    assert_close(out2, ref + a.double() @ w.double().T, 2e-4 * tol, 1e-5 * tol, "gemm accumulate")
+
+
+def test_gemm_bf16x3_error_level():
+    """The 2-term split must sit ~2^-16 relative, far below single-pass bf16 (~2^-9)."""
+    M, N, K = 4096, 128, 256
+    a, w = rnd(M, K), rnd(N, K, scale=0.1)
+    ref = a.double() @ w.double().T
+    errs = {}
+    for name, prec in (("fp32", PREC_FP32), ("bf16x3", PREC_BF16X3), ("bf16", PREC_BF16)):
+        out = torch.empty(M, N, device=DEV)
+        engine.gemm(a, w, out, precision=prec)
+        errs[name] = float((out.double() - ref).abs().max() / ref.abs().max())
+    print(errs)
+    assert errs["fp32"] < 2e-6 and errs["bf16x3"] < 3e-5 and 1e-4 < errs["bf16"] < 2e-2
 
 
 def test_gemm_strided_views():
@@ -62,43 +81,51 @@ def test_gemm_strided_views():
     engine.gemm(a, w, big_out[50:])
     assert_close(big_out[50:], a.double() @ w.double().T, 1e-4, 1e-5, "gemm views")
     assert float(big_out[:50].abs().max()) == 0.0
+    # tensor-core path: strided A / C, row-slice view of a dense weight
+    w_rows = rnd(3 * N, K, scale=0.1)
+    big_out.zero_()
+    engine.gemm(a, w_rows[N:2 * N], big_out[50:], precision=PREC_BF16X3)
+    assert_close(big_out[50:], a.double() @ w_rows[N:2 * N].double().T, 3e-4, 3e-5, "gemm tc views")
+    assert float(big_out[:50].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("prec,tol", PRECISIONS)
 @pytest.mark.parametrize("M,N,K", [(700, 128, 256), (65, 256, 128)])
-def test_gemm_silu_and_dsilu(M, N, K):
+def test_gemm_silu_and_dsilu(M, N, K, prec, tol):
     a, w, b = rnd(M, K), rnd(N, K, scale=0.1), rnd(N)
     out, pre = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
-    engine.gemm(a, w, out, bias=b, epilogue=EPI_SILU, aux_out=pre)
+    engine.gemm(a, w, out, bias=b, epilogue=EPI_SILU, aux_out=pre, precision=prec)
     ref_pre = a.double() @ w.double().T + b.double()
-    assert_close(pre, ref_pre, 1e-4, 1e-5, "silu pre")
-    assert_close(out, F.silu(ref_pre), 1e-4, 1e-5, "silu out")
+    assert_close(pre, ref_pre, 1e-4 * tol, 1e-5 * tol, "silu pre")
+    assert_close(out, F.silu(ref_pre), 1e-4 * tol, 1e-5 * tol, "silu out")
     # dgrad through the SiLU: d_pre = (g @ W2) * silu'(pre)
     g, w2 = rnd(M, K, seed=3), rnd(N, K, seed=4, scale=0.1)
     d = torch.empty(M, N, device=DEV)
-    engine.gemm(g, w2, d, epilogue=EPI_MUL_DSILU, aux_in=pre)
+    engine.gemm(g, w2, d, epilogue=EPI_MUL_DSILU, aux_in=pre, precision=prec)
     p = pre.double().clone().requires_grad_(True)
     (F.silu(p) * (g.double() @ w2.double().T)).sum().backward()
-    assert_close(d, p.grad, 1e-4, 1e-5, "mul_dsilu")
+    assert_close(d, p.grad, 1e-4 * tol, 1e-5 * tol, "mul_dsilu")
 
 
+@pytest.mark.parametrize("prec,tol", PRECISIONS)
 @pytest.mark.parametrize("M,Fdim,K", [(500, 256, 128), (90, 512, 256)])
-def test_gemm_swiglu_fwd_bwd(M, Fdim, K):
+def test_gemm_swiglu_fwd_bwd(M, Fdim, K, prec, tol):
     a, w, b = rnd(M, K), rnd(2 * Fdim, K, scale=0.1), rnd(2 * Fdim)
     rs = rnd(M).abs() + 0.5
     out, ug = torch.empty(M, Fdim, device=DEV), torch.empty(M, 2 * Fdim, device=DEV)
-    engine.gemm(a, w, out, bias=b, row_scale=rs, epilogue=EPI_SWIGLU, aux_out=ug)
+    engine.gemm(a, w, out, bias=b, row_scale=rs, epilogue=EPI_SWIGLU, aux_out=ug, precision=prec)
     ref_ug = rs[:, None].double() * (a.double() @ w.double().T) + b.double()
     u, g = ref_ug.chunk(2, dim=-1)
-    assert_close(ug, ref_ug, 1e-4, 1e-5, "swiglu preact")
-    assert_close(out, u * torch.sigmoid(g), 1e-4, 1e-5, "swiglu out")
+    assert_close(ug, ref_ug, 1e-4 * tol, 1e-5 * tol, "swiglu preact")
+    assert_close(out, u * torch.sigmoid(g), 1e-4 * tol, 1e-5 * tol, "swiglu out")
     # backward: d_ug from d_s = go @ Wout   (Wout^T passed as the [F, d] operand)
     go, wout_t = rnd(M, 128, seed=5), rnd(Fdim, 128, seed=6, scale=0.1)
     d_ug = torch.empty(M, 2 * Fdim, device=DEV)
-    engine.gemm(go, wout_t, d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=ug)
+    engine.gemm(go, wout_t, d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=ug, precision=prec)
     x = ug.double().clone().requires_grad_(True)
     uu, gg = x.chunk(2, dim=-1)
     ((uu * torch.sigmoid(gg)) * (go.double() @ wout_t.double().T)).sum().backward()
-    assert_close(d_ug, x.grad, 1e-4, 1e-5, "swiglu bwd")
+    assert_close(d_ug, x.grad, 1e-4 * tol, 1e-5 * tol, "swiglu bwd")
 
 
 def test_gemm_rejects_bad_shapes():
