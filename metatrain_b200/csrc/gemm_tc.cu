@@ -8,13 +8,19 @@
 // keeps forces within 1e-4 eV/A of the fp32 reference (precision
 // ladder).  PETB200_PREC_BF16 issues only hi*hi.
 //
-// Persistent, warp-specialised CTA (one per SM), 288 threads:
-//   warps 0-3  epilogue   TMEM -> registers (tcgen05.ld 32x32b) -> bias / row scale /
-//                         activation / residual -> global
-//   warp  4    MMA issue  one elected lane issues tcgen05.mma (M=128, N=128, K=16) and
-//                         tcgen05.commit; owns the TMEM allocation (2 x 128 columns)
-//   warps 5-8  producers  global fp32 A tile -> bf16 hi/lo -> 128B-swizzled K-major smem;
-//                         pre-split bf16 W tile -> smem; 3-stage mbarrier ring
+// Persistent, warp-specialised CTA (one per SM), 416 threads:
+//   warps 0-7   epilogue   TMEM -> registers (tcgen05.ld 32x32b.x16) -> per-warp smem
+//                          transpose tile -> coalesced bias / row scale / activation /
+//                          residual -> global.  Warps w and w+4 share TMEM lane quarter
+//                          w%4 and split the 128 accumulator columns in halves.
+//   warp  8     MMA issue  one lane issues tcgen05.mma (M=128, N=128, K=16) and
+//                          tcgen05.commit; owns the TMEM allocation (2 x 128 columns)
+//   warps 9-12  producers  global fp32 A tile -> bf16 hi/lo -> 128B-swizzled K-major smem
+//                          (mbarrier ring).  Two operand-B modes:
+//                          * stationary (K <= 256): the CTA owns one 128-column chunk for
+//                            its whole life, W hi/lo sits in smem once, only A streams
+//                            (register double buffering keeps loads in flight);
+//                          * streaming  (K  > 256): W tiles ride the ring with A.
 // Work item = (128-row tile, 128-column chunk); the accumulator is double buffered in
 // TMEM so the epilogue of item i overlaps the main loop of item i+1.
 //
@@ -29,13 +35,18 @@ namespace petb200 {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;  // BK bf16 = 128 B = one swizzle row
-constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 2;      // one bf16 operand tile: 16 KiB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
-constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 4;
+constexpr int OPERAND_BYTES = 192 * 1024;    // A ring (+ resident or streamed W tiles)
+constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;
+constexpr int NUM_PROD_THREADS = NUM_PROD_WARPS * 32;
 constexpr int NUM_THREADS = 32 * (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS);
+constexpr int MAX_STAGES = 4;
 constexpr int TMEM_COLS = 256;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_COLS = 16;   // accumulator columns per tcgen05.ld in the epilogue
+constexpr int STAGE_LD = 20;   // floats per row of the epilogue transpose tile
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * STAGE_LD * 4;
+constexpr size_t SMEM_BYTES =
+    (size_t)OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -63,6 +74,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+// arrive on the mbarrier once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -104,6 +124,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start address >> 4 | LBO (unused, 1) << 16 | SBO (8 rows x 128 B = 1024 B) >> 4 << 32 |
 // version 1 << 46 | layout type SWIZZLE_128B (2) << 61
@@ -129,47 +161,103 @@ __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
+// Tile column -> weight row.  Plain layouts: identity.  SwiGLU forward: within each
+// 64-column half of the tile, columns [0,32) are "value" columns and [32,64) the matching
+// "gate" columns F + ... (transformer.py:40-44: v, g = w_in(x).chunk(2)), so that one
+// epilogue warp sees both members of every pair.
+// epilogue activations with SFU intrinsics (ex2.approx / rcp.approx: ~1e-7 relative, far
+// below the bf16x3 operand error); the fp32 FFMA kernel keeps the exact expf versions
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fsilu(float x) { return x * fsigmoid(x); }
+__device__ __forceinline__ float fdsilu(float x) {
+  const float s = fsigmoid(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
 template <int EPI>
 __device__ __forceinline__ int weight_row(int n0, int c, int F) {
-  if (EPI == PETB200_EPI_SWIGLU) return (c < 64) ? (n0 / 2 + c) : (F + n0 / 2 + (c - 64));
+  if (EPI == PETB200_EPI_SWIGLU) {
+    const int value_col = n0 / 2 + (c >> 6) * 32 + (c & 31);
+    return (c & 32) ? F + value_col : value_col;
+  }
   return n0 + c;
 }
 
-struct PipeState {
+struct Ring {
   int stage = 0;
   uint32_t phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) {
+  __device__ __forceinline__ void advance(int num_stages) {
+    if (++stage == num_stages) {
       stage = 0;
       phase ^= 1;
     }
   }
 };
 
-template <int EPI, int NPROD /*3 = bf16x3, 1 = bf16*/>
+// Work distribution.  Stationary-B: CTA b owns column chunk b % n_chunks and walks row
+// tiles (b / n_chunks) + j * (grid / n_chunks).  Streaming: items b, b + grid, ...
+struct Schedule {
+  int num_n_chunks, first, stride, count;
+  bool stationary;
+  __device__ __forceinline__ Schedule(const GemmArgs& g, bool stat) {
+    const int num_m_tiles = (int)ceil_div(g.M, BM);
+    num_n_chunks = g.N / BN;
+    stationary = stat;
+    if (stat) {
+      const int per = gridDim.x / num_n_chunks;  // CTAs per column chunk
+      first = blockIdx.x / num_n_chunks;
+      stride = per;
+      count = first < num_m_tiles ? (num_m_tiles - first + per - 1) / per : 0;
+    } else {
+      const int items = num_m_tiles * num_n_chunks;
+      first = blockIdx.x;
+      stride = gridDim.x;
+      count = first < items ? (items - first + stride - 1) / stride : 0;
+    }
+  }
+  __device__ __forceinline__ void item(int j, int64_t& m0, int& n0) const {
+    if (stationary) {
+      m0 = (int64_t)(first + j * stride) * BM;
+      n0 = (blockIdx.x % num_n_chunks) * BN;
+    } else {
+      const int it = first + j * stride;
+      m0 = (int64_t)(it / num_n_chunks) * BM;
+      n0 = (it % num_n_chunks) * BN;
+    }
+  }
+};
+
+template <int EPI, int NPROD /*3 = bf16x3, 1 = bf16*/, bool BSTAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t bar_base = smem_base + OPERAND_BYTES;
+  // barriers: loaded / full / empty [MAX_STAGES], tmem_full[2], tmem_empty[2], TMEM base
+  auto loaded_bar = [&](int s) { return bar_base + 8u * s; };
+  auto full_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + 2 + a); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + OPERAND_BYTES + 8 * (3 * MAX_STAGES + 4));
+  float* stage_all = reinterpret_cast<float*>(smem_gen + OPERAND_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m_tiles = (int)ceil_div(g.M, BM);
-  const int num_n_chunks = g.N / BN;
-  const int num_items = num_m_tiles * num_n_chunks;
   const int num_k = g.K / BK;
   const int F = g.N / 2;
+  // operand memory map.  Stationary: [W: num_k x (hi, lo)] then the A ring of (hi, lo)
+  // pairs; streaming: ring of (A_hi, A_lo, W_hi, W_lo).
+  const int b_bytes = BSTAT ? num_k * 2 * TILE_BYTES : 0;
+  const int stage_bytes = BSTAT ? 2 * TILE_BYTES : 4 * TILE_BYTES;
+  int num_stages = (OPERAND_BYTES - b_bytes) / stage_bytes;
+  if (num_stages > MAX_STAGES) num_stages = MAX_STAGES;
+  const Schedule sched(g, BSTAT);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), NUM_PROD_WARPS * 32);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(loaded_bar(s), NUM_PROD_THREADS);
+      mbar_init(full_bar(s), NUM_PROD_THREADS);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -185,6 +273,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
                  "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  if (BSTAT && warp > NUM_EPI_WARPS) {
+    // resident W: every producer thread copies its share of the (hi, lo) tiles once
+    const int t = threadIdx.x - 32 * (NUM_EPI_WARPS + 1);
+    const int n0 = (blockIdx.x % sched.num_n_chunks) * BN;
+    for (int kc = 0; kc < num_k; ++kc) {
+#pragma unroll
+      for (int i = 0; i < 1024 / NUM_PROD_THREADS; ++i) {
+        const int idx = t + NUM_PROD_THREADS * i, row = idx >> 3, c = idx & 7;
+        const uint8_t* wrow =
+            reinterpret_cast<const uint8_t*>(g.W + (int64_t)weight_row<EPI>(n0, row, F) * g.ldw);
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(wrow + (size_t)kc * BK * 2) + c);
+        *reinterpret_cast<uint4*>(smem_gen + (size_t)kc * 2 * TILE_BYTES + swz(row, c)) = hi;
+        if (NPROD == 3) {
+          const uint4 lo = __ldg(
+              reinterpret_cast<const uint4*>(wrow + (size_t)g.K * 2 + (size_t)kc * BK * 2) + c);
+          *reinterpret_cast<uint4*>(smem_gen + (size_t)kc * 2 * TILE_BYTES + TILE_BYTES + swz(row, c)) = lo;
+        }
+      }
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -192,82 +301,104 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 
   if (warp > NUM_EPI_WARPS) {
     // =============================================================== producers
-    const int t = threadIdx.x - 32 * (NUM_EPI_WARPS + 1);  // 0..127
-    PipeState ps;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int64_t m0 = (int64_t)(item / num_n_chunks) * BM;
-      const int n0 = (item % num_n_chunks) * BN;
-      for (int kc = 0; kc < num_k; ++kc) {
-        mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
-        uint8_t* st = smem_gen + (size_t)ps.stage * STAGE_BYTES;
-        const int k0 = kc * BK;
-        // ---- issue all global loads of this stage first (32 x 16 B in flight per thread)
-        float4 av[16];
+    // Stage layout: [A_hi tile | A_lo tile | (streaming) W_hi tile | W_lo tile].  The fp32
+    // A chunk (128 rows x 64 floats) is copied asynchronously (cp.async, no registers) so
+    // that row r's floats 0..31 land in the 128 bytes of A_hi row r and floats 32..63 in
+    // A_lo row r; a warp then converts the row IN PLACE to its bf16 hi / lo 128-byte
+    // swizzled rows.  Copies run `num_stages - 1` chunks ahead of the conversion.
+    const int t = threadIdx.x - 32 * (NUM_EPI_WARPS + 1);  // 0..NUM_PROD_THREADS-1
+    const int pw = t >> 5;
+    const uint32_t ring_u32 = smem_base + (uint32_t)b_bytes;
+    uint8_t* ring_base = smem_gen + b_bytes;
+    const int total = sched.count * num_k;  // (item, k-chunk) pairs of this CTA, flattened
+    const int depth = num_stages - 1;
+    Ring load_ring, conv_ring;
+    for (int q = 0; q < total + depth; ++q) {
+      if (q < total) {
+        int64_t m0;
+        int n0;
+        sched.item(q / num_k, m0, n0);
+        const int k0 = (q % num_k) * BK;
+        mbar_wait(empty_bar(load_ring.stage), load_ring.phase ^ 1);
+        const uint32_t st = ring_u32 + (uint32_t)load_ring.stage * stage_bytes;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = t + 128 * i, row = idx >> 4, c4 = idx & 15;
+        for (int i = 0; i < 2048 / NUM_PROD_THREADS; ++i) {
+          const int idx = t + NUM_PROD_THREADS * i, row = idx >> 4, piece = idx & 15;
           const int64_t m = m0 + row;
-          av[i] = m < g.M ? __ldg(reinterpret_cast<const float4*>(g.A + m * g.lda + k0) + c4)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool ok = m < g.M;
+          const float* src = g.A + (ok ? m : 0) * g.lda + k0 + 4 * piece;
+          cp_async16(st + (piece >> 3) * TILE_BYTES + row * 128 + (piece & 7) * 16, src, ok ? 16u : 0u);
         }
-        uint4 bh[8], bl[8];
+        if (!BSTAT) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = t + 128 * i, row = idx >> 3, c = idx & 7;
-          // split weight row: [K bf16 hi | K bf16 lo] in the bytes of an fp32 row
-          const uint8_t* wrow = reinterpret_cast<const uint8_t*>(
-              g.W + (int64_t)weight_row<EPI>(n0, row, F) * g.ldw);
-          bh[i] = __ldg(reinterpret_cast<const uint4*>(wrow + (size_t)k0 * 2) + c);
-          if (NPROD == 3)
-            bl[i] = __ldg(reinterpret_cast<const uint4*>(wrow + (size_t)g.K * 2 + (size_t)k0 * 2) + c);
+          for (int i = 0; i < 1024 / NUM_PROD_THREADS; ++i) {
+            const int idx = t + NUM_PROD_THREADS * i, row = idx >> 3, c = idx & 7;
+            const uint8_t* wrow =
+                reinterpret_cast<const uint8_t*>(g.W + (int64_t)weight_row<EPI>(n0, row, F) * g.ldw);
+            cp_async16(st + 2 * TILE_BYTES + swz(row, c), wrow + (size_t)k0 * 2 + c * 16, 16u);
+            if (NPROD == 3)
+              cp_async16(st + 3 * TILE_BYTES + swz(row, c),
+                         wrow + (size_t)g.K * 2 + (size_t)k0 * 2 + c * 16, 16u);
+          }
         }
-        // ---- A: fp32 -> bf16 hi / lo, swizzled K-major tiles
+        cp_async_arrive(loaded_bar(load_ring.stage));
+        load_ring.advance(num_stages);
+      }
+      if (q >= depth) {
+        mbar_wait(loaded_bar(conv_ring.stage), conv_ring.phase);
+        uint8_t* st = ring_base + (size_t)conv_ring.stage * stage_bytes;
+        // warp pw converts its ROWS_PER_WARP rows; lane l owns k = 2l, 2l+1 of each row
+        constexpr int ROWS_PER_WARP = BM / NUM_PROD_WARPS;
+        const uint8_t* src_tile = st + (lane < 16 ? 0 : TILE_BYTES);
+        const int chunk = lane >> 2, within = (lane & 3) * 4;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = t + 128 * i, row = idx >> 4, c4 = idx & 15;
-          const float4 x = av[i];
-          const float hx = bf16_round(x.x), hy = bf16_round(x.y), hz = bf16_round(x.z),
-                      hw = bf16_round(x.w);
-          const uint32_t off = swz(row, c4 >> 1) + ((c4 & 1) << 3);
-          *reinterpret_cast<uint2*>(st + off) = make_uint2(pack_bf16(hx, hy), pack_bf16(hz, hw));
-          if (NPROD == 3)
-            *reinterpret_cast<uint2*>(st + TILE_BYTES + off) =
-                make_uint2(pack_bf16(x.x - hx, x.y - hy), pack_bf16(x.z - hz, x.w - hw));
-        }
+        for (int b = 0; b < ROWS_PER_WARP / 4; ++b) {
+          float2 x[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = t + 128 * i, row = idx >> 3, c = idx & 7;
-          const uint32_t off = swz(row, c);
-          *reinterpret_cast<uint4*>(st + 2 * TILE_BYTES + off) = bh[i];
-          if (NPROD == 3) *reinterpret_cast<uint4*>(st + 3 * TILE_BYTES + off) = bl[i];
+          for (int jj = 0; jj < 4; ++jj) {
+            const int r = pw * ROWS_PER_WARP + b * 4 + jj;
+            x[jj] = *reinterpret_cast<const float2*>(src_tile + r * 128 + (lane & 15) * 8);
+          }
+          __syncwarp();  // the whole row is in registers before it is overwritten
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int r = pw * ROWS_PER_WARP + b * 4 + jj;
+            const float hx = bf16_round(x[jj].x), hy = bf16_round(x[jj].y);
+            const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+            *reinterpret_cast<uint32_t*>(st + off) = pack_bf16(hx, hy);
+            if (NPROD == 3)
+              *reinterpret_cast<uint32_t*>(st + TILE_BYTES + off) =
+                  pack_bf16(x[jj].x - hx, x[jj].y - hy);
+          }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
-        mbar_arrive(full_bar(ps.stage));
-        ps.advance();
+        mbar_arrive(full_bar(conv_ring.stage));
+        conv_ring.advance(num_stages);
       }
     }
   } else if (warp == NUM_EPI_WARPS) {
     // =============================================================== MMA issuer
     constexpr uint32_t idesc = make_idesc(BM, BN);
-    PipeState ps;
+    Ring ring;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int j = 0; j < sched.count; ++j) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kc = 0; kc < num_k; ++kc) {
-        mbar_wait(full_bar(ps.stage), ps.phase);
+        mbar_wait(full_bar(ring.stage), ring.phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t st = smem_base + (uint32_t)ps.stage * STAGE_BYTES;
+          const uint32_t st = smem_base + (uint32_t)b_bytes + (uint32_t)ring.stage * stage_bytes;
+          const uint32_t bt = BSTAT ? smem_base + (uint32_t)kc * 2 * TILE_BYTES : st + 2 * TILE_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t a_hi = make_smem_desc(st + kk * 32);
-            const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES + kk * 32);
+            const uint64_t b_hi = make_smem_desc(bt + kk * 32);
             if (NPROD == 3) {
               const uint64_t a_lo = make_smem_desc(st + TILE_BYTES + kk * 32);
-              const uint64_t b_lo = make_smem_desc(st + 3 * TILE_BYTES + kk * 32);
+              const uint64_t b_lo = make_smem_desc(bt + TILE_BYTES + kk * 32);
               // small terms first, then the leading term
               tc_mma(d_tmem, a_lo, b_hi, idesc, (kc | kk) != 0);
               tc_mma(d_tmem, a_hi, b_lo, idesc, 1);
@@ -276,11 +407,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
               tc_mma(d_tmem, a_hi, b_hi, idesc, (kc | kk) != 0);
             }
           }
-          tc_commit(empty_bar(ps.stage));  // frees the smem stage when these MMAs retire
+          tc_commit(empty_bar(ring.stage));  // frees the smem stage when these MMAs retire
           if (kc == num_k - 1) tc_commit(tfull_bar(acc));
         }
         __syncwarp();
-        ps.advance();
+        ring.advance(num_stages);
       }
       if (++acc == 2) {
         acc = 0;
@@ -289,118 +420,178 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
     }
   } else {
     // =============================================================== epilogue
+    // TMEM gives each thread one accumulator row (16 columns per tcgen05.ld).  Rows are
+    // transposed through a per-warp shared-memory tile (stride 20 floats: conflict-free
+    // float4 both ways) so that every global access of the epilogue (C, residual, aux) is a
+    // coalesced 64-byte row segment: lane -> (row = 8*it + rsel, float4 column lane%4).
+    float* stage = stage_all + warp * (32 * STAGE_LD);
+    const int quarter = warp & 3, half = warp >> 2;
+    const int c4 = lane & 3, rsel = (lane >> 3) + 4 * ((lane >> 2) & 1);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int64_t m = (int64_t)(item / num_n_chunks) * BM + warp * 32 + lane;
-      const int n0 = (item % num_n_chunks) * BN;
-      const bool ok = m < g.M;
+    auto ld4 = [&](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int NCH = 64 / EPI_COLS;  // column chunks per warp
+    // one additive operand is prefetched per item: the residual, or (C += ...) the old C;
+    // the rare "residual AND accumulate" case adds the old C late, unprefetched
+    const float* pre_src = g.residual ? g.residual : (g.accumulate ? g.C : nullptr);
+    const int64_t pre_ld = g.residual ? g.ldr : g.ldc;
+    const bool late_acc = g.residual && g.accumulate;
+    for (int j = 0; j < sched.count; ++j) {
+      int64_t m0;
+      int n0;
+      sched.item(j, m0, n0);
+      const int64_t m_base = m0 + quarter * 32;
+      float rs[4];
+      bool ok[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int64_t m = m_base + it * 8 + rsel;
+        ok[it] = m < g.M;
+        rs[it] = (g.row_scale && ok[it]) ? __ldg(g.row_scale + m) : 1.0f;
+      }
+      // Global operands of the whole item are requested BEFORE waiting for the MMA, so
+      // their latency hides behind the main loop of this item.
+      float4 pre[NCH][4];
+      if (EPI == PETB200_EPI_NONE || EPI == PETB200_EPI_SILU || EPI == PETB200_EPI_MUL_DSILU) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int64_t m = m_base + it * 8 + rsel;
+            const int c0 = n0 + 64 * half + EPI_COLS * ch + 4 * c4;
+            pre[ch][it] = zero4;
+            if (!ok[it]) continue;
+            if (EPI == PETB200_EPI_MUL_DSILU) {
+              pre[ch][it] = ld4(g.aux_in + m * g.ld_aux + c0);
+            } else if (pre_src) {
+              pre[ch][it] = ld4(pre_src + m * pre_ld + c0);
+            }
+          }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-      const float rs = (ok && g.row_scale) ? g.row_scale[m] : 1.0f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      auto stage_chunk = [&](int tile_col) {
+        float v[EPI_COLS];
+        tmem_ld16(taddr + tile_col, v);
+        __syncwarp();  // readers of the previous chunk are done with the tile
+#pragma unroll
+        for (int q = 0; q < EPI_COLS / 4; ++q)
+          *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * q) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+      };
+      auto staged = [&](int it) {
+        return *reinterpret_cast<const float4*>(stage + (it * 8 + rsel) * STAGE_LD + 4 * c4);
+      };
+
       if (EPI == PETB200_EPI_SWIGLU) {
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          float u[32], gt[32];
-          tmem_ld32(taddr + 32 * h, u);
-          tmem_ld32(taddr + 64 + 32 * h, gt);
-          if (ok) {
-            const int cu = n0 / 2 + 32 * h;
+        for (int ch = 0; ch < 2; ++ch) {
+          const int tile_u = 64 * half + EPI_COLS * ch;       // value columns of this warp
+          const int cu = n0 / 2 + 32 * half + EPI_COLS * ch + 4 * c4;
+          const float4 bu = g.bias ? ld4(g.bias + cu) : zero4;
+          const float4 bg = g.bias ? ld4(g.bias + F + cu) : zero4;
+          float4 u[4];
+          stage_chunk(tile_u);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              u[j] = rs * u[j] + (g.bias ? __ldg(g.bias + cu + j) : 0.f);
-              gt[j] = rs * gt[j] + (g.bias ? __ldg(g.bias + F + cu + j) : 0.f);
-            }
+          for (int it = 0; it < 4; ++it) {
+            const float4 x = staged(it);
+            u[it] = make_float4(rs[it] * x.x + bu.x, rs[it] * x.y + bu.y, rs[it] * x.z + bu.z,
+                                rs[it] * x.w + bu.w);
+          }
+          stage_chunk(tile_u + 32);  // the matching gate columns
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (!ok[it]) continue;
+            const int64_t m = m_base + it * 8 + rsel;
+            const float4 x = staged(it);
+            const float4 gt = make_float4(rs[it] * x.x + bg.x, rs[it] * x.y + bg.y,
+                                          rs[it] * x.z + bg.z, rs[it] * x.w + bg.w);
             if (g.aux_out) {
-              float4* pu = reinterpret_cast<float4*>(g.aux_out + m * g.ld_aux + cu);
-              float4* pg = reinterpret_cast<float4*>(g.aux_out + m * g.ld_aux + F + cu);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                pu[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
-                pg[j] = make_float4(gt[4 * j], gt[4 * j + 1], gt[4 * j + 2], gt[4 * j + 3]);
-              }
+              *reinterpret_cast<float4*>(g.aux_out + m * g.ld_aux + cu) = u[it];
+              *reinterpret_cast<float4*>(g.aux_out + m * g.ld_aux + F + cu) = gt;
             }
-            float4* po = reinterpret_cast<float4*>(g.C + m * g.ldc + cu);
+            *reinterpret_cast<float4*>(g.C + m * g.ldc + cu) =
+                make_float4(u[it].x * fsigmoid(gt.x), u[it].y * fsigmoid(gt.y),
+                            u[it].z * fsigmoid(gt.z), u[it].w * fsigmoid(gt.w));
+          }
+        }
+      } else if (EPI == PETB200_EPI_SWIGLU_BWD) {
+        // two operands per output: fetch them two column chunks at a time
+#pragma unroll 1
+        for (int pair = 0; pair < NCH / 2; ++pair) {
+          float4 uu[2][4], gg[2][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              po[j] = make_float4(u[4 * j] * sigmoidf_(gt[4 * j]), u[4 * j + 1] * sigmoidf_(gt[4 * j + 1]),
-                                  u[4 * j + 2] * sigmoidf_(gt[4 * j + 2]),
-                                  u[4 * j + 3] * sigmoidf_(gt[4 * j + 3]));
+          for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int64_t m = m_base + it * 8 + rsel;
+              const int c0 = n0 + 64 * half + EPI_COLS * (2 * pair + h2) + 4 * c4;
+              uu[h2][it] = ok[it] ? ld4(g.aux_in + m * g.ld_aux + c0) : zero4;
+              gg[h2][it] = ok[it] ? ld4(g.aux_in + m * g.ld_aux + g.N + c0) : zero4;
+            }
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int tile_col = 64 * half + EPI_COLS * (2 * pair + h2);
+            const int c0 = n0 + tile_col + 4 * c4;
+            stage_chunk(tile_col);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              if (!ok[it]) continue;
+              const int64_t m = m_base + it * 8 + rsel;
+              const float4 v = staged(it);
+              const float4 u4 = uu[h2][it], g4 = gg[h2][it];
+              const float s0 = fsigmoid(g4.x), s1 = fsigmoid(g4.y), s2 = fsigmoid(g4.z),
+                          s3 = fsigmoid(g4.w);
+              *reinterpret_cast<float4*>(g.C + m * g.ldc + c0) =
+                  make_float4(v.x * s0, v.y * s1, v.z * s2, v.w * s3);
+              *reinterpret_cast<float4*>(g.C + m * g.ldc + g.N + c0) =
+                  make_float4(v.x * u4.x * s0 * (1.f - s0), v.y * u4.y * s1 * (1.f - s1),
+                              v.z * u4.z * s2 * (1.f - s2), v.w * u4.w * s3 * (1.f - s3));
+            }
           }
         }
       } else {
-#pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          float v[32];
-          tmem_ld32(taddr + 32 * ch, v);
-          if (!ok) continue;
-          const int c0 = n0 + 32 * ch;
-          if (EPI == PETB200_EPI_SWIGLU_BWD) {
-            const float4* pu = reinterpret_cast<const float4*>(g.aux_in + m * g.ld_aux + c0);
-            const float4* pg = reinterpret_cast<const float4*>(g.aux_in + m * g.ld_aux + g.N + c0);
-            float4* du = reinterpret_cast<float4*>(g.C + m * g.ldc + c0);
-            float4* dg = reinterpret_cast<float4*>(g.C + m * g.ldc + g.N + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 uu = pu[j], gg = pg[j];
-              const float s0 = sigmoidf_(gg.x), s1 = sigmoidf_(gg.y), s2 = sigmoidf_(gg.z),
-                          s3 = sigmoidf_(gg.w);
-              du[j] = make_float4(v[4 * j] * s0, v[4 * j + 1] * s1, v[4 * j + 2] * s2, v[4 * j + 3] * s3);
-              dg[j] = make_float4(v[4 * j] * uu.x * s0 * (1.f - s0), v[4 * j + 1] * uu.y * s1 * (1.f - s1),
-                                  v[4 * j + 2] * uu.z * s2 * (1.f - s2),
-                                  v[4 * j + 3] * uu.w * s3 * (1.f - s3));
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int tile_col = 64 * half + EPI_COLS * ch;
+          const int c0 = n0 + tile_col + 4 * c4;  // this lane's 4 output columns
+          const float4 b4 = g.bias ? ld4(g.bias + c0) : zero4;
+          stage_chunk(tile_col);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (!ok[it]) continue;
+            const int64_t m = m_base + it * 8 + rsel;
+            float4 v = staged(it);
+            v = make_float4(rs[it] * v.x + b4.x, rs[it] * v.y + b4.y, rs[it] * v.z + b4.z,
+                            rs[it] * v.w + b4.w);
+            if (EPI == PETB200_EPI_SILU) {
+              if (g.aux_out) *reinterpret_cast<float4*>(g.aux_out + m * g.ld_aux + c0) = v;
+              v = make_float4(fsilu(v.x), fsilu(v.y), fsilu(v.z), fsilu(v.w));
             }
-            continue;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = rs * v[j] + (g.bias ? __ldg(g.bias + c0 + j) : 0.f);
-          if (EPI == PETB200_EPI_SILU) {
-            if (g.aux_out) {
-              float4* pa = reinterpret_cast<float4*>(g.aux_out + m * g.ld_aux + c0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                pa[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (EPI == PETB200_EPI_MUL_DSILU) {
+              v.x *= fdsilu(pre[ch][it].x);
+              v.y *= fdsilu(pre[ch][it].y);
+              v.z *= fdsilu(pre[ch][it].z);
+              v.w *= fdsilu(pre[ch][it].w);
+              if (pre_src) {  // rare with this epilogue: not prefetched
+                const float4 r = ld4(pre_src + m * pre_ld + c0);
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+              }
+            } else {
+              v.x += pre[ch][it].x;
+              v.y += pre[ch][it].y;
+              v.z += pre[ch][it].z;
+              v.w += pre[ch][it].w;
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = siluf_(v[j]);
-          }
-          if (EPI == PETB200_EPI_MUL_DSILU) {
-            const float4* pp = reinterpret_cast<const float4*>(g.aux_in + m * g.ld_aux + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 p = pp[j];
-              v[4 * j] *= dsiluf_(p.x);
-              v[4 * j + 1] *= dsiluf_(p.y);
-              v[4 * j + 2] *= dsiluf_(p.z);
-              v[4 * j + 3] *= dsiluf_(p.w);
+            if (late_acc) {
+              const float4 o = *reinterpret_cast<const float4*>(g.C + m * g.ldc + c0);
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
             }
+            *reinterpret_cast<float4*>(g.C + m * g.ldc + c0) = v;
           }
-          if (g.residual) {
-            const float4* pr = reinterpret_cast<const float4*>(g.residual + m * g.ldr + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = pr[j];
-              v[4 * j] += r.x;
-              v[4 * j + 1] += r.y;
-              v[4 * j + 2] += r.z;
-              v[4 * j + 3] += r.w;
-            }
-          }
-          float4* pc = reinterpret_cast<float4*>(g.C + m * g.ldc + c0);
-          if (g.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 o = pc[j];
-              v[4 * j] += o.x;
-              v[4 * j + 1] += o.y;
-              v[4 * j + 2] += o.z;
-              v[4 * j + 3] += o.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            pc[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
       tc_fence_before();
@@ -435,20 +626,31 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, int64_t rows, int
   row[cols + c] = lo;
 }
 
+template <int EPI, int NPROD, bool BSTAT>
+int launch_one(const GemmArgs& g, int grid, cudaStream_t stream) {
+  auto kern = gemm_tc_kernel<EPI, NPROD, BSTAT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
+  return check_launch("gemm_tc");
+}
+
 template <int EPI>
 int launch_epi(const GemmArgs& g, int precision, cudaStream_t stream) {
-  const int items = (int)ceil_div(g.M, BM) * (g.N / BN);
-  const int grid = items < kNumSMs ? items : kNumSMs;
-  if (precision == PETB200_PREC_BF16X3) {
-    auto kern = gemm_tc_kernel<EPI, 3>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
+  const int m_tiles = (int)ceil_div(g.M, BM), n_chunks = g.N / BN;
+  // stationary W needs K/64 x 32 KiB of smem and at least two A stages in 192 KiB
+  const bool stationary = g.K <= 256 && n_chunks <= kNumSMs;
+  int grid;
+  if (stationary) {
+    int per = kNumSMs / n_chunks;
+    if (per > m_tiles) per = m_tiles;
+    grid = per * n_chunks;
   } else {
-    auto kern = gemm_tc_kernel<EPI, 1>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
+    const int items = m_tiles * n_chunks;
+    grid = items < kNumSMs ? items : kNumSMs;
   }
-  return check_launch("gemm_tc");
+  const bool x3 = precision == PETB200_PREC_BF16X3;
+  if (stationary) return x3 ? launch_one<EPI, 3, true>(g, grid, stream) : launch_one<EPI, 1, true>(g, grid, stream);
+  return x3 ? launch_one<EPI, 3, false>(g, grid, stream) : launch_one<EPI, 1, false>(g, grid, stream);
 }
 
 }  // namespace
