@@ -134,6 +134,18 @@ PETB200_API int petb200_edges_bwd(const float* d_vec, const float* d_dist, const
                       int cutoff_function, float* edge_grad, float* d_pos, float* d_cells,
                       petb200_stream_t stream);
 
+/* The same backward in two calls, for the atom-sharded path: edge gradients of halo edges
+ * are exchanged between ranks in between (edge_grad has n_edges + n_ghost rows then, and
+ * rev may point into the ghost rows).                                                   */
+PETB200_API int petb200_edge_grad(const float* d_vec, const float* d_dist, const float* d_fc,
+                      const float* edge_vec, const float* edge_dist, int64_t n_edges,
+                      float cutoff, float width, int cutoff_function, float* edge_grad,
+                      petb200_stream_t stream);
+PETB200_API int petb200_force_scatter(const float* edge_grad, const int32_t* row_ptr,
+                      const int32_t* ctr, const int32_t* rev, const int32_t* shift_csr,
+                      const int32_t* system_of_atom, int64_t n_atoms, int64_t n_edges,
+                      float* d_pos, float* d_cells, petb200_stream_t stream);
+
 /* --------------------------------------------------------------- dense contractions
  * C[M,N] = epilogue(row_scale * (A[M,K] . W[N,K]^T) + bias) (+ residual) — every
  * torch.nn.Linear of transformer.py / backend.py, and its dgrad with W^T.             */

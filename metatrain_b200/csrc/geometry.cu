@@ -188,3 +188,35 @@ extern "C" PETB200_API int petb200_edges_bwd(const float* d_vec, const float* d_
   }
   return check_launch("edges_bwd");
 }
+
+// --- split form of petb200_edges_bwd for the atom-sharded path: the edge gradients of halo
+// edges are exchanged between the two calls (metatrain_b200/sharded.py).
+extern "C" PETB200_API int petb200_edge_grad(const float* d_vec, const float* d_dist,
+                                             const float* d_fc, const float* edge_vec,
+                                             const float* edge_dist, int64_t n_edges, float cutoff,
+                                             float width, int cutoff_function, float* edge_grad,
+                                             cudaStream_t stream) {
+  PETB200_REQUIRE(cutoff_function == PETB200_CUTOFF_BUMP || cutoff_function == PETB200_CUTOFF_COSINE,
+                  "edge_grad: unknown cutoff function %d", cutoff_function);
+  if (n_edges == 0) return PETB200_OK;
+  edge_grad_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
+      d_vec, d_dist, d_fc, edge_vec, edge_dist, n_edges, cutoff, width, cutoff_function, edge_grad);
+  return check_launch("edge_grad");
+}
+
+extern "C" PETB200_API int petb200_force_scatter(const float* edge_grad, const int32_t* row_ptr,
+                                                 const int32_t* ctr, const int32_t* rev,
+                                                 const int32_t* shift_csr,
+                                                 const int32_t* system_of_atom, int64_t n_atoms,
+                                                 int64_t n_edges, float* d_pos, float* d_cells,
+                                                 cudaStream_t stream) {
+  if (n_atoms > 0 && d_pos) {
+    force_scatter_kernel<<<(unsigned)ceil_div(n_atoms * 32, 256), 256, 0, stream>>>(
+        edge_grad, row_ptr, rev, n_atoms, d_pos);
+  }
+  if (n_edges > 0 && d_cells) {
+    cell_grad_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
+        edge_grad, shift_csr, ctr, system_of_atom, n_edges, d_cells);
+  }
+  return check_launch("force_scatter");
+}

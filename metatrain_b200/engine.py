@@ -85,16 +85,20 @@ class Topology:
     z_nodes: Tensor           # [N] species index of each atom
     z_neighbors: Tensor       # [E] species index of each edge's neighbour
     perm: Tensor              # [E] index of each CSR edge in the caller's neighbor list
+    n_positions: int = 0      # rows of the positions array (> n_atoms when ghost atoms follow)
+    rev_bwd: Optional[Tensor] = None   # atom-sharded runs: rev with the backward ghost base
+    halo: Optional[object] = None      # atom-sharded runs: metatrain_b200.sharded.Halo
 
 
 def build_topology(positions: Tensor, centers: Tensor, neighbors: Tensor, cell_shifts: Tensor,
                    cells: Tensor, system_indices: Tensor, z_nodes: Tensor, cutoff: float,
-                   check_symmetric: bool = True) -> Topology:
+                   check_symmetric: bool = True, n_rows: Optional[int] = None) -> Topology:
     """a4-a6 of SURVEY.md 8(a): filter pairs beyond the cutoff, CSR by centre (stable),
     reverse-edge map.  One device->host read of (E, max neighbours, missing reverses) —
     the reference syncs at the same place (structures.py:292-294)."""
     dev = positions.device
-    n_atoms = positions.shape[0]
+    # atoms that own CSR rows; in atom-sharded runs ghost atoms follow them in `positions`
+    n_atoms = positions.shape[0] if n_rows is None else int(n_rows)
     n_pairs = centers.shape[0]
     i32 = torch.int32
     centers = centers.to(i32).contiguous()
@@ -135,7 +139,8 @@ def build_topology(positions: Tensor, centers: Tensor, neighbors: Tensor, cell_s
     z_neighbors = z_nodes[col.long()] if n_edges > 0 else torch.empty(0, device=dev, dtype=i32)
     n_structures = cells.shape[0]
     return Topology(n_atoms, n_edges, n_structures, max_row, row_ptr, ctr, col, rev, shift,
-                    sys_atom, z_nodes, z_neighbors.contiguous(), perm[:n_edges])
+                    sys_atom, z_nodes[:n_atoms].contiguous(), z_neighbors.contiguous(),
+                    perm[:n_edges], n_positions=positions.shape[0])
 
 
 # ---------------------------------------------------------------------- weight packing
@@ -253,12 +258,24 @@ def edges_forward(topo: Topology, positions: Tensor, cells: Tensor, cutoff, widt
 def edges_backward(topo: Topology, vec, dist, d_vec, d_dist, d_fc, cutoff, width, func,
                    need_cells: bool):
     E, N = topo.n_edges, topo.n_atoms
-    scratch = _empty((max(E, 1), 3), vec)
-    d_pos = _empty((N, 3), vec)
+    halo = topo.halo
+    H = halo.n_ghost if halo is not None else 0
+    scratch = _empty((max(E + H, 1), 3), vec)
+    d_pos = (torch.zeros((topo.n_positions, 3), device=vec.device) if topo.n_positions > N
+             else _empty((N, 3), vec))
     d_cells = torch.zeros((topo.n_structures, 3, 3), device=vec.device) if need_cells else None
-    call("edges_bwd", ptr(d_vec), ptr(d_dist), ptr(d_fc), ptr(vec), ptr(dist), ptr(topo.row_ptr),
-         ptr(topo.ctr), ptr(topo.rev), ptr(topo.shift), ptr(topo.system_of_atom), N, E,
-         float(cutoff), float(width), func, ptr(scratch), ptr(d_pos), ptr(d_cells))
+    if halo is None:
+        call("edges_bwd", ptr(d_vec), ptr(d_dist), ptr(d_fc), ptr(vec), ptr(dist),
+             ptr(topo.row_ptr), ptr(topo.ctr), ptr(topo.rev), ptr(topo.shift),
+             ptr(topo.system_of_atom), N, E, float(cutoff), float(width), func, ptr(scratch),
+             ptr(d_pos), ptr(d_cells))
+    else:
+        # sharded: edge gradients of halo edges come from the peers that own the reversed edges
+        call("edge_grad", ptr(d_vec), ptr(d_dist), ptr(d_fc), ptr(vec), ptr(dist), E,
+             float(cutoff), float(width), func, ptr(scratch))
+        halo.exchange(scratch[:E].index_select(0, halo.send_idx), out=scratch[E:E + H])
+        call("force_scatter", ptr(scratch), ptr(topo.row_ptr), ptr(topo.ctr), ptr(topo.rev_bwd),
+             ptr(topo.shift), ptr(topo.system_of_atom), N, E, ptr(d_pos), ptr(d_cells))
     return d_pos, d_cells
 
 
@@ -278,6 +295,8 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
     """backend.py:496-587 + transformer.py:463-562,203-234 on the CSR layout.
     Returns (node features [N,d_node], edge messages [E,d_pet], saved-for-backward)."""
     N, E = topo.n_atoms, topo.n_edges
+    halo = topo.halo
+    H = halo.n_ghost if halo is not None else 0  # ghost rows behind the [E | N] token rows
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
     h = _empty((N, dn), vec)
@@ -294,7 +313,8 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
         c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
         gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec, pack=pw)
         del cat
-        X = _empty((E + N, d), vec)
+        Xf = _empty((E + N + H, d), vec)
+        X = Xf[:E + N]
         gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec, pack=pw)
         del a1
         S["c1"] = c1
@@ -330,14 +350,18 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
             s = _empty((E, dff), vec)
             gemm(tp, T["w_in"], s, bias=T["b_in"], row_scale=rstd2, epilogue=EPI_SWIGLU,
                  aux_out=ug, precision=prec, pack=pw)
-            Xnn = _empty((E + N, d), vec)
+            Xnnf = _empty((E + N + H, d), vec)
+            Xnn = Xnnf[:E + N]
             gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec, pack=pw)
             del s, sc
             K.update(X=X, rstd1=rstd1, qkv=qkv, o=o, lse=lse, tp=tp, rstd2=rstd2, ug=ug,
                      h1=h1, rstd3=rstd3, ugc=ugc)
             S["tl"].append(K)
-            X, h = Xnn, h2
+            X, Xf, h = Xnn, Xnnf, h2
         t = X[:E]
+        if halo is not None:
+            # reversed messages of halo edges live on the peers: all-to-all-v into the ghost rows
+            halo.exchange(t.index_select(0, halo.send_idx), out=Xf[E + N:])
         cc = _empty((E, 2 * d), vec)
         mean, rstd = _empty((E,), vec), _empty((E,), vec)
         call("combine_ln_fwd", ptr(t), ptr(topo.rev), ptr(C["gamma"]), ptr(C["beta"]), E, d,
@@ -358,6 +382,9 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
     """Hand-scheduled dgrad of :func:`features_forward`.  Consumes d_h
     [N,d_node] and d_m [E,d_pet]; returns (d_vec [E,3], d_dist [E], d_fc [E])."""
     N, E = topo.n_atoms, topo.n_edges
+    halo = topo.halo
+    H = halo.n_ghost if halo is not None else 0
+    rev_bwd = topo.rev_bwd if halo is not None else topo.rev
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
     ref = fc
@@ -370,16 +397,21 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
     for l in range(n_layers - 1, -1, -1):
         L, C, S = pw.gnn[l], pw.combine[l], saved[l]
         # ---- message update:  m_out = m_in + t + W_b silu(W_a LN(cat[t, t_rev]) + b_a) + b_b
-        d_p1 = _empty((E, 2 * d), ref)
+        d_p1f = _empty((E + H, 2 * d), ref)
+        d_p1 = d_p1f[:E]
         gemm(d_m, C["w_b_t"], d_p1, epilogue=EPI_MUL_DSILU, aux_in=S["p1"], precision=prec, pack=pw)
         d_cc = _empty((E, 2 * d), ref)
         gemm(d_p1, C["w_a_t"], d_cc, precision=prec, pack=pw)
         d_cat = d_p1  # reuse
         call("combine_ln_bwd", ptr(d_cc), ptr(S["t"]), ptr(topo.rev), ptr(C["gamma"]),
              ptr(S["mean"]), ptr(S["rstd"]), E, d, ptr(d_cat))
+        if halo is not None:
+            # the "reversed half" gradients of our halo edges were computed by the peers
+            got = halo.exchange(d_cat.index_select(0, halo.send_idx)[:, d:])
+            d_p1f[E:, d:] = got
         d_t = _empty((E, d), ref)
-        call("combine_scatter_bwd", ptr(d_cat), ptr(d_m), ptr(topo.rev), E, d, ptr(d_t))
-        del d_cc, d_cat, d_p1
+        call("combine_scatter_bwd", ptr(d_cat), ptr(d_m), ptr(rev_bwd), E, d, ptr(d_t))
+        del d_cc, d_cat, d_p1, d_p1f
         for k in range(len(L["tl"]) - 1, -1, -1):
             T, K = L["tl"][k], S["tl"][k]
             dff = T["w_out"].shape[1]

@@ -39,6 +39,8 @@ _SIGNATURES = {
     "petb200_edges_fwd": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _I, _P, _P, _P, _P],
     "petb200_edges_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _I,
                           _P, _P, _P, _P],
+    "petb200_edge_grad": [_P, _P, _P, _P, _P, _I64, _F, _F, _I, _P, _P],
+    "petb200_force_scatter": [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P],
     "petb200_gemm": [_P, _I64, _P, _I64, _P, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P,
                      _I64, _I, _I, _I, _P],
     "petb200_split_bf16": [_P, _I64, _I, _P, _P],
@@ -107,7 +109,7 @@ def stream_ptr() -> int:
 
 
 # kernels launched by each entry point (for bench.py's ``gpu_launches`` claim)
-_KERNELS_PER_CALL = {"edges_bwd": 3, "csr_build": 6, "readout_bwd": 2}
+_KERNELS_PER_CALL = {"edges_bwd": 3, "csr_build": 6, "readout_bwd": 2, "force_scatter": 2}
 launch_count = 0
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
 profile_hook = None
