@@ -19,9 +19,11 @@ configs[1]; the reference's 384-atom water fixture tiled 3x3x3).  Metric: atom-s
                   reference's algorithm with the reference's torch CPU primitives) on the
                   host cores, bounded sample of the same workload.
 
-N > 1: one process per GPU (torchrun), each rank evaluates its own independent box (the
-batched evaluator loop of src/metatrain/cli/eval.py:148-310 shards by structures with no
-data-path collective) -> weak scaling; value = atoms of all ranks / max-over-ranks time.
+N > 1: one process per GPU (torchrun).  Default `--multi sharded`: ONE box N times larger
+(3x3x3N tiling, 10 368 atoms per GPU) is sharded by atoms (metatrain_b200/sharded.py): slabs,
+halo-edge all-to-all-v over NCCL per GNN layer forward and backward, energy / force all-reduce
+-> weak scaling; value = atoms of the whole box x steps / max-over-ranks time.
+`--multi independent`: each rank evaluates its own 10k box (no data-path collective).
 """
 import argparse
 import contextlib
@@ -53,6 +55,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("PETB200_PRECISION", "fp32"))
     ap.add_argument("--reps", type=int, nargs=3, default=list(REPS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "independent"])
     return ap.parse_args()
 
 
@@ -188,19 +191,25 @@ class KernelTimer:
         a.record()
         yield
         b.record()
-        work = 0.0
+        work, byt = 0.0, 0.0
         if name == "gemm":
-            work = 2.0 * args[6] * args[7] * args[8]  # M, N, K
+            m, n, k = args[6], args[7], args[8]
+            work = 2.0 * m * n * k
+            epi = args[16]
+            out_cols = n // 2 if epi == 2 else (2 * n if epi == 4 else n)
+            aux_cols = {1: n, 2: n, 3: n, 4: 2 * n}.get(epi, 0) if (args[13] or args[14]) else 0
+            extra = (n if args[11] else 0) + (n if args[17] else 0)
+            byt = 4.0 * m * (k + out_cols + aux_cols + extra)  # algorithmic fp32 bytes
         elif name in ("combine_ln_fwd",):
             work = float(args[4])  # edges
-        self.records.append((name, a, b, work))
+        self.records.append((name, a, b, work, byt))
 
     def totals(self):
         torch.cuda.synchronize()
         out = {}
-        for name, a, b, work in self.records:
-            t, w, n = out.get(name, (0.0, 0.0, 0))
-            out[name] = (t + a.elapsed_time(b) * 1e-3, w + work, n + 1)
+        for name, a, b, work, byt in self.records:
+            t, w, n, by = out.get(name, (0.0, 0.0, 0, 0.0))
+            out[name] = (t + a.elapsed_time(b) * 1e-3, w + work, n + 1, by + byt)
         return out
 
 
@@ -225,6 +234,7 @@ def run_petb200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PETB200_NCCL_DEBUG", "WARN")  # keep stdout = 1 JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     seed_all(0)
@@ -233,24 +243,64 @@ def run_petb200(args):
     be = be.to(dev).eval()
     be.emit_nef = False  # energies + forces only need the CSR handles
 
-    box = replicate(water_384(), tuple(args.reps))
-    host = make_batch([box], CUTOFF, pin_memory=True)
-    resident = {k: v.to(dev) for k, v in host.items()}
-    n_atoms = host["positions"].shape[0]
-    n_edges = host["centers"].shape[0]
+    sharded = world > 1 and args.multi == "sharded"
+    if sharded:
+        from metatrain_b200.neighbors import neighbor_list
+        from metatrain_b200.sharded import (build_shard, evaluate_sharded, shard_to_device,
+                                            shard_to_host_tensors)
+        reps = (args.reps[0], args.reps[1], args.reps[2] * world)
+        box = replicate(water_384(), reps)
+        nl = neighbor_list(box["positions"], box["cell"], True, CUTOFF)
+        shard = build_shard(box["positions"], box["cell"], nl, rank, world)
+        host = shard_to_host_tensors(shard, pin_memory=True)
+        host_pos = torch.tensor(box["positions"], dtype=torch.float32).pin_memory()
+        host_z = torch.tensor(box["Z"], dtype=torch.int32).pin_memory()
+        host_cell = torch.tensor(box["cell"], dtype=torch.float32).pin_memory()
+        lists = shard_to_device(shard, dev, host)
+        pos_d, z_d, cell_d = host_pos.to(dev), host_z.to(dev), host_cell.to(dev)
+        n_atoms = len(box["Z"]) // world          # per-GPU share of the one big box
+        n_edges = len(shard.centers)
+        n_total = len(box["Z"])
 
-    def step_resident():
-        return evaluate(be, **resident, target=TARGET)
+        def step_resident():
+            return evaluate_sharded(be, shard, pos_d, z_d, cell_d, target=TARGET, device_lists=lists)
 
-    e_host = torch.empty((1, 1), dtype=torch.float32).pin_memory()
-    f_host = torch.empty((n_atoms, 3), dtype=torch.float32).pin_memory()
+        e_host = torch.empty((1, 1), dtype=torch.float32).pin_memory()
+        f_host = torch.empty((n_total, 3), dtype=torch.float32).pin_memory()
 
-    def step_e2e():
-        dev_in = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        out = evaluate(be, **dev_in, target=TARGET)
-        e_host.copy_(out["energies"], non_blocking=True)
-        f_host.copy_(out["dE_dpos"], non_blocking=True)
-        torch.cuda.synchronize()
+        def step_e2e():
+            lists_in = shard_to_device(shard, dev, host)
+            out = evaluate_sharded(be, shard, host_pos.to(dev, non_blocking=True),
+                                   host_z.to(dev, non_blocking=True),
+                                   host_cell.to(dev, non_blocking=True), target=TARGET,
+                                   device_lists=lists_in)
+            e_host.copy_(out["energies"], non_blocking=True)
+            f_host.copy_(out["dE_dpos"], non_blocking=True)
+            torch.cuda.synchronize()
+
+        h2d_tensors = list(host.values()) + [host_pos, host_z, host_cell]
+    else:
+        box = replicate(water_384(), tuple(args.reps))
+        host = make_batch([box], CUTOFF, pin_memory=True)
+        resident = {k: v.to(dev) for k, v in host.items()}
+        n_atoms = host["positions"].shape[0]
+        n_edges = host["centers"].shape[0]
+        n_total = n_atoms
+
+        def step_resident():
+            return evaluate(be, **resident, target=TARGET)
+
+        e_host = torch.empty((1, 1), dtype=torch.float32).pin_memory()
+        f_host = torch.empty((n_atoms, 3), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            dev_in = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            out = evaluate(be, **dev_in, target=TARGET)
+            e_host.copy_(out["energies"], non_blocking=True)
+            f_host.copy_(out["dE_dpos"], non_blocking=True)
+            torch.cuda.synchronize()
+
+        h2d_tensors = list(host.values())
 
     def barrier():
         if world > 1:
@@ -262,7 +312,7 @@ def run_petb200(args):
     # accuracy next to the throughput: tiled forces vs the reference's golden for the seed box
     from helpers import load_golden
     g = load_golden("water_384")
-    tiles = n_atoms // 384
+    tiles = n_total // 384
     f = out["dE_dpos"].cpu().numpy().reshape(tiles, 384, 3)
     force_err = float(np.abs(f - g["ref32_dE_dpos"][None]).max())
     energy_err = float(abs(float(out["energies"]) / tiles - float(g["ref32_energies"].ravel()[0])) / 384)
@@ -301,7 +351,7 @@ def run_petb200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t)
     e2e_value = world * n_atoms * args.steps / e2e_sec
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = sum(v.numel() * v.element_size() for v in h2d_tensors)
     d2h = e_host.numel() * 4 + f_host.numel() * 4
 
     # per-kernel roofline: instrumented extra steps (not part of the timed regions above)
@@ -312,18 +362,25 @@ def run_petb200(args):
     lib.profile_hook = None
     tot = timer.totals()
     hbm, tf_burst, tf_sust, which = peaks()
-    g_t, g_flops, g_n = tot["gemm"]
-    c_t, c_edges, c_n = tot["combine_ln_fwd"]
+    g_t, g_flops, g_n, g_bytes = tot["gemm"]
+    c_t, c_edges, c_n, _ = tot["combine_ln_fwd"]
     gemm_tflops = g_flops / g_t * 1e-12
+    gemm_gbs = g_bytes / g_t * 1e-9
     scatter_bytes = 2060.0 * c_edges  # 2x512 B read + 4 B rev + 1024 B write + 8 B stats per edge
     scatter_gbs = scatter_bytes / c_t * 1e-9
     step_ms = sec / args.steps * 1e3
+    # The contractions are tall-skinny (M = edges, N, K <= 1024): arithmetic intensity
+    # 32..128 flop/B is below the ridge (~215), so the dominant kernel is HBM-bound; the
+    # tensor-pipe view is reported next to it.
     roofline = {
-        "kernel": "gemm (all dense contractions of the step)", "bound": "tensor",
-        "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
-        "frac": gemm_tflops / tf_sust, "traffic": None, "peak_source": which + " (sustained bf16)",
-        "launches_per_step": g_n // 3, "ms_per_step": g_t / 3 * 1e3,
-        "share_of_step": (g_t / 3 * 1e3) / step_ms, "precision": args.precision,
+        "kernel": "gemm (all dense contractions of the step: gemm_tc_kernel / gemm_simt_kernel)",
+        "bound": "hbm", "achieved": gemm_gbs, "peak": hbm, "unit": "GB/s", "frac": gemm_gbs / hbm,
+        "traffic": None, "peak_source": which,
+        "algorithmic_bytes_per_step": g_bytes / 3, "launches_per_step": g_n // 3,
+        "ms_per_step": g_t / 3 * 1e3, "share_of_step": (g_t / 3 * 1e3) / step_ms,
+        "precision": args.precision,
+        "tensor_view": {"achieved_tflops": gemm_tflops, "peak_tflops": tf_sust,
+                        "frac": gemm_tflops / tf_sust, "flops_per_step": g_flops / 3},
     }
     edge_scatter = {
         "kernel": "combine_ln_fwd (message reversal + LayerNorm)", "bound": "hbm",
@@ -348,7 +405,10 @@ def run_petb200(args):
                                f"{args.reps[2]} tiling of the 384-atom fixture, cutoff 4.5 A, "
                                "energy + forces (BASELINE.json configs[1])",
                    "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges,
-                   "parallelism": f"{world} independent boxes (1 per GPU)" if world > 1 else "1 GPU",
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   f"one {n_total}-atom box sharded by atoms over {world} GPUs, halo "
+                                   "all-to-all-v + all-reduce over NCCL" if sharded else
+                                   f"{world} independent boxes (1 per GPU)"),
                    "cache": "per-step working set (~8 GB of activations) >> 126 MB L2; no explicit flush"},
         "force_max_abs_err_eV_per_A": force_err, "energy_abs_err_eV_per_atom": energy_err,
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d,

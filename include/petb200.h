@@ -101,9 +101,10 @@ PETB200_API int petb200_csr_gather(const int32_t* perm, const int32_t* centers,
                        petb200_stream_t stream);
 
 /* Step 4: rev[e] = index of (col[e] -> ctr[e], -S_e) (nef.py:88-166).  *n_missing is
- * incremented for every edge whose reverse does not exist (non-symmetric list).        */
+ * incremented for every edge whose reverse does not exist (non-symmetric list, or — in an
+ * atom-sharded run — a neighbour col[e] >= n_rows that has no CSR row on this rank).     */
 PETB200_API int petb200_reverse_map(const int32_t* row_ptr, const int32_t* ctr, const int32_t* col,
-                        const int32_t* shift_csr, int64_t n_edges, int32_t* rev,
+                        const int32_t* shift_csr, int64_t n_edges, int64_t n_rows, int32_t* rev,
                         int32_t* n_missing, petb200_stream_t stream);
 
 /* CSR <-> padded NEF ([N, M, D], zero padded; nef.py:169-218).                         */

@@ -90,13 +90,17 @@ __global__ void reverse_map_kernel(const int32_t* __restrict__ row_ptr,
                                    const int32_t* __restrict__ ctr,
                                    const int32_t* __restrict__ col,
                                    const int32_t* __restrict__ shift, int64_t n_edges,
-                                   int32_t* __restrict__ rev, int32_t* __restrict__ n_missing) {
+                                   int64_t n_rows, int32_t* __restrict__ rev,
+                                   int32_t* __restrict__ n_missing) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   const int i = ctr[e], j = col[e];
   const int sa = -shift[3 * e], sb = -shift[3 * e + 1], sc = -shift[3 * e + 2];
   int found = -1;
-  const int lo = row_ptr[j], hi = row_ptr[j + 1];
+  // a neighbour without a CSR row is a ghost atom of an atom-sharded run: its edges (and the
+  // reverse of this one) live on another rank
+  const bool has_row = j < n_rows;
+  const int lo = has_row ? row_ptr[j] : 0, hi = has_row ? row_ptr[j + 1] : 0;
   for (int k = lo; k < hi; ++k) {
     if (col[k] == i && shift[3 * (int64_t)k] == sa && shift[3 * (int64_t)k + 1] == sb &&
         shift[3 * (int64_t)k + 2] == sc) {
@@ -236,11 +240,11 @@ extern "C" PETB200_API int petb200_csr_gather(const int32_t* perm, const int32_t
 }
 
 extern "C" PETB200_API int petb200_reverse_map(const int32_t* row_ptr, const int32_t* ctr, const int32_t* col,
-                                   const int32_t* shift_csr, int64_t n_edges, int32_t* rev,
-                                   int32_t* n_missing, cudaStream_t stream) {
+                                   const int32_t* shift_csr, int64_t n_edges, int64_t n_rows,
+                                   int32_t* rev, int32_t* n_missing, cudaStream_t stream) {
   if (n_edges == 0) return PETB200_OK;
   reverse_map_kernel<<<(unsigned)ceil_div(n_edges, 128), 128, 0, stream>>>(
-      row_ptr, ctr, col, shift_csr, n_edges, rev, n_missing);
+      row_ptr, ctr, col, shift_csr, n_edges, n_rows, rev, n_missing);
   return check_launch("reverse_map");
 }
 

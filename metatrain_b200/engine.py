@@ -127,7 +127,7 @@ def build_topology(positions: Tensor, centers: Tensor, neighbors: Tensor, cell_s
     rev = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
     call("csr_gather", ptr(perm), ptr(centers), ptr(neighbors), ptr(cell_shifts), n_edges,
          ptr(ctr), ptr(col), ptr(shift))
-    call("reverse_map", ptr(row_ptr), ptr(ctr), ptr(col), ptr(shift), n_edges, ptr(rev),
+    call("reverse_map", ptr(row_ptr), ptr(ctr), ptr(col), ptr(shift), n_edges, n_atoms, ptr(rev),
          ptr(stats[2:]))
     if check_symmetric and n_edges > 0:
         missing = int(stats[2].item())

@@ -33,7 +33,7 @@ _SIGNATURES = {
     "petb200_csr_build_workspace": [_I64, _I64],
     "petb200_csr_build": [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, _SZ, _P],
     "petb200_csr_gather": [_P, _P, _P, _P, _I64, _P, _P, _P, _P],
-    "petb200_reverse_map": [_P, _P, _P, _P, _I64, _P, _P, _P],
+    "petb200_reverse_map": [_P, _P, _P, _P, _I64, _I64, _P, _P, _P],
     "petb200_csr_to_nef": [_P, _P, _I64, _I64, _I, _I, _P, _P],
     "petb200_nef_to_csr": [_P, _P, _P, _I64, _I64, _I, _I, _P, _P],
     "petb200_edges_fwd": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _I, _P, _P, _P, _P],

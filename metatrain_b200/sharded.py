@@ -136,8 +136,23 @@ def attach_halo(topo, shard: Shard, device, group=None) -> None:
                      [len(a) for a in shard.halo_recv], halo_edges, group)
 
 
+def shard_to_host_tensors(shard: Shard, pin_memory: bool = False) -> Dict[str, Tensor]:
+    """The rank's index lists as (optionally pinned) host tensors."""
+    out = dict(ids=torch.from_numpy(np.ascontiguousarray(shard.local_ids)),
+               centers=torch.from_numpy(shard.centers.astype(np.int32)),
+               neighbors=torch.from_numpy(shard.neighbors.astype(np.int32)),
+               shifts=torch.from_numpy(np.ascontiguousarray(shard.cell_shifts.astype(np.int32))))
+    return {k: v.pin_memory() for k, v in out.items()} if pin_memory else out
+
+
+def shard_to_device(shard: Shard, device, host: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    host = host if host is not None else shard_to_host_tensors(shard)
+    return {k: v.to(device, non_blocking=True) for k, v in host.items()}
+
+
 def evaluate_sharded(backend, shard: Shard, positions: Tensor, species: Tensor, cell: Tensor,
-                     target: str = "energy", gradients: bool = True, group=None) -> Dict[str, Tensor]:
+                     target: str = "energy", gradients: bool = True, group=None,
+                     device_lists: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
     """Energy (+ dE/dr for ALL atoms, summed over ranks) of one structure sharded by atoms.
 
     ``positions`` / ``species`` are the full (replicated) arrays on this rank's device; every rank
@@ -147,13 +162,11 @@ def evaluate_sharded(backend, shard: Shard, positions: Tensor, species: Tensor, 
 
     dev = positions.device
     pos = positions.detach().clone().requires_grad_(gradients)
-    ids = torch.from_numpy(shard.local_ids).to(dev)
+    lists = device_lists if device_lists is not None else shard_to_device(shard, dev)
+    ids, centers, neighbors, shifts = (lists[k] for k in ("ids", "centers", "neighbors", "shifts"))
     pos_local = pos.index_select(0, ids)
     z_nodes = backend.species_to_species_index[species.long()].index_select(0, ids)
     cells = cell.reshape(1, 3, 3)
-    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)  # noqa: E731
-    centers, neighbors = t(shard.centers, torch.int32), t(shard.neighbors, torch.int32)
-    shifts = t(shard.cell_shifts, torch.int32)
     sysidx = torch.zeros(len(shard.local_ids), dtype=torch.int64, device=dev)
     backend._check_inference()
     topo = engine.build_topology(pos_local, centers, neighbors, shifts, cells, sysidx, z_nodes,
