@@ -181,6 +181,7 @@ class KernelTimer:
     def __init__(self, names):
         self.names = set(names)
         self.records = []
+        self.shapes = []
 
     @contextlib.contextmanager
     def __call__(self, name, args):
@@ -203,6 +204,19 @@ class KernelTimer:
         elif name in ("combine_ln_fwd",):
             work = float(args[4])  # edges
         self.records.append((name, a, b, work, byt))
+        if name == "gemm":
+            self.shapes.append((len(self.records) - 1,
+                                (int(args[6]), int(args[7]), int(args[8]), int(args[16]),
+                                 int(args[17]), int(bool(args[11])))))
+
+    def shape_totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for idx, key in self.shapes:
+            _, a, b, _, byt = self.records[idx]
+            t, n, by = out.get(key, (0.0, 0, 0.0))
+            out[key] = (t + a.elapsed_time(b) * 1e-3, n + 1, by + byt)
+        return out
 
     def totals(self):
         torch.cuda.synchronize()
@@ -361,6 +375,16 @@ def run_petb200(args):
         step_resident()
     lib.profile_hook = None
     tot = timer.totals()
+    if os.environ.get("PETB200_GEMM_SHAPES") and rank == 0:
+        shapes = {}
+        for name, a, b, work, byt in timer.records:
+            if name == "gemm":
+                pass
+        # re-walk with the raw args kept by the timer
+        for key, (t_s, n_l, by) in sorted(timer.shape_totals().items(), key=lambda kv: -kv[1][0]):
+            print(f"# gemm M={key[0]:7d} N={key[1]:5d} K={key[2]:5d} epi={key[3]} acc={key[4]} res={key[5]}: "
+                  f"{n_l // 3:3d} launches/step {t_s / 3 * 1e3:8.3f} ms/step  {by / t_s * 1e-9:7.0f} GB/s",
+                  file=sys.stderr)
     hbm, tf_burst, tf_sust, which = peaks()
     g_t, g_flops, g_n, g_bytes = tot["gemm"]
     c_t, c_edges, c_n, _ = tot["combine_ln_fwd"]

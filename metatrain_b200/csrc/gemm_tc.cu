@@ -347,28 +347,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
       if (q >= depth) {
         mbar_wait(loaded_bar(conv_ring.stage), conv_ring.phase);
         uint8_t* st = ring_base + (size_t)conv_ring.stage * stage_bytes;
-        // warp pw converts its ROWS_PER_WARP rows; lane l owns k = 2l, 2l+1 of each row
+        // warp pw converts its ROWS_PER_WARP rows, two rows per instruction: lane l works on
+        // row (l >> 4) of the pair and owns k = 4*quad .. 4*quad+3 (quad = l & 15).  One
+        // cvt.rn.bf16x2 (F2FP) rounds and packs two values; hi is rebuilt with shifts.
         constexpr int ROWS_PER_WARP = BM / NUM_PROD_WARPS;
-        const uint8_t* src_tile = st + (lane < 16 ? 0 : TILE_BYTES);
-        const int chunk = lane >> 2, within = (lane & 3) * 4;
+        const int quad = lane & 15, rsub = lane >> 4;
+        const uint8_t* src_tile = st + (quad < 8 ? 0 : TILE_BYTES) + (quad & 7) * 16;
+        const int chunk = quad >> 1, within = (quad & 1) * 8;
 #pragma unroll
-        for (int b = 0; b < ROWS_PER_WARP / 4; ++b) {
-          float2 x[4];
+        for (int b = 0; b < ROWS_PER_WARP / 16; ++b) {
+          float4 x[8];
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int r = pw * ROWS_PER_WARP + b * 4 + jj;
-            x[jj] = *reinterpret_cast<const float2*>(src_tile + r * 128 + (lane & 15) * 8);
+          for (int jj = 0; jj < 8; ++jj) {
+            const int r = pw * ROWS_PER_WARP + b * 16 + jj * 2 + rsub;
+            x[jj] = *reinterpret_cast<const float4*>(src_tile + r * 128);
           }
-          __syncwarp();  // the whole row is in registers before it is overwritten
+          __syncwarp();  // whole rows are in registers before they are overwritten
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int r = pw * ROWS_PER_WARP + b * 4 + jj;
-            const float hx = bf16_round(x[jj].x), hy = bf16_round(x[jj].y);
+          for (int jj = 0; jj < 8; ++jj) {
+            const int r = pw * ROWS_PER_WARP + b * 16 + jj * 2 + rsub;
+            const uint32_t h01 = pack_bf16(x[jj].x, x[jj].y), h23 = pack_bf16(x[jj].z, x[jj].w);
             const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + within);
-            *reinterpret_cast<uint32_t*>(st + off) = pack_bf16(hx, hy);
-            if (NPROD == 3)
-              *reinterpret_cast<uint32_t*>(st + TILE_BYTES + off) =
-                  pack_bf16(x[jj].x - hx, x[jj].y - hy);
+            *reinterpret_cast<uint2*>(st + off) = make_uint2(h01, h23);
+            if (NPROD == 3) {
+              const float l0 = x[jj].x - __uint_as_float(h01 << 16);
+              const float l1 = x[jj].y - __uint_as_float(h01 & 0xffff0000u);
+              const float l2 = x[jj].z - __uint_as_float(h23 << 16);
+              const float l3 = x[jj].w - __uint_as_float(h23 & 0xffff0000u);
+              *reinterpret_cast<uint2*>(st + TILE_BYTES + off) =
+                  make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+            }
           }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
