@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="petb200", choices=["petb200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PETB200_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("PETB200_PRECISION", "bf16x3"),
+                    choices=["bf16x3", "fp32", "bf16"])
     ap.add_argument("--reps", type=int, nargs=3, default=list(REPS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "independent"])

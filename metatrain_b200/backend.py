@@ -163,14 +163,14 @@ class B200PETBackend(PETParameters):
 
     :param hypers: PET ``ModelHypers`` (``src/metatrain/pet/documentation.py:156-259``).
     :param atomic_types: sorted list of supported atomic numbers.
-    :param precision: GEMM arithmetic — ``"fp32"`` (FFMA, parity reference),
-        ``"bf16x3"`` (tcgen05, 2-term bf16 split, fp32 accumulate; meets 1e-4 eV/A) or
-        ``"bf16"`` (single-pass tcgen05; fast, ~1e-2 eV/A).
+    :param precision: GEMM arithmetic — ``"bf16x3"`` (default: tcgen05, 2-term bf16 split,
+        fp32 accumulate; forces within ~1e-5 eV/A of the fp32 reference), ``"fp32"`` (FFMA,
+        the exact-fp32 parity path) or ``"bf16"`` (single-pass tcgen05; ~1e-2 eV/A).
     """
 
     NUM_FEATURE_TYPES: int = 2
 
-    def __init__(self, hypers: dict, atomic_types: List[int], precision: str = "fp32") -> None:
+    def __init__(self, hypers: dict, atomic_types: List[int], precision: str = "bf16x3") -> None:
         # same validation and exception types as the reference
         if hypers["normalization"] not in _AVAILABLE_NORMALIZATIONS:  # transformer.py:329-333
             raise ValueError(f"Unknown normalization flag: {hypers['normalization']}. "

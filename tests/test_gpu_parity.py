@@ -167,6 +167,27 @@ def test_empty_and_errors():
         evaluate(be, **inp, target=g["target"])
 
 
+def test_evaluator_loop_matches_reference_semantics():
+    """eval_targets mirrors cli/eval.py:_eval_targets: batching (last batch smaller), per-atom
+    energy metrics, force metrics, predictions equal to direct evaluation."""
+    from metatrain_b200 import eval_targets
+    g = load_golden("carbon_5")
+    be = make_backend(g)
+    structures, targets = [], []
+    for b in range(5):
+        sel = g["system_indices"] == b
+        structures.append(dict(Z=g["species"][sel], positions=g["positions"][sel].astype(np.float64),
+                               cell=g["cells"][b].astype(np.float64), pbc=True))
+        targets.append(dict(energy=g["ref32_energies"][b], forces=-g["ref32_dE_dpos"][sel]))
+    res = eval_targets(be, structures, targets, target=g["target"], batch_size=2, device=DEV)
+    assert len(res["energies"]) == 5 and len(res["forces"]) == 5
+    e = np.array([float(x) for x in res["energies"]])
+    assert np.abs(e - g["ref32_energies"].ravel()).max() <= 1e-4
+    assert res["metrics"][g["target"] + " forces RMSE"] <= 2e-5
+    assert res["metrics"][g["target"] + " (per atom) MAE"] <= 1e-5
+    assert res["ms_per_atom"][0] > 0
+
+
 def test_neighbor_order_invariance():
     """Shuffling the neighbor list changes nothing but fp summation order."""
     g = load_golden("si_64")
