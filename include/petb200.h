@@ -203,12 +203,13 @@ PETB200_API int petb200_attention_fwd(const float* qkv, const int32_t* row_ptr,
                           const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
                           int num_heads, int head_dim, float scale, int max_row,
                           float* out, float* lse, petb200_stream_t stream);
-/* d_qkv from d_out; d_fc[e] += (sum_{heads,queries} dS[.,e]) / f_e  (f_e > 1e-15).     */
+/* d_qkv from d_out; d_fc[e] += (sum_{heads,queries} dS[.,e]) / f_e  (f_e > 1e-15).
+ * dsum is [E+N, num_heads] scratch (row sums dO.O, passed between the two kernels).     */
 PETB200_API int petb200_attention_bwd(const float* qkv, const float* out, const float* lse,
                           const float* d_out, const int32_t* row_ptr,
                           const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
                           int num_heads, int head_dim, float scale, int max_row,
-                          float* d_qkv, float* d_fc, petb200_stream_t stream);
+                          float* d_qkv, float* d_fc, float* dsum, petb200_stream_t stream);
 
 /* ------------------------------------------------ message reversal + combine (a8)
  * backend.py:559-575: cc[e] = LayerNorm_{2d}(cat[t_e, t_rev(e)]) (eps 1e-5, affine).

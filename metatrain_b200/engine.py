@@ -437,9 +437,10 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
             gemm(d_tp, T["w_o_t"], d_o[:E], precision=prec, pack=pw)
             gemm(d_yc, T["w_o_t"], d_o[E:], precision=prec, pack=pw)
             d_qkv = _empty((E + N, 3 * d), ref)
+            dsum = _empty((E + N, nh), ref)
             call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o),
                  ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row,
-                 ptr(d_qkv), ptr(d_fc))
+                 ptr(d_qkv), ptr(d_fc), ptr(dsum))
             d_xh1 = d_o  # reuse
             gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec, pack=pw)
             del d_qkv

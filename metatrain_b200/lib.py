@@ -51,7 +51,7 @@ _SIGNATURES = {
     "petb200_rms_rstd": [_P, _I64, _I, _P, _P],
     "petb200_rms_bwd": [_P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_attention_fwd": [_P, _P, _P, _I64, _I64, _I, _I, _F, _I, _P, _P, _P],
-    "petb200_attention_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _I, _P, _P, _P],
+    "petb200_attention_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _I, _P, _P, _P, _P],
     "petb200_combine_ln_fwd": [_P, _P, _P, _P, _I64, _I, _P, _P, _P, _P],
     "petb200_combine_ln_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_combine_scatter_bwd": [_P, _P, _P, _I64, _I, _P, _P],
@@ -109,7 +109,7 @@ def stream_ptr() -> int:
 
 
 # kernels launched by each entry point (for bench.py's ``gpu_launches`` claim)
-_KERNELS_PER_CALL = {"edges_bwd": 3, "csr_build": 6, "readout_bwd": 2, "force_scatter": 2}
+_KERNELS_PER_CALL = {"attention_bwd": 2, "edges_bwd": 3, "csr_build": 6, "readout_bwd": 2, "force_scatter": 2}
 launch_count = 0
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
 profile_hook = None

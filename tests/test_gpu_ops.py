@@ -176,8 +176,9 @@ def test_attention_fwd_bwd(n_atoms, max_count):
     ref.backward(go.double().cpu())
     d_qkv = torch.empty_like(qkv)
     d_fc = torch.zeros(E, device=DEV)
+    dsum = torch.empty(E + n_atoms, nh, device=DEV)
     call("attention_bwd", ptr(qkv), ptr(out), ptr(lse), ptr(go), ptr(row_ptr), ptr(fc), n_atoms, E,
-         nh, hd, scale, mx, ptr(d_qkv), ptr(d_fc))
+         nh, hd, scale, mx, ptr(d_qkv), ptr(d_fc), ptr(dsum))
     assert_close(d_qkv, x.grad, 5e-5, 1e-4, "attention d_qkv")
     ref_dfc = f.grad.clone()
     assert_close(d_fc, ref_dfc, 5e-4, 1e-4, "attention d_fc")

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel.
+"""Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_*] --csv` launch list.
 
     python tools/summarize_launches.py gpurun_out/launches.csv > profiles/rNN_launches.md
 """
@@ -8,30 +8,38 @@ import csv
 import re
 import sys
 
+SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
 
 def main(path):
     with open(path) as fh:
         lines = [ln for ln in fh if ln.startswith('"')]
-    tot = collections.defaultdict(lambda: [0, 0.0])
+    tot = collections.defaultdict(lambda: collections.defaultdict(float))
+    ids = collections.defaultdict(set)
     for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
-            continue
         name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("petb200::<unnamed>::", "")
         name = re.sub(r"^void ", "", name)
-        v = float(row["Metric Value"].replace(",", ""))
-        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(row["Metric Unit"], 1.0)
-        tot[name][0] += 1
-        tot[name][1] += v
-    total = sum(v[1] for v in tot.values())
+        v = float(row["Metric Value"].replace(",", "")) * SCALE.get(row["Metric Unit"], 1.0)
+        tot[name][row["Metric Name"]] += v
+        ids[name].add(row["ID"])
+    total = sum(v["gpu__time_duration.sum"] for v in tot.values())
+    has_dram = any("dram__bytes_read.sum" in v for v in tot.values())
     print(f"# ncu launch list summary: {path}\n")
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES.\n")
-    print("| kernel | launches | total ms | share | avg us |")
-    print("|---|---:|---:|---:|---:|")
-    for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        if v[1] / total < 0.0005:
+    cols = "| kernel | launches | total ms | share | avg us |" + (" DRAM read MB | DRAM write MB | DRAM GB/s |" if has_dram else "")
+    print(cols)
+    print("|---|---:|---:|---:|---:|" + ("---:|---:|---:|" if has_dram else ""))
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
+        t = v["gpu__time_duration.sum"]
+        if t / total < 0.0005:
             continue
-        print(f"| `{k[:80]}` | {v[0]} | {v[1] / 1e3:.3f} | {v[1] / total * 100:.1f}% | {v[1] / v[0]:.1f} |")
-    print(f"\ntotal {total / 1e3:.2f} ms over {sum(v[0] for v in tot.values())} launches")
+        n = len(ids[k])
+        line = f"| `{k[:80]}` | {n} | {t / 1e3:.3f} | {t / total * 100:.1f}% | {t / n:.1f} |"
+        if has_dram:
+            rd, wr = v.get("dram__bytes_read.sum", 0.0), v.get("dram__bytes_write.sum", 0.0)
+            line += f" {rd / 1e6:.0f} | {wr / 1e6:.0f} | {(rd + wr) / (t * 1e-6) / 1e9:.0f} |"
+        print(line)
+    print(f"\ntotal {total / 1e3:.2f} ms over {sum(len(i) for i in ids.values())} launches")
 
 
 if __name__ == "__main__":
