@@ -329,8 +329,18 @@ def run_petb200(args):
     g = load_golden("water_384")
     tiles = n_total // 384
     f = out["dE_dpos"].cpu().numpy().reshape(tiles, 384, 3)
-    force_err = float(np.abs(f - g["ref32_dE_dpos"][None]).max())
+    # tiles far from the origin see differently rounded fp32 positions than the seed box (the
+    # golden), so the golden check uses the first 27 tiles (the single-GPU box); sharded runs
+    # are additionally compared with a single-GPU evaluation of the SAME big box
+    force_err = float(np.abs(f[:27] - g["ref32_dE_dpos"][None]).max())
     energy_err = float(abs(float(out["energies"]) / tiles - float(g["ref32_energies"].ravel()[0])) / 384)
+    force_err_single = None
+    if sharded and rank == 0:
+        whole = {k: v.to(dev) for k, v in make_batch([box], CUTOFF).items()}
+        ref_out = evaluate(be, **whole, target=TARGET)
+        force_err_single = float((ref_out["dE_dpos"] - out["dE_dpos"]).abs().max())
+        del whole, ref_out
+        torch.cuda.empty_cache()
 
     sampler = ClockSampler(local)
     barrier()
@@ -436,6 +446,7 @@ def run_petb200(args):
                                    f"{world} independent boxes (1 per GPU)"),
                    "cache": "per-step working set (~8 GB of activations) >> 126 MB L2; no explicit flush"},
         "force_max_abs_err_eV_per_A": force_err, "energy_abs_err_eV_per_atom": energy_err,
+        "force_max_abs_err_vs_single_gpu_eV_per_A": force_err_single,
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec / args.steps * 1e3},
         "gpu_launches": launches, "clocks": clocks,
