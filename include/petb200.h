@@ -107,6 +107,26 @@ PETB200_API int petb200_reverse_map(const int32_t* row_ptr, const int32_t* ctr, 
                         const int32_t* shift_csr, int64_t n_edges, int64_t n_rows, int32_t* rev,
                         int32_t* n_missing, petb200_stream_t stream);
 
+/* ------------------------------------------------------------ neighbor list (a1)
+ * GPU replacement of vesin.ase_neighbor_list("ijS", ...) (src/metatrain/utils/neighbor_lists.py:131):
+ * all ordered pairs (i, j, S) with |r_j + S.cell - r_i| <= cutoff (+2e-6 relative margin; the
+ * model's own filter decides), no (i, i, 0), grouped by centre.  `cell_host` (9 floats, rows =
+ * lattice vectors) and `origin_host` (3 floats, may be NULL) are HOST pointers; periodic = 1
+ * (all three directions) or 0 (open: pass the bounding box as cell + origin).  Two phases
+ * around one device->host read of offsets[n_atoms] (= number of pairs):
+ *   nl_count: offsets[N+1] = exclusive scan of the per-atom neighbour counts;
+ *   nl_fill : centers / neighbors [P], shifts [P,3].  The workspace must persist in between. */
+PETB200_API int64_t petb200_nl_num_bins(const float* cell_host, int periodic, float cutoff,
+                        int64_t n_atoms);
+PETB200_API size_t petb200_nl_workspace(int64_t n_atoms, int64_t n_bins);
+PETB200_API int petb200_nl_count(const float* positions, int64_t n_atoms, const float* cell_host,
+                        const float* origin_host, int periodic, float cutoff, void* workspace,
+                        size_t workspace_bytes, int32_t* offsets, petb200_stream_t stream);
+PETB200_API int petb200_nl_fill(int64_t n_atoms, const float* cell_host, const float* origin_host,
+                        int periodic, float cutoff, const void* workspace, size_t workspace_bytes,
+                        const int32_t* offsets, int32_t* centers, int32_t* neighbors,
+                        int32_t* shifts, petb200_stream_t stream);
+
 /* CSR <-> padded NEF ([N, M, D], zero padded; nef.py:169-218).                         */
 PETB200_API int petb200_csr_to_nef(const float* x_csr, const int32_t* row_ptr, int64_t n_atoms,
                        int64_t n_edges, int width_m, int d, float* x_nef,

@@ -34,6 +34,10 @@ _SIGNATURES = {
     "petb200_csr_build": [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, _SZ, _P],
     "petb200_csr_gather": [_P, _P, _P, _P, _I64, _P, _P, _P, _P],
     "petb200_reverse_map": [_P, _P, _P, _P, _I64, _I64, _P, _P, _P],
+    "petb200_nl_num_bins": [_P, _I, _F, _I64],
+    "petb200_nl_workspace": [_I64, _I64],
+    "petb200_nl_count": [_P, _I64, _P, _P, _I, _F, _P, _SZ, _P, _P],
+    "petb200_nl_fill": [_I64, _P, _P, _I, _F, _P, _SZ, _P, _P, _P, _P, _P],
     "petb200_csr_to_nef": [_P, _P, _I64, _I64, _I, _I, _P, _P],
     "petb200_nef_to_csr": [_P, _P, _P, _I64, _I64, _I, _I, _P, _P],
     "petb200_edges_fwd": [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _I, _P, _P, _P, _P],
@@ -61,7 +65,8 @@ _SIGNATURES = {
     "petb200_last_error": [],
     "petb200_version": [],
 }
-_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_last_error": ctypes.c_char_p}
+_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_last_error": ctypes.c_char_p,
+            "petb200_nl_num_bins": _I64, "petb200_nl_workspace": _SZ}
 
 
 def library_path() -> str:
@@ -109,7 +114,7 @@ def stream_ptr() -> int:
 
 
 # kernels launched by each entry point (for bench.py's ``gpu_launches`` claim)
-_KERNELS_PER_CALL = {"attention_bwd": 2, "edges_bwd": 3, "csr_build": 6, "readout_bwd": 2, "force_scatter": 2}
+_KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "csr_build": 6, "readout_bwd": 2, "force_scatter": 2}
 launch_count = 0
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
 profile_hook = None

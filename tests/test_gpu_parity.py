@@ -188,6 +188,45 @@ def test_evaluator_loop_matches_reference_semantics():
     assert res["ms_per_atom"][0] > 0
 
 
+@pytest.mark.parametrize("case", ["water_384", "carbon_5", "si_64", "qm9_5", "co_periodic", "ragged_mix"])
+def test_gpu_neighbor_list_equals_host_list(case):
+    """petb200_nl_count/fill (GPU cell list) produce the same pair set as the host list that
+    the golden files were generated with (after the model's own cutoff filter)."""
+    from metatrain_b200.neighbors_gpu import neighbor_list_gpu
+    g = load_golden(case)
+    for b in range(g["cells"].shape[0]):
+        sel = g["system_indices"] == b
+        pos = torch.tensor(g["positions"][sel], device=DEV)
+        cell = torch.tensor(g["cells"][b], device=DEV)
+        periodic = bool(np.abs(g["cells"][b]).sum() > 0)
+        i, j, s = neighbor_list_gpu(pos, cell, periodic, 4.5)
+        # exact cutoff decision in fp64 on the same fp32 inputs
+        p64, c64 = g["positions"][sel].astype(np.float64), g["cells"][b].astype(np.float64)
+        i, j, s = i.cpu().numpy(), j.cpu().numpy(), s.cpu().numpy()
+        d = np.linalg.norm(p64[j] - p64[i] + s @ c64, axis=1) if len(i) else np.zeros(0)
+        assert (d <= 4.5 * (1 + 1e-5)).all()
+        keep = d <= 4.5
+        got = set(zip(i[keep].tolist(), j[keep].tolist(), map(tuple, s[keep].tolist())))
+        off = int(np.nonzero(sel)[0][0]) if sel.any() else 0
+        e = np.isin(g["centers"], np.nonzero(sel)[0])
+        ref = set(zip((g["centers"][e] - off).tolist(), (g["neighbors"][e] - off).tolist(),
+                      map(tuple, g["cell_shifts"][e].tolist())))
+        assert len(got) == keep.sum() and got == ref
+        assert (np.diff(i) >= 0).all()  # grouped by centre
+
+
+def test_gpu_neighbor_list_end_to_end_10k(water_10k):
+    """Positions in, energies + forces out, nothing but positions crosses PCIe."""
+    from metatrain_b200.neighbors_gpu import neighbor_list_gpu
+    g, be, batch, out = water_10k
+    i, j, s = neighbor_list_gpu(batch["positions"], batch["cells"][0], True, 4.5)
+    assert i.shape[0] >= 392040
+    out2 = evaluate(be, batch["positions"], i, j, batch["species"], batch["cells"], s,
+                    batch["system_indices"], target=g["target"])
+    assert abs(float(out2["energies"]) - float(out["energies"])) <= 2e-6 * abs(float(out["energies"]))
+    assert (out2["dE_dpos"] - out["dE_dpos"]).abs().max() <= 2e-5
+
+
 def test_neighbor_order_invariance():
     """Shuffling the neighbor list changes nothing but fp summation order."""
     g = load_golden("si_64")
