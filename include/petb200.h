@@ -218,18 +218,23 @@ PETB200_API int petb200_rms_bwd(const float* d_xhat, const float* x, const float
  * Per-atom multi-head attention over tokens {centre i} U {edges of row i} with the
  * key-only additive bias log(max(w_q, 1e-15)), w = 1 for the centre token and f_e for
  * edge tokens (transformer.py:86-152, 524-540).  qkv is [E+N, 3*d] = [q | k | v], each
- * split into num_heads heads of 16; out is [E+N, d]; lse is [E+N, num_heads].           */
+ * split into num_heads heads of 16; out is [E+N, d]; lse is [E+N, num_heads] (base-2
+ * units).  precision = PETB200_PREC_FP32: packed-fp32 CUDA-core kernels (any row length that
+ * fits shared memory); otherwise, for rows of at most 63 neighbours, warp-level tensor-core
+ * kernels (mma.sync bf16, 2-term operand split, fp32 accumulation), falling back to the
+ * CUDA-core kernels for longer rows.                                                     */
 PETB200_API int petb200_attention_fwd(const float* qkv, const int32_t* row_ptr,
                           const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
                           int num_heads, int head_dim, float scale, int max_row,
-                          float* out, float* lse, petb200_stream_t stream);
+                          int precision, float* out, float* lse, petb200_stream_t stream);
 /* d_qkv from d_out; d_fc[e] += (sum_{heads,queries} dS[.,e]) / f_e  (f_e > 1e-15).
  * dsum is [E+N, num_heads] scratch (row sums dO.O, passed between the two kernels).     */
 PETB200_API int petb200_attention_bwd(const float* qkv, const float* out, const float* lse,
                           const float* d_out, const int32_t* row_ptr,
                           const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
                           int num_heads, int head_dim, float scale, int max_row,
-                          float* d_qkv, float* d_fc, float* dsum, petb200_stream_t stream);
+                          int precision, float* d_qkv, float* d_fc, float* dsum,
+                          petb200_stream_t stream);
 
 /* ------------------------------------------------ message reversal + combine (a8)
  * backend.py:559-575: cc[e] = LayerNorm_{2d}(cat[t_e, t_rev(e)]) (eps 1e-5, affine).

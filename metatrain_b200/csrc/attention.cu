@@ -18,6 +18,7 @@
 // memory -> 4 CTAs per SM.  No atomics: every output row has exactly one writer, results
 // are bit-reproducible.  The log-sum-exp is stored in base-2 units.
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace petb200 {
 namespace {
@@ -334,7 +335,10 @@ using namespace petb200;
 extern "C" PETB200_API int petb200_attention_fwd(const float* qkv, const int32_t* row_ptr,
                                      const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
                                      int num_heads, int head_dim, float scale, int max_row,
-                                     float* out, float* lse, cudaStream_t stream) {
+                                     int precision, float* out, float* lse, cudaStream_t stream) {
+  if (precision != PETB200_PREC_FP32 && n_atoms > 0 && attention_tc_supports(num_heads, head_dim, max_row))
+    return launch_attention_fwd_tc(qkv, row_ptr, cutoff_factor, n_atoms, n_edges, scale, max_row, out,
+                                   lse, stream);
   const size_t smem = fwd_smem_bytes(max_row + 1, 8);
   if (int rc = check_shape("attention_fwd", num_heads, head_dim, smem, max_row)) return rc;
   if (n_atoms == 0) return PETB200_OK;
@@ -348,7 +352,11 @@ extern "C" PETB200_API int petb200_attention_bwd(const float* qkv, const float* 
                                      const float* d_out, const int32_t* row_ptr,
                                      const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,
                                      int num_heads, int head_dim, float scale, int max_row,
-                                     float* d_qkv, float* d_fc, float* dsum, cudaStream_t stream) {
+                                     int precision, float* d_qkv, float* d_fc, float* dsum,
+                                     cudaStream_t stream) {
+  if (precision != PETB200_PREC_FP32 && n_atoms > 0 && attention_tc_supports(num_heads, head_dim, max_row))
+    return launch_attention_bwd_tc(qkv, out, lse, d_out, row_ptr, cutoff_factor, n_atoms, n_edges, scale,
+                                   max_row, d_qkv, d_fc, stream);
   const size_t smem_a = fwd_smem_bytes(max_row + 1, 8), smem_b = dkv_smem_bytes(max_row + 1, 8);
   if (int rc = check_shape("attention_bwd", num_heads, head_dim, smem_b > smem_a ? smem_b : smem_a, max_row))
     return rc;

@@ -29,4 +29,14 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream);
 bool gemm_tc_supports(const GemmArgs& g);
 
+// tensor-core attention (attention_tc.cu): mma.sync bf16 hi/lo split, T <= 64 tokens per atom
+bool attention_tc_supports(int num_heads, int head_dim, int max_row);
+int launch_attention_fwd_tc(const float* qkv, const int32_t* row_ptr, const float* fc,
+                            int64_t n_atoms, int64_t n_edges, float scale, int max_row, float* out,
+                            float* lse, cudaStream_t stream);
+int launch_attention_bwd_tc(const float* qkv, const float* out, const float* lse, const float* d_out,
+                            const int32_t* row_ptr, const float* fc, int64_t n_atoms,
+                            int64_t n_edges, float scale, int max_row, float* d_qkv, float* d_fc,
+                            cudaStream_t stream);
+
 }  // namespace petb200

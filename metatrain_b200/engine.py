@@ -327,7 +327,7 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
             o = _empty((E + N, d), vec)
             lse = _empty((E + N, nh), vec)
             call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,
-                 scale, topo.max_row, ptr(o), ptr(lse))
+                 scale, topo.max_row, prec, ptr(o), ptr(lse))
             Xn = _empty((E + N, d), vec)  # rows [:E] = t' ; rows [E:] = next centre token
             gemm(o[:E], T["w_o"], Xn[:E], bias=T["b_o"], residual=X[:E], precision=prec, pack=pw)
             yc = _empty((N, d), vec)
@@ -439,7 +439,7 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
             d_qkv = _empty((E + N, 3 * d), ref)
             dsum = _empty((E + N, nh), ref)
             call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o),
-                 ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row,
+                 ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row, prec,
                  ptr(d_qkv), ptr(d_fc), ptr(dsum))
             d_xh1 = d_o  # reuse
             gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec, pack=pw)

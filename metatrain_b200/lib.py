@@ -54,8 +54,8 @@ _SIGNATURES = {
     "petb200_geom_embed_bwd": [_P, _I64, _P, _I64, _I, _I, _P, _P, _P],
     "petb200_rms_rstd": [_P, _I64, _I, _P, _P],
     "petb200_rms_bwd": [_P, _P, _P, _P, _I64, _I, _P, _P],
-    "petb200_attention_fwd": [_P, _P, _P, _I64, _I64, _I, _I, _F, _I, _P, _P, _P],
-    "petb200_attention_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _I, _P, _P, _P, _P],
+    "petb200_attention_fwd": [_P, _P, _P, _I64, _I64, _I, _I, _F, _I, _I, _P, _P, _P],
+    "petb200_attention_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _I, _I, _P, _P, _P, _P],
     "petb200_combine_ln_fwd": [_P, _P, _P, _P, _I64, _I, _P, _P, _P, _P],
     "petb200_combine_ln_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_combine_scatter_bwd": [_P, _P, _P, _I64, _I, _P, _P],

@@ -152,8 +152,12 @@ def _attention_reference(qkv, row_ptr, fc, n_atoms, n_edges, nh, scale):
     return out
 
 
-@pytest.mark.parametrize("n_atoms,max_count", [(37, 48), (5, 70), (3, 1)])
-def test_attention_fwd_bwd(n_atoms, max_count):
+@pytest.mark.parametrize("prec", [PREC_FP32, PREC_BF16X3])
+@pytest.mark.parametrize("n_atoms,max_count", [(37, 48), (5, 70), (3, 1), (41, 63), (23, 15), (19, 31)])
+def test_attention_fwd_bwd(n_atoms, max_count, prec):
+    """PREC_FP32: packed-fp32 CUDA-core kernels; PREC_BF16X3: mma.sync tensor-core kernels
+    (rows of <= 63 neighbours; the (5, 70) case exercises the documented fallback)."""
+    tol = 1.0 if prec == PREC_FP32 else 4.0
     nh, hd = 8, 16
     d = nh * hd
     row_ptr, E, mx = ragged_rows(n_atoms, max_count, seed=n_atoms)
@@ -167,21 +171,22 @@ def test_attention_fwd_bwd(n_atoms, max_count):
     scale = 0.25
     out = torch.empty(E + n_atoms, d, device=DEV)
     lse = torch.empty(E + n_atoms, nh, device=DEV)
-    call("attention_fwd", ptr(qkv), ptr(row_ptr), ptr(fc), n_atoms, E, nh, hd, scale, mx, ptr(out), ptr(lse))
+    call("attention_fwd", ptr(qkv), ptr(row_ptr), ptr(fc), n_atoms, E, nh, hd, scale, mx, prec,
+         ptr(out), ptr(lse))
     x = qkv.double().cpu().requires_grad_(True)
     f = fc.double().cpu().requires_grad_(True)
     ref = _attention_reference(x, row_ptr, f, n_atoms, E, nh, scale)
-    assert_close(out, ref.detach(), 2e-5, 1e-5, "attention out")
+    assert_close(out, ref.detach(), 2e-5 * tol, 1e-5 * tol, "attention out")
     go = rnd(E + n_atoms, d, seed=9)
     ref.backward(go.double().cpu())
     d_qkv = torch.empty_like(qkv)
     d_fc = torch.zeros(E, device=DEV)
     dsum = torch.empty(E + n_atoms, nh, device=DEV)
     call("attention_bwd", ptr(qkv), ptr(out), ptr(lse), ptr(go), ptr(row_ptr), ptr(fc), n_atoms, E,
-         nh, hd, scale, mx, ptr(d_qkv), ptr(d_fc), ptr(dsum))
-    assert_close(d_qkv, x.grad, 5e-5, 1e-4, "attention d_qkv")
+         nh, hd, scale, mx, prec, ptr(d_qkv), ptr(d_fc), ptr(dsum))
+    assert_close(d_qkv, x.grad, 5e-5 * tol, 1e-4 * tol, "attention d_qkv")
     ref_dfc = f.grad.clone()
-    assert_close(d_fc, ref_dfc, 5e-4, 1e-4, "attention d_fc")
+    assert_close(d_fc, ref_dfc, 5e-4 * tol, 1e-4 * tol, "attention d_fc")
 
 
 # ------------------------------------------------------------------------ row-wise
