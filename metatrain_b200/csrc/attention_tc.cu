@@ -33,6 +33,7 @@ namespace {
 constexpr int H = 8, HD = 16, D = H * HD;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kPrefetchDistance = 2 * kNumSMs;  // ~ CTAs resident at a time
 
 __device__ __forceinline__ int64_t token_row(int p, int row_lo, int64_t n_edges, int64_t atom) {
   return p == 0 ? n_edges + atom : (int64_t)row_lo + (p - 1);
@@ -99,12 +100,25 @@ __device__ __forceinline__ float key_bias(int k, int T, int lo, const float* __r
   return log2f(fmaxf(__ldg(fc + lo + k - 1), 1e-15f));
 }
 
+// L2 prefetch of the token rows of a later atom (one whose CTA starts when the CTAs resident
+// now retire): the edge-token rows of an atom are contiguous, so one bulk prefetch per array
+// covers them.  Decouples DRAM traffic from the (register-limited) occupancy of these kernels.
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_atom_rows(const float* base, int ld, int64_t atom,
+                                                   const int32_t* __restrict__ row_ptr, int64_t n_edges) {
+  const int lo = __ldg(row_ptr + atom), hi = __ldg(row_ptr + atom + 1);
+  if (hi > lo) prefetch_l2(base + (int64_t)lo * ld, (uint32_t)(hi - lo) * ld * 4u);
+  prefetch_l2(base + (n_edges + atom) * ld, (uint32_t)ld * 4u);
+}
+
 // ------------------------------------------------------------------------- forward
 // Per warp (= head) shared memory: K fragments [2*NKB][32] uint4 (hi0, hi1, lo0, lo1 per
 // 8-key tile), V^T fragments [2*NKB][32] uint4, key bias [16*NKB] floats.  These are the
 // warp's own registers parked in smem (each lane reads back what it wrote).
 template <int NKB>
-__global__ void __launch_bounds__(256) attention_fwd_tc_kernel(
+__global__ void __launch_bounds__(256, 3) attention_fwd_tc_kernel(
     const float* __restrict__ qkv, const int32_t* __restrict__ row_ptr,
     const float* __restrict__ fc, int64_t n_edges, float scale, float* __restrict__ out,
     float* __restrict__ lse) {
@@ -116,39 +130,58 @@ __global__ void __launch_bounds__(256) attention_fwd_tc_kernel(
   const int T = __ldg(row_ptr + atom + 1) - lo + 1;
   const int nkb = (T + 15) >> 4;
   const int h = warp;
+  if (threadIdx.x == 0 && atom + kPrefetchDistance < (int64_t)gridDim.x)
+    prefetch_atom_rows(qkv, 3 * D, atom + kPrefetchDistance, row_ptr, n_edges);
   uint4* kfrag = smem4 + (size_t)warp * WARP_U4;
   uint4* vfrag = kfrag + 2 * NKB * 32;
   float* lbias = reinterpret_cast<float*>(vfrag + 2 * NKB * 32);
 
-  for (int j = 0; j < 2 * nkb; ++j) {
-    const int key = 8 * j + g;
-    const bool ok = key < T;
-    const float* row = qkv + token_row(ok ? key : 0, lo, n_edges, atom) * (3 * D) + h * HD + 4 * t;
-    const float4 k4 = ok ? ldg4(row + D) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 v4 = ok ? ldg4(row + 2 * D) : make_float4(0.f, 0.f, 0.f, 0.f);
-    uint4 kf, vf;
-    split2(k4.x, k4.y, kf.x, kf.z);
-    split2(k4.z, k4.w, kf.y, kf.w);
-    split2(v4.x, v4.y, vf.x, vf.z);
-    split2(v4.z, v4.w, vf.y, vf.w);
-    vf.x = movm(vf.x);
-    vf.y = movm(vf.y);
-    vf.z = movm(vf.z);
-    vf.w = movm(vf.w);
-    kfrag[j * 32 + lane] = kf;
-    vfrag[j * 32 + lane] = vf;
+  // two 8-key tiles per iteration: all four global loads are issued before the conversions
+  for (int jb = 0; jb < nkb; ++jb) {
+    float4 k4[2], v4[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int key = 16 * jb + 8 * u + g;
+      const bool ok = key < T;
+      const float* row = qkv + token_row(ok ? key : 0, lo, n_edges, atom) * (3 * D) + h * HD + 4 * t;
+      k4[u] = ok ? ldg4(row + D) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v4[u] = ok ? ldg4(row + 2 * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = 2 * jb + u;
+      uint4 kf, vf;
+      split2(k4[u].x, k4[u].y, kf.x, kf.z);
+      split2(k4[u].z, k4[u].w, kf.y, kf.w);
+      split2(v4[u].x, v4[u].y, vf.x, vf.z);
+      split2(v4[u].z, v4[u].w, vf.y, vf.w);
+      vf.x = movm(vf.x);
+      vf.y = movm(vf.y);
+      vf.z = movm(vf.z);
+      vf.w = movm(vf.w);
+      kfrag[j * 32 + lane] = kf;
+      vfrag[j * 32 + lane] = vf;
+    }
   }
   for (int k = lane; k < 16 * nkb; k += 32) lbias[k] = key_bias(k, T, lo, fc);
   __syncwarp();
 
   const float qs = scale * kLog2e;
+  // the queries of the next tile are fetched while the current one is processed
+  float4 qn0, qn1;
+  auto fetch_q = [&](int qt) {
+    const int p0 = 16 * qt + g, p1 = p0 + 8;
+    qn0 = ldg4(qkv + token_row(p0 < T ? p0 : 0, lo, n_edges, atom) * (3 * D) + h * HD + 4 * t);
+    qn1 = ldg4(qkv + token_row(p1 < T ? p1 : 0, lo, n_edges, atom) * (3 * D) + h * HD + 4 * t);
+  };
+  fetch_q(0);
   for (int qt = 0; qt < nkb; ++qt) {
     const int p0 = 16 * qt + g, p1 = p0 + 8;
     const bool ok0 = p0 < T, ok1 = p1 < T;
     const int64_t r0 = token_row(ok0 ? p0 : 0, lo, n_edges, atom);
     const int64_t r1 = token_row(ok1 ? p1 : 0, lo, n_edges, atom);
-    float4 q0 = ldg4(qkv + r0 * (3 * D) + h * HD + 4 * t);
-    float4 q1 = ldg4(qkv + r1 * (3 * D) + h * HD + 4 * t);
+    const float4 q0 = qn0, q1 = qn1;
+    if (qt + 1 < nkb) fetch_q(qt + 1);
     uint32_t ah[4], al[4];
     split2(q0.x * qs, q0.y * qs, ah[0], al[0]);
     split2(q1.x * qs, q1.y * qs, ah[1], al[1]);
@@ -224,7 +257,7 @@ __global__ void __launch_bounds__(256) attention_fwd_tc_kernel(
 //   d_fc[e] += sum_{h,q} dS[q,e] / f_e.
 // Per-warp smem: 4 arrays (Qh, Ql, dOh, dOl) x 2 halves x Tp rows x 16 B; L, Dq [Tp] floats.
 template <int NKB>
-__global__ void __launch_bounds__(256) attention_bwd_tc_kernel(
+__global__ void __launch_bounds__(256, 2) attention_bwd_tc_kernel(
     const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ lse,
     const float* __restrict__ d_out, const int32_t* __restrict__ row_ptr,
     const float* __restrict__ fc, int64_t n_edges, float scale, float* __restrict__ d_qkv,
@@ -240,6 +273,10 @@ __global__ void __launch_bounds__(256) attention_bwd_tc_kernel(
   const int T = __ldg(row_ptr + atom + 1) - lo + 1;
   const int nkb = (T + 15) >> 4;
   const int h = warp;
+  if (threadIdx.x < 3 && atom + kPrefetchDistance < (int64_t)gridDim.x) {
+    const float* base = threadIdx.x == 0 ? qkv : (threadIdx.x == 1 ? d_out : out);
+    prefetch_atom_rows(base, threadIdx.x == 0 ? 3 * D : D, atom + kPrefetchDistance, row_ptr, n_edges);
+  }
   uint8_t* wbase = smem + (size_t)warp * WARP_BYTES;
   const uint32_t w_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(wbase));
   float* Ls = reinterpret_cast<float*>(wbase + 4 * ARR);
@@ -248,34 +285,44 @@ __global__ void __launch_bounds__(256) attention_bwd_tc_kernel(
   const float qs = scale * kLog2e;
 
   // ---- stage Q (scaled) and dO, L and D for every token of this (atom, head)
-  for (int it = 0; it < 2 * nkb; ++it) {
-    const int p = 8 * it + g;
-    const bool ok = p < T;
-    const int64_t row = token_row(ok ? p : 0, lo, n_edges, atom);
-    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = q4, o4 = q4;
-    if (ok) {
-      q4 = ldg4(qkv + row * (3 * D) + h * HD + 4 * t);
-      g4 = ldg4(d_out + row * D + h * HD + 4 * t);
-      o4 = ldg4(out + row * D + h * HD + 4 * t);
+  for (int ib = 0; ib < nkb; ++ib) {
+    float4 q4[2], g4[2], o4[2];
+    int64_t rows[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int p = 16 * ib + 8 * u + g;
+      const bool ok = p < T;
+      rows[u] = token_row(ok ? p : 0, lo, n_edges, atom);
+      q4[u] = g4[u] = o4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        q4[u] = ldg4(qkv + rows[u] * (3 * D) + h * HD + 4 * t);
+        g4[u] = ldg4(d_out + rows[u] * D + h * HD + 4 * t);
+        o4[u] = ldg4(out + rows[u] * D + h * HD + 4 * t);
+      }
     }
-    uint32_t h0, l0, h1, l1;
-    split2(q4.x * qs, q4.y * qs, h0, l0);
-    split2(q4.z * qs, q4.w * qs, h1, l1);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(wbase) + p * 4 + t;  // 16 B rows, word t
-    dst[0] = h0;
-    dst[Tp * 4] = h1;                      // half 1
-    dst[ARR / 4] = l0;
-    dst[ARR / 4 + Tp * 4] = l1;
-    split2(g4.x, g4.y, h0, l0);
-    split2(g4.z, g4.w, h1, l1);
-    dst[2 * (ARR / 4)] = h0;
-    dst[2 * (ARR / 4) + Tp * 4] = h1;
-    dst[3 * (ARR / 4)] = l0;
-    dst[3 * (ARR / 4) + Tp * 4] = l1;
-    const float dsum = quad_sum(g4.x * o4.x + g4.y * o4.y + g4.z * o4.z + g4.w * o4.w);
-    if (t == 0) {
-      Dq[p] = dsum;
-      Ls[p] = ok ? __ldg(lse + row * H + h) : INFINITY;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int p = 16 * ib + 8 * u + g;
+      uint32_t h0, l0, h1, l1;
+      split2(q4[u].x * qs, q4[u].y * qs, h0, l0);
+      split2(q4[u].z * qs, q4[u].w * qs, h1, l1);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(wbase) + p * 4 + t;  // 16 B rows, word t
+      dst[0] = h0;
+      dst[Tp * 4] = h1;                      // half 1
+      dst[ARR / 4] = l0;
+      dst[ARR / 4 + Tp * 4] = l1;
+      split2(g4[u].x, g4[u].y, h0, l0);
+      split2(g4[u].z, g4[u].w, h1, l1);
+      dst[2 * (ARR / 4)] = h0;
+      dst[2 * (ARR / 4) + Tp * 4] = h1;
+      dst[3 * (ARR / 4)] = l0;
+      dst[3 * (ARR / 4) + Tp * 4] = l1;
+      const float dsum = quad_sum(g4[u].x * o4[u].x + g4[u].y * o4[u].y + g4[u].z * o4[u].z +
+                                  g4[u].w * o4[u].w);
+      if (t == 0) {
+        Dq[p] = dsum;
+        Ls[p] = p < T ? __ldg(lse + rows[u] * H + h) : INFINITY;
+      }
     }
   }
   __syncwarp();
@@ -295,17 +342,25 @@ __global__ void __launch_bounds__(256) attention_bwd_tc_kernel(
   // transposed:     matrices (tokens 0-7, half 0), (8-15, half 0), (0-7, half 1), (8-15, half 1)
   const uint32_t off_t = (uint32_t)(((mi >> 1) * Tp + (mi & 1) * 8 + mr) * 16);
 
+  // K / V rows of the next key tile are fetched while the current tile is processed
+  float4 ka, kb4, va, vb;
+  auto fetch_kv = [&](int kt) {
+    const int k0 = 16 * kt + g, k1 = k0 + 8;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* r0 = qkv + token_row(k0 < T ? k0 : 0, lo, n_edges, atom) * (3 * D) + h * HD + 4 * t;
+    const float* r1 = qkv + token_row(k1 < T ? k1 : 0, lo, n_edges, atom) * (3 * D) + h * HD + 4 * t;
+    ka = k0 < T ? ldg4(r0 + D) : z4;
+    va = k0 < T ? ldg4(r0 + 2 * D) : z4;
+    kb4 = k1 < T ? ldg4(r1 + D) : z4;
+    vb = k1 < T ? ldg4(r1 + 2 * D) : z4;
+  };
+  fetch_kv(0);
 #pragma unroll 1
   for (int kt = 0; kt < nkb; ++kt) {
     const int k0 = 16 * kt + g, k1 = k0 + 8;
     const bool ok0 = k0 < T, ok1 = k1 < T;
     const int64_t r0 = token_row(ok0 ? k0 : 0, lo, n_edges, atom);
     const int64_t r1 = token_row(ok1 ? k1 : 0, lo, n_edges, atom);
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 ka = ok0 ? ldg4(qkv + r0 * (3 * D) + D + h * HD + 4 * t) : z4;
-    const float4 kb4 = ok1 ? ldg4(qkv + r1 * (3 * D) + D + h * HD + 4 * t) : z4;
-    const float4 va = ok0 ? ldg4(qkv + r0 * (3 * D) + 2 * D + h * HD + 4 * t) : z4;
-    const float4 vb = ok1 ? ldg4(qkv + r1 * (3 * D) + 2 * D + h * HD + 4 * t) : z4;
     uint32_t kh[4], kl[4], vh[4], vl[4];
     split2(ka.x, ka.y, kh[0], kl[0]);
     split2(kb4.x, kb4.y, kh[1], kl[1]);
@@ -322,6 +377,7 @@ __global__ void __launch_bounds__(256) attention_bwd_tc_kernel(
       kth[c] = movm(kh[c]);
       ktl[c] = movm(kl[c]);
     }
+    if (kt + 1 < nkb) fetch_kv(kt + 1);
     const float lb0 = key_bias(k0, T, lo, fc), lb1 = key_bias(k1, T, lo, fc);
     float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
