@@ -182,6 +182,28 @@ PETB200_API int petb200_gemm(const float* A, int64_t lda, const float* W, int64_
 PETB200_API int petb200_split_bf16(const float* w, int64_t rows, int cols, float* out,
                        petb200_stream_t stream);
 
+/* ---------------------------------------------------- fused edge feed-forward block
+ * One persistent tcgen05 kernel per direction for the PreLN feed-forward of a transformer
+ * layer (transformer.py:229-232 with FeedForward :21-50, SwiGLU):
+ *   fwd:  y   = x + W_out . swiglu(W_in . rmsnorm(x) + b_in) + b_out
+ *   bwd:  d_x = d_y + (d rmsnorm/dx)^T W_in^T swiglu'(.) W_out^T d_y   (pre-activations are
+ *         recomputed from x; nothing but x has to be kept from the forward pass)
+ * w_in is [2*d_ff, d] with the RMSNorm weight folded into its columns (value rows first, gate
+ * rows second: v, g = chunk(2)), w_out is [d, d_ff]; both fp32.  petb200_mlp_pack turns them
+ * into the bf16 hi/lo operand-tile images (petb200_mlp_image_bytes bytes each, 16-byte
+ * aligned, either pointer may be NULL) that the kernels stream from L2.  Built for d = 128,
+ * d_ff a multiple of 64 up to 512; PETB200_ERR_UNSUPPORTED otherwise (callers then use
+ * petb200_gemm + petb200_rms_*).  Arithmetic: bf16 2-term split, fp32 accumulation.        */
+PETB200_API size_t petb200_mlp_image_bytes(int d_ff, int backward);
+PETB200_API int petb200_mlp_pack(const float* w_in, const float* w_out, int d, int d_ff,
+                     void* image_fwd, void* image_bwd, petb200_stream_t stream);
+PETB200_API int petb200_mlp_fwd(const float* x, int64_t ldx, const void* image_fwd, const float* b_in,
+                    const float* b_out, int64_t n_rows, int d, int d_ff, float* y, int64_t ldy,
+                    petb200_stream_t stream);
+PETB200_API int petb200_mlp_bwd(const float* x, int64_t ldx, const float* d_y, int64_t ld_dy,
+                    const void* image_bwd, const float* b_in, int64_t n_rows, int d, int d_ff,
+                    float* d_x, int64_t ld_dx, petb200_stream_t stream);
+
 /* out[m,:] = table[idx[m],:] (torch.nn.Embedding, backend.py:515-516).                 */
 PETB200_API int petb200_embedding(const float* table, const int32_t* idx, int64_t n_rows, int d,
                       float* out, int64_t ld_out, petb200_stream_t stream);

@@ -1,0 +1,841 @@
+// Fused edge-token feed-forward block of a PET transformer layer, forward and backward, as
+// single persistent tcgen05 kernels (sm_100a).
+//
+//   forward :  y  = x + W_out . swiglu(W_in . rmsnorm(x) + b_in) + b_out
+//   backward:  dx = dy + rmsnorm'(x)^T [ W_in^T . swiglu'(u, g) (W_out^T . dy) ]
+// (TransformerLayer._forward_pre_ln_impl, src/metatrain/pet/modules/transformer.py:229-232;
+//  FeedForward with SwiGLU :21-50 — v, g = w_in(x).chunk(2); w_out(v * sigmoid(g)).)
+//
+// The unfused path (gemm_tc.cu) moves ~25 KB per edge and layer through HBM for this block
+// (the [E, 2F] pre-activations are written, read, and their gradient written and read
+// again).  Here the hidden activations never leave the SM: per 128-row tile the kernel
+// walks the hidden dimension in chunks of 32 units,
+//   GEMM1  acc1[128 x 64]   = X[128 x 128] . W_in[chunk]^T        (tcgen05.mma, A and B in smem)
+//   epi1   a[128 x 32]      = (rs*v + b_v) * sigmoid(rs*g + b_g)  (TMEM -> regs -> TMEM, bf16 hi/lo)
+//   GEMM2  acc2[128 x 128] += a . W_out[:, chunk]^T               (tcgen05.mma, A in TMEM, B in smem)
+// and the backward recomputes the pre-activations instead of loading them,
+//   GEMM1a ug = X . W_in[chunk]^T, GEMM1b ds = dY . W_out[:, chunk], epi1 d_ug = swiglu'(ug) ds,
+//   GEMM2  d_xhat += d_ug . W_in[chunk]      followed by the RMSNorm backward in the epilogue.
+// HBM traffic drops to the algorithmic minimum: forward 1 KB per row (read x, write y),
+// backward 1.5 KB per row (read x, dy, write dx).  All products use the bf16 hi/lo 2-term split
+// of gemm_tc.cu (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM).
+//
+// Weights are streamed from L2 as 16 KB "stages": a pre-swizzled image of the exact
+// shared-memory operand tiles in the order the MMA warp consumes them (petb200_mlp_pack),
+// moved by one thread with 1-D bulk async copies (cp.async.bulk, TMA engine) into a ring.
+//
+// Warp roles (448 threads): warps 0-7 epilogues, warp 8 MMA issue + TMEM owner, warps 9-12
+// activation producers (cp.async fp32 rows -> in-place bf16 hi/lo swizzled operand tiles +
+// per-row RMS statistics), warp 13 weight-stage producer.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace petb200 {
+namespace {
+
+using namespace tc;
+
+constexpr int D = 128;          // d_pet
+constexpr int MAX_F = 512;      // largest hidden width (after SwiGLU) the bias buffer holds
+constexpr int BM = 128;
+constexpr int CH = 32;          // hidden units per chunk
+constexpr int TILE = 16384;     // [128 x 64] bf16 operand tile, K-major SWIZZLE_128B
+constexpr int STAGE = 16384;    // weight ring stage
+constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;
+constexpr int NUM_PROD_THREADS = NUM_PROD_WARPS * 32;
+constexpr int MMA_WARP = NUM_EPI_WARPS, FIRST_PROD_WARP = NUM_EPI_WARPS + 1;
+constexpr int TMA_WARP = FIRST_PROD_WARP + NUM_PROD_WARPS;
+constexpr int NUM_THREADS = 32 * (TMA_WARP + 1);
+constexpr int STAGE_LD = 20;    // floats per row of the epilogue transpose tile
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * STAGE_LD * 4;
+constexpr float kRmsEps = 1.1920928955078125e-07f;  // torch.nn.RMSNorm default: finfo(fp32).eps
+
+// forward image: per pair of chunks: W1(2p,k0) W1(2p,k1) W1(2p+1,k0) W1(2p+1,k1) W2hi(p) W2lo(p)
+__host__ __device__ constexpr int fwd_stages(int F) { return (F / 64) * 6; }
+// backward image: G1 stages of chunk 0; then for c >= 1: G1 stages of c, WT(c-1); finally WT(last)
+__host__ __device__ constexpr int bwd_stages(int F) { return (F / CH) * 5; }
+
+struct Ring {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+// --------------------------------------------------------------------- weight images
+// source row of w_in ([2F, D], RMSNorm weight folded in) behind GEMM1 column n (0..63) of
+// chunk c: columns [0,16) = value units 0..15 of the chunk's first half, [16,32) the matching
+// gate units, [32,64) the same for the second half — so each epilogue warp sees both members
+// of every (value, gate) pair.
+__device__ __forceinline__ int w1_row(int c, int n, int F) {
+  const int hf = n >> 5, s = (n >> 4) & 1, i = n & 15;
+  return s * F + c * CH + hf * 16 + i;
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v, bool lo) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float a = v[2 * q], b = v[2 * q + 1];
+    if (lo) {
+      a -= __bfloat162float(__float2bfloat16_rn(a));
+      b -= __bfloat162float(__float2bfloat16_rn(b));
+    }
+    w[q] = pack_bf16(a, b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// one thread per 16-byte chunk (8 bf16) of the image
+__global__ void mlp_pack_kernel(const float* __restrict__ w_in, const float* __restrict__ w_out, int F,
+                                int backward, uint4* __restrict__ image) {
+  const int n_stage = backward ? bwd_stages(F) : fwd_stages(F);
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_stage * (STAGE / 16)) return;
+  const int s = (int)(idx / (STAGE / 16));
+  const int o = (int)(idx % (STAGE / 16)) * 16;  // byte offset inside the stage
+  // stage kind: 0 = W1(c, kh) ; 1 = W2 hi/lo (pair p) ; 2 = WO(c) ; 3 = WT hi/lo (c)
+  int kind, c = 0, sub = 0;
+  if (!backward) {
+    const int p = s / 6, r = s % 6;
+    if (r < 4) { kind = 0; c = 2 * p + r / 2; sub = r % 2; }
+    else { kind = 1; c = p; sub = r - 4; }
+  } else {
+    const int last = F / CH - 1;
+    int r;
+    if (s < 3) { c = 0; r = s; }
+    else if (s < 3 + 5 * last) { c = 1 + (s - 3) / 5; r = (s - 3) % 5; }
+    else { c = last + 1; r = 3 + (s - 3 - 5 * last); }
+    if (r < 2) { kind = 0; sub = r; }
+    else if (r == 2) { kind = 2; }
+    else { kind = 3; c -= 1; sub = r - 3; }
+  }
+  float v[8];
+  bool lo;
+  if (kind == 0) {          // [64 rows x 64 k] hi (8 KB) | lo (8 KB)
+    lo = o >= 8192;
+    const int t = o & 8191, n = (t >> 10) * 8 + ((t >> 7) & 7), j = ((t >> 4) & 7) ^ (n & 7);
+    const float* src = w_in + (int64_t)w1_row(c, n, F) * D + sub * 64 + j * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = src[e];
+  } else if (kind == 1) {   // [128 rows (out dim) x 64 k (hidden units of the pair)]
+    lo = sub == 1;
+    const int n = (o >> 10) * 8 + ((o >> 7) & 7), j = ((o >> 4) & 7) ^ (n & 7);
+    const float* src = w_out + (int64_t)n * F + c * 64 + j * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = src[e];
+  } else if (kind == 2) {   // per k-half: [32 rows (hidden unit) x 64 k (out dim)] hi (4 KB) | lo (4 KB)
+    const int kh = o >> 13, t = o & 8191;
+    lo = t >= 4096;
+    const int u = t & 4095, n = (u >> 10) * 8 + ((u >> 7) & 7), j = ((u >> 4) & 7) ^ (n & 7);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = w_out[(int64_t)(kh * 64 + j * 8 + e) * F + c * CH + n];
+  } else {                  // [128 rows (in dim) x 64 k (d_v / d_g order of epi1)]
+    lo = sub == 1;
+    const int n = (o >> 10) * 8 + ((o >> 7) & 7), j = ((o >> 4) & 7) ^ (n & 7);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = w_in[(int64_t)w1_row(c, j * 8 + e, F) * D + n];
+  }
+  image[idx] = pack8(v, lo);
+}
+
+// ------------------------------------------------------------------ shared pieces
+struct TileSchedule {
+  int first, stride, count;
+  __device__ __forceinline__ TileSchedule(int64_t M) {
+    const int tiles = (int)ceil_div(M, BM);
+    first = blockIdx.x;
+    stride = gridDim.x;
+    count = first < tiles ? (tiles - first + stride - 1) / stride : 0;
+  }
+  __device__ __forceinline__ int64_t m0(int i) const { return (int64_t)(first + i * stride) * BM; }
+};
+
+// Producer: bring the 128 x 128 fp32 tile `src` (rows m0.., leading dimension ld) into the four
+// bf16 operand tiles at `dst` ([k-chunk][hi|lo], 16 KB each).  Warp `pw` owns rows 32 pw .. 32 pw + 31:
+// cp.async lands floats 0..31 of a k-chunk in the bytes of the hi row and floats 32..63 in the lo
+// row, then the warp converts the rows in place (same scheme as gemm_tc.cu).  Returns, in
+// ss[b][jj], this lane's partial sum of squares of row 32 pw + 16 b + 2 jj + (lane >> 4).
+__device__ __forceinline__ void issue_tile_copies(uint32_t dst_u32, const float* __restrict__ src,
+                                                  int64_t ld, int64_t m0, int64_t M, int pw, int lane) {
+#pragma unroll
+  for (int kc = 0; kc < 2; ++kc) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int row = pw * 32 + 2 * i + (lane >> 4), piece = lane & 15;
+      const int64_t m = m0 + row;
+      const bool ok = m < M;
+      const float* s = src + (ok ? m : 0) * ld + kc * 64 + 4 * piece;
+      cp_async16(dst_u32 + (uint32_t)((kc * 2 + (piece >> 3)) * TILE + row * 128 + (piece & 7) * 16), s,
+                 ok ? 16u : 0u);
+    }
+  }
+}
+template <bool STATS>
+__device__ __forceinline__ void convert_tile(uint8_t* dst, int pw, int lane, float (&ss)[2][8]) {
+  const int quad = lane & 15, rsub = lane >> 4;
+  const int chunk = quad >> 1, within = (quad & 1) * 8;
+#pragma unroll
+  for (int kc = 0; kc < 2; ++kc) {
+    uint8_t* st = dst + kc * 2 * TILE;
+    const uint8_t* src_tile = st + (quad < 8 ? 0 : TILE) + (quad & 7) * 16;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      float4 x[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int r = pw * 32 + b * 16 + jj * 2 + rsub;
+        x[jj] = *reinterpret_cast<const float4*>(src_tile + r * 128);
+      }
+      __syncwarp();  // whole rows are in registers before they are overwritten
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int r = pw * 32 + b * 16 + jj * 2 + rsub;
+        if (STATS) ss[b][jj] += x[jj].x * x[jj].x + x[jj].y * x[jj].y + x[jj].z * x[jj].z + x[jj].w * x[jj].w;
+        const uint32_t h01 = pack_bf16(x[jj].x, x[jj].y), h23 = pack_bf16(x[jj].z, x[jj].w);
+        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+        *reinterpret_cast<uint2*>(st + off) = make_uint2(h01, h23);
+        const float l0 = x[jj].x - __uint_as_float(h01 << 16);
+        const float l1 = x[jj].y - __uint_as_float(h01 & 0xffff0000u);
+        const float l2 = x[jj].z - __uint_as_float(h23 << 16);
+        const float l3 = x[jj].w - __uint_as_float(h23 & 0xffff0000u);
+        *reinterpret_cast<uint2*>(st + TILE + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+      }
+    }
+  }
+}
+__device__ __forceinline__ void store_rstd(float* rstd, int pw, int lane, float (&ss)[2][8]) {
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      float v = ss[b][jj];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      if ((lane & 15) == 0) rstd[pw * 32 + b * 16 + jj * 2 + (lane >> 4)] = rsqrtf(v * (1.0f / D) + kRmsEps);
+    }
+}
+
+// three MMAs of the 2-term split, A and B in shared memory (K-major SWIZZLE_128B tiles)
+__device__ __forceinline__ void mma3_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                        uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  const uint64_t ah = make_smem_desc(a_hi), al = make_smem_desc(a_lo);
+  const uint64_t bh = make_smem_desc(b_hi), bl = make_smem_desc(b_lo);
+  tc_mma(d_tmem, al, bh, idesc, accumulate);
+  tc_mma(d_tmem, ah, bl, idesc, 1);
+  tc_mma(d_tmem, ah, bh, idesc, 1);
+}
+// the same with A in tensor memory
+__device__ __forceinline__ void mma3_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                        uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  const uint64_t bh = make_smem_desc(b_hi), bl = make_smem_desc(b_lo);
+  tc_mma_ts(d_tmem, a_lo, bh, idesc, accumulate);
+  tc_mma_ts(d_tmem, a_hi, bl, idesc, 1);
+  tc_mma_ts(d_tmem, a_hi, bh, idesc, 1);
+}
+
+struct Barriers {
+  uint32_t base;
+  int ring;
+  __device__ __forceinline__ uint32_t at(int i) const { return base + 8u * i; }
+  __device__ __forceinline__ uint32_t x_full(int b) const { return at(b); }
+  __device__ __forceinline__ uint32_t x_empty(int b) const { return at(2 + b); }
+  __device__ __forceinline__ uint32_t acc1_full(int b) const { return at(4 + b); }
+  __device__ __forceinline__ uint32_t acc1_empty(int b) const { return at(6 + b); }
+  __device__ __forceinline__ uint32_t a2_full(int b) const { return at(8 + b); }
+  __device__ __forceinline__ uint32_t a2_empty(int b) const { return at(10 + b); }
+  __device__ __forceinline__ uint32_t acc2_full(int b) const { return at(12 + b); }
+  __device__ __forceinline__ uint32_t acc2_empty(int b) const { return at(14 + b); }
+  __device__ __forceinline__ uint32_t w_full(int s) const { return at(16 + s); }
+  __device__ __forceinline__ uint32_t w_empty(int s) const { return at(16 + ring + s); }
+  __device__ __forceinline__ void init_all() const {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(x_full(b), NUM_PROD_THREADS);
+      mbar_init(x_empty(b), 1);
+      mbar_init(acc1_full(b), 1);
+      mbar_init(acc1_empty(b), NUM_EPI_WARPS * 32);
+      mbar_init(a2_full(b), NUM_EPI_WARPS * 32);
+      mbar_init(a2_empty(b), 1);
+      mbar_init(acc2_full(b), 1);
+      mbar_init(acc2_empty(b), NUM_EPI_WARPS * 32);
+    }
+    for (int s = 0; s < ring; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+};
+
+__device__ __forceinline__ void weight_producer(const uint8_t* __restrict__ image, int n_stage, int count,
+                                                uint32_t ring_u32, const Barriers& bar) {
+  Ring ring;
+  for (int i = 0; i < count; ++i)
+    for (int s = 0; s < n_stage; ++s) {
+      mbar_wait(bar.w_empty(ring.stage), ring.phase ^ 1);
+      mbar_expect_tx(bar.w_full(ring.stage), STAGE);
+      bulk_g2s(ring_u32 + (uint32_t)ring.stage * STAGE, image + (size_t)s * STAGE, STAGE, bar.w_full(ring.stage));
+      ring.advance(bar.ring);
+    }
+}
+
+// TMEM -> per-warp smem transpose tile: after the call lane l finds row (8 it + rsel), float4
+// column c4 of the 32 x 16 block at staged(it)
+struct EpiStage {
+  float* stage;
+  int lane, c4, rsel;
+  __device__ __forceinline__ void fill(uint32_t taddr) const {
+    float v[16];
+    tmem_ld16(taddr, v);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * q) =
+          make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+  }
+  __device__ __forceinline__ float4 get(int it) const {
+    return *reinterpret_cast<const float4*>(stage + (it * 8 + rsel) * STAGE_LD + 4 * c4);
+  }
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ======================================================================== forward
+constexpr int FWD_RING = 4;
+constexpr int FWD_X_OFF = 0;                                 // 2 buffers x 4 tiles
+constexpr int FWD_RING_OFF = FWD_X_OFF + 2 * 4 * TILE;
+constexpr int FWD_EPI_OFF = FWD_RING_OFF + FWD_RING * STAGE;
+constexpr int FWD_BIAS_OFF = FWD_EPI_OFF + EPI_STAGE_BYTES;  // b_in [2 MAX_F], b_out [D]
+constexpr int FWD_RSTD_OFF = FWD_BIAS_OFF + (2 * MAX_F + D) * 4;
+constexpr int FWD_BAR_OFF = FWD_RSTD_OFF + 2 * BM * 4;
+constexpr int FWD_SMEM = FWD_BAR_OFF + 8 * (16 + 2 * FWD_RING) + 16 + 1024;
+// TMEM columns: acc1[2] at 0, 64 ; acc2[2] at 128, 256 ; A2[b] hi at 384 + 32 b, lo 16 further
+constexpr int FWD_ACC2_COL = 128, FWD_A2_COL = 384;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ image,
+               const float* __restrict__ b_in, const float* __restrict__ b_out, int64_t M, int F,
+               float* __restrict__ y, int64_t ldy) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const Barriers bar{smem_base + FWD_BAR_OFF, FWD_RING};
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FWD_BAR_OFF + 8 * (16 + 2 * FWD_RING));
+  float* bias_s = reinterpret_cast<float*>(smem + FWD_BIAS_OFF);
+  float* rstd_s = reinterpret_cast<float*>(smem + FWD_RSTD_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = F / CH;
+  const TileSchedule sched(M);
+
+  if (threadIdx.x == 0) bar.init_all();
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        smem_u32(const_cast<uint32_t*>(tmem_slot))));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < 2 * F; i += NUM_THREADS) bias_s[i] = b_in[i];
+  for (int i = threadIdx.x; i < D; i += NUM_THREADS) bias_s[2 * MAX_F + i] = b_out[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
+    // ============================================================ activation producers
+    const int pw = warp - FIRST_PROD_WARP;
+    for (int i = 0; i < sched.count; ++i) {
+      const int buf = i & 1;
+      mbar_wait(bar.x_empty(buf), ((i >> 1) & 1) ^ 1);
+      issue_tile_copies(smem_base + FWD_X_OFF + buf * 4 * TILE, x, ldx, sched.m0(i), M, pw, lane);
+      cp_async_wait_all();
+      __syncwarp();
+      float ss[2][8] = {};
+      convert_tile<true>(smem + FWD_X_OFF + buf * 4 * TILE, pw, lane, ss);
+      store_rstd(rstd_s + buf * BM, pw, lane, ss);
+      fence_proxy_async();
+      mbar_arrive(bar.x_full(buf));
+    }
+  } else if (warp == TMA_WARP) {
+    // ============================================================ weight-stage producer
+    if (lane == 0) weight_producer(image, fwd_stages(F), sched.count, smem_base + FWD_RING_OFF, bar);
+  } else if (warp == MMA_WARP) {
+    // ============================================================ MMA issuer
+    constexpr uint32_t idesc1 = make_idesc(BM, 64), idesc2 = make_idesc(BM, D);
+    const uint32_t ring_u32 = smem_base + FWD_RING_OFF;
+    Ring ring;
+    int w2_hi = 0, w2_lo = 0;
+    auto gemm2 = [&](int i, int c) {
+      const int b = c & 1, t = i & 1;
+      const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+      if (b == 0) {
+        mbar_wait(bar.w_full(ring.stage), ring.phase);
+        w2_hi = ring.stage;
+        ring.advance(FWD_RING);
+        mbar_wait(bar.w_full(ring.stage), ring.phase);
+        w2_lo = ring.stage;
+        ring.advance(FWD_RING);
+      }
+      mbar_wait(bar.a2_full(b), u & 1);
+      if (c == 0) mbar_wait(bar.acc2_empty(t), ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t koff = (uint32_t)(b * 64 + kk * 32);
+          const uint32_t a_hi = tmem_base + FWD_A2_COL + b * 32 + kk * 8;
+          mma3_ts(tmem_base + FWD_ACC2_COL + t * D, a_hi, a_hi + 16, ring_u32 + w2_hi * STAGE + koff,
+                  ring_u32 + w2_lo * STAGE + koff, idesc2, (c | kk) != 0);
+        }
+        tc_commit(bar.a2_empty(b));
+        if (b == 1) {
+          tc_commit(bar.w_empty(w2_hi));
+          tc_commit(bar.w_empty(w2_lo));
+        }
+      }
+      __syncwarp();
+    };
+    for (int i = 0; i < sched.count; ++i) {
+      const int buf = i & 1;
+      const uint32_t xt = smem_base + FWD_X_OFF + buf * 4 * TILE;
+      mbar_wait(bar.x_full(buf), (i >> 1) & 1);
+      tc_fence_after();
+      for (int c = 0; c < nch; ++c) {
+        const int b = c & 1;
+        const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+        mbar_wait(bar.acc1_empty(b), (u & 1) ^ 1);
+        tc_fence_after();
+        for (int kh = 0; kh < 2; ++kh) {
+          mbar_wait(bar.w_full(ring.stage), ring.phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t st = ring_u32 + ring.stage * STAGE;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma3_ss(tmem_base + b * 64, xt + (kh * 2) * TILE + kk * 32, xt + (kh * 2 + 1) * TILE + kk * 32,
+                      st + kk * 32, st + 8192 + kk * 32, idesc1, (kh | kk) != 0);
+            tc_commit(bar.w_empty(ring.stage));
+          }
+          __syncwarp();
+          ring.advance(FWD_RING);
+        }
+        if (lane == 0) {
+          tc_commit(bar.acc1_full(b));
+          if (c == nch - 1) tc_commit(bar.x_empty(buf));
+        }
+        __syncwarp();
+        if (c >= 1) gemm2(i, c - 1);
+      }
+      gemm2(i, nch - 1);
+      if (lane == 0) tc_commit(bar.acc2_full(i & 1));
+      __syncwarp();
+    }
+  } else {
+    // ============================================================ epilogues
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const EpiStage es{reinterpret_cast<float*>(smem + FWD_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    for (int i = 0; i < sched.count; ++i) {
+      const int buf = i & 1, t = i & 1;
+      const int64_t m0 = sched.m0(i);
+      mbar_wait(bar.x_full(buf), (i >> 1) & 1);
+      const float rs = rstd_s[buf * BM + quarter * 32 + lane];
+      for (int c = 0; c < nch; ++c) {
+        const int b = c & 1;
+        const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+        mbar_wait(bar.acc1_full(b), u & 1);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + b * 64 + half * 32, v);
+        tc_fence_before();
+        mbar_arrive(bar.acc1_empty(b));
+        const float* bv = bias_s + c * CH + half * 16;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a0 = (rs * v[2 * q] + bv[2 * q]) * fsigmoid(rs * v[16 + 2 * q] + bv[F + 2 * q]);
+          const float a1 = (rs * v[2 * q + 1] + bv[2 * q + 1]) * fsigmoid(rs * v[17 + 2 * q] + bv[F + 2 * q + 1]);
+          hi[q] = pack_bf16(a0, a1);
+          lo[q] = pack_bf16(a0 - __uint_as_float(hi[q] << 16), a1 - __uint_as_float(hi[q] & 0xffff0000u));
+        }
+        mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a2 = tmem_base + lane_base + FWD_A2_COL + b * 32 + half * 8;
+        tmem_st8(a2, hi);
+        tmem_st8(a2 + 16, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar.a2_full(b));
+      }
+      // ---- y = acc2 + b_out + x
+      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
+      tc_fence_after();
+      const int64_t m_base = m0 + quarter * 32;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int col = 64 * half + 16 * ch;
+        const int c0 = col + 4 * es.c4;
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * MAX_F + c0);
+        float4 res[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          res[it] = m < M ? ld4(x + m * ldx + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        es.fill(tmem_base + lane_base + FWD_ACC2_COL + t * D + col);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          if (m >= M) continue;
+          const float4 a = es.get(it);
+          *reinterpret_cast<float4*>(y + m * ldy + c0) =
+              make_float4(a.x + b4.x + res[it].x, a.y + b4.y + res[it].y, a.z + b4.z + res[it].z,
+                          a.w + b4.w + res[it].w);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar.acc2_empty(t));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+// ======================================================================= backward
+constexpr int BWD_RING = 4;
+constexpr int BWD_X_OFF = 0;                                  // X tiles (4), then dY tiles (4)
+constexpr int BWD_RING_OFF = BWD_X_OFF + 8 * TILE;
+constexpr int BWD_EPI_OFF = BWD_RING_OFF + BWD_RING * STAGE;
+constexpr int BWD_BIAS_OFF = BWD_EPI_OFF + EPI_STAGE_BYTES;   // b_in [2 MAX_F]
+constexpr int BWD_RSTD_OFF = BWD_BIAS_OFF + 2 * MAX_F * 4;    // rstd [2][BM]
+constexpr int BWD_DOT_OFF = BWD_RSTD_OFF + 2 * BM * 4;        // dot exchange [2][BM]
+constexpr int BWD_BAR_OFF = BWD_DOT_OFF + 2 * BM * 4;
+constexpr int BWD_SMEM = BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING) + 16 + 1024;
+// TMEM columns: acc1[b] at 128 b (ug: 64, then ds: 32) ; acc2 at 256 ; A2[b] hi at 384 + 64 b, lo 32 further
+constexpr int BWD_ACC1_STRIDE = 128, BWD_ACC2_COL = 256, BWD_A2_COL = 384;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t ld_dy,
+               const uint8_t* __restrict__ image, const float* __restrict__ b_in, int64_t M, int F,
+               float* __restrict__ dx, int64_t ld_dx) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const Barriers bar{smem_base + BWD_BAR_OFF, BWD_RING};
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING));
+  float* bias_s = reinterpret_cast<float*>(smem + BWD_BIAS_OFF);
+  float* rstd_s = reinterpret_cast<float*>(smem + BWD_RSTD_OFF);
+  float* dot_s = reinterpret_cast<float*>(smem + BWD_DOT_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = F / CH;
+  const TileSchedule sched(M);
+
+  if (threadIdx.x == 0) bar.init_all();
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        smem_u32(const_cast<uint32_t*>(tmem_slot))));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < 2 * F; i += NUM_THREADS) bias_s[i] = b_in[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
+    // ============================================================ activation producers
+    const int pw = warp - FIRST_PROD_WARP;
+    for (int i = 0; i < sched.count; ++i) {
+      mbar_wait(bar.x_empty(0), (i & 1) ^ 1);
+      issue_tile_copies(smem_base + BWD_X_OFF, x, ldx, sched.m0(i), M, pw, lane);
+      issue_tile_copies(smem_base + BWD_X_OFF + 4 * TILE, dy, ld_dy, sched.m0(i), M, pw, lane);
+      // the next tile's rows are pulled into L2 while this one is processed
+      if (i + 1 < sched.count) {
+        const int64_t m = sched.m0(i + 1) + pw * 32 + lane;
+        if (m < M) {
+          prefetch_l2_bulk(x + m * ldx, D * 4);
+          prefetch_l2_bulk(dy + m * ld_dy, D * 4);
+        }
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      float ss[2][8] = {};
+      convert_tile<true>(smem + BWD_X_OFF, pw, lane, ss);
+      store_rstd(rstd_s + (i & 1) * BM, pw, lane, ss);
+      convert_tile<false>(smem + BWD_X_OFF + 4 * TILE, pw, lane, ss);
+      fence_proxy_async();
+      mbar_arrive(bar.x_full(0));
+    }
+  } else if (warp == TMA_WARP) {
+    if (lane == 0) weight_producer(image, bwd_stages(F), sched.count, smem_base + BWD_RING_OFF, bar);
+  } else if (warp == MMA_WARP) {
+    // ============================================================ MMA issuer
+    constexpr uint32_t idesc_ug = make_idesc(BM, 64), idesc_ds = make_idesc(BM, 32), idesc2 = make_idesc(BM, D);
+    const uint32_t ring_u32 = smem_base + BWD_RING_OFF;
+    const uint32_t xt = smem_base + BWD_X_OFF, dyt = xt + 4 * TILE;
+    Ring ring;
+    auto gemm2 = [&](int i, int c) {
+      const int b = c & 1;
+      const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+      mbar_wait(bar.w_full(ring.stage), ring.phase);
+      const int s_hi = ring.stage;
+      ring.advance(BWD_RING);
+      mbar_wait(bar.w_full(ring.stage), ring.phase);
+      const int s_lo = ring.stage;
+      ring.advance(BWD_RING);
+      mbar_wait(bar.a2_full(b), u & 1);
+      if (c == 0) mbar_wait(bar.acc2_empty(0), (i & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t a_hi = tmem_base + BWD_A2_COL + b * 64 + kk * 8;
+          mma3_ts(tmem_base + BWD_ACC2_COL, a_hi, a_hi + 32, ring_u32 + s_hi * STAGE + kk * 32,
+                  ring_u32 + s_lo * STAGE + kk * 32, idesc2, (c | kk) != 0);
+        }
+        tc_commit(bar.a2_empty(b));
+        tc_commit(bar.w_empty(s_hi));
+        tc_commit(bar.w_empty(s_lo));
+      }
+      __syncwarp();
+    };
+    for (int i = 0; i < sched.count; ++i) {
+      mbar_wait(bar.x_full(0), i & 1);
+      tc_fence_after();
+      for (int c = 0; c < nch; ++c) {
+        const int b = c & 1;
+        const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+        mbar_wait(bar.acc1_empty(b), (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc1 = tmem_base + b * BWD_ACC1_STRIDE;
+        for (int kh = 0; kh < 2; ++kh) {   // ug = X . W_in[chunk]^T
+          mbar_wait(bar.w_full(ring.stage), ring.phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t st = ring_u32 + ring.stage * STAGE;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma3_ss(acc1, xt + (kh * 2) * TILE + kk * 32, xt + (kh * 2 + 1) * TILE + kk * 32, st + kk * 32,
+                      st + 8192 + kk * 32, idesc_ug, (kh | kk) != 0);
+            tc_commit(bar.w_empty(ring.stage));
+          }
+          __syncwarp();
+          ring.advance(BWD_RING);
+        }
+        mbar_wait(bar.w_full(ring.stage), ring.phase);   // ds = dY . W_out[:, chunk]
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = ring_u32 + ring.stage * STAGE;
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma3_ss(acc1 + 64, dyt + (kh * 2) * TILE + kk * 32, dyt + (kh * 2 + 1) * TILE + kk * 32,
+                      st + kh * 8192 + kk * 32, st + kh * 8192 + 4096 + kk * 32, idesc_ds, (kh | kk) != 0);
+          tc_commit(bar.w_empty(ring.stage));
+          tc_commit(bar.acc1_full(b));
+          if (c == nch - 1) tc_commit(bar.x_empty(0));
+        }
+        __syncwarp();
+        ring.advance(BWD_RING);
+        if (c >= 1) gemm2(i, c - 1);
+      }
+      gemm2(i, nch - 1);
+      if (lane == 0) tc_commit(bar.acc2_full(0));
+      __syncwarp();
+    }
+  } else {
+    // ============================================================ epilogues
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const EpiStage es{reinterpret_cast<float*>(smem + BWD_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    for (int i = 0; i < sched.count; ++i) {
+      const int64_t m0 = sched.m0(i);
+      const float* rstd_t = rstd_s + (i & 1) * BM;
+      mbar_wait(bar.x_full(0), i & 1);
+      const float rs = rstd_t[quarter * 32 + lane];
+      for (int c = 0; c < nch; ++c) {
+        const int b = c & 1;
+        const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+        mbar_wait(bar.acc1_full(b), u & 1);
+        tc_fence_after();
+        float v[32], ds[16];
+        tmem_ld32(tmem_base + lane_base + b * BWD_ACC1_STRIDE + half * 32, v);
+        tmem_ld16(tmem_base + lane_base + b * BWD_ACC1_STRIDE + 64 + half * 16, ds);
+        tc_fence_before();
+        mbar_arrive(bar.acc1_empty(b));
+        const float* bv = bias_s + c * CH + half * 16;
+        // K order of GEMM2: [d_v 0..15 | d_g 0..15] of this warp half
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float dv[2], dg[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 2 * q + e;
+            const float val = rs * v[k] + bv[k];
+            const float s = fsigmoid(rs * v[16 + k] + bv[F + k]);
+            dv[e] = ds[k] * s;
+            dg[e] = ds[k] * val * s * (1.0f - s);
+          }
+          hi[q] = pack_bf16(dv[0], dv[1]);
+          lo[q] = pack_bf16(dv[0] - __uint_as_float(hi[q] << 16), dv[1] - __uint_as_float(hi[q] & 0xffff0000u));
+          hi[8 + q] = pack_bf16(dg[0], dg[1]);
+          lo[8 + q] = pack_bf16(dg[0] - __uint_as_float(hi[8 + q] << 16),
+                                dg[1] - __uint_as_float(hi[8 + q] & 0xffff0000u));
+        }
+        mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a2 = tmem_base + lane_base + BWD_A2_COL + b * 64 + half * 16;
+        tmem_st16(a2, hi);
+        tmem_st16(a2 + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar.a2_full(b));
+      }
+      // ---- dx = dy + rs * d - x * rs^3 * (d . x) / D     (d = acc2 = gradient w.r.t. x_hat)
+      mbar_wait(bar.acc2_full(0), i & 1);
+      tc_fence_after();
+      const int64_t m_base = m0 + quarter * 32;
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int col = 64 * half + 16 * ch, c0 = col + 4 * es.c4;
+        float4 xr[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          xr[it] = m < M ? ld4(x + m * ldx + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        es.fill(tmem_base + lane_base + BWD_ACC2_COL + col);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 a = es.get(it);
+          dot[it] += a.x * xr[it].x + a.y * xr[it].y + a.z * xr[it].z + a.w * xr[it].w;
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 1);
+        dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 2);
+        if (es.c4 == 0) dot_s[half * BM + quarter * 32 + it * 8 + es.rsel] = dot[it];
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      float rr[4], kap[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = quarter * 32 + it * 8 + es.rsel;
+        rr[it] = rstd_t[r];
+        kap[it] = rr[it] * rr[it] * rr[it] * (dot_s[r] + dot_s[BM + r]) * (1.0f / D);
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int col = 64 * half + 16 * ch, c0 = col + 4 * es.c4;
+        float4 xr[4], gr[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          const bool ok = m < M;
+          xr[it] = ok ? ld4(x + m * ldx + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gr[it] = ok ? ld4(dy + m * ld_dy + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        es.fill(tmem_base + lane_base + BWD_ACC2_COL + col);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          if (m >= M) continue;
+          const float4 a = es.get(it);
+          *reinterpret_cast<float4*>(dx + m * ld_dx + c0) =
+              make_float4(gr[it].x + rr[it] * a.x - xr[it].x * kap[it], gr[it].y + rr[it] * a.y - xr[it].y * kap[it],
+                          gr[it].z + rr[it] * a.z - xr[it].z * kap[it], gr[it].w + rr[it] * a.w - xr[it].w * kap[it]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar.acc2_empty(0));
+      // the dot exchange buffer is rewritten one tile later, after this pair of warps has
+      // passed another acc2_full wait: no extra synchronisation needed
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+int check_dims(const char* what, int d, int d_ff) {
+  if (d != D || d_ff % 64 != 0 || d_ff < 64 || d_ff > MAX_F) {
+    set_error("%s: built for d_pet = %d and a hidden width that is a multiple of 64 up to %d (got %d, %d)",
+              what, D, MAX_F, d, d_ff);
+    return PETB200_ERR_UNSUPPORTED;
+  }
+  return PETB200_OK;
+}
+
+}  // namespace
+}  // namespace petb200
+
+using namespace petb200;
+
+extern "C" PETB200_API size_t petb200_mlp_image_bytes(int d_ff, int backward) {
+  return (size_t)(backward ? bwd_stages(d_ff) : fwd_stages(d_ff)) * STAGE;
+}
+
+extern "C" PETB200_API int petb200_mlp_pack(const float* w_in, const float* w_out, int d, int d_ff,
+                                            void* image_fwd, void* image_bwd, cudaStream_t stream) {
+  if (int rc = check_dims("mlp_pack", d, d_ff)) return rc;
+  for (int backward = 0; backward < 2; ++backward) {
+    void* image = backward ? image_bwd : image_fwd;
+    if (!image) continue;
+    const int64_t chunks = (int64_t)petb200_mlp_image_bytes(d_ff, backward) / 16;
+    mlp_pack_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, stream>>>(w_in, w_out, d_ff, backward,
+                                                                        reinterpret_cast<uint4*>(image));
+  }
+  return check_launch("mlp_pack");
+}
+
+extern "C" PETB200_API int petb200_mlp_fwd(const float* x, int64_t ldx, const void* image_fwd,
+                                           const float* b_in, const float* b_out, int64_t n_rows, int d,
+                                           int d_ff, float* y, int64_t ldy, cudaStream_t stream) {
+  if (int rc = check_dims("mlp_fwd", d, d_ff)) return rc;
+  PETB200_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "mlp_fwd: leading dimensions must be multiples of 4");
+  if (n_rows == 0) return PETB200_OK;
+  const int tiles = (int)ceil_div(n_rows, BM);
+  cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+  mlp_fwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, NUM_THREADS, FWD_SMEM, stream>>>(
+      x, ldx, reinterpret_cast<const uint8_t*>(image_fwd), b_in, b_out, n_rows, d_ff, y, ldy);
+  return check_launch("mlp_fwd");
+}
+
+extern "C" PETB200_API int petb200_mlp_bwd(const float* x, int64_t ldx, const float* d_y, int64_t ld_dy,
+                                           const void* image_bwd, const float* b_in, int64_t n_rows, int d,
+                                           int d_ff, float* d_x, int64_t ld_dx, cudaStream_t stream) {
+  if (int rc = check_dims("mlp_bwd", d, d_ff)) return rc;
+  PETB200_REQUIRE(ldx % 4 == 0 && ld_dy % 4 == 0 && ld_dx % 4 == 0,
+                  "mlp_bwd: leading dimensions must be multiples of 4");
+  if (n_rows == 0) return PETB200_OK;
+  const int tiles = (int)ceil_div(n_rows, BM);
+  cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+  mlp_bwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, NUM_THREADS, BWD_SMEM, stream>>>(
+      x, ldx, d_y, ld_dy, reinterpret_cast<const uint8_t*>(image_bwd), b_in, n_rows, d_ff, d_x, ld_dx);
+  return check_launch("mlp_bwd");
+}

@@ -156,6 +156,20 @@ def _t_and_scaled(weight: Tensor, col_scale: Optional[Tensor] = None, want_scale
     return out_t, out_s
 
 
+def _mlp_images(w_in_folded: Tensor, w_out: Tensor):
+    """(forward image, backward image) for the fused feed-forward kernels, or None when the
+    layer shape is outside what they are built for (the unfused GEMM path is used then)."""
+    d, d_ff = w_in_folded.shape[1], w_out.shape[1]
+    if d != 128 or d_ff % 64 != 0 or not 64 <= d_ff <= 512 or w_in_folded.shape[0] != 2 * d_ff:
+        return None
+    handle = lib.load()
+    w_out = w_out.contiguous()
+    imgs = [torch.empty(handle.petb200_mlp_image_bytes(d_ff, b), device=w_out.device, dtype=torch.uint8)
+            for b in (0, 1)]
+    call("mlp_pack", ptr(w_in_folded), ptr(w_out), d, d_ff, ptr(imgs[0]), ptr(imgs[1]))
+    return imgs
+
+
 class PackedWeights:
     """Device-side views/derivatives of the module parameters the kernels consume:
     RMSNorm weights folded into the following Linear (W.diag(gamma)), and W^T for every
@@ -192,6 +206,8 @@ class PackedWeights:
                 T["w_out"] = g(tl.mlp.w_out.weight)
                 T["b_out"] = g(tl.mlp.w_out.bias)
                 T["w_out_t"], _ = _t_and_scaled(tl.mlp.w_out.weight)
+                # operand-tile images of the fused feed-forward kernels (petb200_mlp_fwd / _bwd)
+                T["mlp_img"] = _mlp_images(T["w_in"], T["w_out"])
                 T["w_con"] = g(tl.center_contraction.weight)
                 T["b_con"] = g(tl.center_contraction.bias)
                 T["w_con_t"], _ = _t_and_scaled(tl.center_contraction.weight)
@@ -344,16 +360,23 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
             gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec, pack=pw)
             # edge MLP (d_pet -> 2 d_ff -> d_pet, SwiGLU)
             tp = Xn[:E]
-            rstd2 = _rstd(tp)
             dff = T["w_out"].shape[1]
-            ug = _empty((E, 2 * dff), vec)
-            s = _empty((E, dff), vec)
-            gemm(tp, T["w_in"], s, bias=T["b_in"], row_scale=rstd2, epilogue=EPI_SWIGLU,
-                 aux_out=ug, precision=prec, pack=pw)
             Xnnf = _empty((E + N + H, d), vec)
             Xnn = Xnnf[:E + N]
-            gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec, pack=pw)
-            del s, sc
+            if prec != PREC_FP32 and T["mlp_img"] is not None:
+                # one fused tcgen05 kernel; the backward recomputes the hidden activations
+                rstd2 = ug = None
+                call("mlp_fwd", ptr(tp), tp.stride(0), ptr(T["mlp_img"][0]), ptr(T["b_in"]),
+                     ptr(T["b_out"]), E, d, dff, ptr(Xnn), Xnn.stride(0))
+            else:
+                rstd2 = _rstd(tp)
+                ug = _empty((E, 2 * dff), vec)
+                s = _empty((E, dff), vec)
+                gemm(tp, T["w_in"], s, bias=T["b_in"], row_scale=rstd2, epilogue=EPI_SWIGLU,
+                     aux_out=ug, precision=prec, pack=pw)
+                gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec, pack=pw)
+                del s
+            del sc
             K.update(X=X, rstd1=rstd1, qkv=qkv, o=o, lse=lse, tp=tp, rstd2=rstd2, ug=ug,
                      h1=h1, rstd3=rstd3, ugc=ugc)
             S["tl"].append(K)
@@ -416,13 +439,18 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
             T, K = L["tl"][k], S["tl"][k]
             dff = T["w_out"].shape[1]
             # ---- edge MLP: t'' = t' + W_out swiglu(W_in rms(t'))
-            d_ug = _empty((E, 2 * dff), ref)
-            gemm(d_t, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec, pack=pw)
-            d_xh = _empty((E, d), ref)
-            gemm(d_ug, T["w_in_t"], d_xh, precision=prec, pack=pw)
-            del d_ug
             d_tp = _empty((E, d), ref)
-            _rms_bwd(d_xh, K["tp"], K["rstd2"], d_t, d_tp)
+            d_xh = _empty((E, d), ref)
+            if K["ug"] is None:
+                call("mlp_bwd", ptr(K["tp"]), K["tp"].stride(0), ptr(d_t), d_t.stride(0),
+                     ptr(T["mlp_img"][1]), ptr(T["b_in"]), E, d, dff, ptr(d_tp), d_tp.stride(0))
+            else:
+                d_ug = _empty((E, 2 * dff), ref)
+                gemm(d_t, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec,
+                     pack=pw)
+                gemm(d_ug, T["w_in_t"], d_xh, precision=prec, pack=pw)
+                del d_ug
+                _rms_bwd(d_xh, K["tp"], K["rstd2"], d_t, d_tp)
             # ---- centre MLP: h2 = h1 + Wc_out swiglu(Wc_in rms(h1))
             d_ugc = _empty((N, 4 * dn), ref)
             gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec, pack=pw)

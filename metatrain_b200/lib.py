@@ -48,6 +48,10 @@ _SIGNATURES = {
     "petb200_gemm": [_P, _I64, _P, _I64, _P, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P,
                      _I64, _I, _I, _I, _P],
     "petb200_split_bf16": [_P, _I64, _I, _P, _P],
+    "petb200_mlp_image_bytes": [_I, _I],
+    "petb200_mlp_pack": [_P, _P, _I, _I, _P, _P, _P],
+    "petb200_mlp_fwd": [_P, _I64, _P, _P, _P, _I64, _I, _I, _P, _I64, _P],
+    "petb200_mlp_bwd": [_P, _I64, _P, _I64, _P, _P, _I64, _I, _I, _P, _I64, _P],
     "petb200_embedding": [_P, _P, _I64, _I, _P, _I64, _P],
     "petb200_transpose_scale": [_P, _I, _I, _P, _P, _P, _P],
     "petb200_compress_input": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
@@ -65,7 +69,7 @@ _SIGNATURES = {
     "petb200_last_error": [],
     "petb200_version": [],
 }
-_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_last_error": ctypes.c_char_p,
+_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
             "petb200_nl_num_bins": _I64, "petb200_nl_workspace": _SZ}
 
 

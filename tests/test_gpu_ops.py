@@ -326,3 +326,43 @@ def test_csr_nef_roundtrip():
     back = torch.empty(E, 3, device=DEV)
     call("nef_to_csr", ptr(nef), ptr(row_ptr), ptr(ctr), n_atoms, E, mx, 3, ptr(back))
     assert torch.equal(back, x)
+
+
+# ------------------------------------------------------------- fused feed-forward block
+def _mlp_reference(x, w_in, b_in, w_out, b_out, gamma):
+    """transformer.py:229-232 (PreLN) with FeedForward :21-50 in fp64."""
+    xh = F.rms_norm(x, (x.shape[1],), gamma, torch.finfo(torch.float32).eps)
+    v, g = (xh @ w_in.T + b_in).chunk(2, dim=-1)
+    return x + (v * torch.sigmoid(g)) @ w_out.T + b_out
+
+
+@pytest.mark.parametrize("M,d_ff", [(1000, 256), (128, 64), (77, 512), (40000, 256)])
+def test_mlp_fused_fwd_bwd(M, d_ff):
+    """petb200_mlp_fwd / petb200_mlp_bwd (one tcgen05 kernel each) against fp64 autograd."""
+    d = 128
+    x, dy = rnd(M, d, seed=1), rnd(M, d, seed=2)
+    x[: min(M, 5)] *= 30.0   # rows with a very different norm
+    gamma = rnd(d, seed=3).abs() + 0.5
+    w_in, b_in = rnd(2 * d_ff, d, seed=4, scale=d ** -0.5), rnd(2 * d_ff, seed=5, scale=0.1)
+    w_out, b_out = rnd(d, d_ff, seed=6, scale=d_ff ** -0.5), rnd(d, seed=7, scale=0.1)
+    w_in_folded = (w_in * gamma[None, :]).contiguous()
+    handle = lib.load()
+    img_f = torch.empty(handle.petb200_mlp_image_bytes(d_ff, 0), device=DEV, dtype=torch.uint8)
+    img_b = torch.empty(handle.petb200_mlp_image_bytes(d_ff, 1), device=DEV, dtype=torch.uint8)
+    call("mlp_pack", ptr(w_in_folded), ptr(w_out), d, d_ff, ptr(img_f), ptr(img_b))
+    y = torch.empty(M, d, device=DEV)
+    call("mlp_fwd", ptr(x), d, ptr(img_f), ptr(b_in), ptr(b_out), M, d, d_ff, ptr(y), d)
+    xx = x.double().cpu().requires_grad_(True)
+    ref = _mlp_reference(xx, w_in.double().cpu(), b_in.double().cpu(), w_out.double().cpu(),
+                         b_out.double().cpu(), gamma.double().cpu())
+    assert_close(y, ref.detach(), 1e-4, 2e-5, "fused mlp forward")
+    ref.backward(dy.double().cpu())
+    dx = torch.empty(M, d, device=DEV)
+    call("mlp_bwd", ptr(x), d, ptr(dy), d, ptr(img_b), ptr(b_in), M, d, d_ff, ptr(dx), d)
+    assert_close(dx, xx.grad, 1e-4, 2e-5, "fused mlp backward")
+
+
+def test_mlp_fused_rejects_unsupported_width():
+    x = rnd(8, 128)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        call("mlp_fwd", ptr(x), 128, ptr(x), ptr(x), ptr(x), 8, 128, 96, ptr(x), 128)
