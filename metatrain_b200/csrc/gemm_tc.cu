@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
       for (int kc = 0; kc < num_k; ++kc) {
         mbar_wait(full_bar(ring.stage), ring.phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = smem_base + (uint32_t)b_bytes + (uint32_t)ring.stage * stage_bytes;
           const uint32_t bt = BSTAT ? smem_base + (uint32_t)kc * 2 * TILE_BYTES : st + 2 * TILE_BYTES;
 #pragma unroll

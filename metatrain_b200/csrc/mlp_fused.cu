@@ -262,8 +262,8 @@ struct Barriers {
       mbar_init(x_full(b), NUM_PROD_THREADS);
       mbar_init(x_empty(b), 1);
       mbar_init(acc1_full(b), 1);
-      mbar_init(acc1_empty(b), NUM_EPI_WARPS * 32);
-      mbar_init(a2_full(b), NUM_EPI_WARPS * 32);
+      mbar_init(acc1_empty(b), NUM_EPI_WARPS * 16);  // one epilogue group (4 warps)
+      mbar_init(a2_full(b), NUM_EPI_WARPS * 16);
       mbar_init(a2_empty(b), 1);
       mbar_init(acc2_full(b), 1);
       mbar_init(acc2_empty(b), NUM_EPI_WARPS * 32);
@@ -368,7 +368,7 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
     }
   } else if (warp == TMA_WARP) {
     // ============================================================ weight-stage producer
-    if (lane == 0) weight_producer(image, fwd_stages(F), sched.count, smem_base + FWD_RING_OFF, bar);
+    if (elect_one()) weight_producer(image, fwd_stages(F), sched.count, smem_base + FWD_RING_OFF, bar);
   } else if (warp == MMA_WARP) {
     // ============================================================ MMA issuer
     constexpr uint32_t idesc1 = make_idesc(BM, 64), idesc2 = make_idesc(BM, D);
@@ -389,7 +389,7 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
       mbar_wait(bar.a2_full(b), u & 1);
       if (c == 0) mbar_wait(bar.acc2_empty(t), ((i >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const uint32_t koff = (uint32_t)(b * 64 + kk * 32);
@@ -418,7 +418,7 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
         for (int kh = 0; kh < 2; ++kh) {
           mbar_wait(bar.w_full(ring.stage), ring.phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
@@ -429,7 +429,7 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
           __syncwarp();
           ring.advance(FWD_RING);
         }
-        if (lane == 0) {
+        if (elect_one()) {
           tc_commit(bar.acc1_full(b));
           if (c == nch - 1) tc_commit(bar.x_empty(buf));
         }
@@ -437,7 +437,7 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
         if (c >= 1) gemm2(i, c - 1);
       }
       gemm2(i, nch - 1);
-      if (lane == 0) tc_commit(bar.acc2_full(i & 1));
+      if (elect_one()) tc_commit(bar.acc2_full(i & 1));
       __syncwarp();
     }
   } else {
@@ -451,29 +451,38 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
       const int64_t m0 = sched.m0(i);
       mbar_wait(bar.x_full(buf), (i >> 1) & 1);
       const float rs = rstd_s[buf * BM + quarter * 32 + lane];
-      for (int c = 0; c < nch; ++c) {
-        const int b = c & 1;
+      // the two groups of four warps take alternate chunks (group = chunk parity = buffer), so
+      // the epilogue of chunk c overlaps GEMM1 of c+1, GEMM2 of c-1 AND the epilogue of c+1;
+      // a thread owns one row: 64 accumulator columns in, 32 activations out
+      for (int c = half; c < nch; c += 2) {
+        const int b = half;
         const uint32_t u = (uint32_t)(i * nch + c) >> 1;
         mbar_wait(bar.acc1_full(b), u & 1);
         tc_fence_after();
-        float v[32];
-        tmem_ld32(tmem_base + lane_base + b * 64 + half * 32, v);
+        float v[64];
+        tmem_ld32(tmem_base + lane_base + b * 64, v);
+        tmem_ld32(tmem_base + lane_base + b * 64 + 32, v + 32);
         tc_fence_before();
         mbar_arrive(bar.acc1_empty(b));
-        const float* bv = bias_s + c * CH + half * 16;
-        uint32_t hi[8], lo[8];
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float a0 = (rs * v[2 * q] + bv[2 * q]) * fsigmoid(rs * v[16 + 2 * q] + bv[F + 2 * q]);
-          const float a1 = (rs * v[2 * q + 1] + bv[2 * q + 1]) * fsigmoid(rs * v[17 + 2 * q] + bv[F + 2 * q + 1]);
-          hi[q] = pack_bf16(a0, a1);
-          lo[q] = pack_bf16(a0 - __uint_as_float(hi[q] << 16), a1 - __uint_as_float(hi[q] & 0xffff0000u));
+        for (int hf = 0; hf < 2; ++hf) {
+          const float* bv = bias_s + c * CH + hf * 16;
+          const float* vv = v + hf * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float a0 = (rs * vv[2 * q] + bv[2 * q]) * fsigmoid(rs * vv[16 + 2 * q] + bv[F + 2 * q]);
+            const float a1 = (rs * vv[2 * q + 1] + bv[2 * q + 1]) * fsigmoid(rs * vv[17 + 2 * q] + bv[F + 2 * q + 1]);
+            const uint32_t h2 = pack_bf16(a0, a1);
+            hi[hf * 8 + q] = h2;
+            lo[hf * 8 + q] = pack_bf16(a0 - __uint_as_float(h2 << 16), a1 - __uint_as_float(h2 & 0xffff0000u));
+          }
         }
         mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a2 = tmem_base + lane_base + FWD_A2_COL + b * 32 + half * 8;
-        tmem_st8(a2, hi);
-        tmem_st8(a2 + 16, lo);
+        const uint32_t a2 = tmem_base + lane_base + FWD_A2_COL + b * 32;
+        tmem_st16(a2, hi);
+        tmem_st16(a2 + 16, lo);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar.a2_full(b));
@@ -583,7 +592,7 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       mbar_arrive(bar.x_full(0));
     }
   } else if (warp == TMA_WARP) {
-    if (lane == 0) weight_producer(image, bwd_stages(F), sched.count, smem_base + BWD_RING_OFF, bar);
+    if (elect_one()) weight_producer(image, bwd_stages(F), sched.count, smem_base + BWD_RING_OFF, bar);
   } else if (warp == MMA_WARP) {
     // ============================================================ MMA issuer
     constexpr uint32_t idesc_ug = make_idesc(BM, 64), idesc_ds = make_idesc(BM, 32), idesc2 = make_idesc(BM, D);
@@ -602,7 +611,7 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       mbar_wait(bar.a2_full(b), u & 1);
       if (c == 0) mbar_wait(bar.acc2_empty(0), (i & 1) ^ 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint32_t a_hi = tmem_base + BWD_A2_COL + b * 64 + kk * 8;
@@ -627,7 +636,7 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
         for (int kh = 0; kh < 2; ++kh) {   // ug = X . W_in[chunk]^T
           mbar_wait(bar.w_full(ring.stage), ring.phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
@@ -640,7 +649,7 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
         }
         mbar_wait(bar.w_full(ring.stage), ring.phase);   // ds = dY . W_out[:, chunk]
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh)
@@ -657,7 +666,7 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
         if (c >= 1) gemm2(i, c - 1);
       }
       gemm2(i, nch - 1);
-      if (lane == 0) tc_commit(bar.acc2_full(0));
+      if (elect_one()) tc_commit(bar.acc2_full(0));
       __syncwarp();
     }
   } else {
@@ -671,41 +680,50 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       const float* rstd_t = rstd_s + (i & 1) * BM;
       mbar_wait(bar.x_full(0), i & 1);
       const float rs = rstd_t[quarter * 32 + lane];
-      for (int c = 0; c < nch; ++c) {
-        const int b = c & 1;
+      // alternate chunks per group of four warps, as in the forward kernel; a thread owns one
+      // row and walks the two 16-unit halves of the chunk in turn
+      for (int c = half; c < nch; c += 2) {
+        const int b = half;
         const uint32_t u = (uint32_t)(i * nch + c) >> 1;
         mbar_wait(bar.acc1_full(b), u & 1);
         tc_fence_after();
-        float v[32], ds[16];
-        tmem_ld32(tmem_base + lane_base + b * BWD_ACC1_STRIDE + half * 32, v);
-        tmem_ld16(tmem_base + lane_base + b * BWD_ACC1_STRIDE + 64 + half * 16, ds);
-        tc_fence_before();
-        mbar_arrive(bar.acc1_empty(b));
-        const float* bv = bias_s + c * CH + half * 16;
-        // K order of GEMM2: [d_v 0..15 | d_g 0..15] of this warp half
-        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float dv[2], dg[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int k = 2 * q + e;
-            const float val = rs * v[k] + bv[k];
-            const float s = fsigmoid(rs * v[16 + k] + bv[F + k]);
-            dv[e] = ds[k] * s;
-            dg[e] = ds[k] * val * s * (1.0f - s);
+        for (int hf = 0; hf < 2; ++hf) {
+          float v[32], ds[16];
+          tmem_ld32(tmem_base + lane_base + b * BWD_ACC1_STRIDE + hf * 32, v);
+          tmem_ld16(tmem_base + lane_base + b * BWD_ACC1_STRIDE + 64 + hf * 16, ds);
+          if (hf == 1) {
+            tc_fence_before();
+            mbar_arrive(bar.acc1_empty(b));
           }
-          hi[q] = pack_bf16(dv[0], dv[1]);
-          lo[q] = pack_bf16(dv[0] - __uint_as_float(hi[q] << 16), dv[1] - __uint_as_float(hi[q] & 0xffff0000u));
-          hi[8 + q] = pack_bf16(dg[0], dg[1]);
-          lo[8 + q] = pack_bf16(dg[0] - __uint_as_float(hi[8 + q] << 16),
-                                dg[1] - __uint_as_float(hi[8 + q] & 0xffff0000u));
+          const float* bv = bias_s + c * CH + hf * 16;
+          // K order of GEMM2: [d_v 0..15 | d_g 0..15] of this half
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float dv[2], dg[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int k = 2 * q + e;
+              const float val = rs * v[k] + bv[k];
+              const float sg = fsigmoid(rs * v[16 + k] + bv[F + k]);
+              dv[e] = ds[k] * sg;
+              dg[e] = ds[k] * val * sg * (1.0f - sg);
+            }
+            hi[q] = pack_bf16(dv[0], dv[1]);
+            lo[q] = pack_bf16(dv[0] - __uint_as_float(hi[q] << 16), dv[1] - __uint_as_float(hi[q] & 0xffff0000u));
+            hi[8 + q] = pack_bf16(dg[0], dg[1]);
+            lo[8 + q] = pack_bf16(dg[0] - __uint_as_float(hi[8 + q] << 16),
+                                  dg[1] - __uint_as_float(hi[8 + q] & 0xffff0000u));
+          }
+          if (hf == 0) {
+            mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t a2 = tmem_base + lane_base + BWD_A2_COL + b * 64 + hf * 16;
+          tmem_st16(a2, hi);
+          tmem_st16(a2 + 32, lo);
         }
-        mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t a2 = tmem_base + lane_base + BWD_A2_COL + b * 64 + half * 16;
-        tmem_st16(a2, hi);
-        tmem_st16(a2 + 32, lo);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar.a2_full(b));

@@ -122,6 +122,21 @@ __device__ __forceinline__ float bf16_round(float x) {
 }
 
 
+// true in exactly one lane of a converged warp (elect.sync): the compiler treats the guarded
+// region as single-threaded, so tcgen05 instructions inside it are issued without the
+// per-instruction "waterfall" loop it wraps around uniform-operand instructions otherwise
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- additions used by the fused kernels
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
