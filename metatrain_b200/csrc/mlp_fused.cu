@@ -58,6 +58,19 @@ __host__ __device__ constexpr int fwd_stages(int F) { return (F / 64) * 6; }
 // backward image: G1 stages of chunk 0; then for c >= 1: G1 stages of c, WT(c-1); finally WT(last)
 __host__ __device__ constexpr int bwd_stages(int F) { return (F / CH) * 5; }
 
+// Optional in-kernel timeline (tools/mlp_trace.py): CTA 0 records clock64() at pipeline events of
+// its first tiles into a caller-provided buffer.  Off (null pointer) in normal operation.
+#ifdef PETB200_MLP_TRACE
+__device__ long long* g_trace = nullptr;
+constexpr int TRACE_SLOTS = 16;    // events per (role, tile, chunk)
+__device__ __forceinline__ void trace(int role, int tile, int chunk, int ev) {
+  if (g_trace != nullptr && blockIdx.x == 0 && tile < 4)
+    g_trace[((role * 4 + tile) * 16 + chunk) * TRACE_SLOTS + ev] = clock64();
+}
+#else   // compiled out: even a disabled run-time check costs a global load per event
+__device__ __forceinline__ void trace(int, int, int, int) {}
+#endif
+
 struct Ring {
   int stage = 0;
   uint32_t phase = 0;
@@ -312,18 +325,40 @@ struct EpiStage {
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // ======================================================================== forward
-constexpr int FWD_RING = 4;
-constexpr int FWD_X_OFF = 0;                                 // 2 buffers x 4 tiles
-constexpr int FWD_RING_OFF = FWD_X_OFF + 2 * 4 * TILE;
-constexpr int FWD_EPI_OFF = FWD_RING_OFF + FWD_RING * STAGE;
-constexpr int FWD_BIAS_OFF = FWD_EPI_OFF + EPI_STAGE_BYTES;  // b_in [2 MAX_F], b_out [D]
+// Forward-kernel layout.  The activation tile never sits in shared memory as an MMA operand:
+// tcgen05.mma with A in shared memory is bound by the 128 B/clk shared-memory read port for
+// N <= 64 (measured 48 clk per M128 N64 K16 instruction instead of 32, tools/umma_rate.cu),
+// and that port also carries the weight stages.  So the producers stage the raw fp32 rows
+// with cp.async (double buffered, pitch 132 floats: conflict-free row-per-thread reads),
+// convert them to bf16 hi / lo in registers and park them in TENSOR memory (lane = row),
+// where GEMM1 reads its A operand at full rate.  19 warps: 0-7 SwiGLU epilogue groups,
+// 8 GEMM1 issue, 9-12 activation producers, 13 weight stages, 14-17 output store, 18 GEMM2
+// issue (two issuing threads: the per-chunk barrier hops of one GEMM no longer delay the other).
+constexpr int FWD_NUM_THREADS = 32 * 19;
+constexpr int FWD_STORE_WARP0 = 14, FWD_MMA2_WARP = 18;
+constexpr int FWD_RING_A = 5, FWD_RING_B = 4;   // W1 stages / W2 stages
+constexpr int FWD_RING = FWD_RING_A + FWD_RING_B;
+constexpr int XPITCH = D + 4;                                // floats per staged row
+constexpr int FWD_STAGING_BYTES = BM * XPITCH * 4;           // 67 584
+constexpr int FWD_XS_OFF = 0;                                // raw fp32 staging buffer
+constexpr int FWD_RING_OFF = ((FWD_XS_OFF + FWD_STAGING_BYTES + 1023) / 1024) * 1024;
+constexpr int FWD_EPI_OFF = FWD_RING_OFF + FWD_RING * STAGE; // 4 store warps x 32 x STAGE_LD floats
+constexpr int FWD_BIAS_OFF = FWD_EPI_OFF + 4 * 32 * STAGE_LD * 4;  // b_in [2 MAX_F], b_out [D]
 constexpr int FWD_RSTD_OFF = FWD_BIAS_OFF + (2 * MAX_F + D) * 4;
 constexpr int FWD_BAR_OFF = FWD_RSTD_OFF + 2 * BM * 4;
 constexpr int FWD_SMEM = FWD_BAR_OFF + 8 * (16 + 2 * FWD_RING) + 16 + 1024;
-// TMEM columns: acc1[2] at 0, 64 ; acc2[2] at 128, 256 ; A2[b] hi at 384 + 32 b, lo 16 further
-constexpr int FWD_ACC2_COL = 128, FWD_A2_COL = 384;
+// TMEM columns: X hi 0..63, X lo 64..127 ; acc1 at 128 (single buffer: GEMM1 of the next chunk
+// only waits for the tcgen05.ld of the previous one) ; A2[b] hi at 192 + 32 b, lo 16 further ;
+// acc2[t] at 256 + 128 t (double buffer: the output store overlaps the next tile)
+constexpr int FWD_XLO_COL = 64, FWD_ACC1_COL = 128, FWD_A2_COL = 192, FWD_ACC2_COL = 256;
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(FWD_NUM_THREADS, 1)
 mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ image,
                const float* __restrict__ b_in, const float* __restrict__ b_out, int64_t M, int F,
                float* __restrict__ y, int64_t ldy) {
@@ -333,19 +368,26 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
   const Barriers bar{smem_base + FWD_BAR_OFF, FWD_RING};
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FWD_BAR_OFF + 8 * (16 + 2 * FWD_RING));
   float* bias_s = reinterpret_cast<float*>(smem + FWD_BIAS_OFF);
-  float* rstd_s = reinterpret_cast<float*>(smem + FWD_RSTD_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+  const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
   const int nch = F / CH;
   const TileSchedule sched(M);
 
-  if (threadIdx.x == 0) bar.init_all();
+  if (threadIdx.x == 0) {
+    bar.init_all();
+    // only the four store warps drain acc2
+    mbar_init(bar.acc2_empty(0), 4 * 32);
+    mbar_init(bar.acc2_empty(1), 4 * 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
         smem_u32(const_cast<uint32_t*>(tmem_slot))));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < 2 * F; i += NUM_THREADS) bias_s[i] = b_in[i];
-  for (int i = threadIdx.x; i < D; i += NUM_THREADS) bias_s[2 * MAX_F + i] = b_out[i];
+  for (int i = threadIdx.x; i < 2 * F; i += FWD_NUM_THREADS) bias_s[i] = b_in[i];
+  for (int i = threadIdx.x; i < D; i += FWD_NUM_THREADS) bias_s[2 * MAX_F + i] = b_out[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -353,117 +395,180 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
 
   if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
     // ============================================================ activation producers
-    const int pw = warp - FIRST_PROD_WARP;
+    // warp -> rows 32 * quarter .. + 31 (the TMEM lanes it may write); lane -> one row
+    auto issue = [&](int i) {
+      const uint32_t dst = smem_base + FWD_XS_OFF;
+      const int64_t m0 = sched.m0(i);
+#pragma unroll 8
+      for (int it = 0; it < 32; ++it) {  // one row (32 x 16 B) per instruction
+        const int row = quarter * 32 + it;
+        const int64_t m = m0 + row;
+        const bool ok = m < M;
+        cp_async16(dst + (uint32_t)(row * XPITCH * 4 + lane * 16), x + (ok ? m : 0) * ldx + 4 * lane,
+                   ok ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    if (sched.count > 0) issue(0);
     for (int i = 0; i < sched.count; ++i) {
-      const int buf = i & 1;
-      mbar_wait(bar.x_empty(buf), ((i >> 1) & 1) ^ 1);
-      issue_tile_copies(smem_base + FWD_X_OFF + buf * 4 * TILE, x, ldx, sched.m0(i), M, pw, lane);
-      cp_async_wait_all();
+      cp_async_wait_group<0>();
       __syncwarp();
-      float ss[2][8] = {};
-      convert_tile<true>(smem + FWD_X_OFF + buf * 4 * TILE, pw, lane, ss);
-      store_rstd(rstd_s + buf * BM, pw, lane, ss);
-      fence_proxy_async();
-      mbar_arrive(bar.x_full(buf));
+      if (lane == 0 && quarter == 1) trace(3, i, 0, 0);
+      mbar_wait(bar.x_empty(0), (i & 1) ^ 1);   // GEMM1 of the previous tile has consumed X
+      tc_fence_after();
+      if (lane == 0 && quarter == 1) trace(3, i, 0, 1);
+      const float* row = reinterpret_cast<const float*>(smem + FWD_XS_OFF) + (quarter * 32 + lane) * XPITCH;
+      // pass 1: RMS statistic of the row; pass 2: x_hat = x * rstd -> bf16 hi / lo -> TMEM (the
+      // norm weight is folded into W_in, so GEMM1 consumes the normalised row directly)
+      float ss = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(row + 4 * q);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+      const float rs = rsqrtf(ss * (1.0f / D) + kRmsEps);
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {   // 32 floats -> 16 hi + 16 lo columns
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v = *reinterpret_cast<const float4*>(row + part * 32 + 4 * q);
+          v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+          hi[2 * q] = pack_bf16(v.x, v.y);
+          hi[2 * q + 1] = pack_bf16(v.z, v.w);
+          lo[2 * q] = pack_bf16(v.x - __uint_as_float(hi[2 * q] << 16), v.y - __uint_as_float(hi[2 * q] & 0xffff0000u));
+          lo[2 * q + 1] = pack_bf16(v.z - __uint_as_float(hi[2 * q + 1] << 16),
+                                    v.w - __uint_as_float(hi[2 * q + 1] & 0xffff0000u));
+        }
+        tmem_st16(tmem_base + lane_base + part * 16, hi);
+        tmem_st16(tmem_base + lane_base + FWD_XLO_COL + part * 16, lo);
+      }
+      // this warp's rows of the staging buffer are consumed: fetch the next tile behind the
+      // whole chunk loop of this one
+      __syncwarp();
+      if (i + 1 < sched.count) issue(i + 1);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar.x_full(0));
+      if (lane == 0 && quarter == 1) trace(3, i, 0, 3);
     }
   } else if (warp == TMA_WARP) {
     // ============================================================ weight-stage producer
-    if (elect_one()) weight_producer(image, fwd_stages(F), sched.count, smem_base + FWD_RING_OFF, bar);
+    // one thread walks the image in order and routes W1 stages to ring A (slots 0..RA-1) and
+    // W2 stages to ring B (slots RA..RA+RB-1); a stage only ever waits for EARLIER stages to be
+    // consumed, so the two rings cannot deadlock each other
+    if (elect_one()) {
+      Ring ra, rb;
+      const int n_stage = fwd_stages(F);
+      for (int i = 0; i < sched.count; ++i)
+        for (int st = 0; st < n_stage; ++st) {
+          const bool is_b = (st % 6) >= 4;
+          Ring& r = is_b ? rb : ra;
+          const int slot = is_b ? FWD_RING_A + r.stage : r.stage;
+          mbar_wait(bar.w_empty(slot), r.phase ^ 1);
+          mbar_expect_tx(bar.w_full(slot), STAGE);
+          bulk_g2s(smem_base + FWD_RING_OFF + (uint32_t)slot * STAGE, image + (size_t)st * STAGE, STAGE,
+                   bar.w_full(slot));
+          r.advance(is_b ? FWD_RING_B : FWD_RING_A);
+        }
+    }
   } else if (warp == MMA_WARP) {
-    // ============================================================ MMA issuer
-    constexpr uint32_t idesc1 = make_idesc(BM, 64), idesc2 = make_idesc(BM, D);
-    const uint32_t ring_u32 = smem_base + FWD_RING_OFF;
-    Ring ring;
-    int w2_hi = 0, w2_lo = 0;
-    auto gemm2 = [&](int i, int c) {
-      const int b = c & 1, t = i & 1;
-      const uint32_t u = (uint32_t)(i * nch + c) >> 1;
-      if (b == 0) {
-        mbar_wait(bar.w_full(ring.stage), ring.phase);
-        w2_hi = ring.stage;
-        ring.advance(FWD_RING);
-        mbar_wait(bar.w_full(ring.stage), ring.phase);
-        w2_lo = ring.stage;
-        ring.advance(FWD_RING);
-      }
-      mbar_wait(bar.a2_full(b), u & 1);
-      if (c == 0) mbar_wait(bar.acc2_empty(t), ((i >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const uint32_t koff = (uint32_t)(b * 64 + kk * 32);
-          const uint32_t a_hi = tmem_base + FWD_A2_COL + b * 32 + kk * 8;
-          mma3_ts(tmem_base + FWD_ACC2_COL + t * D, a_hi, a_hi + 16, ring_u32 + w2_hi * STAGE + koff,
-                  ring_u32 + w2_lo * STAGE + koff, idesc2, (c | kk) != 0);
-        }
-        tc_commit(bar.a2_empty(b));
-        if (b == 1) {
-          tc_commit(bar.w_empty(w2_hi));
-          tc_commit(bar.w_empty(w2_lo));
-        }
-      }
-      __syncwarp();
-    };
-    for (int i = 0; i < sched.count; ++i) {
-      const int buf = i & 1;
-      const uint32_t xt = smem_base + FWD_X_OFF + buf * 4 * TILE;
-      mbar_wait(bar.x_full(buf), (i >> 1) & 1);
-      tc_fence_after();
-      for (int c = 0; c < nch; ++c) {
-        const int b = c & 1;
-        const uint32_t u = (uint32_t)(i * nch + c) >> 1;
-        mbar_wait(bar.acc1_empty(b), (u & 1) ^ 1);
-        tc_fence_after();
-        for (int kh = 0; kh < 2; ++kh) {
-          mbar_wait(bar.w_full(ring.stage), ring.phase);
+    // ============================================================ GEMM1 issuer (one thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc1 = make_idesc(BM, 64);
+      const uint32_t ring_u32 = smem_base + FWD_RING_OFF;
+      Ring ring;
+      for (int i = 0; i < sched.count; ++i) {
+        mbar_wait(bar.x_full(0), i & 1);
+        for (int c = 0; c < nch; ++c) {
+          const int b = c & 1;
+          trace(0, i, c, 0);
+          // single acc1 buffer: the epilogue group of the PREVIOUS chunk (barrier pair b ^ 1)
+          // must have pulled it into registers
+          const int n = i * nch + c;
+          if (n > 0) mbar_wait(bar.acc1_empty(b ^ 1), ((uint32_t)(n - 1) >> 1) & 1);
           tc_fence_after();
-          if (elect_one()) {
+          trace(0, i, c, 1);
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            mbar_wait(bar.w_full(ring.stage), ring.phase);
             const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma3_ss(tmem_base + b * 64, xt + (kh * 2) * TILE + kk * 32, xt + (kh * 2 + 1) * TILE + kk * 32,
-                      st + kk * 32, st + 8192 + kk * 32, idesc1, (kh | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t a_hi = tmem_base + (kh * 4 + kk) * 8;
+              mma3_ts(tmem_base + FWD_ACC1_COL, a_hi, a_hi + FWD_XLO_COL, st + kk * 32,
+                      st + 8192 + kk * 32, idesc1, (kh | kk) != 0);
+            }
             tc_commit(bar.w_empty(ring.stage));
+            ring.advance(FWD_RING_A);
           }
-          __syncwarp();
-          ring.advance(FWD_RING);
-        }
-        if (elect_one()) {
           tc_commit(bar.acc1_full(b));
-          if (c == nch - 1) tc_commit(bar.x_empty(buf));
+          if (c == nch - 1) tc_commit(bar.x_empty(0));
+          trace(0, i, c, 7);
         }
-        __syncwarp();
-        if (c >= 1) gemm2(i, c - 1);
       }
-      gemm2(i, nch - 1);
-      if (elect_one()) tc_commit(bar.acc2_full(i & 1));
-      __syncwarp();
     }
-  } else {
-    // ============================================================ epilogues
-    const int quarter = warp & 3, half = warp >> 2;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const EpiStage es{reinterpret_cast<float*>(smem + FWD_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+  } else if (warp == FWD_MMA2_WARP) {
+    // ============================================================ GEMM2 issuer (one thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc2 = make_idesc(BM, D);
+      const uint32_t ring_u32 = smem_base + FWD_RING_OFF + FWD_RING_A * STAGE;
+      Ring ring;
+      int w2_hi = 0, w2_lo = 0;
+      for (int i = 0; i < sched.count; ++i) {
+        for (int c = 0; c < nch; ++c) {
+          const int b = c & 1;
+          const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+          if (b == 0) {
+            mbar_wait(bar.w_full(FWD_RING_A + ring.stage), ring.phase);
+            w2_hi = ring.stage;
+            ring.advance(FWD_RING_B);
+            mbar_wait(bar.w_full(FWD_RING_A + ring.stage), ring.phase);
+            w2_lo = ring.stage;
+            ring.advance(FWD_RING_B);
+          }
+          trace(0, i, c, 3);
+          mbar_wait(bar.a2_full(b), u & 1);
+          if (c == 0) mbar_wait(bar.acc2_empty(i & 1), ((i >> 1) & 1) ^ 1);
+          tc_fence_after();
+          trace(0, i, c, 4);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint32_t koff = (uint32_t)(b * 64 + kk * 32);
+            const uint32_t a_hi = tmem_base + FWD_A2_COL + b * 32 + kk * 8;
+            mma3_ts(tmem_base + FWD_ACC2_COL + (i & 1) * D, a_hi, a_hi + 16, ring_u32 + w2_hi * STAGE + koff,
+                    ring_u32 + w2_lo * STAGE + koff, idesc2, (c | kk) != 0);
+          }
+          tc_commit(bar.a2_empty(b));
+          if (b == 1) {
+            tc_commit(bar.w_empty(FWD_RING_A + w2_hi));
+            tc_commit(bar.w_empty(FWD_RING_A + w2_lo));
+          }
+          trace(0, i, c, 8);
+        }
+        tc_commit(bar.acc2_full(i & 1));
+      }
+    }
+  } else if (warp < NUM_EPI_WARPS) {
+    // ============================================================ SwiGLU epilogues
+    const int half = warp >> 2;
     for (int i = 0; i < sched.count; ++i) {
-      const int buf = i & 1, t = i & 1;
-      const int64_t m0 = sched.m0(i);
-      mbar_wait(bar.x_full(buf), (i >> 1) & 1);
-      const float rs = rstd_s[buf * BM + quarter * 32 + lane];
       // the two groups of four warps take alternate chunks (group = chunk parity = buffer), so
       // the epilogue of chunk c overlaps GEMM1 of c+1, GEMM2 of c-1 AND the epilogue of c+1;
       // a thread owns one row: 64 accumulator columns in, 32 activations out
       for (int c = half; c < nch; c += 2) {
         const int b = half;
         const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 0);
         mbar_wait(bar.acc1_full(b), u & 1);
         tc_fence_after();
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 1);
         float v[64];
-        tmem_ld32(tmem_base + lane_base + b * 64, v);
-        tmem_ld32(tmem_base + lane_base + b * 64 + 32, v + 32);
+        tmem_ld32(tmem_base + lane_base + FWD_ACC1_COL, v);
+        tmem_ld32(tmem_base + lane_base + FWD_ACC1_COL + 32, v + 32);
         tc_fence_before();
         mbar_arrive(bar.acc1_empty(b));
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 2);
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -471,13 +576,14 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
           const float* vv = v + hf * 32;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float a0 = (rs * vv[2 * q] + bv[2 * q]) * fsigmoid(rs * vv[16 + 2 * q] + bv[F + 2 * q]);
-            const float a1 = (rs * vv[2 * q + 1] + bv[2 * q + 1]) * fsigmoid(rs * vv[17 + 2 * q] + bv[F + 2 * q + 1]);
+            const float a0 = (vv[2 * q] + bv[2 * q]) * fsigmoid(vv[16 + 2 * q] + bv[F + 2 * q]);
+            const float a1 = (vv[2 * q + 1] + bv[2 * q + 1]) * fsigmoid(vv[17 + 2 * q] + bv[F + 2 * q + 1]);
             const uint32_t h2 = pack_bf16(a0, a1);
             hi[hf * 8 + q] = h2;
             lo[hf * 8 + q] = pack_bf16(a0 - __uint_as_float(h2 << 16), a1 - __uint_as_float(h2 & 0xffff0000u));
           }
         }
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 3);
         mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
         tc_fence_after();
         const uint32_t a2 = tmem_base + lane_base + FWD_A2_COL + b * 32;
@@ -486,35 +592,54 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar.a2_full(b));
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 4);
       }
-      // ---- y = acc2 + b_out + x
-      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
-      tc_fence_after();
-      const int64_t m_base = m0 + quarter * 32;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int col = 64 * half + 16 * ch;
-        const int c0 = col + 4 * es.c4;
-        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * MAX_F + c0);
-        float4 res[4];
+    }
+  } else if (warp >= FWD_STORE_WARP0 && warp < FWD_STORE_WARP0 + 4) {
+    // ============================================================ output store warps
+    // y = acc2 + b_out + x, overlapped with the chunk loop of the next tile.  Warp -> 32 rows
+    // (its TMEM lane quarter) x 128 columns in 8 slices of 16; the residual of the next slice is
+    // in flight while the current one is transposed and stored.
+    const int sw = warp - FWD_STORE_WARP0;
+    const EpiStage es{reinterpret_cast<float*>(smem + FWD_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    for (int i = 0; i < sched.count; ++i) {
+      const int64_t m_base = sched.m0(i) + quarter * 32;
+      const int t = i & 1;
+      float4 res[3][4];
+      auto fetch = [&](int sl) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int64_t m = m_base + it * 8 + es.rsel;
-          res[it] = m < M ? ld4(x + m * ldx + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res[sl % 3][it] = m < M ? ld4(x + m * ldx + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        es.fill(tmem_base + lane_base + FWD_ACC2_COL + t * D + col);
+      };
+      fetch(0);
+      fetch(1);
+      if (lane == 0 && sw == 0) trace(1, i, 15, 0);
+      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0 && sw == 0) trace(1, i, 15, 1);
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) {
+        if (sl + 2 < 8) fetch(sl + 2);
+        const int c0 = 16 * sl + 4 * es.c4;
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * MAX_F + c0);
+        es.fill(tmem_base + lane_base + FWD_ACC2_COL + t * D + 16 * sl);
+        if (sl == 7) {   // the accumulator is in registers / smem now: release it early
+          tc_fence_before();
+          mbar_arrive(bar.acc2_empty(t));
+        }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int64_t m = m_base + it * 8 + es.rsel;
           if (m >= M) continue;
-          const float4 a = es.get(it);
+          const float4 a = es.get(it), r = res[sl % 3][it];
           *reinterpret_cast<float4*>(y + m * ldy + c0) =
-              make_float4(a.x + b4.x + res[it].x, a.y + b4.y + res[it].y, a.z + b4.z + res[it].z,
-                          a.w + b4.w + res[it].w);
+              make_float4(a.x + b4.x + r.x, a.y + b4.y + r.y, a.z + b4.z + r.z, a.w + b4.w + r.w);
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar.acc2_empty(t));
+      if (lane == 0 && sw == 0) trace(1, i, 15, 2);
     }
   }
 
@@ -814,6 +939,19 @@ int check_dims(const char* what, int d, int d_ff) {
 
 using namespace petb200;
 
+// debugging aid, not part of the documented ABI: buffer of 4 roles x 4 tiles x 16 chunks x 16
+// int64 slots that CTA 0 of petb200_mlp_fwd fills with clock64() stamps (NULL switches it off)
+extern "C" PETB200_API int petb200_debug_mlp_trace(void* buffer) {
+#ifdef PETB200_MLP_TRACE
+  cudaMemcpyToSymbol(g_trace, &buffer, sizeof(void*));
+  return check_launch("debug_mlp_trace");
+#else
+  (void)buffer;
+  set_error("debug_mlp_trace: rebuild with -DPETB200_MLP_TRACE");
+  return PETB200_ERR_UNSUPPORTED;
+#endif
+}
+
 extern "C" PETB200_API size_t petb200_mlp_image_bytes(int d_ff, int backward) {
   return (size_t)(backward ? bwd_stages(d_ff) : fwd_stages(d_ff)) * STAGE;
 }
@@ -839,7 +977,7 @@ extern "C" PETB200_API int petb200_mlp_fwd(const float* x, int64_t ldx, const vo
   if (n_rows == 0) return PETB200_OK;
   const int tiles = (int)ceil_div(n_rows, BM);
   cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-  mlp_fwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, NUM_THREADS, FWD_SMEM, stream>>>(
+  mlp_fwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, FWD_NUM_THREADS, FWD_SMEM, stream>>>(
       x, ldx, reinterpret_cast<const uint8_t*>(image_fwd), b_in, b_out, n_rows, d_ff, y, ldy);
   return check_launch("mlp_fwd");
 }
