@@ -652,19 +652,26 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
 }
 
 // ======================================================================= backward
-constexpr int BWD_RING = 4;
+// 19 warps, as in the forward kernel: 0-7 swiglu' epilogue groups, 8 GEMM1 issue (ug and ds),
+// 9-12 activation producers (X and dY tiles as bf16 hi / lo operand tiles in shared memory),
+// 13 weight stages, 14-17 output store (RMSNorm backward, overlapped with the next tile),
+// 18 GEMM2 issue.
+constexpr int BWD_NUM_THREADS = 32 * 19;
+constexpr int BWD_STORE_WARP0 = 14, BWD_MMA2_WARP = 18;
+constexpr int BWD_RING_A = 3, BWD_RING_B = 2;                 // G1 stages / WT stages
+constexpr int BWD_RING = BWD_RING_A + BWD_RING_B;
 constexpr int BWD_X_OFF = 0;                                  // X tiles (4), then dY tiles (4)
 constexpr int BWD_RING_OFF = BWD_X_OFF + 8 * TILE;
-constexpr int BWD_EPI_OFF = BWD_RING_OFF + BWD_RING * STAGE;
-constexpr int BWD_BIAS_OFF = BWD_EPI_OFF + EPI_STAGE_BYTES;   // b_in [2 MAX_F]
+constexpr int BWD_EPI_OFF = BWD_RING_OFF + BWD_RING * STAGE;  // 4 store warps x 32 x STAGE_LD floats
+constexpr int BWD_BIAS_OFF = BWD_EPI_OFF + 4 * 32 * STAGE_LD * 4;   // b_in [2 MAX_F]
 constexpr int BWD_RSTD_OFF = BWD_BIAS_OFF + 2 * MAX_F * 4;    // rstd [2][BM]
-constexpr int BWD_DOT_OFF = BWD_RSTD_OFF + 2 * BM * 4;        // dot exchange [2][BM]
-constexpr int BWD_BAR_OFF = BWD_DOT_OFF + 2 * BM * 4;
+constexpr int BWD_BAR_OFF = BWD_RSTD_OFF + 2 * BM * 4;
 constexpr int BWD_SMEM = BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING) + 16 + 1024;
-// TMEM columns: acc1[b] at 128 b (ug: 64, then ds: 32) ; acc2 at 256 ; A2[b] hi at 384 + 64 b, lo 32 further
-constexpr int BWD_ACC1_STRIDE = 128, BWD_ACC2_COL = 256, BWD_A2_COL = 384;
+// TMEM columns: acc1 at 0 (ug: 0..63, ds: 64..95; single buffer) ; A2[b] hi at 128 + 64 b, lo 32
+// further ; acc2[t] at 256 + 128 t
+constexpr int BWD_A2_COL = 128, BWD_ACC2_COL = 256;
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(BWD_NUM_THREADS, 1)
 mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t ld_dy,
                const uint8_t* __restrict__ image, const float* __restrict__ b_in, int64_t M, int F,
                float* __restrict__ dx, int64_t ld_dx) {
@@ -675,18 +682,24 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING));
   float* bias_s = reinterpret_cast<float*>(smem + BWD_BIAS_OFF);
   float* rstd_s = reinterpret_cast<float*>(smem + BWD_RSTD_OFF);
-  float* dot_s = reinterpret_cast<float*>(smem + BWD_DOT_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3;
+  const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
   const int nch = F / CH;
   const TileSchedule sched(M);
 
-  if (threadIdx.x == 0) bar.init_all();
+  if (threadIdx.x == 0) {
+    bar.init_all();
+    mbar_init(bar.acc2_empty(0), 4 * 32);   // drained by the four store warps
+    mbar_init(bar.acc2_empty(1), 4 * 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
         smem_u32(const_cast<uint32_t*>(tmem_slot))));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < 2 * F; i += NUM_THREADS) bias_s[i] = b_in[i];
+  for (int i = threadIdx.x; i < 2 * F; i += BWD_NUM_THREADS) bias_s[i] = b_in[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -717,96 +730,106 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       mbar_arrive(bar.x_full(0));
     }
   } else if (warp == TMA_WARP) {
-    if (elect_one()) weight_producer(image, bwd_stages(F), sched.count, smem_base + BWD_RING_OFF, bar);
-  } else if (warp == MMA_WARP) {
-    // ============================================================ MMA issuer
-    constexpr uint32_t idesc_ug = make_idesc(BM, 64), idesc_ds = make_idesc(BM, 32), idesc2 = make_idesc(BM, D);
-    const uint32_t ring_u32 = smem_base + BWD_RING_OFF;
-    const uint32_t xt = smem_base + BWD_X_OFF, dyt = xt + 4 * TILE;
-    Ring ring;
-    auto gemm2 = [&](int i, int c) {
-      const int b = c & 1;
-      const uint32_t u = (uint32_t)(i * nch + c) >> 1;
-      mbar_wait(bar.w_full(ring.stage), ring.phase);
-      const int s_hi = ring.stage;
-      ring.advance(BWD_RING);
-      mbar_wait(bar.w_full(ring.stage), ring.phase);
-      const int s_lo = ring.stage;
-      ring.advance(BWD_RING);
-      mbar_wait(bar.a2_full(b), u & 1);
-      if (c == 0) mbar_wait(bar.acc2_empty(0), (i & 1) ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint32_t a_hi = tmem_base + BWD_A2_COL + b * 64 + kk * 8;
-          mma3_ts(tmem_base + BWD_ACC2_COL, a_hi, a_hi + 32, ring_u32 + s_hi * STAGE + kk * 32,
-                  ring_u32 + s_lo * STAGE + kk * 32, idesc2, (c | kk) != 0);
+    // ============================================================ weight-stage producer
+    // image order: G1 stages of chunk 0; for c >= 1: G1 stages of c, then WT(c-1); WT(last).
+    // G1 stages (W_in k-halves, W_out^T chunk) -> ring A, WT stages -> ring B.
+    if (elect_one()) {
+      Ring ra, rb;
+      const int n_stage = bwd_stages(F), tail = n_stage - 2;
+      for (int i = 0; i < sched.count; ++i)
+        for (int st = 0; st < n_stage; ++st) {
+          const bool is_b = st >= tail || (st >= 3 && (st - 3) % 5 >= 3);
+          Ring& r = is_b ? rb : ra;
+          const int slot = is_b ? BWD_RING_A + r.stage : r.stage;
+          mbar_wait(bar.w_empty(slot), r.phase ^ 1);
+          mbar_expect_tx(bar.w_full(slot), STAGE);
+          bulk_g2s(smem_base + BWD_RING_OFF + (uint32_t)slot * STAGE, image + (size_t)st * STAGE, STAGE,
+                   bar.w_full(slot));
+          r.advance(is_b ? BWD_RING_B : BWD_RING_A);
         }
-        tc_commit(bar.a2_empty(b));
-        tc_commit(bar.w_empty(s_hi));
-        tc_commit(bar.w_empty(s_lo));
-      }
-      __syncwarp();
-    };
-    for (int i = 0; i < sched.count; ++i) {
-      mbar_wait(bar.x_full(0), i & 1);
-      tc_fence_after();
-      for (int c = 0; c < nch; ++c) {
-        const int b = c & 1;
-        const uint32_t u = (uint32_t)(i * nch + c) >> 1;
-        mbar_wait(bar.acc1_empty(b), (u & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t acc1 = tmem_base + b * BWD_ACC1_STRIDE;
-        for (int kh = 0; kh < 2; ++kh) {   // ug = X . W_in[chunk]^T
-          mbar_wait(bar.w_full(ring.stage), ring.phase);
+    }
+  } else if (warp == MMA_WARP) {
+    // ============================================================ GEMM1 issuer (one thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc_ug = make_idesc(BM, 64), idesc_ds = make_idesc(BM, 32);
+      const uint32_t ring_u32 = smem_base + BWD_RING_OFF;
+      const uint32_t xt = smem_base + BWD_X_OFF, dyt = xt + 4 * TILE;
+      Ring ring;
+      for (int i = 0; i < sched.count; ++i) {
+        mbar_wait(bar.x_full(0), i & 1);
+        for (int c = 0; c < nch; ++c) {
+          const int b = c & 1;
+          const int n = i * nch + c;
+          if (n > 0) mbar_wait(bar.acc1_empty(b ^ 1), ((uint32_t)(n - 1) >> 1) & 1);
           tc_fence_after();
-          if (elect_one()) {
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {   // ug = X . W_in[chunk]^T
+            mbar_wait(bar.w_full(ring.stage), ring.phase);
             const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              mma3_ss(acc1, xt + (kh * 2) * TILE + kk * 32, xt + (kh * 2 + 1) * TILE + kk * 32, st + kk * 32,
+              mma3_ss(tmem_base, xt + (kh * 2) * TILE + kk * 32, xt + (kh * 2 + 1) * TILE + kk * 32, st + kk * 32,
                       st + 8192 + kk * 32, idesc_ug, (kh | kk) != 0);
             tc_commit(bar.w_empty(ring.stage));
+            ring.advance(BWD_RING_A);
           }
-          __syncwarp();
-          ring.advance(BWD_RING);
-        }
-        mbar_wait(bar.w_full(ring.stage), ring.phase);   // ds = dY . W_out[:, chunk]
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t st = ring_u32 + ring.stage * STAGE;
+          mbar_wait(bar.w_full(ring.stage), ring.phase);   // ds = dY . W_out[:, chunk]
+          {
+            const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
-          for (int kh = 0; kh < 2; ++kh)
+            for (int kh = 0; kh < 2; ++kh)
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma3_ss(acc1 + 64, dyt + (kh * 2) * TILE + kk * 32, dyt + (kh * 2 + 1) * TILE + kk * 32,
-                      st + kh * 8192 + kk * 32, st + kh * 8192 + 4096 + kk * 32, idesc_ds, (kh | kk) != 0);
-          tc_commit(bar.w_empty(ring.stage));
+              for (int kk = 0; kk < 4; ++kk)
+                mma3_ss(tmem_base + 64, dyt + (kh * 2) * TILE + kk * 32, dyt + (kh * 2 + 1) * TILE + kk * 32,
+                        st + kh * 8192 + kk * 32, st + kh * 8192 + 4096 + kk * 32, idesc_ds, (kh | kk) != 0);
+            tc_commit(bar.w_empty(ring.stage));
+            ring.advance(BWD_RING_A);
+          }
           tc_commit(bar.acc1_full(b));
           if (c == nch - 1) tc_commit(bar.x_empty(0));
         }
-        __syncwarp();
-        ring.advance(BWD_RING);
-        if (c >= 1) gemm2(i, c - 1);
       }
-      gemm2(i, nch - 1);
-      if (elect_one()) tc_commit(bar.acc2_full(0));
-      __syncwarp();
     }
-  } else {
-    // ============================================================ epilogues
-    const int quarter = warp & 3, half = warp >> 2;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const EpiStage es{reinterpret_cast<float*>(smem + BWD_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+  } else if (warp == BWD_MMA2_WARP) {
+    // ============================================================ GEMM2 issuer (one thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc2 = make_idesc(BM, D);
+      const uint32_t ring_u32 = smem_base + BWD_RING_OFF + BWD_RING_A * STAGE;
+      Ring ring;
+      for (int i = 0; i < sched.count; ++i) {
+        for (int c = 0; c < nch; ++c) {
+          const int b = c & 1;
+          const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+          mbar_wait(bar.w_full(BWD_RING_A + ring.stage), ring.phase);
+          const int s_hi = ring.stage;
+          ring.advance(BWD_RING_B);
+          mbar_wait(bar.w_full(BWD_RING_A + ring.stage), ring.phase);
+          const int s_lo = ring.stage;
+          ring.advance(BWD_RING_B);
+          mbar_wait(bar.a2_full(b), u & 1);
+          if (c == 0) mbar_wait(bar.acc2_empty(i & 1), ((i >> 1) & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t a_hi = tmem_base + BWD_A2_COL + b * 64 + kk * 8;
+            mma3_ts(tmem_base + BWD_ACC2_COL + (i & 1) * D, a_hi, a_hi + 32, ring_u32 + s_hi * STAGE + kk * 32,
+                    ring_u32 + s_lo * STAGE + kk * 32, idesc2, (c | kk) != 0);
+          }
+          tc_commit(bar.a2_empty(b));
+          tc_commit(bar.w_empty(BWD_RING_A + s_hi));
+          tc_commit(bar.w_empty(BWD_RING_A + s_lo));
+        }
+        tc_commit(bar.acc2_full(i & 1));
+      }
+    }
+  } else if (warp < NUM_EPI_WARPS) {
+    // ============================================================ swiglu' epilogues
+    // alternate chunks per group of four warps; a thread owns one row and walks the two
+    // 16-unit halves of the chunk in turn
+    const int half = warp >> 2;
     for (int i = 0; i < sched.count; ++i) {
-      const int64_t m0 = sched.m0(i);
-      const float* rstd_t = rstd_s + (i & 1) * BM;
       mbar_wait(bar.x_full(0), i & 1);
-      const float rs = rstd_t[quarter * 32 + lane];
-      // alternate chunks per group of four warps, as in the forward kernel; a thread owns one
-      // row and walks the two 16-unit halves of the chunk in turn
+      const float rs = rstd_s[(i & 1) * BM + quarter * 32 + lane];
       for (int c = half; c < nch; c += 2) {
         const int b = half;
         const uint32_t u = (uint32_t)(i * nch + c) >> 1;
@@ -815,8 +838,8 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           float v[32], ds[16];
-          tmem_ld32(tmem_base + lane_base + b * BWD_ACC1_STRIDE + hf * 32, v);
-          tmem_ld16(tmem_base + lane_base + b * BWD_ACC1_STRIDE + 64 + hf * 16, ds);
+          tmem_ld32(tmem_base + lane_base + hf * 32, v);
+          tmem_ld16(tmem_base + lane_base + 64 + hf * 16, ds);
           if (hf == 1) {
             tc_fence_before();
             mbar_arrive(bar.acc1_empty(b));
@@ -853,67 +876,81 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
         tc_fence_before();
         mbar_arrive(bar.a2_full(b));
       }
-      // ---- dx = dy + rs * d - x * rs^3 * (d . x) / D     (d = acc2 = gradient w.r.t. x_hat)
-      mbar_wait(bar.acc2_full(0), i & 1);
-      tc_fence_after();
-      const int64_t m_base = m0 + quarter * 32;
-      float dot[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int col = 64 * half + 16 * ch, c0 = col + 4 * es.c4;
-        float4 xr[4];
+    }
+  } else if (warp >= BWD_STORE_WARP0 && warp < BWD_STORE_WARP0 + 4) {
+    // ============================================================ output store warps
+    // dx = dy + rs * d - x * rs^3 * (d . x) / D   (d = acc2 = gradient w.r.t. x_hat), overlapped
+    // with the chunk loop of the next tile.  Warp -> 32 rows x 128 columns in 8 slices of 16:
+    // pass 1 accumulates d . x per row, pass 2 forms the output; x (and dy) of the next slice
+    // are in flight while the current one is transposed.
+    const int sw = warp - BWD_STORE_WARP0;
+    const EpiStage es{reinterpret_cast<float*>(smem + BWD_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    for (int i = 0; i < sched.count; ++i) {
+      const int t = i & 1;
+      const int64_t m_base = sched.m0(i) + quarter * 32;
+      float4 xr[2][4], gr[2][4];
+      auto fetch_x = [&](int sl) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int64_t m = m_base + it * 8 + es.rsel;
-          xr[it] = m < M ? ld4(x + m * ldx + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xr[sl & 1][it] = m < M ? ld4(x + m * ldx + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        es.fill(tmem_base + lane_base + BWD_ACC2_COL + col);
+      };
+      auto fetch_g = [&](int sl) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const float4 a = es.get(it);
-          dot[it] += a.x * xr[it].x + a.y * xr[it].y + a.z * xr[it].z + a.w * xr[it].w;
+          const int64_t m = m_base + it * 8 + es.rsel;
+          gr[sl & 1][it] = m < M ? ld4(dy + m * ld_dy + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      fetch_x(0);
+      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
+      tc_fence_after();
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) {
+        if (sl + 1 < 8) fetch_x(sl + 1);
+        es.fill(tmem_base + lane_base + BWD_ACC2_COL + t * D + 16 * sl);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 a = es.get(it), xv = xr[sl & 1][it];
+          dot[it] += a.x * xv.x + a.y * xv.y + a.z * xv.z + a.w * xv.w;
         }
       }
+      fetch_x(0);
+      fetch_g(0);
+      float rr[4], kap[4];
+      const float* rstd_t = rstd_s + t * BM;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 1);
         dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 2);
-        if (es.c4 == 0) dot_s[half * BM + quarter * 32 + it * 8 + es.rsel] = dot[it];
+        rr[it] = rstd_t[quarter * 32 + it * 8 + es.rsel];
+        kap[it] = rr[it] * rr[it] * rr[it] * dot[it] * (1.0f / D);
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      float rr[4], kap[4];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int r = quarter * 32 + it * 8 + es.rsel;
-        rr[it] = rstd_t[r];
-        kap[it] = rr[it] * rr[it] * rr[it] * (dot_s[r] + dot_s[BM + r]) * (1.0f / D);
-      }
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int col = 64 * half + 16 * ch, c0 = col + 4 * es.c4;
-        float4 xr[4], gr[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          const bool ok = m < M;
-          xr[it] = ok ? ld4(x + m * ldx + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          gr[it] = ok ? ld4(dy + m * ld_dy + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sl = 0; sl < 8; ++sl) {
+        if (sl + 1 < 8) {
+          fetch_x(sl + 1);
+          fetch_g(sl + 1);
         }
-        es.fill(tmem_base + lane_base + BWD_ACC2_COL + col);
+        const int c0 = 16 * sl + 4 * es.c4;
+        es.fill(tmem_base + lane_base + BWD_ACC2_COL + t * D + 16 * sl);
+        if (sl == 7) {
+          tc_fence_before();
+          mbar_arrive(bar.acc2_empty(t));
+        }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int64_t m = m_base + it * 8 + es.rsel;
           if (m >= M) continue;
-          const float4 a = es.get(it);
+          const float4 a = es.get(it), xv = xr[sl & 1][it], g = gr[sl & 1][it];
           *reinterpret_cast<float4*>(dx + m * ld_dx + c0) =
-              make_float4(gr[it].x + rr[it] * a.x - xr[it].x * kap[it], gr[it].y + rr[it] * a.y - xr[it].y * kap[it],
-                          gr[it].z + rr[it] * a.z - xr[it].z * kap[it], gr[it].w + rr[it] * a.w - xr[it].w * kap[it]);
+              make_float4(g.x + rr[it] * a.x - xv.x * kap[it], g.y + rr[it] * a.y - xv.y * kap[it],
+                          g.z + rr[it] * a.z - xv.z * kap[it], g.w + rr[it] * a.w - xv.w * kap[it]);
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar.acc2_empty(0));
-      // the dot exchange buffer is rewritten one tile later, after this pair of warps has
-      // passed another acc2_full wait: no extra synchronisation needed
     }
   }
 
@@ -991,7 +1028,7 @@ extern "C" PETB200_API int petb200_mlp_bwd(const float* x, int64_t ldx, const fl
   if (n_rows == 0) return PETB200_OK;
   const int tiles = (int)ceil_div(n_rows, BM);
   cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-  mlp_bwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, NUM_THREADS, BWD_SMEM, stream>>>(
+  mlp_bwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, BWD_NUM_THREADS, BWD_SMEM, stream>>>(
       x, ldx, d_y, ld_dy, reinterpret_cast<const uint8_t*>(image_bwd), b_in, n_rows, d_ff, d_x, ld_dx);
   return check_launch("mlp_bwd");
 }
