@@ -204,6 +204,20 @@ class KernelTimer:
             byt = 4.0 * m * (k + out_cols + aux_cols + extra)  # algorithmic fp32 bytes
         elif name in ("combine_ln_fwd",):
             work = float(args[4])  # edges
+        elif name in ("mlp_fwd", "mlp_bwd"):
+            # fused feed-forward block: rows, d, d_ff -> algorithmic flops (2 GEMMs forward, 3
+            # backward incl. the recomputation) and MINIMUM bytes (x in, y out / x, dy in, dx out)
+            fwd = name == "mlp_fwd"
+            rows, d, dff = (args[5], args[6], args[7]) if fwd else (args[6], args[7], args[8])
+            work = 2.0 * rows * d * 3 * dff * (1.0 if fwd else 5.0 / 3.0)
+            byt = 4.0 * rows * d * (2 if fwd else 3)
+        elif name in ("attention_fwd", "attention_bwd"):
+            # tokens = E + N rows; fwd reads qkv (3d) writes out (d) + lse; bwd reads qkv, out, d_out
+            # and writes d_qkv
+            fwd = name == "attention_fwd"
+            n_atoms, n_edges, heads, hd = (args[3], args[4], args[5], args[6]) if fwd else (args[6], args[7], args[8], args[9])
+            d = heads * hd
+            byt = 4.0 * (n_atoms + n_edges) * ((4 * d + heads) if fwd else (8 * d + 2 * heads))
         self.records.append((name, a, b, work, byt))
         if name == "gemm":
             self.shapes.append((len(self.records) - 1,
@@ -408,7 +422,7 @@ def run_petb200(args):
               "what": "positions H2D -> GPU cell-list neighbor list -> energy+forces -> D2H"}
 
     # per-kernel roofline: instrumented extra steps (not part of the timed regions above)
-    timer = KernelTimer(["gemm", "combine_ln_fwd", "attention_fwd", "attention_bwd"])
+    timer = KernelTimer(["gemm", "combine_ln_fwd", "attention_fwd", "attention_bwd", "mlp_fwd", "mlp_bwd"])
     lib.profile_hook = timer
     for _ in range(3):
         step_resident()
@@ -450,7 +464,17 @@ def run_petb200(args):
         "achieved": scatter_gbs, "peak": hbm, "unit": "GB/s", "frac": scatter_gbs / hbm,
         "traffic": None, "peak_source": which, "avg_launch_us": c_t / c_n * 1e6,
     }
-    attn = {k: {"ms_per_step": tot[k][0] / 3 * 1e3} for k in ("attention_fwd", "attention_bwd")}
+    attn = {k: {"ms_per_step": tot[k][0] / 3 * 1e3, "launches_per_step": tot[k][2] // 3,
+                "bound": "hbm", "achieved": tot[k][3] / tot[k][0] * 1e-9, "peak": hbm, "unit": "GB/s",
+                "frac": tot[k][3] / tot[k][0] * 1e-9 / hbm, "peak_source": which}
+            for k in ("attention_fwd", "attention_bwd") if k in tot}
+    # fused feed-forward kernels (mlp_fused.cu): HBM view on the algorithmic MINIMUM bytes and the
+    # tensor view on algorithmic flops (the 2-term split issues 3x as many MMAs)
+    fused = {k: {"ms_per_step": tot[k][0] / 3 * 1e3, "launches_per_step": tot[k][2] // 3,
+                 "achieved_gbs": tot[k][3] / tot[k][0] * 1e-9, "hbm_frac": tot[k][3] / tot[k][0] * 1e-9 / hbm,
+                 "achieved_tflops": tot[k][1] / tot[k][0] * 1e-12,
+                 "tensor_frac": tot[k][1] / tot[k][0] * 1e-12 / tf_sust, "peak_source": which}
+             for k in ("mlp_fwd", "mlp_bwd") if k in tot}
 
     if world > 1:
         dist.barrier()
@@ -480,6 +504,7 @@ def run_petb200(args):
         "e2e_device_neighbor_list": md,
         "gpu_launches": launches, "clocks": clocks,
         "roofline": roofline, "edge_scatter": edge_scatter, "attention": attn,
+        "fused_feed_forward": fused,
     }
     if not args.no_cpu_baseline and world == 1:
         v, dt, n = time_oracle((2, 2, 2), 1, 1)

@@ -118,7 +118,8 @@ def stream_ptr() -> int:
 
 
 # kernels launched by each entry point (for bench.py's ``gpu_launches`` claim)
-_KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "csr_build": 6, "readout_bwd": 2, "force_scatter": 2}
+_KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "csr_build": 6, "readout_bwd": 2,
+                     "force_scatter": 2, "mlp_pack": 2}
 launch_count = 0
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
 profile_hook = None
@@ -128,7 +129,10 @@ def call(name: str, *args) -> None:
     """Invoke ``petb200_<name>`` on torch's current stream; raise on a non-zero status."""
     global launch_count
     lib = load()
-    launch_count += _KERNELS_PER_CALL.get(name, 1)
+    n_kernels = _KERNELS_PER_CALL.get(name, 1)
+    if name == "attention_bwd" and args[12] != PREC_FP32 and args[11] + 1 <= 64:
+        n_kernels = 1  # single tensor-core kernel (attention_tc.cu) instead of dQ + dKdV
+    launch_count += n_kernels
     if profile_hook is not None:
         with profile_hook(name, args):
             status = getattr(lib, "petb200_" + name)(*args, stream_ptr())
