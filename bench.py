@@ -355,6 +355,11 @@ def run_petb200(args):
         force_err_single = float((ref_out["dE_dpos"] - out["dE_dpos"]).abs().max())
         del whole, ref_out
         torch.cuda.empty_cache()
+    if sharded:
+        # the comparison above released the allocator cache on rank 0: warm it up again so the
+        # timed region does not pay cudaMalloc
+        for _ in range(2):
+            step_resident()
 
     sampler = ClockSampler(local)
     barrier()
