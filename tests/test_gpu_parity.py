@@ -42,7 +42,7 @@ def test_matches_reference_golden(case):
         assert np.abs(out["dE_dpos"].cpu().numpy() - g["ref64_dE_dpos"]).max() <= FORCE_TOL
 
 
-@pytest.mark.parametrize("case", ["water_384", "si_64", "carbon_5", "qm9_5"])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_tensor_core_split_meets_force_tolerance(case):
     """bf16x3 (tcgen05, 2-term split): forces within the north-star 1e-4 eV/A of the
     reference; single-pass bf16 is reported but only sanity-bounded."""
@@ -242,10 +242,12 @@ def test_neighbor_order_invariance():
 
 
 # ------------------------------------------------ BASELINE.json config 2: 10k-atom water
-@pytest.fixture(scope="module")
-def water_10k():
+@pytest.fixture(scope="module", params=["fp32", "bf16x3"])
+def water_10k(request):
+    """The bench configuration, on the fp32 parity path and on the tensor-core product path
+    (tcgen05 GEMMs, mma.sync attention, fused feed-forward kernels) that bench.py measures."""
     g = load_golden("water_384")
-    be = make_backend(g)
+    be = make_backend(g, precision=request.param)
     be.emit_nef = False
     box = replicate(water_384(), (3, 3, 3))
     batch = {k: v.to(DEV) for k, v in make_batch([box], 4.5).items()}
