@@ -692,6 +692,10 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
     bar.init_all();
     mbar_init(bar.acc2_empty(0), 4 * 32);   // drained by the four store warps
     mbar_init(bar.acc2_empty(1), 4 * 32);
+    for (int b = 0; b < 2; ++b) {           // every epilogue warp takes part in every chunk
+      mbar_init(bar.acc1_empty(b), NUM_EPI_WARPS * 32);
+      mbar_init(bar.a2_full(b), NUM_EPI_WARPS * 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -709,7 +713,9 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
     // ============================================================ activation producers
     const int pw = warp - FIRST_PROD_WARP;
     for (int i = 0; i < sched.count; ++i) {
+      if (lane == 0 && pw == 0) trace(3, i, 0, 0);
       mbar_wait(bar.x_empty(0), (i & 1) ^ 1);
+      if (lane == 0 && pw == 0) trace(3, i, 0, 1);
       issue_tile_copies(smem_base + BWD_X_OFF, x, ldx, sched.m0(i), M, pw, lane);
       issue_tile_copies(smem_base + BWD_X_OFF + 4 * TILE, dy, ld_dy, sched.m0(i), M, pw, lane);
       // the next tile's rows are pulled into L2 while this one is processed
@@ -722,12 +728,14 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       }
       cp_async_wait_all();
       __syncwarp();
+      if (lane == 0 && pw == 0) trace(3, i, 0, 2);
       float ss[2][8] = {};
       convert_tile<true>(smem + BWD_X_OFF, pw, lane, ss);
       store_rstd(rstd_s + (i & 1) * BM, pw, lane, ss);
       convert_tile<false>(smem + BWD_X_OFF + 4 * TILE, pw, lane, ss);
       fence_proxy_async();
       mbar_arrive(bar.x_full(0));
+      if (lane == 0 && pw == 0) trace(3, i, 0, 3);
     }
   } else if (warp == TMA_WARP) {
     // ============================================================ weight-stage producer
@@ -760,8 +768,10 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
         for (int c = 0; c < nch; ++c) {
           const int b = c & 1;
           const int n = i * nch + c;
+          trace(0, i, c, 0);
           if (n > 0) mbar_wait(bar.acc1_empty(b ^ 1), ((uint32_t)(n - 1) >> 1) & 1);
           tc_fence_after();
+          trace(0, i, c, 1);
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh) {   // ug = X . W_in[chunk]^T
             mbar_wait(bar.w_full(ring.stage), ring.phase);
@@ -773,7 +783,9 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
             tc_commit(bar.w_empty(ring.stage));
             ring.advance(BWD_RING_A);
           }
+          trace(0, i, c, 6);
           mbar_wait(bar.w_full(ring.stage), ring.phase);   // ds = dY . W_out[:, chunk]
+          trace(0, i, c, 2);
           {
             const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
@@ -787,6 +799,7 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
           }
           tc_commit(bar.acc1_full(b));
           if (c == nch - 1) tc_commit(bar.x_empty(0));
+          trace(0, i, c, 7);
         }
       }
     }
@@ -806,9 +819,11 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
           mbar_wait(bar.w_full(BWD_RING_A + ring.stage), ring.phase);
           const int s_lo = ring.stage;
           ring.advance(BWD_RING_B);
+          trace(0, i, c, 3);
           mbar_wait(bar.a2_full(b), u & 1);
           if (c == 0) mbar_wait(bar.acc2_empty(i & 1), ((i >> 1) & 1) ^ 1);
           tc_fence_after();
+          trace(0, i, c, 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t a_hi = tmem_base + BWD_A2_COL + b * 64 + kk * 8;
@@ -818,63 +833,61 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
           tc_commit(bar.a2_empty(b));
           tc_commit(bar.w_empty(BWD_RING_A + s_hi));
           tc_commit(bar.w_empty(BWD_RING_A + s_lo));
+          trace(0, i, c, 8);
         }
         tc_commit(bar.acc2_full(i & 1));
       }
     }
   } else if (warp < NUM_EPI_WARPS) {
     // ============================================================ swiglu' epilogues
-    // alternate chunks per group of four warps; a thread owns one row and walks the two
-    // 16-unit halves of the chunk in turn
+    // all eight warps work on every chunk: group `half` (four warps = 128 rows) takes the
+    // 16-unit half `half` of the chunk, so the single acc1 buffer is released as soon as each
+    // thread has pulled its 48 accumulator columns into registers
     const int half = warp >> 2;
     for (int i = 0; i < sched.count; ++i) {
       mbar_wait(bar.x_full(0), i & 1);
       const float rs = rstd_s[(i & 1) * BM + quarter * 32 + lane];
-      for (int c = half; c < nch; c += 2) {
-        const int b = half;
+      for (int c = 0; c < nch; ++c) {
+        const int b = c & 1;
         const uint32_t u = (uint32_t)(i * nch + c) >> 1;
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 0);
         mbar_wait(bar.acc1_full(b), u & 1);
         tc_fence_after();
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 1);
+        float v[32], ds[16];
+        tmem_ld32(tmem_base + lane_base + half * 32, v);
+        tmem_ld16(tmem_base + lane_base + 64 + half * 16, ds);
+        tc_fence_before();
+        mbar_arrive(bar.acc1_empty(b));
+        const float* bv = bias_s + c * CH + half * 16;
+        // K order of GEMM2: [d_v 0..15 | d_g 0..15] of this half
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float v[32], ds[16];
-          tmem_ld32(tmem_base + lane_base + hf * 32, v);
-          tmem_ld16(tmem_base + lane_base + 64 + hf * 16, ds);
-          if (hf == 1) {
-            tc_fence_before();
-            mbar_arrive(bar.acc1_empty(b));
-          }
-          const float* bv = bias_s + c * CH + hf * 16;
-          // K order of GEMM2: [d_v 0..15 | d_g 0..15] of this half
-          uint32_t hi[16], lo[16];
+        for (int q = 0; q < 8; ++q) {
+          float dv[2], dg[2];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float dv[2], dg[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int k = 2 * q + e;
-              const float val = rs * v[k] + bv[k];
-              const float sg = fsigmoid(rs * v[16 + k] + bv[F + k]);
-              dv[e] = ds[k] * sg;
-              dg[e] = ds[k] * val * sg * (1.0f - sg);
-            }
-            hi[q] = pack_bf16(dv[0], dv[1]);
-            lo[q] = pack_bf16(dv[0] - __uint_as_float(hi[q] << 16), dv[1] - __uint_as_float(hi[q] & 0xffff0000u));
-            hi[8 + q] = pack_bf16(dg[0], dg[1]);
-            lo[8 + q] = pack_bf16(dg[0] - __uint_as_float(hi[8 + q] << 16),
-                                  dg[1] - __uint_as_float(hi[8 + q] & 0xffff0000u));
+          for (int e = 0; e < 2; ++e) {
+            const int k = 2 * q + e;
+            const float val = rs * v[k] + bv[k];
+            const float sg = fsigmoid(rs * v[16 + k] + bv[F + k]);
+            dv[e] = ds[k] * sg;
+            dg[e] = ds[k] * val * sg * (1.0f - sg);
           }
-          if (hf == 0) {
-            mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
-            tc_fence_after();
-          }
-          const uint32_t a2 = tmem_base + lane_base + BWD_A2_COL + b * 64 + hf * 16;
-          tmem_st16(a2, hi);
-          tmem_st16(a2 + 32, lo);
+          hi[q] = pack_bf16(dv[0], dv[1]);
+          lo[q] = pack_bf16(dv[0] - __uint_as_float(hi[q] << 16), dv[1] - __uint_as_float(hi[q] & 0xffff0000u));
+          hi[8 + q] = pack_bf16(dg[0], dg[1]);
+          lo[8 + q] = pack_bf16(dg[0] - __uint_as_float(hi[8 + q] << 16),
+                                dg[1] - __uint_as_float(hi[8 + q] & 0xffff0000u));
         }
+        mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a2 = tmem_base + lane_base + BWD_A2_COL + b * 64 + half * 16;
+        tmem_st16(a2, hi);
+        tmem_st16(a2 + 32, lo);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar.a2_full(b));
+        if (lane == 0 && quarter == 0) trace(1 + half, i, c, 4);
       }
     }
   } else if (warp >= BWD_STORE_WARP0 && warp < BWD_STORE_WARP0 + 4) {
@@ -905,8 +918,10 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
         }
       };
       fetch_x(0);
+      if (lane == 0 && sw == 0) trace(1, i, 15, 0);
       mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
       tc_fence_after();
+      if (lane == 0 && sw == 0) trace(1, i, 15, 1);
       float dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl) {
@@ -951,6 +966,7 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
                           g.z + rr[it] * a.z - xv.z * kap[it], g.w + rr[it] * a.w - xv.w * kap[it]);
         }
       }
+      if (lane == 0 && sw == 0) trace(1, i, 15, 2);
     }
   }
 

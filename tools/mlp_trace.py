@@ -28,13 +28,17 @@ buf = torch.zeros(4 * 4 * 16 * 16, device=dev, dtype=torch.int64)
 fn = h.petb200_debug_mlp_trace
 fn.argtypes = [ctypes.c_void_p]
 fn(buf.data_ptr())
-call("mlp_fwd", ptr(x), d, ptr(img[0]), ptr(b_in), ptr(b_out), M, d, F, ptr(y), d)
+if len(sys.argv) > 1 and sys.argv[1] == "bwd":
+    dy = torch.randn(M, d, device=dev)
+    call("mlp_bwd", ptr(x), d, ptr(dy), d, ptr(img[1]), ptr(b_in), M, d, F, ptr(y), d)
+else:
+    call("mlp_fwd", ptr(x), d, ptr(img[0]), ptr(b_in), ptr(b_out), M, d, F, ptr(y), d)
 torch.cuda.synchronize()
 fn(None)
 t = buf.cpu().view(4, 4, 16, 16)
 t0 = int(t[t > 0].min())
 names = {0: ["G1 wait acc1_empty", "acc1_empty ok", "W k1 ready", "G2 wait a2_full", "a2_full ok", "W k0 ready",
-             "k0 MMAs issued", "k1 MMAs issued", "G2 MMAs issued"],
+             "k0 MMAs issued / ug issued", "k1 MMAs issued / G1 done", "G2 MMAs issued"],
          1: ["wait acc1_full", "acc1_full ok", "loaded", "computed", "A2 stored"],
          2: ["wait acc1_full", "acc1_full ok", "loaded", "computed", "A2 stored"],
          3: ["wait x_empty", "x_empty ok", "copies landed", "converted"]}
