@@ -191,38 +191,41 @@ __device__ __forceinline__ void issue_tile_copies(uint32_t dst_u32, const float*
     }
   }
 }
+// In-place conversion of 16 rows (row_base ..) of one k-chunk: fp32 landed as [hi tile row | lo
+// tile row] -> bf16 hi / lo swizzled rows.  Lane l works on row 2 jj + (l >> 4) of the batch and
+// owns k = 4 (l & 15) .. + 3.  ss[jj] accumulates this lane's partial sum of squares.
 template <bool STATS>
-__device__ __forceinline__ void convert_tile(uint8_t* dst, int pw, int lane, float (&ss)[2][8]) {
+__device__ __forceinline__ void convert_batch(uint8_t* st, int row_base, int lane, float (&ss)[8]) {
   const int quad = lane & 15, rsub = lane >> 4;
   const int chunk = quad >> 1, within = (quad & 1) * 8;
+  const uint8_t* src_tile = st + (quad < 8 ? 0 : TILE) + (quad & 7) * 16;
+  float4 x[8];
 #pragma unroll
-  for (int kc = 0; kc < 2; ++kc) {
-    uint8_t* st = dst + kc * 2 * TILE;
-    const uint8_t* src_tile = st + (quad < 8 ? 0 : TILE) + (quad & 7) * 16;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      float4 x[8];
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int r = pw * 32 + b * 16 + jj * 2 + rsub;
-        x[jj] = *reinterpret_cast<const float4*>(src_tile + r * 128);
-      }
-      __syncwarp();  // whole rows are in registers before they are overwritten
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int r = pw * 32 + b * 16 + jj * 2 + rsub;
-        if (STATS) ss[b][jj] += x[jj].x * x[jj].x + x[jj].y * x[jj].y + x[jj].z * x[jj].z + x[jj].w * x[jj].w;
-        const uint32_t h01 = pack_bf16(x[jj].x, x[jj].y), h23 = pack_bf16(x[jj].z, x[jj].w);
-        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + within);
-        *reinterpret_cast<uint2*>(st + off) = make_uint2(h01, h23);
-        const float l0 = x[jj].x - __uint_as_float(h01 << 16);
-        const float l1 = x[jj].y - __uint_as_float(h01 & 0xffff0000u);
-        const float l2 = x[jj].z - __uint_as_float(h23 << 16);
-        const float l3 = x[jj].w - __uint_as_float(h23 & 0xffff0000u);
-        *reinterpret_cast<uint2*>(st + TILE + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
-      }
-    }
+  for (int jj = 0; jj < 8; ++jj) {
+    const int r = row_base + jj * 2 + rsub;
+    x[jj] = *reinterpret_cast<const float4*>(src_tile + r * 128);
   }
+  __syncwarp();  // whole rows are in registers before they are overwritten
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int r = row_base + jj * 2 + rsub;
+    if (STATS) ss[jj] += x[jj].x * x[jj].x + x[jj].y * x[jj].y + x[jj].z * x[jj].z + x[jj].w * x[jj].w;
+    const uint32_t h01 = pack_bf16(x[jj].x, x[jj].y), h23 = pack_bf16(x[jj].z, x[jj].w);
+    const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+    *reinterpret_cast<uint2*>(st + off) = make_uint2(h01, h23);
+    const float l0 = x[jj].x - __uint_as_float(h01 << 16);
+    const float l1 = x[jj].y - __uint_as_float(h01 & 0xffff0000u);
+    const float l2 = x[jj].z - __uint_as_float(h23 << 16);
+    const float l3 = x[jj].w - __uint_as_float(h23 & 0xffff0000u);
+    *reinterpret_cast<uint2*>(st + TILE + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+  }
+}
+template <bool STATS>
+__device__ __forceinline__ void convert_tile(uint8_t* dst, int pw, int lane, float (&ss)[2][8]) {
+#pragma unroll
+  for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) convert_batch<STATS>(dst + kc * 2 * TILE, pw * 32 + b * 16, lane, ss[b]);
 }
 __device__ __forceinline__ void store_rstd(float* rstd, int pw, int lane, float (&ss)[2][8]) {
 #pragma unroll
@@ -666,20 +669,23 @@ constexpr int BWD_EPI_OFF = BWD_RING_OFF + BWD_RING * STAGE;  // 4 store warps x
 constexpr int BWD_BIAS_OFF = BWD_EPI_OFF + 4 * 32 * STAGE_LD * 4;   // b_in [2 MAX_F]
 constexpr int BWD_RSTD_OFF = BWD_BIAS_OFF + 2 * MAX_F * 4;    // rstd [2][BM]
 constexpr int BWD_BAR_OFF = BWD_RSTD_OFF + 2 * BM * 4;
-constexpr int BWD_SMEM = BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING) + 16 + 1024;
+constexpr int BWD_SMEM = BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING) + 8 + 16 + 1024;
 // TMEM columns: acc1 at 0 (ug: 0..63, ds: 64..95; single buffer) ; A2[b] hi at 128 + 64 b, lo 32
 // further ; acc2[t] at 256 + 128 t
 constexpr int BWD_A2_COL = 128, BWD_ACC2_COL = 256;
 
 __global__ void __launch_bounds__(BWD_NUM_THREADS, 1)
-mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t ld_dy,
+mlp_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+               const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t ld_dy,
                const uint8_t* __restrict__ image, const float* __restrict__ b_in, int64_t M, int F,
                float* __restrict__ dx, int64_t ld_dx) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const Barriers bar{smem_base + BWD_BAR_OFF, BWD_RING};
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING));
+  const uint32_t landed_bar = bar.at(16 + 2 * BWD_RING);   // TMA of the X / dY tile has landed
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem + BWD_BAR_OFF + 8 * (16 + 2 * BWD_RING) + 8);
   float* bias_s = reinterpret_cast<float*>(smem + BWD_BIAS_OFF);
   float* rstd_s = reinterpret_cast<float*>(smem + BWD_RSTD_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -696,6 +702,9 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       mbar_init(bar.acc1_empty(b), NUM_EPI_WARPS * 32);
       mbar_init(bar.a2_full(b), NUM_EPI_WARPS * 32);
     }
+    // X rows are converted by the producer warps, dY rows by the (then idle) epilogue warps
+    mbar_init(bar.x_full(0), NUM_PROD_THREADS + NUM_EPI_WARPS * 32);
+    mbar_init(landed_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -716,8 +725,18 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       if (lane == 0 && pw == 0) trace(3, i, 0, 0);
       mbar_wait(bar.x_empty(0), (i & 1) ^ 1);
       if (lane == 0 && pw == 0) trace(3, i, 0, 1);
-      issue_tile_copies(smem_base + BWD_X_OFF, x, ldx, sched.m0(i), M, pw, lane);
-      issue_tile_copies(smem_base + BWD_X_OFF + 4 * TILE, dy, ld_dy, sched.m0(i), M, pw, lane);
+      // eight TMA boxes of [128 rows x 32 floats] land the fp32 rows as [hi tile row | lo tile
+      // row] per k-chunk (rows beyond M arrive as zeros); one thread issues them
+      if (pw == 0 && elect_one()) {
+        mbar_expect_tx(landed_bar, 8 * TILE);
+        const int m0 = (int)sched.m0(i);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tma_load_2d(smem_base + BWD_X_OFF + q * TILE, &map_x, 32 * q, m0, landed_bar);
+          tma_load_2d(smem_base + BWD_X_OFF + (4 + q) * TILE, &map_dy, 32 * q, m0, landed_bar);
+        }
+      }
+      __syncwarp();
       // the next tile's rows are pulled into L2 while this one is processed
       if (i + 1 < sched.count) {
         const int64_t m = sched.m0(i + 1) + pw * 32 + lane;
@@ -726,13 +745,11 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
           prefetch_l2_bulk(dy + m * ld_dy, D * 4);
         }
       }
-      cp_async_wait_all();
-      __syncwarp();
+      mbar_wait(landed_bar, i & 1);
       if (lane == 0 && pw == 0) trace(3, i, 0, 2);
       float ss[2][8] = {};
       convert_tile<true>(smem + BWD_X_OFF, pw, lane, ss);
       store_rstd(rstd_s + (i & 1) * BM, pw, lane, ss);
-      convert_tile<false>(smem + BWD_X_OFF + 4 * TILE, pw, lane, ss);
       fence_proxy_async();
       mbar_arrive(bar.x_full(0));
       if (lane == 0 && pw == 0) trace(3, i, 0, 3);
@@ -845,6 +862,14 @@ mlp_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
     // thread has pulled its 48 accumulator columns into registers
     const int half = warp >> 2;
     for (int i = 0; i < sched.count; ++i) {
+      {  // dY rows 16 warp .. + 15 -> bf16 hi / lo operand tiles (both k-chunks)
+        mbar_wait(landed_bar, i & 1);
+        float unused[8];
+        convert_batch<false>(smem + BWD_X_OFF + 4 * TILE, warp * 16, lane, unused);
+        convert_batch<false>(smem + BWD_X_OFF + 6 * TILE, warp * 16, lane, unused);
+        fence_proxy_async();
+        mbar_arrive(bar.x_full(0));
+      }
       mbar_wait(bar.x_full(0), i & 1);
       const float rs = rstd_s[(i & 1) * BM + quarter * 32 + lane];
       for (int c = 0; c < nch; ++c) {
@@ -1043,8 +1068,13 @@ extern "C" PETB200_API int petb200_mlp_bwd(const float* x, int64_t ldx, const fl
                   "mlp_bwd: leading dimensions must be multiples of 4");
   if (n_rows == 0) return PETB200_OK;
   const int tiles = (int)ceil_div(n_rows, BM);
+  CUtensorMap map_x, map_dy;
+  if (make_tma_map_f32(&map_x, x, n_rows, d, ldx, 32, BM) || make_tma_map_f32(&map_dy, d_y, n_rows, d, ld_dy, 32, BM)) {
+    set_error("mlp_bwd: cuTensorMapEncodeTiled failed (x / d_y must be 16-byte aligned)");
+    return PETB200_ERR_CUDA;
+  }
   cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   mlp_bwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, BWD_NUM_THREADS, BWD_SMEM, stream>>>(
-      x, ldx, d_y, ld_dy, reinterpret_cast<const uint8_t*>(image_bwd), b_in, n_rows, d_ff, d_x, ld_dx);
+      map_x, map_dy, x, ldx, d_y, ld_dy, reinterpret_cast<const uint8_t*>(image_bwd), b_in, n_rows, d_ff, d_x, ld_dx);
   return check_launch("mlp_bwd");
 }

@@ -1,6 +1,7 @@
 // tcgen05 / mbarrier / cp.async PTX wrappers and UMMA descriptors shared by the tensor-core
 // kernels of libpetb200 (gemm_tc.cu, mlp_fused.cu).  sm_100a only.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -151,6 +152,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box (c0.., c1..) of the tensor map ->
+// dense [box rows][box cols] block at `dst`; out-of-range rows arrive as zeros; completion is
+// signalled on the mbarrier as box bytes of transaction count
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// host: tensor map of a row-major fp32 matrix [rows, cols] with leading dimension ld (floats)
+inline int make_tma_map_f32(CUtensorMap* map, const float* base, int64_t rows, int cols, int64_t ld,
+                            int box_cols, int box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult rc = cuTensorMapEncodeTiled(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? 0 : (int)rc;
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column = two
