@@ -117,7 +117,8 @@ struct Schedule {
 };
 
 template <int EPI, int NPROD /*3 = bf16x3, 1 = bf16*/, bool BSTAT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(loaded_bar(s), NUM_PROD_THREADS);
+      // one expect_tx arrival for the TMA boxes of A (+ the cp.async arrivals of streamed W)
+      mbar_init(loaded_bar(s), BSTAT ? 1 : NUM_PROD_THREADS + 1);
       mbar_init(full_bar(s), NUM_PROD_THREADS);
       mbar_init(empty_bar(s), 1);
     }
@@ -210,13 +212,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
         const int k0 = (q % num_k) * BK;
         mbar_wait(empty_bar(load_ring.stage), load_ring.phase ^ 1);
         const uint32_t st = ring_u32 + (uint32_t)load_ring.stage * stage_bytes;
-#pragma unroll
-        for (int i = 0; i < 2048 / NUM_PROD_THREADS; ++i) {
-          const int idx = t + NUM_PROD_THREADS * i, row = idx >> 4, piece = idx & 15;
-          const int64_t m = m0 + row;
-          const bool ok = m < g.M;
-          const float* src = g.A + (ok ? m : 0) * g.lda + k0 + 4 * piece;
-          cp_async16(st + (piece >> 3) * TILE_BYTES + row * 128 + (piece & 7) * 16, src, ok ? 16u : 0u);
+        // the fp32 A chunk arrives as two TMA boxes of [128 rows x 32 floats] (rows beyond M as
+        // zeros): floats 0..31 of a row into the bytes of its hi-tile row, 32..63 into the lo-tile row
+        if (t == 0) {
+          mbar_expect_tx(loaded_bar(load_ring.stage), 2 * TILE_BYTES);
+          tma_load_2d(st, &map_a, k0, (int)m0, loaded_bar(load_ring.stage));
+          tma_load_2d(st + TILE_BYTES, &map_a, k0 + 32, (int)m0, loaded_bar(load_ring.stage));
         }
         if (!BSTAT) {
 #pragma unroll
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmArgs g) {
                          wrow + (size_t)g.K * 2 + (size_t)k0 * 2 + c * 16, 16u);
           }
         }
-        cp_async_arrive(loaded_bar(load_ring.stage));
+        if (!BSTAT) cp_async_arrive(loaded_bar(load_ring.stage));
         load_ring.advance(num_stages);
       }
       if (q >= depth) {
@@ -526,8 +527,13 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, int64_t rows, int
 template <int EPI, int NPROD, bool BSTAT>
 int launch_one(const GemmArgs& g, int grid, cudaStream_t stream) {
   auto kern = gemm_tc_kernel<EPI, NPROD, BSTAT>;
+  CUtensorMap map_a;
+  if (make_tma_map_f32(&map_a, g.A, g.M, g.K, g.lda, 32, BM)) {
+    set_error("gemm: cuTensorMapEncodeTiled failed for A (pointer / leading dimension must be 16-byte aligned)");
+    return PETB200_ERR_CUDA;
+  }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(map_a, g);
   return check_launch("gemm_tc");
 }
 
@@ -553,7 +559,7 @@ int launch_epi(const GemmArgs& g, int precision, cudaStream_t stream) {
 }  // namespace
 
 bool gemm_tc_supports(const GemmArgs& g) {
-  return g.N % BN == 0 && g.K % BK == 0 && g.M < (1ll << 31) * 100;
+  return g.N % BN == 0 && g.K % BK == 0 && g.M < (1ll << 31);
 }
 
 int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream) {
