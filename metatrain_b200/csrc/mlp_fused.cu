@@ -735,16 +735,18 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           tma_load_2d(smem_base + BWD_X_OFF + q * TILE, &map_x, 32 * q, m0, landed_bar);
           tma_load_2d(smem_base + BWD_X_OFF + (4 + q) * TILE, &map_dy, 32 * q, m0, landed_bar);
         }
-      }
-      __syncwarp();
-      // the next tile's rows are pulled into L2 while this one is processed
-      if (i + 1 < sched.count) {
-        const int64_t m = sched.m0(i + 1) + pw * 32 + lane;
-        if (m < M) {
-          prefetch_l2_bulk(x + m * ldx, D * 4);
-          prefetch_l2_bulk(dy + m * ld_dy, D * 4);
+        // the next tile's boxes are pulled into L2 while this one is processed: all CTAs reach
+        // their tile boundary together, and a 19 MB burst straight from DRAM would cost ~3 us
+        if (i + 1 < sched.count) {
+          const int m1 = (int)sched.m0(i + 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            tma_prefetch_2d(&map_x, 32 * q, m1);
+            tma_prefetch_2d(&map_dy, 32 * q, m1);
+          }
         }
       }
+      __syncwarp();
       mbar_wait(landed_bar, i & 1);
       if (lane == 0 && pw == 0) trace(3, i, 0, 2);
       float ss[2][8] = {};

@@ -162,6 +162,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
           "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// L2 prefetch of the same box (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 // host: tensor map of a row-major fp32 matrix [rows, cols] with leading dimension ld (floats)
 inline int make_tma_map_f32(CUtensorMap* map, const float* base, int64_t rows, int cols, int64_t ld,
                             int box_cols, int box_rows) {
