@@ -426,6 +426,38 @@ def run_petb200(args):
               "h2d_bytes_per_step": host["positions"].numel() * 4, "d2h_bytes_per_step": d2h,
               "what": "positions H2D -> GPU cell-list neighbor list -> energy+forces -> D2H"}
 
+        # the same with a Verlet (skin) list: thermal-size displacements every step, the list is
+        # rebuilt only when an atom has moved more than skin / 2
+        from metatrain_b200.neighbors_gpu import VerletNeighborList
+        vl = VerletNeighborList(CUTOFF, skin=0.5, periodic=True)
+        gen = torch.Generator().manual_seed(0)
+        base_pos = host["positions"].clone()
+        drift = torch.zeros_like(base_pos).pin_memory()
+
+        def step_md_verlet():
+            drift.add_(0.01 * torch.randn(base_pos.shape, generator=gen))
+            pos_d = (base_pos + drift).pin_memory().to(dev, non_blocking=True)
+            i, j, sft = vl.update(pos_d, resident["cells"][0])
+            o = evaluate(be, pos_d, i, j, resident["species"], resident["cells"], sft,
+                         resident["system_indices"], target=TARGET)
+            e_host.copy_(o["energies"], non_blocking=True)
+            f_host.copy_(o["dE_dpos"], non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            step_md_verlet()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_md_verlet()
+        barrier()
+        mdv_sec = time.perf_counter() - t0
+        md["verlet"] = {"value": world * n_atoms * args.steps / mdv_sec, "unit": "atom-steps/s",
+                        "ms_per_step": mdv_sec / args.steps * 1e3, "skin_A": 0.5,
+                        "list_builds": vl.n_builds, "list_reuses": vl.n_reuses,
+                        "what": "random-walk positions (0.01 A per step) H2D -> skin list reused while "
+                                "max displacement < skin/2 -> energy+forces -> D2H"}
+
     # per-kernel roofline: instrumented extra steps (not part of the timed regions above)
     timer = KernelTimer(["gemm", "combine_ln_fwd", "attention_fwd", "attention_bwd", "mlp_fwd", "mlp_bwd"])
     lib.profile_hook = timer

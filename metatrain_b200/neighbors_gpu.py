@@ -59,3 +59,43 @@ def neighbor_list_gpu(positions: Tensor, cell: Tensor, periodic: bool, cutoff: f
     call("nl_fill", n, cell_c, origin_c, int(periodic), float(cutoff), ptr(workspace), ws_bytes,
          ptr(offsets), ptr(centers), ptr(neighbors), ptr(shifts))
     return centers, neighbors, shifts
+
+
+class VerletNeighborList:
+    """Skin-based reuse of the device neighbor list across MD steps (a Verlet list).
+
+    The list is built for ``cutoff + skin`` and handed out unchanged while no atom has moved more
+    than ``skin / 2`` since the build (and the cell is unchanged) — then no pair inside the
+    model cutoff can be missing.  The backend treats such a list like the reference treats a
+    non-strict neighbor list: pairs beyond the model cutoff are dropped in ``preprocess``
+    (``src/metatrain/pet/modules/structures.py:265-272``; here ``petb200_nl_filter_count``).
+    One 4-byte device->host read per step decides whether to rebuild.
+    """
+
+    def __init__(self, cutoff: float, skin: float = 0.5, periodic: bool = True):
+        if skin < 0:
+            raise ValueError("VerletNeighborList: skin must be non-negative")
+        self.cutoff, self.skin, self.periodic = float(cutoff), float(skin), bool(periodic)
+        self._ref_pos = None
+        self._ref_cell = None
+        self._lists = None
+        self.n_builds = 0
+        self.n_reuses = 0
+
+    def update(self, positions: Tensor, cell: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """``(centers, neighbors, cell_shifts)`` valid for ``positions`` (non-strict: may contain
+        pairs up to ``cutoff + skin``)."""
+        pos = positions.detach()
+        stale = (self._lists is None or self._ref_pos.shape != pos.shape
+                 or not torch.equal(self._ref_cell, cell.detach()))
+        if not stale:
+            moved = float((pos - self._ref_pos).square().sum(dim=1).max().sqrt())
+            stale = moved > 0.5 * self.skin
+        if stale:
+            self._lists = neighbor_list_gpu(pos, cell, self.periodic, self.cutoff + self.skin)
+            self._ref_pos = pos.clone()
+            self._ref_cell = cell.detach().clone()
+            self.n_builds += 1
+        else:
+            self.n_reuses += 1
+        return self._lists

@@ -227,6 +227,32 @@ def test_gpu_neighbor_list_end_to_end_10k(water_10k):
     assert (out2["dE_dpos"] - out["dE_dpos"]).abs().max() <= 2e-5
 
 
+def test_verlet_list_reuse_matches_fresh_lists():
+    """MD-style loop: the skin list is reused while atoms move < skin/2 and gives the energies and
+    forces of a freshly built exact list at every step (the backend drops the extra pairs)."""
+    from metatrain_b200.neighbors_gpu import VerletNeighborList, neighbor_list_gpu
+    g = load_golden("water_384")
+    be = make_backend(g, precision="bf16x3")
+    be.emit_nef = False
+    box = water_384()
+    cell = torch.tensor(box["cell"], dtype=torch.float32, device=DEV)
+    pos = torch.tensor(box["positions"], dtype=torch.float32, device=DEV)
+    z = torch.tensor(box["Z"], device=DEV)
+    sysidx = torch.zeros(len(z), dtype=torch.int64, device=DEV)
+    cutoff = float(g["hypers"]["cutoff"])
+    vl = VerletNeighborList(cutoff, skin=0.6, periodic=True)
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    for step in range(6):
+        i, j, s = vl.update(pos, cell)
+        out = evaluate(be, pos, i, j, z, cell[None], s, sysidx, target=g["target"])
+        fi, fj, fs = neighbor_list_gpu(pos, cell, True, cutoff)
+        ref = evaluate(be, pos, fi, fj, z, cell[None], fs, sysidx, target=g["target"])
+        assert abs(float(out["energies"]) - float(ref["energies"])) <= 2e-5 * abs(float(ref["energies"]))
+        assert (out["dE_dpos"] - ref["dE_dpos"]).abs().max() <= 2e-5
+        pos = pos + 0.04 * torch.randn(pos.shape, generator=gen).to(DEV)
+    assert vl.n_builds >= 1 and vl.n_reuses >= 2 and vl.n_builds + vl.n_reuses == 6
+
+
 def test_neighbor_order_invariance():
     """Shuffling the neighbor list changes nothing but fp summation order."""
     g = load_golden("si_64")
