@@ -199,7 +199,7 @@ class KernelTimer:
             work = 2.0 * m * n * k
             epi = args[16]
             out_cols = n // 2 if epi == 2 else (2 * n if epi == 4 else n)
-            aux_cols = {1: n, 2: n, 3: n, 4: 2 * n}.get(epi, 0) if (args[13] or args[14]) else 0
+            aux_cols = {1: n, 2: n, 3: n, 4: 2 * n, 5: n}.get(epi, 0) if (args[13] or args[14]) else 0
             extra = (n if args[11] else 0) + (n if args[17] else 0)
             byt = 4.0 * m * (k + out_cols + aux_cols + extra)  # algorithmic fp32 bytes
         elif name in ("combine_ln_fwd",):

@@ -54,7 +54,10 @@ enum {
   PETB200_EPI_SILU = 1,       /* pre = rs*acc + bias -> aux_out ; C = silu(pre) (+res)  */
   PETB200_EPI_SWIGLU = 2,     /* [u|g] = rs*acc + bias -> aux_out ; C = u * sigmoid(g)  */
   PETB200_EPI_MUL_DSILU = 3,  /* C = acc * silu'(aux_in)          (dgrad through SiLU)  */
-  PETB200_EPI_SWIGLU_BWD = 4  /* C = [acc*sig(g) | acc*u*sig'(g)] (dgrad through SwiGLU)*/
+  PETB200_EPI_SWIGLU_BWD = 4, /* C = [acc*sig(g) | acc*u*sig'(g)] (dgrad through SwiGLU)*/
+  PETB200_EPI_RMS_BWD = 5     /* C = residual + rs*acc - x*rs^3*(acc.x)/N : dgrad through the
+                                 RMSNorm in front of the Linear (x = aux_in [M,N], rs = row_scale;
+                                 N = 128; tensor-core precisions only)                         */
 };
 
 /* GEMM arithmetic */

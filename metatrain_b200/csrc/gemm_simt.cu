@@ -227,6 +227,10 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     case PETB200_EPI_SWIGLU_BWD:
       gemm_simt_kernel<PETB200_EPI_SWIGLU_BWD><<<grid, block, 0, stream>>>(g);
       break;
+    case PETB200_EPI_RMS_BWD:
+      set_error("gemm: the RMSNorm-backward epilogue is built for the tensor-core precisions only "
+                "(use petb200_rms_bwd after a plain fp32 gemm)");
+      return PETB200_ERR_UNSUPPORTED;
     default:
       set_error("gemm: unknown epilogue %d", g.epilogue);
       return PETB200_ERR_INVALID_ARGUMENT;

@@ -49,7 +49,8 @@ constexpr int EPI_COLS = 16;   // accumulator columns per tcgen05.ld in the epil
 constexpr int STAGE_LD = 20;   // floats per row of the epilogue transpose tile
 constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * STAGE_LD * 4;
 constexpr size_t SMEM_BYTES =
-    (size_t)OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+    (size_t)OPERAND_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES +
+    2 * 2 * BM * 4 /*row-dot exchange of the RMSNorm-backward epilogue*/;
 
 // Tile column -> weight row.  Plain layouts: identity.  SwiGLU forward: within each
 // 64-column half of the tile, columns [0,32) are "value" columns and [32,64) the matching
@@ -132,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
   volatile uint32_t* tmem_slot =
       reinterpret_cast<volatile uint32_t*>(smem_gen + OPERAND_BYTES + 8 * (3 * MAX_STAGES + 4));
   float* stage_all = reinterpret_cast<float*>(smem_gen + OPERAND_BYTES + 256);
+  float* dots_all = stage_all + EPI_STAGE_BYTES / 4;  // [item parity][half][BM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = g.K / BK;
@@ -351,7 +353,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
       // Global operands of the whole item are requested BEFORE waiting for the MMA, so
       // their latency hides behind the main loop of this item.
       float4 pre[NCH][4];
-      if (EPI == PETB200_EPI_NONE || EPI == PETB200_EPI_SILU || EPI == PETB200_EPI_MUL_DSILU) {
+      if (EPI == PETB200_EPI_NONE || EPI == PETB200_EPI_SILU || EPI == PETB200_EPI_MUL_DSILU ||
+          EPI == PETB200_EPI_RMS_BWD) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -360,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
             const int c0 = n0 + 64 * half + EPI_COLS * ch + 4 * c4;
             pre[ch][it] = zero4;
             if (!ok[it]) continue;
-            if (EPI == PETB200_EPI_MUL_DSILU) {
+            if (EPI == PETB200_EPI_MUL_DSILU || EPI == PETB200_EPI_RMS_BWD) {
               pre[ch][it] = ld4(g.aux_in + m * g.ld_aux + c0);
             } else if (pre_src) {
               pre[ch][it] = ld4(pre_src + m * pre_ld + c0);
@@ -414,6 +417,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
             *reinterpret_cast<float4*>(g.C + m * g.ldc + cu) =
                 make_float4(u[it].x * fsigmoid(gt.x), u[it].y * fsigmoid(gt.y),
                             u[it].z * fsigmoid(gt.z), u[it].w * fsigmoid(gt.w));
+          }
+        }
+      } else if (EPI == PETB200_EPI_RMS_BWD) {
+        // C = residual + rs * d - x * rs^3 * (d . x) / N with d = the accumulator row (gradient
+        // w.r.t. the normalised row), x = aux_in, rs = row_scale; N = BN (one column chunk).
+        // Pass 1: row dots (this warp's 64 columns, then exchanged with the partner warp of the
+        // same lane quarter); pass 2: re-read the accumulator and form the output.
+        float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          stage_chunk(64 * half + EPI_COLS * ch);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const float4 v = staged(it), x4 = pre[ch][it];
+            dot[it] += v.x * x4.x + v.y * x4.y + v.z * x4.z + v.w * x4.w;
+          }
+        }
+        float* dots = dots_all + (j & 1) * 2 * BM;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 1);
+          dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 2);
+          if (c4 == 0) dots[half * BM + quarter * 32 + it * 8 + rsel] = dot[it];
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        float kap[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = quarter * 32 + it * 8 + rsel;
+          kap[it] = rs[it] * rs[it] * rs[it] * (dots[r] + dots[BM + r]) * (1.0f / BN);
+        }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int tile_col = 64 * half + EPI_COLS * ch;
+          const int c0 = n0 + tile_col + 4 * c4;
+          stage_chunk(tile_col);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (!ok[it]) continue;
+            const int64_t m = m_base + it * 8 + rsel;
+            const float4 v = staged(it), x4 = pre[ch][it];
+            float4 o = make_float4(rs[it] * v.x - x4.x * kap[it], rs[it] * v.y - x4.y * kap[it],
+                                   rs[it] * v.z - x4.z * kap[it], rs[it] * v.w - x4.w * kap[it]);
+            if (g.residual) {
+              const float4 r4 = ld4(g.residual + m * g.ldr + c0);
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            }
+            *reinterpret_cast<float4*>(g.C + m * g.ldc + c0) = o;
           }
         }
       } else if (EPI == PETB200_EPI_SWIGLU_BWD) {
@@ -570,6 +621,12 @@ int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream) {
     case PETB200_EPI_SWIGLU: return launch_epi<PETB200_EPI_SWIGLU>(g, precision, stream);
     case PETB200_EPI_MUL_DSILU: return launch_epi<PETB200_EPI_MUL_DSILU>(g, precision, stream);
     case PETB200_EPI_SWIGLU_BWD: return launch_epi<PETB200_EPI_SWIGLU_BWD>(g, precision, stream);
+    case PETB200_EPI_RMS_BWD:
+      if (g.N != BN || !g.aux_in || !g.row_scale || g.accumulate) {
+        set_error("gemm: the RMSNorm-backward epilogue needs N = %d, aux_in (x) and row_scale (rstd)", BN);
+        return PETB200_ERR_INVALID_ARGUMENT;
+      }
+      return launch_epi<PETB200_EPI_RMS_BWD>(g, precision, stream);
     default:
       set_error("gemm: unknown epilogue %d", g.epilogue);
       return PETB200_ERR_INVALID_ARGUMENT;

@@ -17,8 +17,8 @@ from typing import Dict, List, Optional
 import torch
 
 from . import lib
-from .lib import (EPI_MUL_DSILU, EPI_NONE, EPI_SILU, EPI_SWIGLU, EPI_SWIGLU_BWD, PREC_FP32,
-                  call, ptr)
+from .lib import (EPI_MUL_DSILU, EPI_NONE, EPI_RMS_BWD, EPI_SILU, EPI_SWIGLU, EPI_SWIGLU_BWD,
+                  PREC_FP32, call, ptr)
 
 Tensor = torch.Tensor
 
@@ -469,13 +469,21 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
             call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o),
                  ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row, prec,
                  ptr(d_qkv), ptr(d_fc), ptr(dsum))
-            d_xh1 = d_o  # reuse
-            gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec, pack=pw)
-            del d_qkv
             d_t_new = d_xh  # reuse
-            _rms_bwd(d_xh1[:E], K["X"][:E], K["rstd1"][:E], d_tp, d_t_new)
             d_c = d_yc  # reuse
-            _rms_bwd(d_xh1[E:], K["X"][E:], K["rstd1"][E:], None, d_c)
+            if prec != PREC_FP32 and d == 128:
+                # dgrad through the QKV projection and the RMSNorm in front of it in one kernel
+                # (RMSNorm backward in the GEMM epilogue), edge rows and centre rows
+                gemm(d_qkv[:E], T["w_qkv_t"], d_t_new, epilogue=EPI_RMS_BWD, aux_in=K["X"][:E],
+                     row_scale=K["rstd1"][:E], residual=d_tp, precision=prec, pack=pw)
+                gemm(d_qkv[E:], T["w_qkv_t"], d_c, epilogue=EPI_RMS_BWD, aux_in=K["X"][E:],
+                     row_scale=K["rstd1"][E:], precision=prec, pack=pw)
+            else:
+                d_xh1 = d_o  # reuse
+                gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec, pack=pw)
+                _rms_bwd(d_xh1[:E], K["X"][:E], K["rstd1"][:E], d_tp, d_t_new)
+                _rms_bwd(d_xh1[E:], K["X"][E:], K["rstd1"][E:], None, d_c)
+            del d_qkv
             if l > 0 or k > 0:
                 d_h_new = _empty((N, dn), ref)
                 gemm(d_c, T["w_con_t"], d_h_new, residual=d_h1, precision=prec, pack=pw)

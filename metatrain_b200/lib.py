@@ -17,7 +17,7 @@ _lock = threading.Lock()
 _lib = None
 
 # enums of include/petb200.h
-EPI_NONE, EPI_SILU, EPI_SWIGLU, EPI_MUL_DSILU, EPI_SWIGLU_BWD = range(5)
+EPI_NONE, EPI_SILU, EPI_SWIGLU, EPI_MUL_DSILU, EPI_SWIGLU_BWD, EPI_RMS_BWD = range(6)
 PREC_FP32, PREC_BF16X3, PREC_BF16 = range(3)
 CUTOFF_BUMP, CUTOFF_COSINE = range(2)
 

@@ -366,3 +366,25 @@ def test_mlp_fused_rejects_unsupported_width():
     x = rnd(8, 128)
     with pytest.raises(RuntimeError, match="multiple of 64"):
         call("mlp_fwd", ptr(x), 128, ptr(x), ptr(x), ptr(x), 8, 128, 96, ptr(x), 128)
+
+
+@pytest.mark.parametrize("M,K", [(1000, 384), (77, 128), (30000, 384)])
+def test_gemm_rms_bwd_epilogue(M, K):
+    """EPI_RMS_BWD: dgrad through Linear(RMSNorm(x)) in one kernel == gemm followed by rms_bwd."""
+    d = 128
+    g_out, w_t = rnd(M, K, seed=1), rnd(d, K, seed=2, scale=K ** -0.5)
+    x, base = rnd(M, d, seed=3), rnd(M, d, seed=4)
+    x[: min(M, 3)] *= 25.0
+    rstd = torch.empty(M, device=DEV)
+    call("rms_rstd", ptr(x), M, d, ptr(rstd))
+    out = torch.empty(M, d, device=DEV)
+    engine.gemm(g_out, w_t, out, epilogue=lib.EPI_RMS_BWD, aux_in=x, row_scale=rstd, residual=base,
+                precision=PREC_BF16X3)
+    dxh = g_out.double() @ w_t.double().T
+    xh = x.double() * rstd.double()[:, None]
+    ref = base.double() + rstd.double()[:, None] * (dxh - xh * (dxh * xh).mean(-1, keepdim=True))
+    assert_close(out, ref, 2e-4, 3e-5, "gemm + rms_bwd epilogue")
+    engine.gemm(g_out, w_t, out, epilogue=lib.EPI_RMS_BWD, aux_in=x, row_scale=rstd, precision=PREC_BF16X3)
+    assert_close(out, ref - base.double(), 2e-4, 3e-5, "gemm + rms_bwd epilogue, no base")
+    with pytest.raises(RuntimeError, match="tensor-core precisions only"):
+        engine.gemm(g_out, w_t, out, epilogue=lib.EPI_RMS_BWD, aux_in=x, row_scale=rstd, precision=PREC_FP32)
