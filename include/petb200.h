@@ -55,9 +55,11 @@ enum {
   PETB200_EPI_SWIGLU = 2,     /* [u|g] = rs*acc + bias -> aux_out ; C = u * sigmoid(g)  */
   PETB200_EPI_MUL_DSILU = 3,  /* C = acc * silu'(aux_in)          (dgrad through SiLU)  */
   PETB200_EPI_SWIGLU_BWD = 4, /* C = [acc*sig(g) | acc*u*sig'(g)] (dgrad through SwiGLU)*/
-  PETB200_EPI_RMS_BWD = 5     /* C = residual + rs*acc - x*rs^3*(acc.x)/N : dgrad through the
+  PETB200_EPI_RMS_BWD = 5,    /* C = residual + rs*acc - x*rs^3*(acc.x)/N : dgrad through the
                                  RMSNorm in front of the Linear (x = aux_in [M,N], rs = row_scale;
                                  N = 128; tensor-core precisions only)                         */
+  PETB200_EPI_SILU_GEO = 6    /* SILU with a per-row geometry / table term in the pre-activation
+                                 (petb200_compress_gemm only)                                   */
 };
 
 /* GEMM arithmetic */
@@ -223,6 +225,19 @@ PETB200_API int petb200_compress_input(const float* edge_vec, const float* edge_
                            const float* w_geo, const float* b_geo, const float* nbr_table,
                            const int32_t* z_neighbor, const float* messages,
                            int64_t n_edges, int d, float* cat, petb200_stream_t stream);
+
+/* The first Linear of the GNN-layer token builder with the concatenation folded away
+ * (transformer.py:500-521):  W_1 . cat[geo | nbr | m] + b_1  =  W_1m . m  +  G . (r_e, d_e)
+ * + Tbl[z_j] + b'  with G = W_1geo . W_geo [d, 4], Tbl = NbrEmb . W_1nbr^T [species, d] (nullable)
+ * and b' = b_1 + W_1geo . b_geo prepared by the caller.  pre[e] (the pre-activation, kept for
+ * the backward) and out[e] = silu(pre[e]) are [E, d]; w1m is the bf16 hi/lo split of W_1m
+ * ([d, d], petb200_split_bf16).  One tcgen05 GEMM with K = d instead of a gather kernel plus a
+ * GEMM with K = 2d / 3d.  precision: PETB200_PREC_BF16X3 or PETB200_PREC_BF16.               */
+PETB200_API int petb200_compress_gemm(const float* messages, int64_t ld_m, const float* w1m_split,
+                          const float* bias, const float* geo_w, const float* nbr_table,
+                          const int32_t* z_neighbor, const float* edge_vec, const float* edge_dist,
+                          int64_t n_edges, int d, float* pre, float* out, int precision,
+                          petb200_stream_t stream);
 
 /* d_(r,d)[e] (+)= W_geo^T . d_geo[e]  (backward of the 4 -> d geometry embedder).      */
 PETB200_API int petb200_geom_embed_bwd(const float* d_geo, int64_t ld, const float* w_geo,

@@ -60,3 +60,26 @@ extern "C" PETB200_API int petb200_gemm(const float* A, int64_t lda, const float
   set_error("gemm: unknown precision %d", precision);
   return PETB200_ERR_INVALID_ARGUMENT;
 }
+
+extern "C" PETB200_API int petb200_compress_gemm(const float* messages, int64_t ld_m, const float* w1m_split,
+                                     const float* bias, const float* geo_w, const float* nbr_table,
+                                     const int32_t* z_neighbor, const float* edge_vec,
+                                     const float* edge_dist, int64_t n_edges, int d, float* pre,
+                                     float* out, int precision, cudaStream_t stream) {
+  PETB200_REQUIRE(d == 128, "compress_gemm: only d_pet = 128 is built (got %d)", d);
+  PETB200_REQUIRE(precision == PETB200_PREC_BF16X3 || precision == PETB200_PREC_BF16,
+                  "compress_gemm: tensor-core precisions only (the fp32 path uses compress_input + gemm)");
+  PETB200_REQUIRE(messages && w1m_split && geo_w && edge_vec && edge_dist && pre && out,
+                  "compress_gemm: null argument");
+  PETB200_REQUIRE(!nbr_table || z_neighbor, "compress_gemm: a table needs its row index");
+  PETB200_REQUIRE(ld_m % 4 == 0, "compress_gemm: ld_m must be a multiple of 4");
+  GemmArgs g;
+  g.A = messages; g.lda = ld_m; g.W = w1m_split; g.ldw = d; g.C = out; g.ldc = d;
+  g.M = n_edges; g.N = d; g.K = d;
+  g.bias = bias; g.row_scale = nullptr; g.residual = nullptr; g.ldr = 0;
+  g.aux_in = nullptr; g.aux_out = pre; g.ld_aux = d;
+  g.epilogue = PETB200_EPI_SILU_GEO; g.accumulate = 0;
+  g.geo_vec = edge_vec; g.geo_dist = edge_dist; g.geo_w = geo_w;
+  g.row_table = nbr_table; g.row_index = z_neighbor;
+  return launch_gemm_tc(g, precision, stream);
+}

@@ -350,11 +350,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
         ok[it] = m < g.M;
         rs[it] = (g.row_scale && ok[it]) ? __ldg(g.row_scale + m) : 1.0f;
       }
+      float4 geo[4];
+      int zrow[4];
+      if (EPI == PETB200_EPI_SILU_GEO) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + rsel;
+          geo[it] = zero4;
+          zrow[it] = 0;
+          if (!ok[it]) continue;
+          geo[it] = make_float4(__ldg(g.geo_vec + 3 * m), __ldg(g.geo_vec + 3 * m + 1),
+                                __ldg(g.geo_vec + 3 * m + 2), __ldg(g.geo_dist + m));
+          if (g.row_table) zrow[it] = __ldg(g.row_index + m);
+        }
+      }
       // Global operands of the whole item are requested BEFORE waiting for the MMA, so
       // their latency hides behind the main loop of this item.
       float4 pre[NCH][4];
       if (EPI == PETB200_EPI_NONE || EPI == PETB200_EPI_SILU || EPI == PETB200_EPI_MUL_DSILU ||
-          EPI == PETB200_EPI_RMS_BWD) {
+          EPI == PETB200_EPI_RMS_BWD || EPI == PETB200_EPI_SILU_GEO) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -516,7 +530,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
             float4 v = staged(it);
             v = make_float4(rs[it] * v.x + b4.x, rs[it] * v.y + b4.y, rs[it] * v.z + b4.z,
                             rs[it] * v.w + b4.w);
-            if (EPI == PETB200_EPI_SILU) {
+            if (EPI == PETB200_EPI_SILU_GEO) {
+              // + G[c] . (r, d) of this row + table row of its neighbour species
+              const float4 gv = geo[it];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = ld4(g.geo_w + (c0 + q) * 4);
+                (&v.x)[q] += w.x * gv.x + w.y * gv.y + w.z * gv.z + w.w * gv.w;
+              }
+              if (g.row_table) {
+                const float4 tb = ld4(g.row_table + (int64_t)zrow[it] * g.N + c0);
+                v.x += tb.x; v.y += tb.y; v.z += tb.z; v.w += tb.w;
+              }
+            }
+            if (EPI == PETB200_EPI_SILU || EPI == PETB200_EPI_SILU_GEO) {
               if (g.aux_out) *reinterpret_cast<float4*>(g.aux_out + m * g.ld_aux + c0) = v;
               v = make_float4(fsilu(v.x), fsilu(v.y), fsilu(v.z), fsilu(v.w));
             }
@@ -621,6 +648,7 @@ int launch_gemm_tc(const GemmArgs& g, int precision, cudaStream_t stream) {
     case PETB200_EPI_SWIGLU: return launch_epi<PETB200_EPI_SWIGLU>(g, precision, stream);
     case PETB200_EPI_MUL_DSILU: return launch_epi<PETB200_EPI_MUL_DSILU>(g, precision, stream);
     case PETB200_EPI_SWIGLU_BWD: return launch_epi<PETB200_EPI_SWIGLU_BWD>(g, precision, stream);
+    case PETB200_EPI_SILU_GEO: return launch_epi<PETB200_EPI_SILU_GEO>(g, precision, stream);
     case PETB200_EPI_RMS_BWD:
       if (g.N != BN || !g.aux_in || !g.row_scale || g.accumulate) {
         set_error("gemm: the RMSNorm-backward epilogue needs N = %d, aux_in (x) and row_scale (rstd)", BN);

@@ -23,6 +23,13 @@ struct GemmArgs {
   int64_t ld_aux;
   int epilogue;
   int accumulate;
+  // PETB200_EPI_SILU_GEO: per-row additive term of the pre-activation,
+  //   geo_w[c] . (edge_vec[m], edge_dist[m]) + row_table[row_index[m]][c]
+  const float* geo_vec = nullptr;     // [M, 3]
+  const float* geo_dist = nullptr;    // [M]
+  const float* geo_w = nullptr;       // [N, 4]
+  const float* row_table = nullptr;   // [S, N] or null
+  const int32_t* row_index = nullptr; // [M]
 };
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);

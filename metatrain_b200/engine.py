@@ -192,6 +192,15 @@ class PackedWeights:
             L["w2_t"], _ = _t_and_scaled(layer.compress[2].weight)
             L["nbr"] = (g(layer.neighbor_embedder.weight).contiguous()
                         if hasattr(layer, "neighbor_embedder") else None)
+            # concatenation folded into the first Linear (petb200_compress_gemm):
+            #   W_1 . cat[geo | nbr | m] + b_1 = W_1m . m + G . (r, d) + Tbl[z_j] + b'
+            dp = L["w_geo"].shape[0]
+            w1_64 = L["w1"].double()
+            L["geo_fold"] = (w1_64[:, :dp] @ L["w_geo"].double()).float().contiguous()
+            L["b_fold"] = (L["b1"].double() + w1_64[:, :dp] @ L["b_geo"].double()).float().contiguous()
+            L["nbr_fold"] = ((L["nbr"].double() @ w1_64[:, dp:2 * dp].T).float().contiguous()
+                             if L["nbr"] is not None else None)
+            L["w1m"] = L["w1"][:, -dp:].contiguous()
             L["tl"] = []
             for tl in layer.trans.layers:
                 T: dict = {}
@@ -322,13 +331,20 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
     saved = []
     for l, (L, C) in enumerate(zip(pw.gnn, pw.combine)):
         S: dict = {"tl": []}
-        width = 3 * d if L["nbr"] is not None else 2 * d
-        cat = _empty((E, width), vec)
-        call("compress_input", ptr(vec), ptr(dist), ptr(L["w_geo"]), ptr(L["b_geo"]),
-             ptr(L["nbr"]), ptr(topo.z_neighbors), ptr(m), E, d, ptr(cat))
         c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
-        gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec, pack=pw)
-        del cat
+        if prec != PREC_FP32 and d == 128:
+            # one K = d GEMM; geometry embedding and neighbour-species embedding enter as a
+            # per-row term of the epilogue (no [E, 2d / 3d] concatenation in HBM)
+            call("compress_gemm", ptr(m), m.stride(0), ptr(split_weight(L["w1m"], pw)), ptr(L["b_fold"]),
+                 ptr(L["geo_fold"]), ptr(L["nbr_fold"]), ptr(topo.z_neighbors), ptr(vec), ptr(dist),
+                 E, d, ptr(c1), ptr(a1), prec)
+        else:
+            width = 3 * d if L["nbr"] is not None else 2 * d
+            cat = _empty((E, width), vec)
+            call("compress_input", ptr(vec), ptr(dist), ptr(L["w_geo"]), ptr(L["b_geo"]),
+                 ptr(L["nbr"]), ptr(topo.z_neighbors), ptr(m), E, d, ptr(cat))
+            gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec, pack=pw)
+            del cat
         Xf = _empty((E + N + H, d), vec)
         X = Xf[:E + N]
         gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec, pack=pw)
@@ -492,9 +508,13 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
         # ---- token builder: t = W_2 silu(W_1 cat[geo, nbr, m] + b_1) + b_2
         d_c1 = _empty((E, d), ref)
         gemm(d_t, L["w2_t"], d_c1, epilogue=EPI_MUL_DSILU, aux_in=S["c1"], precision=prec, pack=pw)
-        d_geo = _empty((E, d), ref)
-        gemm(d_c1, L["w1_t"][:d], d_geo, precision=prec, pack=pw)
-        call("geom_embed_bwd", ptr(d_geo), d, ptr(L["w_geo"]), E, d, 1, ptr(d_vec), ptr(d_dist))
+        if prec != PREC_FP32 and d == 128:
+            # (W_1geo . W_geo)^T applied to d_c1 directly: no d_geo GEMM
+            call("geom_embed_bwd", ptr(d_c1), d, ptr(L["geo_fold"]), E, d, 1, ptr(d_vec), ptr(d_dist))
+        else:
+            d_geo = _empty((E, d), ref)
+            gemm(d_c1, L["w1_t"][:d], d_geo, precision=prec, pack=pw)
+            call("geom_embed_bwd", ptr(d_geo), d, ptr(L["w_geo"]), E, d, 1, ptr(d_vec), ptr(d_dist))
         if l > 0:
             width = L["w1_t"].shape[0]
             gemm(d_c1, L["w1_t"][width - d:], d_m, accumulate=True, precision=prec, pack=pw)

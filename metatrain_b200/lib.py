@@ -48,6 +48,7 @@ _SIGNATURES = {
     "petb200_gemm": [_P, _I64, _P, _I64, _P, _I64, _I64, _I, _I, _P, _P, _P, _I64, _P, _P,
                      _I64, _I, _I, _I, _P],
     "petb200_split_bf16": [_P, _I64, _I, _P, _P],
+    "petb200_compress_gemm": [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P, _I, _P],
     "petb200_mlp_image_bytes": [_I, _I],
     "petb200_mlp_pack": [_P, _P, _I, _I, _P, _P, _P],
     "petb200_mlp_fwd": [_P, _I64, _P, _P, _P, _I64, _I, _I, _P, _I64, _P],

@@ -388,3 +388,29 @@ def test_gemm_rms_bwd_epilogue(M, K):
     assert_close(out, ref - base.double(), 2e-4, 3e-5, "gemm + rms_bwd epilogue, no base")
     with pytest.raises(RuntimeError, match="tensor-core precisions only"):
         engine.gemm(g_out, w_t, out, epilogue=lib.EPI_RMS_BWD, aux_in=x, row_scale=rstd, precision=PREC_FP32)
+
+
+@pytest.mark.parametrize("with_table", [False, True])
+def test_compress_gemm_folds_the_concatenation(with_table):
+    """petb200_compress_gemm == Linear(cat[W_geo.(r,d)+b_geo | NbrEmb[z] | m]) followed by SiLU
+    (transformer.py:500-521) with the concatenation folded into an epilogue term."""
+    E, d, S = 3001, 128, 3
+    vec, dist, m = rnd(E, 3, seed=1), rnd(E, seed=2).abs() + 0.5, rnd(E, d, seed=3)
+    z = torch.randint(0, S, (E,), generator=torch.Generator().manual_seed(4)).to(torch.int32).to(DEV)
+    w_geo, b_geo = rnd(d, 4, seed=5, scale=0.5), rnd(d, seed=6, scale=0.1)
+    nbr = rnd(S, d, seed=7) if with_table else None
+    width = 3 * d if with_table else 2 * d
+    w1, b1 = rnd(d, width, seed=8, scale=width ** -0.5), rnd(d, seed=9, scale=0.1)
+    geo = torch.cat([vec, dist[:, None]], 1).double() @ w_geo.double().T + b_geo.double()
+    parts = [geo] + ([nbr.double()[z.long()]] if with_table else []) + [m.double()]
+    pre_ref = torch.cat(parts, 1) @ w1.double().T + b1.double()
+    w64 = w1.double()
+    geo_fold = (w64[:, :d] @ w_geo.double()).float().contiguous()
+    b_fold = (b1.double() + w64[:, :d] @ b_geo.double()).float().contiguous()
+    nbr_fold = (nbr.double() @ w64[:, d:2 * d].T).float().contiguous() if with_table else None
+    w1m = engine.split_weight(w1[:, -d:].contiguous())
+    pre, out = torch.empty(E, d, device=DEV), torch.empty(E, d, device=DEV)
+    call("compress_gemm", ptr(m), d, ptr(w1m), ptr(b_fold), ptr(geo_fold), ptr(nbr_fold), ptr(z), ptr(vec),
+         ptr(dist), E, d, ptr(pre), ptr(out), PREC_BF16X3)
+    assert_close(pre, pre_ref, 1e-4, 3e-5, "compress_gemm pre-activation")
+    assert_close(out, F.silu(pre_ref), 1e-4, 3e-5, "compress_gemm output")
