@@ -209,6 +209,20 @@ PETB200_API int petb200_mlp_bwd(const float* x, int64_t ldx, const float* d_y, i
                     const void* image_bwd, const float* b_in, int64_t n_rows, int d, int d_ff,
                     float* d_x, int64_t ld_dx, petb200_stream_t stream);
 
+/* ------------------------------------------------ fused RMSNorm + Linear (QKV projection)
+ * out = rmsnorm(x) . W^T + bias for d = 128 and n_out a multiple of 64 up to 1024
+ * (AttentionBlock.input_linear after norm_attention, transformer.py:105-108, :218).  w is
+ * [n_out, d] with the norm weight folded into its columns; petb200_norm_linear_pack builds the
+ * operand-tile image (petb200_norm_linear_image_bytes bytes).  rstd_out (nullable, [n_rows])
+ * receives rsqrt(mean(x^2) + eps) for the backward.  One persistent tcgen05 kernel: every
+ * activation tile is normalised and converted once and produces all n_out columns.        */
+PETB200_API size_t petb200_norm_linear_image_bytes(int n_out);
+PETB200_API int petb200_norm_linear_pack(const float* w, int d, int n_out, void* image,
+                             petb200_stream_t stream);
+PETB200_API int petb200_norm_linear(const float* x, int64_t ldx, const void* image, const float* bias,
+                        int64_t n_rows, int d, int n_out, float* out, int64_t ldo,
+                        float* rstd_out, petb200_stream_t stream);
+
 /* out[m,:] = table[idx[m],:] (torch.nn.Embedding, backend.py:515-516).                 */
 PETB200_API int petb200_embedding(const float* table, const int32_t* idx, int64_t n_rows, int d,
                       float* out, int64_t ld_out, petb200_stream_t stream);

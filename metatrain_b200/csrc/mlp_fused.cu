@@ -654,6 +654,200 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
   }
 }
 
+// ================================================================ RMSNorm + Linear
+// out = rmsnorm(x) . W^T + bias for K = 128 and N a multiple of 64 (the QKV projection,
+// transformer.py:105-108 after norm_attention :218), built from the forward kernel's pieces:
+// the producers normalise each row once (statistics per thread = per row, rstd also written
+// out for the backward), park x_hat as bf16 hi / lo in tensor memory, and ONE pass over the
+// tile produces all N output columns in chunks of 64 — the generic GEMM (gemm_tc.cu) lets a
+// CTA own one 128-column chunk, so a 384-column projection re-reads and re-converts every
+// activation tile three times and needs a separate RMS-statistics kernel in front.
+// 14 warps: 0-7 epilogue (two groups on alternate chunks, TMEM -> smem transpose -> coalesced
+// stores), 8 MMA issue, 9-12 activation producers, 13 weight stages.
+constexpr int NL_RING = 8;
+constexpr int NL_XS_OFF = 0;
+constexpr int NL_RING_OFF = ((NL_XS_OFF + FWD_STAGING_BYTES + 1023) / 1024) * 1024;
+constexpr int NL_EPI_OFF = NL_RING_OFF + NL_RING * STAGE;
+constexpr int NL_BIAS_OFF = NL_EPI_OFF + EPI_STAGE_BYTES;    // bias [NL_MAX_N]
+constexpr int NL_MAX_N = 1024;
+constexpr int NL_BAR_OFF = NL_BIAS_OFF + NL_MAX_N * 4;
+constexpr int NL_SMEM = NL_BAR_OFF + 8 * (16 + 2 * NL_RING) + 16 + 1024;
+// TMEM columns: x_hat hi 0..63, lo 64..127 ; acc[b] at 128 + 64 b
+constexpr int NL_ACC_COL = 128;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ image,
+                   const float* __restrict__ bias, int64_t M, int N, float* __restrict__ out, int64_t ldo,
+                   float* __restrict__ rstd_out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const Barriers bar{smem_base + NL_BAR_OFF, NL_RING};
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + NL_BAR_OFF + 8 * (16 + 2 * NL_RING));
+  float* bias_s = reinterpret_cast<float*>(smem + NL_BIAS_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3;
+  const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+  const int nch = N / 64;
+  const TileSchedule sched(M);
+
+  if (threadIdx.x == 0) bar.init_all();   // acc1_empty: one epilogue group (128 threads) per chunk
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(
+        smem_u32(const_cast<uint32_t*>(tmem_slot))));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < N; i += NUM_THREADS) bias_s[i] = bias ? bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
+    // ============================================================ activation producers
+    auto issue = [&](int i) {
+      const uint32_t dst = smem_base + NL_XS_OFF;
+      const int64_t m0 = sched.m0(i);
+#pragma unroll 8
+      for (int it = 0; it < 32; ++it) {
+        const int row = quarter * 32 + it;
+        const int64_t m = m0 + row;
+        const bool ok = m < M;
+        cp_async16(dst + (uint32_t)(row * XPITCH * 4 + lane * 16), x + (ok ? m : 0) * ldx + 4 * lane,
+                   ok ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    if (sched.count > 0) issue(0);
+    for (int i = 0; i < sched.count; ++i) {
+      cp_async_wait_group<0>();
+      __syncwarp();
+      mbar_wait(bar.x_empty(0), (i & 1) ^ 1);
+      tc_fence_after();
+      const float* row = reinterpret_cast<const float*>(smem + NL_XS_OFF) + (quarter * 32 + lane) * XPITCH;
+      float ss = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(row + 4 * q);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+      const float rs = rsqrtf(ss * (1.0f / D) + kRmsEps);
+      const int64_t m = sched.m0(i) + quarter * 32 + lane;
+      if (rstd_out != nullptr && m < M) rstd_out[m] = rs;
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v = *reinterpret_cast<const float4*>(row + part * 32 + 4 * q);
+          v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+          hi[2 * q] = pack_bf16(v.x, v.y);
+          hi[2 * q + 1] = pack_bf16(v.z, v.w);
+          lo[2 * q] = pack_bf16(v.x - __uint_as_float(hi[2 * q] << 16), v.y - __uint_as_float(hi[2 * q] & 0xffff0000u));
+          lo[2 * q + 1] = pack_bf16(v.z - __uint_as_float(hi[2 * q + 1] << 16),
+                                    v.w - __uint_as_float(hi[2 * q + 1] & 0xffff0000u));
+        }
+        tmem_st16(tmem_base + lane_base + part * 16, hi);
+        tmem_st16(tmem_base + lane_base + FWD_XLO_COL + part * 16, lo);
+      }
+      __syncwarp();
+      if (i + 1 < sched.count) issue(i + 1);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar.x_full(0));
+    }
+  } else if (warp == TMA_WARP) {
+    if (elect_one()) weight_producer(image, 2 * nch, sched.count, smem_base + NL_RING_OFF, bar);
+  } else if (warp == MMA_WARP) {
+    // ============================================================ MMA issuer (one thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(BM, 64);
+      const uint32_t ring_u32 = smem_base + NL_RING_OFF;
+      Ring ring;
+      for (int i = 0; i < sched.count; ++i) {
+        mbar_wait(bar.x_full(0), i & 1);
+        for (int c = 0; c < nch; ++c) {
+          const uint32_t n = (uint32_t)(i * nch + c);
+          const int b = n & 1;
+          mbar_wait(bar.acc1_empty(b), ((n >> 1) & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            mbar_wait(bar.w_full(ring.stage), ring.phase);
+            const uint32_t st = ring_u32 + ring.stage * STAGE;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t a_hi = tmem_base + (kh * 4 + kk) * 8;
+              mma3_ts(tmem_base + NL_ACC_COL + b * 64, a_hi, a_hi + FWD_XLO_COL, st + kk * 32,
+                      st + 8192 + kk * 32, idesc, (kh | kk) != 0);
+            }
+            tc_commit(bar.w_empty(ring.stage));
+            ring.advance(NL_RING);
+          }
+          tc_commit(bar.acc1_full(b));
+          if (c == nch - 1) tc_commit(bar.x_empty(0));
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue: out = acc + bias
+    const int grp = warp >> 2;
+    const EpiStage es{reinterpret_cast<float*>(smem + NL_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    for (int i = 0; i < sched.count; ++i) {
+      const int64_t m_base = sched.m0(i) + quarter * 32;
+      for (int c = 0; c < nch; ++c) {
+        const uint32_t n = (uint32_t)(i * nch + c);
+        const int b = n & 1;
+        if (b != grp) continue;           // chunk n belongs to group n & 1 (its accumulator buffer)
+        mbar_wait(bar.acc1_full(b), (n >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int c0 = c * 64 + 16 * sl + 4 * es.c4;
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0);
+          es.fill(tmem_base + lane_base + NL_ACC_COL + b * 64 + 16 * sl);
+          if (sl == 3) {
+            tc_fence_before();
+            mbar_arrive(bar.acc1_empty(b));
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int64_t m = m_base + it * 8 + es.rsel;
+            if (m >= M) continue;
+            const float4 a = es.get(it);
+            *reinterpret_cast<float4*>(out + m * ldo + c0) =
+                make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+  }
+}
+
+// image of a plain [N, 128] weight for norm_linear_kernel: per 64-row chunk two stages (k-halves),
+// each [64 rows x 64 k] bf16 hi (8 KB) | lo (8 KB), K-major SWIZZLE_128B
+__global__ void linear_pack_kernel(const float* __restrict__ w, int N, uint4* __restrict__ image) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)(N / 64) * 2 * (STAGE / 16)) return;
+  const int s = (int)(idx / (STAGE / 16)), o = (int)(idx % (STAGE / 16)) * 16;
+  const int c = s >> 1, kh = s & 1;
+  const bool lo = o >= 8192;
+  const int t = o & 8191, n = (t >> 10) * 8 + ((t >> 7) & 7), j = ((t >> 4) & 7) ^ (n & 7);
+  const float* src = w + (int64_t)(c * 64 + n) * D + kh * 64 + j * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = src[e];
+  image[idx] = pack8(v, lo);
+}
+
 // ======================================================================= backward
 // 19 warps, as in the forward kernel: 0-7 swiglu' epilogue groups, 8 GEMM1 issue (ug and ds),
 // 9-12 activation producers (X and dY tiles as bf16 hi / lo operand tiles in shared memory),
@@ -1079,4 +1273,33 @@ extern "C" PETB200_API int petb200_mlp_bwd(const float* x, int64_t ldx, const fl
   mlp_bwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, BWD_NUM_THREADS, BWD_SMEM, stream>>>(
       map_x, map_dy, x, ldx, d_y, ld_dy, reinterpret_cast<const uint8_t*>(image_bwd), b_in, n_rows, d_ff, d_x, ld_dx);
   return check_launch("mlp_bwd");
+}
+
+extern "C" PETB200_API size_t petb200_norm_linear_image_bytes(int n_out) {
+  return (size_t)(n_out / 64) * 2 * STAGE;
+}
+
+extern "C" PETB200_API int petb200_norm_linear_pack(const float* w, int d, int n_out, void* image,
+                                                    cudaStream_t stream) {
+  PETB200_REQUIRE(d == D && n_out % 64 == 0 && n_out >= 64 && n_out <= NL_MAX_N,
+                  "norm_linear_pack: built for d = %d and n_out a multiple of 64 up to %d (got %d, %d)", D,
+                  NL_MAX_N, d, n_out);
+  const int64_t chunks = (int64_t)petb200_norm_linear_image_bytes(n_out) / 16;
+  linear_pack_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, stream>>>(w, n_out, reinterpret_cast<uint4*>(image));
+  return check_launch("norm_linear_pack");
+}
+
+extern "C" PETB200_API int petb200_norm_linear(const float* x, int64_t ldx, const void* image, const float* bias,
+                                               int64_t n_rows, int d, int n_out, float* out, int64_t ldo,
+                                               float* rstd_out, cudaStream_t stream) {
+  PETB200_REQUIRE(d == D && n_out % 64 == 0 && n_out >= 64 && n_out <= NL_MAX_N,
+                  "norm_linear: built for d = %d and n_out a multiple of 64 up to %d (got %d, %d)", D, NL_MAX_N,
+                  d, n_out);
+  PETB200_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "norm_linear: leading dimensions must be multiples of 4");
+  if (n_rows == 0) return PETB200_OK;
+  const int tiles = (int)ceil_div(n_rows, BM);
+  cudaFuncSetAttribute(norm_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM);
+  norm_linear_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, NUM_THREADS, NL_SMEM, stream>>>(
+      x, ldx, reinterpret_cast<const uint8_t*>(image), bias, n_rows, n_out, out, ldo, rstd_out);
+  return check_launch("norm_linear");
 }

@@ -170,6 +170,16 @@ def _mlp_images(w_in_folded: Tensor, w_out: Tensor):
     return imgs
 
 
+def _linear_image(w_folded: Tensor):
+    """Operand-tile image for petb200_norm_linear, or None outside its shape range."""
+    n_out, d = w_folded.shape
+    if d != 128 or n_out % 64 != 0 or not 64 <= n_out <= 1024:
+        return None
+    img = torch.empty(lib.load().petb200_norm_linear_image_bytes(n_out), device=w_folded.device, dtype=torch.uint8)
+    call("norm_linear_pack", ptr(w_folded.contiguous()), d, n_out, ptr(img))
+    return img
+
+
 class PackedWeights:
     """Device-side views/derivatives of the module parameters the kernels consume:
     RMSNorm weights folded into the following Linear (W.diag(gamma)), and W^T for every
@@ -207,6 +217,7 @@ class PackedWeights:
                 T["w_qkv_t"], T["w_qkv"] = _t_and_scaled(
                     tl.attention.input_linear.weight, tl.norm_attention.weight, True)
                 T["b_qkv"] = g(tl.attention.input_linear.bias)
+                T["qkv_img"] = _linear_image(T["w_qkv"])   # fused RMSNorm + QKV projection
                 T["w_o"] = g(tl.attention.output_linear.weight)
                 T["b_o"] = g(tl.attention.output_linear.bias)
                 T["w_o_t"], _ = _t_and_scaled(tl.attention.output_linear.weight)
@@ -353,9 +364,15 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
         for T in L["tl"]:
             K: dict = {}
             gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec, pack=pw)
-            rstd1 = _rstd(X)
             qkv = _empty((E + N, 3 * d), vec)
-            gemm(X, T["w_qkv"], qkv, bias=T["b_qkv"], row_scale=rstd1, precision=prec, pack=pw)
+            if prec != PREC_FP32 and T["qkv_img"] is not None:
+                # RMS statistics, normalisation and the whole 3d-column projection in one kernel
+                rstd1 = _empty((E + N,), vec)
+                call("norm_linear", ptr(X), X.stride(0), ptr(T["qkv_img"]), ptr(T["b_qkv"]), E + N, d, 3 * d,
+                     ptr(qkv), qkv.stride(0), ptr(rstd1))
+            else:
+                rstd1 = _rstd(X)
+                gemm(X, T["w_qkv"], qkv, bias=T["b_qkv"], row_scale=rstd1, precision=prec, pack=pw)
             o = _empty((E + N, d), vec)
             lse = _empty((E + N, nh), vec)
             call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,

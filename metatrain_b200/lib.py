@@ -49,6 +49,9 @@ _SIGNATURES = {
                      _I64, _I, _I, _I, _P],
     "petb200_split_bf16": [_P, _I64, _I, _P, _P],
     "petb200_compress_gemm": [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P, _I, _P],
+    "petb200_norm_linear_image_bytes": [_I],
+    "petb200_norm_linear_pack": [_P, _I, _I, _P, _P],
+    "petb200_norm_linear": [_P, _I64, _P, _P, _I64, _I, _I, _P, _I64, _P, _P],
     "petb200_mlp_image_bytes": [_I, _I],
     "petb200_mlp_pack": [_P, _P, _I, _I, _P, _P, _P],
     "petb200_mlp_fwd": [_P, _I64, _P, _P, _P, _I64, _I, _I, _P, _I64, _P],
@@ -70,7 +73,7 @@ _SIGNATURES = {
     "petb200_last_error": [],
     "petb200_version": [],
 }
-_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
+_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_norm_linear_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
             "petb200_nl_num_bins": _I64, "petb200_nl_workspace": _SZ}
 
 

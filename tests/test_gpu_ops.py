@@ -414,3 +414,22 @@ def test_compress_gemm_folds_the_concatenation(with_table):
          ptr(dist), E, d, ptr(pre), ptr(out), PREC_BF16X3)
     assert_close(pre, pre_ref, 1e-4, 3e-5, "compress_gemm pre-activation")
     assert_close(out, F.silu(pre_ref), 1e-4, 3e-5, "compress_gemm output")
+
+
+@pytest.mark.parametrize("M,n_out", [(1000, 384), (128, 64), (50001, 384), (77, 1024)])
+def test_norm_linear(M, n_out):
+    """petb200_norm_linear: rmsnorm(x) @ W^T + b (QKV projection) and the rstd it hands to the backward."""
+    d = 128
+    x = rnd(M, d, seed=1)
+    x[: min(M, 4)] *= 40.0
+    gamma = rnd(d, seed=2).abs() + 0.5
+    w, b = rnd(n_out, d, seed=3, scale=d ** -0.5), rnd(n_out, seed=4, scale=0.1)
+    w_folded = (w * gamma[None, :]).contiguous()
+    img = torch.empty(lib.load().petb200_norm_linear_image_bytes(n_out), device=DEV, dtype=torch.uint8)
+    call("norm_linear_pack", ptr(w_folded), d, n_out, ptr(img))
+    out, rstd = torch.empty(M, n_out, device=DEV), torch.empty(M, device=DEV)
+    call("norm_linear", ptr(x), d, ptr(img), ptr(b), M, d, n_out, ptr(out), n_out, ptr(rstd))
+    ref_rstd = torch.rsqrt((x.double() ** 2).mean(-1) + torch.finfo(torch.float32).eps)
+    ref = F.rms_norm(x.double(), (d,), gamma.double(), torch.finfo(torch.float32).eps) @ w.double().T + b.double()
+    assert_close(rstd, ref_rstd, 1e-6, 1e-5, "norm_linear rstd")
+    assert_close(out, ref, 1e-4, 3e-5, "norm_linear output")
