@@ -672,8 +672,8 @@ constexpr int NL_BIAS_OFF = NL_EPI_OFF + EPI_STAGE_BYTES;    // bias [NL_MAX_N]
 constexpr int NL_MAX_N = 1024;
 constexpr int NL_BAR_OFF = NL_BIAS_OFF + NL_MAX_N * 4;
 constexpr int NL_SMEM = NL_BAR_OFF + 8 * (16 + 2 * NL_RING) + 16 + 1024;
-// TMEM columns: x_hat hi 0..63, lo 64..127 ; acc[b] at 128 + 64 b
-constexpr int NL_ACC_COL = 128;
+// TMEM columns: x_hat[i & 1] hi at 128 (i & 1), lo 64 further ; acc[b] at 256 + 64 b
+constexpr int NL_ACC_COL = 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ image,
@@ -693,7 +693,7 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
 
   if (threadIdx.x == 0) bar.init_all();   // acc1_empty: one epilogue group (128 threads) per chunk
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
         smem_u32(const_cast<uint32_t*>(tmem_slot))));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -722,7 +722,8 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
     for (int i = 0; i < sched.count; ++i) {
       cp_async_wait_group<0>();
       __syncwarp();
-      mbar_wait(bar.x_empty(0), (i & 1) ^ 1);
+      const int xb = i & 1;                      // x_hat is double buffered in tensor memory
+      mbar_wait(bar.x_empty(xb), ((i >> 1) & 1) ^ 1);
       tc_fence_after();
       const float* row = reinterpret_cast<const float*>(smem + NL_XS_OFF) + (quarter * 32 + lane) * XPITCH;
       float ss = 0.f;
@@ -747,14 +748,14 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
           lo[2 * q + 1] = pack_bf16(v.z - __uint_as_float(hi[2 * q + 1] << 16),
                                     v.w - __uint_as_float(hi[2 * q + 1] & 0xffff0000u));
         }
-        tmem_st16(tmem_base + lane_base + part * 16, hi);
-        tmem_st16(tmem_base + lane_base + FWD_XLO_COL + part * 16, lo);
+        tmem_st16(tmem_base + lane_base + xb * 128 + part * 16, hi);
+        tmem_st16(tmem_base + lane_base + xb * 128 + FWD_XLO_COL + part * 16, lo);
       }
       __syncwarp();
       if (i + 1 < sched.count) issue(i + 1);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar.x_full(0));
+      mbar_arrive(bar.x_full(xb));
     }
   } else if (warp == TMA_WARP) {
     if (elect_one()) weight_producer(image, 2 * nch, sched.count, smem_base + NL_RING_OFF, bar);
@@ -765,7 +766,9 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
       const uint32_t ring_u32 = smem_base + NL_RING_OFF;
       Ring ring;
       for (int i = 0; i < sched.count; ++i) {
-        mbar_wait(bar.x_full(0), i & 1);
+        const int xb = i & 1;
+        mbar_wait(bar.x_full(xb), (i >> 1) & 1);
+        tc_fence_after();
         for (int c = 0; c < nch; ++c) {
           const uint32_t n = (uint32_t)(i * nch + c);
           const int b = n & 1;
@@ -777,7 +780,7 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
             const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t a_hi = tmem_base + (kh * 4 + kk) * 8;
+              const uint32_t a_hi = tmem_base + xb * 128 + (kh * 4 + kk) * 8;
               mma3_ts(tmem_base + NL_ACC_COL + b * 64, a_hi, a_hi + FWD_XLO_COL, st + kk * 32,
                       st + 8192 + kk * 32, idesc, (kh | kk) != 0);
             }
@@ -785,7 +788,7 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
             ring.advance(NL_RING);
           }
           tc_commit(bar.acc1_full(b));
-          if (c == nch - 1) tc_commit(bar.x_empty(0));
+          if (c == nch - 1) tc_commit(bar.x_empty(xb));
         }
       }
     }
@@ -828,7 +831,7 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
   __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   }
 }
 
