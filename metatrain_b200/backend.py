@@ -228,6 +228,26 @@ class B200PETBackend(PETParameters):
     def set_precision(self, precision: str) -> None:
         self._precision = _PRECISIONS[precision]
 
+    def _invalidate_packed(self) -> None:
+        self._pw = None
+        self.__dict__.pop("_petb200_param_list", None)
+
+    def add_output(self, *args, **kwargs):
+        self._invalidate_packed()
+        return super().add_output(*args, **kwargs)
+
+    def remove_output(self, *args, **kwargs):
+        self._invalidate_packed()
+        return super().remove_output(*args, **kwargs)
+
+    def _apply(self, *args, **kwargs):
+        self._invalidate_packed()
+        return super()._apply(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._invalidate_packed()
+        return super().load_state_dict(*args, **kwargs)
+
     def _packed(self) -> engine.PackedWeights:
         if self._pw is None or not self._pw.is_current(self):
             self._pw = engine.PackedWeights(self)

@@ -273,7 +273,15 @@ class PackedWeights:
 
     @staticmethod
     def _signature(module):
-        return tuple((p.data_ptr(), p._version) for p in module.parameters())
+        # the list of Parameter objects is cached on the module (walking module.parameters()
+        # costs ~0.5 ms and this runs in every stage of every step); B200PETBackend drops the cache
+        # whenever its parameter SET can change (add_output / remove_output / _apply /
+        # load_state_dict), in-place updates are caught by (data_ptr, _version)
+        params = module.__dict__.get("_petb200_param_list")
+        if params is None:
+            params = list(module.parameters())
+            module.__dict__["_petb200_param_list"] = params
+        return tuple((p.data_ptr(), p._version) for p in params)
 
     def is_current(self, module) -> bool:
         return self.signature == self._signature(module)
