@@ -37,9 +37,10 @@ def sum_over_atoms(atomic: Tensor, system_indices: Tensor, n_structures: int) ->
     """Per-structure sums of per-atom predictions; atoms of a structure are contiguous
     (they are, after ``concatenate_structures``, structures.py:17-112)."""
     idx = system_indices.long()
-    counts = torch.bincount(idx, minlength=n_structures)
-    struct_ptr = torch.zeros(n_structures + 1, device=atomic.device, dtype=torch.int32)
-    struct_ptr[1:] = torch.cumsum(counts, 0)
+    # structure b owns the contiguous, ascending block idx == b: its bounds come from a binary
+    # search (no device->host synchronisation, unlike torch.bincount)
+    bounds = torch.arange(n_structures + 1, device=atomic.device, dtype=idx.dtype)
+    struct_ptr = torch.searchsorted(idx, bounds).to(torch.int32)
     return _SumOverAtoms.apply(atomic, struct_ptr, idx)
 
 
