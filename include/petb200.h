@@ -305,6 +305,15 @@ PETB200_API int petb200_combine_scatter_bwd(const float* d_cat, const float* bas
                                 int64_t n_edges, int d, float* out,
                                 petb200_stream_t stream);
 
+/* ------------------------------------------------ residual featurizer (a8, second variant)
+ * backend.py:589-649: the input messages of GNN layer l+1 are the average of layer l's input
+ * messages and its reversed output tokens, out[e] = 0.5 (m[e] + t[rev[e]]).  Backward:
+ * d_t[e] += 0.5 d_next[rev[e]] (rev is an involution: a gather), d_m[e] = 0.5 d_next[e].     */
+PETB200_API int petb200_avg_reverse_fwd(const float* m, const float* t, const int32_t* rev,
+                            int64_t n_edges, int d, float* out, petb200_stream_t stream);
+PETB200_API int petb200_avg_reverse_bwd(const float* d_next, const int32_t* rev, int64_t n_edges, int d,
+                            float* d_t, float* d_m, petb200_stream_t stream);
+
 /* ------------------------------------------------------------------- readout (a12)
  * backend.py:195-217, 762-772: atomic[i,p] = w_n[p].n2[i] + b_n[p] +
  * sum_{e in row i} f_e * (w_e[p].e2[e] + b_e[p]);  edge_pred[e,p] is kept for backward. */

@@ -14,8 +14,9 @@ may read from ``batch_data`` (``padding_mask``, ``cutoff_factors``, ``edge_dista
 ``model.py:436-459,512-513``) are still produced, from the CSR data, so that the wrapper
 keeps working unchanged.
 
-Not built yet (raise ``NotImplementedError``): adaptive cutoff, residual featurizer,
-PostLN / LayerNorm / SiLU variants, system conditioning, weight gradients (training).
+Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649).  Not built yet
+(raise ``NotImplementedError``): adaptive cutoff, PostLN / LayerNorm / SiLU variants, system
+conditioning, weight gradients (training).
 """
 from typing import Dict, List, Optional, Tuple
 
@@ -68,20 +69,33 @@ class _EdgeGeometry(torch.autograd.Function):
 
 
 class _Features(torch.autograd.Function):
-    """(edge vectors, distances, cutoff factors) -> (node features, edge messages)."""
+    """(edge vectors, distances, cutoff factors) -> (node features, edge messages).  With the
+    residual featurizer the outputs are the node features of every GNN layer followed by the edge
+    features of every GNN layer (2 L tensors)."""
 
     @staticmethod
     def forward(ctx, vec, dist, fc, backend, topo):
         pw = backend._packed()
         prec = backend._precision
-        h, m, saved = engine.features_forward(pw, backend.hypers, topo, vec.contiguous(),
-                                              dist.contiguous(), fc.contiguous(), prec)
-        ctx.backend, ctx.topo, ctx.pw, ctx.saved, ctx.fc, ctx.prec = backend, topo, pw, saved, fc, prec
+        ctx.backend, ctx.topo, ctx.pw, ctx.fc, ctx.prec = backend, topo, pw, fc, prec
+        ctx.residual = backend.featurizer_type == "residual"
+        args = (pw, backend.hypers, topo, vec.contiguous(), dist.contiguous(), fc.contiguous(), prec)
+        if ctx.residual:
+            nodes, edges, ctx.saved = engine.features_forward_residual(*args)
+            return tuple(nodes) + tuple(edges)
+        h, m, ctx.saved = engine.features_forward(*args)
         return h, m
 
     @staticmethod
-    def backward(ctx, d_h, d_m):
+    def backward(ctx, *grads):
         topo = ctx.topo
+        if ctx.residual:
+            n_layers = len(grads) // 2
+            d_vec, d_dist, d_fc = engine.features_backward_residual(
+                ctx.pw, ctx.backend.hypers, topo, ctx.fc.contiguous(), ctx.saved,
+                list(grads[:n_layers]), list(grads[n_layers:]), ctx.prec)
+            return d_vec, d_dist, d_fc, None, None
+        d_h, d_m = grads
         if d_h is None:
             d_h = torch.zeros((topo.n_atoms, ctx.backend.d_node), device=ctx.fc.device)
         if d_m is None:
@@ -92,22 +106,23 @@ class _Features(torch.autograd.Function):
 
 
 class _Predict(torch.autograd.Function):
-    """(node features, edge messages, cutoff factors) -> per-atom predictions [N, P]."""
+    """(node features, edge messages, cutoff factors) -> per-atom predictions [N, P] of one
+    readout layer."""
 
     @staticmethod
-    def forward(ctx, h, m, fc, backend, topo, name):
+    def forward(ctx, h, m, fc, backend, topo, name, layer):
         pw = backend._packed()
         prec = backend._precision
         atomic, saved = engine.predict_forward(pw, topo, name, h.contiguous(), m.contiguous(),
-                                               fc.contiguous(), prec)
-        ctx.topo, ctx.pw, ctx.saved, ctx.fc, ctx.name, ctx.prec = topo, pw, saved, fc, name, prec
+                                               fc.contiguous(), prec, layer)
+        ctx.topo, ctx.pw, ctx.saved, ctx.fc, ctx.name, ctx.prec, ctx.layer = topo, pw, saved, fc, name, prec, layer
         return atomic
 
     @staticmethod
     def backward(ctx, d_atomic):
         d_h, d_m, d_fc = engine.predict_backward(ctx.pw, ctx.topo, ctx.name, ctx.fc.contiguous(),
-                                                 ctx.saved, d_atomic, ctx.prec)
-        return d_h, d_m, d_fc, None, None, None
+                                                 ctx.saved, d_atomic, ctx.prec, ctx.layer)
+        return d_h, d_m, d_fc, None, None, None, None
 
 
 class _CsrToNef(torch.autograd.Function):
@@ -193,8 +208,8 @@ class B200PETBackend(PETParameters):
             unsupported.append("transformer_type=" + hypers["transformer_type"])
         if hypers["activation"] != "SwiGLU":
             unsupported.append("activation=" + hypers["activation"])
-        if hypers["featurizer_type"] != "feedforward":
-            unsupported.append("featurizer_type=" + str(hypers["featurizer_type"]))
+        if hypers["featurizer_type"] not in ("feedforward", "residual"):
+            raise ValueError(f"Unknown featurizer type: {hypers['featurizer_type']}")
         if hypers.get("num_neighbors_adaptive") is not None:
             unsupported.append("num_neighbors_adaptive (adaptive cutoff)")
         if hypers.get("system_conditioning"):
@@ -210,6 +225,7 @@ class B200PETBackend(PETParameters):
             raise ValueError(f"unknown precision {precision!r}; choose from {list(_PRECISIONS)}")
         super().__init__(hypers, atomic_types)
         self.hypers = dict(hypers)
+        self.featurizer_type = hypers["featurizer_type"]
         self.nl_is_strict = bool(hypers["long_range"]["enable"])
         self.cutoff = float(hypers["cutoff"])
         self.cutoff_function = hypers["cutoff_function"]
@@ -344,13 +360,18 @@ class B200PETBackend(PETParameters):
             raise NotImplementedError("B200PETBackend: diagnostic feature capture is not built")
         self._check_inference()
         topo = self._topology_of(batch_data)
-        h, m = _Features.apply(batch_data["_petb200_vec"], batch_data["_petb200_dist"],
+        outs = _Features.apply(batch_data["_petb200_vec"], batch_data["_petb200_dist"],
                                batch_data["_petb200_fc"], self, topo)
+        n_layers = len(outs) // 2   # 1 (feedforward) or num_gnn_layers (residual featurizer)
+        nodes, edges = list(outs[:n_layers]), list(outs[n_layers:])
         if not self.emit_nef:
-            return [h], [m]  # CSR [E, d_pet]; predict() recognises it by its rank
-        m_nef = _CsrToNef.apply(m, topo)
-        m_nef._petb200_csr = m  # lets predict() skip the NEF round trip
-        return [h], [m_nef]
+            return nodes, edges  # CSR [E, d_pet]; predict() recognises it by its rank
+        nef = []
+        for m in edges:
+            m_nef = _CsrToNef.apply(m, topo)
+            m_nef._petb200_csr = m  # lets predict() skip the NEF round trip
+            nef.append(m_nef)
+        return nodes, nef
 
     # ------------------------------------------------------------------ stage 3
     def predict(
@@ -367,18 +388,25 @@ class B200PETBackend(PETParameters):
         self._check_inference()
         topo = self._topology_of(batch_data)
         fc = batch_data["_petb200_fc"]
-        h = node_features_list[0]
-        m_in = edge_features_list[0]
-        m = getattr(m_in, "_petb200_csr", None)
-        if m is None:
-            m = m_in if m_in.dim() == 2 else _NefToCsr.apply(m_in, topo)
+        if len(node_features_list) != self.num_readout_layers or len(edge_features_list) != self.num_readout_layers:
+            raise ValueError(f"predict: expected {self.num_readout_layers} node / edge feature tensors")
+        edges_csr = []
+        for m_in in edge_features_list:
+            m = getattr(m_in, "_petb200_csr", None)
+            if m is None:
+                m = m_in if m_in.dim() == 2 else _NefToCsr.apply(m_in, topo)
+            edges_csr.append(m)
         atomic_predictions: Dict[str, List[Tensor]] = {}
         for name in self.node_last_layers.keys():
             if name not in requested_output_names:
                 continue
             if name == "non_conservative_stress":
                 raise NotImplementedError("B200PETBackend: non_conservative_stress is not built")
-            atomic = _Predict.apply(h, m, fc, self, topo, name)
-            sizes = self._packed().heads[name]["block_sizes"]
+            # node + edge contributions summed over the readout layers (backend.py:469-481)
+            atomic = None
+            for layer, (h, m) in enumerate(zip(node_features_list, edges_csr)):
+                part = _Predict.apply(h, m, fc, self, topo, name, layer)
+                atomic = part if atomic is None else atomic + part
+            sizes = self._packed().heads[name][0]["block_sizes"]
             atomic_predictions[name] = list(torch.split(atomic, sizes, dim=1))
         return atomic_predictions, {}, {}

@@ -126,6 +126,41 @@ __global__ void geom_embed_bwd_kernel(const float* __restrict__ d_geo, int64_t l
   }
 }
 
+// ------------------------------------------ residual featurizer: message averaging
+// backend.py:640-647: m_next[e] = 0.5 (m[e] + t[rev[e]])  (one warp per edge, d = 128 V)
+__global__ void avg_reverse_fwd_kernel(const float* __restrict__ m, const float* __restrict__ t,
+                                       const int32_t* __restrict__ rev, int64_t n_edges, int v4,
+                                       float* __restrict__ out) {
+  const int64_t e = global_warp();
+  if (e >= n_edges) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = rev[e];
+  for (int c = lane; c < v4; c += 32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(m) + e * v4 + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(t) + r * v4 + c);
+    reinterpret_cast<float4*>(out)[e * v4 + c] =
+        make_float4(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z), 0.5f * (a.w + b.w));
+  }
+}
+// its backward: d_t[e] += 0.5 d_next[rev[e]] (rev is an involution: a gather, no atomics),
+// d_m[e] = 0.5 d_next[e]
+__global__ void avg_reverse_bwd_kernel(const float* __restrict__ d_next, const int32_t* __restrict__ rev,
+                                       int64_t n_edges, int v4, float* __restrict__ d_t,
+                                       float* __restrict__ d_m) {
+  const int64_t e = global_warp();
+  if (e >= n_edges) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = rev[e];
+  for (int c = lane; c < v4; c += 32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(d_next) + e * v4 + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(d_next) + r * v4 + c);
+    float4 g = reinterpret_cast<float4*>(d_t)[e * v4 + c];
+    g.x += 0.5f * b.x; g.y += 0.5f * b.y; g.z += 0.5f * b.z; g.w += 0.5f * b.w;
+    reinterpret_cast<float4*>(d_t)[e * v4 + c] = g;
+    reinterpret_cast<float4*>(d_m)[e * v4 + c] = make_float4(0.5f * a.x, 0.5f * a.y, 0.5f * a.z, 0.5f * a.w);
+  }
+}
+
 // ------------------------------------------------------------------------- RMSNorm
 // torch.nn.RMSNorm(d) with eps=None -> finfo(fp32).eps (transformer.py:184-186,193)
 template <int V>  // V float4 per lane: d = 128*V
@@ -413,6 +448,20 @@ extern "C" PETB200_API int petb200_geom_embed_bwd(const float* d_geo, int64_t ld
   PETB200_REQUIRE(ld % 4 == 0, "geom_embed_bwd: ld must be a multiple of 4");
   LAUNCH_ROWS(geom_embed_bwd_kernel, ceil_div(n_edges, 4), d_geo, ld, w_geo, n_edges, accumulate, d_vec, d_dist);
   return check_launch("geom_embed_bwd");
+}
+
+extern "C" PETB200_API int petb200_avg_reverse_fwd(const float* m, const float* t, const int32_t* rev,
+                                       int64_t n_edges, int d, float* out, cudaStream_t stream) {
+  PETB200_REQUIRE(d % 4 == 0, "avg_reverse_fwd: d must be a multiple of 4");
+  LAUNCH_ROWS(avg_reverse_fwd_kernel, n_edges, m, t, rev, n_edges, d / 4, out);
+  return check_launch("avg_reverse_fwd");
+}
+
+extern "C" PETB200_API int petb200_avg_reverse_bwd(const float* d_next, const int32_t* rev, int64_t n_edges,
+                                       int d, float* d_t, float* d_m, cudaStream_t stream) {
+  PETB200_REQUIRE(d % 4 == 0, "avg_reverse_bwd: d must be a multiple of 4");
+  LAUNCH_ROWS(avg_reverse_bwd_kernel, n_edges, d_next, rev, n_edges, d / 4, d_t, d_m);
+  return check_launch("avg_reverse_bwd");
 }
 
 extern "C" PETB200_API int petb200_rms_rstd(const float* x, int64_t n_rows, int d, float* rstd,

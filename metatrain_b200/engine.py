@@ -251,25 +251,29 @@ class PackedWeights:
             C["w_a_t"], _ = _t_and_scaled(mlp[0].weight)
             C["w_b_t"], _ = _t_and_scaled(mlp[2].weight)
             self.combine.append(C)
-        self.node_emb = g(module.node_embedders[0].weight).contiguous()
+        # one node embedding per readout layer (1 with the feedforward featurizer)
+        self.node_emb = [g(e.weight).contiguous() for e in module.node_embedders]
         self.edge_emb = g(module.edge_embedder.weight).contiguous()
-        self.heads: Dict[str, dict] = {}
+        self.heads: Dict[str, List[dict]] = {}   # target -> one entry per readout layer
         for name in module.node_heads.keys():
-            H: dict = {}
-            nh, eh = module.node_heads[name][0], module.edge_heads[name][0]
-            for tag, head in (("n", nh), ("e", eh)):
-                H[tag + "1"], H[tag + "1_b"] = g(head[0].weight), g(head[0].bias)
-                H[tag + "2"], H[tag + "2_b"] = g(head[2].weight), g(head[2].bias)
-                H[tag + "1_t"], _ = _t_and_scaled(head[0].weight)
-                H[tag + "2_t"], _ = _t_and_scaled(head[2].weight)
-            keys = list(module.node_last_layers[name][0].keys())
-            H["block_keys"] = keys
-            H["block_sizes"] = [module.node_last_layers[name][0][k].weight.shape[0] for k in keys]
-            H["wn"] = torch.cat([g(module.node_last_layers[name][0][k].weight) for k in keys]).contiguous()
-            H["bn"] = torch.cat([g(module.node_last_layers[name][0][k].bias) for k in keys]).contiguous()
-            H["we"] = torch.cat([g(module.edge_last_layers[name][0][k].weight) for k in keys]).contiguous()
-            H["be"] = torch.cat([g(module.edge_last_layers[name][0][k].bias) for k in keys]).contiguous()
-            self.heads[name] = H
+            per_layer = []
+            for r in range(len(module.node_heads[name])):
+                H: dict = {}
+                nh, eh = module.node_heads[name][r], module.edge_heads[name][r]
+                for tag, head in (("n", nh), ("e", eh)):
+                    H[tag + "1"], H[tag + "1_b"] = g(head[0].weight), g(head[0].bias)
+                    H[tag + "2"], H[tag + "2_b"] = g(head[2].weight), g(head[2].bias)
+                    H[tag + "1_t"], _ = _t_and_scaled(head[0].weight)
+                    H[tag + "2_t"], _ = _t_and_scaled(head[2].weight)
+                keys = list(module.node_last_layers[name][r].keys())
+                H["block_keys"] = keys
+                H["block_sizes"] = [module.node_last_layers[name][r][k].weight.shape[0] for k in keys]
+                H["wn"] = torch.cat([g(module.node_last_layers[name][r][k].weight) for k in keys]).contiguous()
+                H["bn"] = torch.cat([g(module.node_last_layers[name][r][k].bias) for k in keys]).contiguous()
+                H["we"] = torch.cat([g(module.edge_last_layers[name][r][k].weight) for k in keys]).contiguous()
+                H["be"] = torch.cat([g(module.edge_last_layers[name][r][k].bias) for k in keys]).contiguous()
+                per_layer.append(H)
+            self.heads[name] = per_layer
 
     @staticmethod
     def _signature(module):
@@ -335,93 +339,105 @@ def _rms_bwd(d_xhat, x, rstd, base, out):
     return out
 
 
-def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32):
-    """backend.py:496-587 + transformer.py:463-562,203-234 on the CSR layout.
-    Returns (node features [N,d_node], edge messages [E,d_pet], saved-for-backward)."""
+def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc, h, m, prec):
+    """One CartesianTransformer (transformer.py:463-562) on the CSR layout.  Returns the node
+    features after its attention layers, the token matrix X ([E + N] rows; rows [:E] are the output
+    edge tokens), the buffer behind it (H ghost rows follow in atom-sharded runs) and what the
+    backward needs."""
     N, E = topo.n_atoms, topo.n_edges
     halo = topo.halo
     H = halo.n_ghost if halo is not None else 0  # ghost rows behind the [E | N] token rows
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    S: dict = {"tl": []}
+    c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
+    if prec != PREC_FP32 and d == 128:
+        # one K = d GEMM; geometry embedding and neighbour-species embedding enter as a
+        # per-row term of the epilogue (no [E, 2d / 3d] concatenation in HBM)
+        call("compress_gemm", ptr(m), m.stride(0), ptr(split_weight(L["w1m"], pw)), ptr(L["b_fold"]),
+             ptr(L["geo_fold"]), ptr(L["nbr_fold"]), ptr(topo.z_neighbors), ptr(vec), ptr(dist),
+             E, d, ptr(c1), ptr(a1), prec)
+    else:
+        width = 3 * d if L["nbr"] is not None else 2 * d
+        cat = _empty((E, width), vec)
+        call("compress_input", ptr(vec), ptr(dist), ptr(L["w_geo"]), ptr(L["b_geo"]),
+             ptr(L["nbr"]), ptr(topo.z_neighbors), ptr(m), E, d, ptr(cat))
+        gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec, pack=pw)
+        del cat
+    Xf = _empty((E + N + H, d), vec)
+    X = Xf[:E + N]
+    gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec, pack=pw)
+    del a1
+    S["c1"] = c1
+    for T in L["tl"]:
+        K: dict = {}
+        gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec, pack=pw)
+        qkv = _empty((E + N, 3 * d), vec)
+        if prec != PREC_FP32 and T["qkv_img"] is not None:
+            # RMS statistics, normalisation and the whole 3d-column projection in one kernel
+            rstd1 = _empty((E + N,), vec)
+            call("norm_linear", ptr(X), X.stride(0), ptr(T["qkv_img"]), ptr(T["b_qkv"]), E + N, d, 3 * d,
+                 ptr(qkv), qkv.stride(0), ptr(rstd1))
+        else:
+            rstd1 = _rstd(X)
+            gemm(X, T["w_qkv"], qkv, bias=T["b_qkv"], row_scale=rstd1, precision=prec, pack=pw)
+        o = _empty((E + N, d), vec)
+        lse = _empty((E + N, nh), vec)
+        call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,
+             scale, topo.max_row, prec, ptr(o), ptr(lse))
+        Xn = _empty((E + N, d), vec)  # rows [:E] = t' ; rows [E:] = next centre token
+        gemm(o[:E], T["w_o"], Xn[:E], bias=T["b_o"], residual=X[:E], precision=prec, pack=pw)
+        yc = _empty((N, d), vec)
+        gemm(o[E:], T["w_o"], yc, bias=T["b_o"], precision=prec, pack=pw)
+        h1 = _empty((N, dn), vec)
+        gemm(yc, T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec, pack=pw)
+        # centre MLP (d_node -> 4 d_node -> d_node, SwiGLU)
+        rstd3 = _rstd(h1)
+        ugc = _empty((N, 4 * dn), vec)
+        sc = _empty((N, 2 * dn), vec)
+        gemm(h1, T["wc_in"], sc, bias=T["bc_in"], row_scale=rstd3, epilogue=EPI_SWIGLU,
+             aux_out=ugc, precision=prec, pack=pw)
+        h2 = _empty((N, dn), vec)
+        gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec, pack=pw)
+        # edge MLP (d_pet -> 2 d_ff -> d_pet, SwiGLU)
+        tp = Xn[:E]
+        dff = T["w_out"].shape[1]
+        Xnnf = _empty((E + N + H, d), vec)
+        Xnn = Xnnf[:E + N]
+        if prec != PREC_FP32 and T["mlp_img"] is not None:
+            # one fused tcgen05 kernel; the backward recomputes the hidden activations
+            rstd2 = ug = None
+            call("mlp_fwd", ptr(tp), tp.stride(0), ptr(T["mlp_img"][0]), ptr(T["b_in"]),
+                 ptr(T["b_out"]), E, d, dff, ptr(Xnn), Xnn.stride(0))
+        else:
+            rstd2 = _rstd(tp)
+            ug = _empty((E, 2 * dff), vec)
+            s = _empty((E, dff), vec)
+            gemm(tp, T["w_in"], s, bias=T["b_in"], row_scale=rstd2, epilogue=EPI_SWIGLU,
+                 aux_out=ug, precision=prec, pack=pw)
+            gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec, pack=pw)
+            del s
+        del sc
+        K.update(X=X, rstd1=rstd1, qkv=qkv, o=o, lse=lse, tp=tp, rstd2=rstd2, ug=ug,
+                 h1=h1, rstd3=rstd3, ugc=ugc)
+        S["tl"].append(K)
+        X, Xf, h = Xnn, Xnnf, h2
+    return h, X, Xf, S
+
+
+def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32):
+    """Feedforward featurizer, backend.py:496-587 (+ transformer.py:463-562,203-234) on the CSR
+    layout.  Returns (node features [N,d_node], edge messages [E,d_pet], saved-for-backward)."""
+    N, E = topo.n_atoms, topo.n_edges
+    halo = topo.halo
+    d, dn = hyp["d_pet"], hyp["d_node"]
     h = _empty((N, dn), vec)
-    call("embedding", ptr(pw.node_emb), ptr(topo.z_nodes), N, dn, ptr(h), dn)
+    call("embedding", ptr(pw.node_emb[0]), ptr(topo.z_nodes), N, dn, ptr(h), dn)
     m = _empty((E, d), vec)
     call("embedding", ptr(pw.edge_emb), ptr(topo.z_neighbors), E, d, ptr(m), d)
     saved = []
     for l, (L, C) in enumerate(zip(pw.gnn, pw.combine)):
-        S: dict = {"tl": []}
-        c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
-        if prec != PREC_FP32 and d == 128:
-            # one K = d GEMM; geometry embedding and neighbour-species embedding enter as a
-            # per-row term of the epilogue (no [E, 2d / 3d] concatenation in HBM)
-            call("compress_gemm", ptr(m), m.stride(0), ptr(split_weight(L["w1m"], pw)), ptr(L["b_fold"]),
-                 ptr(L["geo_fold"]), ptr(L["nbr_fold"]), ptr(topo.z_neighbors), ptr(vec), ptr(dist),
-                 E, d, ptr(c1), ptr(a1), prec)
-        else:
-            width = 3 * d if L["nbr"] is not None else 2 * d
-            cat = _empty((E, width), vec)
-            call("compress_input", ptr(vec), ptr(dist), ptr(L["w_geo"]), ptr(L["b_geo"]),
-                 ptr(L["nbr"]), ptr(topo.z_neighbors), ptr(m), E, d, ptr(cat))
-            gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec, pack=pw)
-            del cat
-        Xf = _empty((E + N + H, d), vec)
-        X = Xf[:E + N]
-        gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec, pack=pw)
-        del a1
-        S["c1"] = c1
-        for T in L["tl"]:
-            K: dict = {}
-            gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec, pack=pw)
-            qkv = _empty((E + N, 3 * d), vec)
-            if prec != PREC_FP32 and T["qkv_img"] is not None:
-                # RMS statistics, normalisation and the whole 3d-column projection in one kernel
-                rstd1 = _empty((E + N,), vec)
-                call("norm_linear", ptr(X), X.stride(0), ptr(T["qkv_img"]), ptr(T["b_qkv"]), E + N, d, 3 * d,
-                     ptr(qkv), qkv.stride(0), ptr(rstd1))
-            else:
-                rstd1 = _rstd(X)
-                gemm(X, T["w_qkv"], qkv, bias=T["b_qkv"], row_scale=rstd1, precision=prec, pack=pw)
-            o = _empty((E + N, d), vec)
-            lse = _empty((E + N, nh), vec)
-            call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,
-                 scale, topo.max_row, prec, ptr(o), ptr(lse))
-            Xn = _empty((E + N, d), vec)  # rows [:E] = t' ; rows [E:] = next centre token
-            gemm(o[:E], T["w_o"], Xn[:E], bias=T["b_o"], residual=X[:E], precision=prec, pack=pw)
-            yc = _empty((N, d), vec)
-            gemm(o[E:], T["w_o"], yc, bias=T["b_o"], precision=prec, pack=pw)
-            h1 = _empty((N, dn), vec)
-            gemm(yc, T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec, pack=pw)
-            # centre MLP (d_node -> 4 d_node -> d_node, SwiGLU)
-            rstd3 = _rstd(h1)
-            ugc = _empty((N, 4 * dn), vec)
-            sc = _empty((N, 2 * dn), vec)
-            gemm(h1, T["wc_in"], sc, bias=T["bc_in"], row_scale=rstd3, epilogue=EPI_SWIGLU,
-                 aux_out=ugc, precision=prec, pack=pw)
-            h2 = _empty((N, dn), vec)
-            gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec, pack=pw)
-            # edge MLP (d_pet -> 2 d_ff -> d_pet, SwiGLU)
-            tp = Xn[:E]
-            dff = T["w_out"].shape[1]
-            Xnnf = _empty((E + N + H, d), vec)
-            Xnn = Xnnf[:E + N]
-            if prec != PREC_FP32 and T["mlp_img"] is not None:
-                # one fused tcgen05 kernel; the backward recomputes the hidden activations
-                rstd2 = ug = None
-                call("mlp_fwd", ptr(tp), tp.stride(0), ptr(T["mlp_img"][0]), ptr(T["b_in"]),
-                     ptr(T["b_out"]), E, d, dff, ptr(Xnn), Xnn.stride(0))
-            else:
-                rstd2 = _rstd(tp)
-                ug = _empty((E, 2 * dff), vec)
-                s = _empty((E, dff), vec)
-                gemm(tp, T["w_in"], s, bias=T["b_in"], row_scale=rstd2, epilogue=EPI_SWIGLU,
-                     aux_out=ug, precision=prec, pack=pw)
-                gemm(s, T["w_out"], Xnn[:E], bias=T["b_out"], residual=tp, precision=prec, pack=pw)
-                del s
-            del sc
-            K.update(X=X, rstd1=rstd1, qkv=qkv, o=o, lse=lse, tp=tp, rstd2=rstd2, ug=ug,
-                     h1=h1, rstd3=rstd3, ugc=ugc)
-            S["tl"].append(K)
-            X, Xf, h = Xnn, Xnnf, h2
+        h, X, Xf, S = _gnn_forward(pw, L, hyp, topo, vec, dist, fc, h, m, prec)
         t = X[:E]
         if halo is not None:
             # reversed messages of halo edges live on the peers: all-to-all-v into the ghost rows
@@ -439,6 +455,115 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
         S.update(t=t, mean=mean, rstd=rstd, p1=p1)
         saved.append(S)
     return h, m, saved
+
+
+
+
+def features_forward_residual(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32):
+    """Residual featurizer, backend.py:589-649: every GNN layer starts from its own node embedding,
+    its node / edge outputs are kept for a readout of their own, and the next layer's input
+    messages are 0.5 * (m + out[reversed edge]).  Returns (list of node features, list of edge
+    features, saved-for-backward)."""
+    N, E = topo.n_atoms, topo.n_edges
+    if topo.halo is not None:
+        raise NotImplementedError("atom-sharded evaluation is built for the feedforward featurizer only")
+    d, dn = hyp["d_pet"], hyp["d_node"]
+    m = _empty((E, d), vec)
+    call("embedding", ptr(pw.edge_emb), ptr(topo.z_neighbors), E, d, ptr(m), d)
+    nodes, edges, saved = [], [], []
+    for l, L in enumerate(pw.gnn):
+        h0 = _empty((N, dn), vec)
+        call("embedding", ptr(pw.node_emb[l]), ptr(topo.z_nodes), N, dn, ptr(h0), dn)
+        h, X, _, S = _gnn_forward(pw, L, hyp, topo, vec, dist, fc, h0, m, prec)
+        t = X[:E]
+        nodes.append(h)
+        edges.append(t)
+        saved.append(S)
+        if l + 1 < len(pw.gnn):
+            m_next = _empty((E, d), vec)
+            call("avg_reverse_fwd", ptr(m), ptr(t), ptr(topo.rev), E, d, ptr(m_next))
+            m = m_next
+    return nodes, edges, saved
+
+
+def _gnn_backward(pw: PackedWeights, L: dict, S: dict, hyp, topo: Topology, fc, d_h, d_t, d_m, d_vec,
+                  d_dist, d_fc, h_grad_wanted: bool, prec):
+    """dgrad of :func:`_gnn_forward`.  Consumes d_h [N,d_node] and d_t [E,d_pet] (gradients of the
+    layer's node / edge outputs); accumulates into d_vec, d_dist, d_fc and, when d_m is given, adds
+    the gradient w.r.t. the layer's input messages to it.  Returns the gradient w.r.t. the input
+    node features (None unless ``h_grad_wanted``: the node embedding needs no gradient)."""
+    N, E = topo.n_atoms, topo.n_edges
+    d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
+    scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    ref = fc
+    for k in range(len(L["tl"]) - 1, -1, -1):
+        T, K = L["tl"][k], S["tl"][k]
+        dff = T["w_out"].shape[1]
+        # ---- edge MLP: t'' = t' + W_out swiglu(W_in rms(t'))
+        d_tp = _empty((E, d), ref)
+        d_xh = _empty((E, d), ref)
+        if K["ug"] is None:
+            call("mlp_bwd", ptr(K["tp"]), K["tp"].stride(0), ptr(d_t), d_t.stride(0),
+                 ptr(T["mlp_img"][1]), ptr(T["b_in"]), E, d, dff, ptr(d_tp), d_tp.stride(0))
+        else:
+            d_ug = _empty((E, 2 * dff), ref)
+            gemm(d_t, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec,
+                 pack=pw)
+            gemm(d_ug, T["w_in_t"], d_xh, precision=prec, pack=pw)
+            del d_ug
+            _rms_bwd(d_xh, K["tp"], K["rstd2"], d_t, d_tp)
+        # ---- centre MLP: h2 = h1 + Wc_out swiglu(Wc_in rms(h1))
+        d_ugc = _empty((N, 4 * dn), ref)
+        gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec, pack=pw)
+        d_xhc = _empty((N, dn), ref)
+        gemm(d_ugc, T["wc_in_t"], d_xhc, precision=prec, pack=pw)
+        d_h1 = _empty((N, dn), ref)
+        _rms_bwd(d_xhc, K["h1"], K["rstd3"], d_h, d_h1)
+        # ---- h1 = h + W_exp y_c ;  t' = t + y_e ;  y = W_o o
+        d_yc = _empty((N, d), ref)
+        gemm(d_h1, T["w_exp_t"], d_yc, precision=prec, pack=pw)
+        d_o = _empty((E + N, d), ref)
+        gemm(d_tp, T["w_o_t"], d_o[:E], precision=prec, pack=pw)
+        gemm(d_yc, T["w_o_t"], d_o[E:], precision=prec, pack=pw)
+        d_qkv = _empty((E + N, 3 * d), ref)
+        dsum = _empty((E + N, nh), ref)
+        call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o),
+             ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row, prec,
+             ptr(d_qkv), ptr(d_fc), ptr(dsum))
+        d_t_new = d_xh  # reuse
+        d_c = d_yc  # reuse
+        if prec != PREC_FP32 and d == 128:
+            # dgrad through the QKV projection and the RMSNorm in front of it in one kernel
+            # (RMSNorm backward in the GEMM epilogue), edge rows and centre rows
+            gemm(d_qkv[:E], T["w_qkv_t"], d_t_new, epilogue=EPI_RMS_BWD, aux_in=K["X"][:E],
+                 row_scale=K["rstd1"][:E], residual=d_tp, precision=prec, pack=pw)
+            gemm(d_qkv[E:], T["w_qkv_t"], d_c, epilogue=EPI_RMS_BWD, aux_in=K["X"][E:],
+                 row_scale=K["rstd1"][E:], precision=prec, pack=pw)
+        else:
+            d_xh1 = d_o  # reuse
+            gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec, pack=pw)
+            _rms_bwd(d_xh1[:E], K["X"][:E], K["rstd1"][:E], d_tp, d_t_new)
+            _rms_bwd(d_xh1[E:], K["X"][E:], K["rstd1"][E:], None, d_c)
+        del d_qkv
+        if h_grad_wanted or k > 0:
+            d_h_new = _empty((N, dn), ref)
+            gemm(d_c, T["w_con_t"], d_h_new, residual=d_h1, precision=prec, pack=pw)
+            d_h = d_h_new
+        d_t = d_t_new
+    # ---- token builder: t = W_2 silu(W_1 cat[geo, nbr, m] + b_1) + b_2
+    d_c1 = _empty((E, d), ref)
+    gemm(d_t, L["w2_t"], d_c1, epilogue=EPI_MUL_DSILU, aux_in=S["c1"], precision=prec, pack=pw)
+    if prec != PREC_FP32 and d == 128:
+        # (W_1geo . W_geo)^T applied to d_c1 directly: no d_geo GEMM
+        call("geom_embed_bwd", ptr(d_c1), d, ptr(L["geo_fold"]), E, d, 1, ptr(d_vec), ptr(d_dist))
+    else:
+        d_geo = _empty((E, d), ref)
+        gemm(d_c1, L["w1_t"][:d], d_geo, precision=prec, pack=pw)
+        call("geom_embed_bwd", ptr(d_geo), d, ptr(L["w_geo"]), E, d, 1, ptr(d_vec), ptr(d_dist))
+    if d_m is not None:
+        width = L["w1_t"].shape[0]
+        gemm(d_c1, L["w1_t"][width - d:], d_m, accumulate=True, precision=prec, pack=pw)
+    return d_h if h_grad_wanted else None
 
 
 def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_m,
@@ -476,80 +601,43 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
         d_t = _empty((E, d), ref)
         call("combine_scatter_bwd", ptr(d_cat), ptr(d_m), ptr(rev_bwd), E, d, ptr(d_t))
         del d_cc, d_cat, d_p1, d_p1f
-        for k in range(len(L["tl"]) - 1, -1, -1):
-            T, K = L["tl"][k], S["tl"][k]
-            dff = T["w_out"].shape[1]
-            # ---- edge MLP: t'' = t' + W_out swiglu(W_in rms(t'))
-            d_tp = _empty((E, d), ref)
-            d_xh = _empty((E, d), ref)
-            if K["ug"] is None:
-                call("mlp_bwd", ptr(K["tp"]), K["tp"].stride(0), ptr(d_t), d_t.stride(0),
-                     ptr(T["mlp_img"][1]), ptr(T["b_in"]), E, d, dff, ptr(d_tp), d_tp.stride(0))
-            else:
-                d_ug = _empty((E, 2 * dff), ref)
-                gemm(d_t, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec,
-                     pack=pw)
-                gemm(d_ug, T["w_in_t"], d_xh, precision=prec, pack=pw)
-                del d_ug
-                _rms_bwd(d_xh, K["tp"], K["rstd2"], d_t, d_tp)
-            # ---- centre MLP: h2 = h1 + Wc_out swiglu(Wc_in rms(h1))
-            d_ugc = _empty((N, 4 * dn), ref)
-            gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec, pack=pw)
-            d_xhc = _empty((N, dn), ref)
-            gemm(d_ugc, T["wc_in_t"], d_xhc, precision=prec, pack=pw)
-            d_h1 = _empty((N, dn), ref)
-            _rms_bwd(d_xhc, K["h1"], K["rstd3"], d_h, d_h1)
-            # ---- h1 = h + W_exp y_c ;  t' = t + y_e ;  y = W_o o
-            d_yc = _empty((N, d), ref)
-            gemm(d_h1, T["w_exp_t"], d_yc, precision=prec, pack=pw)
-            d_o = _empty((E + N, d), ref)
-            gemm(d_tp, T["w_o_t"], d_o[:E], precision=prec, pack=pw)
-            gemm(d_yc, T["w_o_t"], d_o[E:], precision=prec, pack=pw)
-            d_qkv = _empty((E + N, 3 * d), ref)
-            dsum = _empty((E + N, nh), ref)
-            call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o),
-                 ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh, scale, topo.max_row, prec,
-                 ptr(d_qkv), ptr(d_fc), ptr(dsum))
-            d_t_new = d_xh  # reuse
-            d_c = d_yc  # reuse
-            if prec != PREC_FP32 and d == 128:
-                # dgrad through the QKV projection and the RMSNorm in front of it in one kernel
-                # (RMSNorm backward in the GEMM epilogue), edge rows and centre rows
-                gemm(d_qkv[:E], T["w_qkv_t"], d_t_new, epilogue=EPI_RMS_BWD, aux_in=K["X"][:E],
-                     row_scale=K["rstd1"][:E], residual=d_tp, precision=prec, pack=pw)
-                gemm(d_qkv[E:], T["w_qkv_t"], d_c, epilogue=EPI_RMS_BWD, aux_in=K["X"][E:],
-                     row_scale=K["rstd1"][E:], precision=prec, pack=pw)
-            else:
-                d_xh1 = d_o  # reuse
-                gemm(d_qkv, T["w_qkv_t"], d_xh1, precision=prec, pack=pw)
-                _rms_bwd(d_xh1[:E], K["X"][:E], K["rstd1"][:E], d_tp, d_t_new)
-                _rms_bwd(d_xh1[E:], K["X"][E:], K["rstd1"][E:], None, d_c)
-            del d_qkv
-            if l > 0 or k > 0:
-                d_h_new = _empty((N, dn), ref)
-                gemm(d_c, T["w_con_t"], d_h_new, residual=d_h1, precision=prec, pack=pw)
-                d_h = d_h_new
-            d_t = d_t_new
-        # ---- token builder: t = W_2 silu(W_1 cat[geo, nbr, m] + b_1) + b_2
-        d_c1 = _empty((E, d), ref)
-        gemm(d_t, L["w2_t"], d_c1, epilogue=EPI_MUL_DSILU, aux_in=S["c1"], precision=prec, pack=pw)
-        if prec != PREC_FP32 and d == 128:
-            # (W_1geo . W_geo)^T applied to d_c1 directly: no d_geo GEMM
-            call("geom_embed_bwd", ptr(d_c1), d, ptr(L["geo_fold"]), E, d, 1, ptr(d_vec), ptr(d_dist))
-        else:
-            d_geo = _empty((E, d), ref)
-            gemm(d_c1, L["w1_t"][:d], d_geo, precision=prec, pack=pw)
-            call("geom_embed_bwd", ptr(d_geo), d, ptr(L["w_geo"]), E, d, 1, ptr(d_vec), ptr(d_dist))
+        d_h_in = _gnn_backward(pw, L, S, hyp, topo, fc, d_h, d_t, d_m if l > 0 else None, d_vec, d_dist,
+                               d_fc, l > 0, prec)
         if l > 0:
-            width = L["w1_t"].shape[0]
-            gemm(d_c1, L["w1_t"][width - d:], d_m, accumulate=True, precision=prec, pack=pw)
+            d_h = d_h_in
+    return d_vec, d_dist, d_fc
+
+
+def features_backward_residual(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_nodes, d_edges,
+                               prec=PREC_FP32):
+    """dgrad of :func:`features_forward_residual`; ``d_nodes`` / ``d_edges`` are lists (entries may be
+    None).  Returns (d_vec [E,3], d_dist [E], d_fc [E])."""
+    N, E = topo.n_atoms, topo.n_edges
+    d, dn = hyp["d_pet"], hyp["d_node"]
+    d_vec = torch.zeros((E, 3), device=fc.device)
+    d_dist = torch.zeros((E,), device=fc.device)
+    d_fc = torch.zeros((E,), device=fc.device)
+    d_m_next = None  # gradient w.r.t. the input messages of layer l + 1
+    for l in range(len(pw.gnn) - 1, -1, -1):
+        d_h = d_nodes[l].contiguous() if d_nodes[l] is not None else torch.zeros((N, dn), device=fc.device)
+        d_t = d_edges[l].contiguous().clone() if d_edges[l] is not None else torch.zeros((E, d), device=fc.device)
+        d_m = None
+        if d_m_next is not None:
+            # m_{l+1} = 0.5 (m_l + t_l[rev]):  d_t[e] += 0.5 d_m_next[rev[e]],  d_m_l = 0.5 d_m_next
+            d_m = _empty((E, d), fc)
+            call("avg_reverse_bwd", ptr(d_m_next), ptr(topo.rev), E, d, ptr(d_t), ptr(d_m))
+        elif l > 0:
+            d_m = torch.zeros((E, d), device=fc.device)
+        _gnn_backward(pw, pw.gnn[l], saved[l], hyp, topo, fc, d_h, d_t, d_m if l > 0 else None, d_vec, d_dist,
+                      d_fc, False, prec)
+        d_m_next = d_m if l > 0 else None
     return d_vec, d_dist, d_fc
 
 
 # ----------------------------------------------------------------------------- readout
-def predict_forward(pw: PackedWeights, topo: Topology, name: str, h, m, fc, prec=PREC_FP32):
-    """backend.py:651-777 for one target: heads, last layers, sum_j f_ij e_ij."""
-    H = pw.heads[name]
+def predict_forward(pw: PackedWeights, topo: Topology, name: str, h, m, fc, prec=PREC_FP32, layer=0):
+    """backend.py:651-777 for one target and one readout layer: heads, last layers, sum_j f_ij e_ij."""
+    H = pw.heads[name][layer]
     N, E = topo.n_atoms, topo.n_edges
     dh = H["n2"].shape[0]
     n1, n1p = _empty((N, dh), h), _empty((N, dh), h)
@@ -570,8 +658,8 @@ def predict_forward(pw: PackedWeights, topo: Topology, name: str, h, m, fc, prec
 
 
 def predict_backward(pw: PackedWeights, topo: Topology, name: str, fc, saved, d_atomic,
-                     prec=PREC_FP32):
-    H = pw.heads[name]
+                     prec=PREC_FP32, layer=0):
+    H = pw.heads[name][layer]
     N, E = topo.n_atoms, topo.n_edges
     dh = H["n2"].shape[0]
     n_out = H["wn"].shape[0]

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "petb200_transpose_scale": [_P, _I, _I, _P, _P, _P, _P],
     "petb200_compress_input": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_geom_embed_bwd": [_P, _I64, _P, _I64, _I, _I, _P, _P, _P],
+    "petb200_avg_reverse_fwd": [_P, _P, _P, _I64, _I, _P, _P],
+    "petb200_avg_reverse_bwd": [_P, _P, _I64, _I, _P, _P, _P],
     "petb200_rms_rstd": [_P, _I64, _I, _P, _P],
     "petb200_rms_bwd": [_P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_attention_fwd": [_P, _P, _P, _I64, _I64, _I, _I, _F, _I, _I, _P, _P, _P],

@@ -99,17 +99,22 @@ class PETParameters(nn.Module):
                 for l in range(self.num_gnn_layers)
             ]
         )
-        self.num_readout_layers = 1  # feedforward featurizer (backend.py:93-94)
-        self.combination_norms = nn.ModuleList(
-            [nn.LayerNorm(2 * self.d_pet) for _ in range(self.num_gnn_layers)]
-        )
-        self.combination_mlps = nn.ModuleList(
-            [
-                nn.Sequential(nn.Linear(2 * self.d_pet, 2 * self.d_pet), nn.SiLU(),
-                              nn.Linear(2 * self.d_pet, self.d_pet))
-                for _ in range(self.num_gnn_layers)
-            ]
-        )
+        if hypers.get("featurizer_type", "feedforward") == "feedforward":
+            self.num_readout_layers = 1  # backend.py:93-107
+            self.combination_norms = nn.ModuleList(
+                [nn.LayerNorm(2 * self.d_pet) for _ in range(self.num_gnn_layers)]
+            )
+            self.combination_mlps = nn.ModuleList(
+                [
+                    nn.Sequential(nn.Linear(2 * self.d_pet, 2 * self.d_pet), nn.SiLU(),
+                                  nn.Linear(2 * self.d_pet, self.d_pet))
+                    for _ in range(self.num_gnn_layers)
+                ]
+            )
+        else:  # residual featurizer: one readout per GNN layer, no combination MLPs (:108-111)
+            self.num_readout_layers = self.num_gnn_layers
+            self.combination_norms = nn.ModuleList()
+            self.combination_mlps = nn.ModuleList()
         self.node_embedders = nn.ModuleList(
             [nn.Embedding(n_species, self.d_node) for _ in range(self.num_readout_layers)]
         )

@@ -143,6 +143,10 @@ def main():
     # non-strict neighbor list: pairs out to 5.5 A are handed in and must be dropped
     make_case("water_384_nonstrict", [water], [1, 8], nl_cutoff=5.5, fp64=False)
 
+    # residual featurizer (backend.py:589-649)
+    make_case("qm9_5_residual", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=dict(featurizer_type="residual"))
+    make_case("water_384_residual", [water], [1, 8], hypers=dict(featurizer_type="residual"), fp64=False)
+
     carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
     make_case("carbon_5", carbon, [6], with_strain=False)
 
