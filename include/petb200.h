@@ -268,6 +268,15 @@ PETB200_API int petb200_rms_bwd(const float* d_xhat, const float* x, const float
                     const float* base, int64_t n_rows, int d, float* out,
                     petb200_stream_t stream);
 
+/* RMSNorm as a standalone op (PostLN transformer, transformer.py:236-262): y = x * rstd * gamma
+ * with rstd kept; backward out = base + rstd * (g - xhat * mean(g * xhat)), g = d_y * gamma
+ * (base nullable).                                                                        */
+PETB200_API int petb200_rms_norm_fwd(const float* x, const float* gamma, int64_t n_rows, int d, float* y,
+                         float* rstd, petb200_stream_t stream);
+PETB200_API int petb200_rms_norm_bwd(const float* d_y, const float* x, const float* rstd, const float* gamma,
+                         const float* base, int64_t n_rows, int d, float* out,
+                         petb200_stream_t stream);
+
 /* ---------------------------------------------------------------------- attention
  * Per-atom multi-head attention over tokens {centre i} U {edges of row i} with the
  * key-only additive bias log(max(w_q, 1e-15)), w = 1 for the centre token and f_e for

@@ -14,9 +14,10 @@ may read from ``batch_data`` (``padding_mask``, ``cutoff_factors``, ``edge_dista
 ``model.py:436-459,512-513``) are still produced, from the CSR data, so that the wrapper
 keeps working unchanged.
 
-Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649).  Not built yet
-(raise ``NotImplementedError``): adaptive cutoff, PostLN / LayerNorm / SiLU variants, system
-conditioning, weight gradients (training).
+Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649); transformer types
+``PreLN`` (default) and ``PostLN`` (transformer.py:236-262).  Not built yet (raise
+``NotImplementedError``): adaptive cutoff, LayerNorm / SiLU variants, system conditioning, weight
+gradients (training).
 """
 from typing import Dict, List, Optional, Tuple
 
@@ -204,8 +205,6 @@ class B200PETBackend(PETParameters):
         unsupported = []
         if hypers["normalization"] != "RMSNorm":
             unsupported.append("normalization=" + hypers["normalization"])
-        if hypers["transformer_type"] != "PreLN":
-            unsupported.append("transformer_type=" + hypers["transformer_type"])
         if hypers["activation"] != "SwiGLU":
             unsupported.append("activation=" + hypers["activation"])
         if hypers["featurizer_type"] not in ("feedforward", "residual"):

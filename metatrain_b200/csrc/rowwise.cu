@@ -180,10 +180,36 @@ __global__ void rms_rstd_kernel(const float* __restrict__ x, int64_t n_rows,
   if (lane == 0) rstd[row] = rsqrtf(ss / (float)(128 * V) + FLT_EPSILON);
 }
 
+// y = x * rstd * gamma (torch.nn.RMSNorm as a standalone op: the PostLN transformer normalises
+// the residual stream itself, transformer.py:236-262), rstd kept for the backward
+template <int V>
+__global__ void rms_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                    int64_t n_rows, float* __restrict__ y, float* __restrict__ rstd) {
+  int64_t row = global_warp();
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 t[V];
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    t[v] = __ldg(reinterpret_cast<const float4*>(x) + row * (32 * V) + v * 32 + lane);
+    ss += t[v].x * t[v].x + t[v].y * t[v].y + t[v].z * t[v].z + t[v].w * t[v].w;
+  }
+  const float rs = rsqrtf(warp_sum(ss) / (float)(128 * V) + FLT_EPSILON);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v * 32 + lane);
+    reinterpret_cast<float4*>(y)[row * (32 * V) + v * 32 + lane] =
+        make_float4(t[v].x * rs * g.x, t[v].y * rs * g.y, t[v].z * rs * g.z, t[v].w * rs * g.w);
+  }
+  if (lane == 0) rstd[row] = rs;
+}
+
 // out = base + rstd * (d_xhat - xhat * mean(d_xhat * xhat)),  xhat = x * rstd
 template <int V>
 __global__ void rms_bwd_kernel(const float* __restrict__ d_xhat, const float* __restrict__ x,
                                const float* __restrict__ rstd, const float* __restrict__ base,
+                               const float* __restrict__ gamma /* nullable: d_xhat = dy * gamma */,
                                int64_t n_rows, float* __restrict__ out) {
   int64_t row = global_warp();
   if (row >= n_rows) return;
@@ -194,6 +220,10 @@ __global__ void rms_bwd_kernel(const float* __restrict__ d_xhat, const float* __
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     g[v] = __ldg(reinterpret_cast<const float4*>(d_xhat) + row * (32 * V) + v * 32 + lane);
+    if (gamma) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(gamma) + v * 32 + lane);
+      g[v] = make_float4(g[v].x * w.x, g[v].y * w.y, g[v].z * w.z, g[v].w * w.w);
+    }
     float4 t = __ldg(reinterpret_cast<const float4*>(x) + row * (32 * V) + v * 32 + lane);
     xh[v] = make_float4(t.x * rs, t.y * rs, t.z * rs, t.w * rs);
     dot += g[v].x * xh[v].x + g[v].y * xh[v].y + g[v].z * xh[v].z + g[v].w * xh[v].w;
@@ -481,14 +511,41 @@ extern "C" PETB200_API int petb200_rms_bwd(const float* d_xhat, const float* x, 
                                const float* base, int64_t n_rows, int d, float* out,
                                cudaStream_t stream) {
   if (d == 128) {
-    LAUNCH_ROWS(rms_bwd_kernel<1>, n_rows, d_xhat, x, rstd, base, n_rows, out);
+    LAUNCH_ROWS(rms_bwd_kernel<1>, n_rows, d_xhat, x, rstd, base, nullptr, n_rows, out);
   } else if (d == 256) {
-    LAUNCH_ROWS(rms_bwd_kernel<2>, n_rows, d_xhat, x, rstd, base, n_rows, out);
+    LAUNCH_ROWS(rms_bwd_kernel<2>, n_rows, d_xhat, x, rstd, base, nullptr, n_rows, out);
   } else {
     set_error("rms_bwd: d must be 128 or 256 (got %d)", d);
     return PETB200_ERR_UNSUPPORTED;
   }
   return check_launch("rms_bwd");
+}
+
+extern "C" PETB200_API int petb200_rms_norm_fwd(const float* x, const float* gamma, int64_t n_rows, int d,
+                                    float* y, float* rstd, cudaStream_t stream) {
+  if (d == 128) {
+    LAUNCH_ROWS(rms_norm_fwd_kernel<1>, n_rows, x, gamma, n_rows, y, rstd);
+  } else if (d == 256) {
+    LAUNCH_ROWS(rms_norm_fwd_kernel<2>, n_rows, x, gamma, n_rows, y, rstd);
+  } else {
+    set_error("rms_norm_fwd: d must be 128 or 256 (got %d)", d);
+    return PETB200_ERR_UNSUPPORTED;
+  }
+  return check_launch("rms_norm_fwd");
+}
+
+extern "C" PETB200_API int petb200_rms_norm_bwd(const float* d_y, const float* x, const float* rstd,
+                                    const float* gamma, const float* base, int64_t n_rows, int d,
+                                    float* out, cudaStream_t stream) {
+  if (d == 128) {
+    LAUNCH_ROWS(rms_bwd_kernel<1>, n_rows, d_y, x, rstd, base, gamma, n_rows, out);
+  } else if (d == 256) {
+    LAUNCH_ROWS(rms_bwd_kernel<2>, n_rows, d_y, x, rstd, base, gamma, n_rows, out);
+  } else {
+    set_error("rms_norm_bwd: d must be 128 or 256 (got %d)", d);
+    return PETB200_ERR_UNSUPPORTED;
+  }
+  return check_launch("rms_norm_bwd");
 }
 
 extern "C" PETB200_API int petb200_combine_ln_fwd(const float* t, const int32_t* rev, const float* gamma,

@@ -189,6 +189,7 @@ class PackedWeights:
         self.signature = self._signature(module)
         self.split_cache: Dict[tuple, Tensor] = {}
         g = lambda t: t.detach()  # noqa: E731
+        post_ln = getattr(module, "hypers", {}).get("transformer_type", "PreLN") == "PostLN"
         self.gnn: List[dict] = []
         for layer in module.gnn_layers:
             L: dict = {}
@@ -218,6 +219,12 @@ class PackedWeights:
                     tl.attention.input_linear.weight, tl.norm_attention.weight, True)
                 T["b_qkv"] = g(tl.attention.input_linear.bias)
                 T["qkv_img"] = _linear_image(T["w_qkv"])   # fused RMSNorm + QKV projection
+                if post_ln:
+                    # PostLN normalises the residual stream itself: the Linears see un-normalised
+                    # inputs, so the norm weights are NOT folded (transformer.py:236-262)
+                    T["w_qkv_raw"] = g(tl.attention.input_linear.weight)
+                    T["w_qkv_raw_t"], _ = _t_and_scaled(tl.attention.input_linear.weight)
+                    T["g_attn"], T["g_mlp"] = g(tl.norm_attention.weight), g(tl.norm_mlp.weight)
                 T["w_o"] = g(tl.attention.output_linear.weight)
                 T["b_o"] = g(tl.attention.output_linear.bias)
                 T["w_o_t"], _ = _t_and_scaled(tl.attention.output_linear.weight)
@@ -228,6 +235,9 @@ class PackedWeights:
                 T["w_out_t"], _ = _t_and_scaled(tl.mlp.w_out.weight)
                 # operand-tile images of the fused feed-forward kernels (petb200_mlp_fwd / _bwd)
                 T["mlp_img"] = _mlp_images(T["w_in"], T["w_out"])
+                if post_ln:
+                    T["w_in_raw"] = g(tl.mlp.w_in.weight)
+                    T["w_in_raw_t"], _ = _t_and_scaled(tl.mlp.w_in.weight)
                 T["w_con"] = g(tl.center_contraction.weight)
                 T["b_con"] = g(tl.center_contraction.bias)
                 T["w_con_t"], _ = _t_and_scaled(tl.center_contraction.weight)
@@ -339,6 +349,100 @@ def _rms_bwd(d_xhat, x, rstd, base, out):
     return out
 
 
+def _rms_norm(x: Tensor, gamma: Tensor, out: Tensor):
+    rstd = _empty((x.shape[0],), x)
+    call("rms_norm_fwd", ptr(x), ptr(gamma), x.shape[0], x.shape[1], ptr(out), ptr(rstd))
+    return rstd
+
+
+def _tl_forward_postln(pw: PackedWeights, T: dict, hyp, topo: Topology, fc, h, X, H, prec):
+    """TransformerLayer._forward_post_ln_impl (transformer.py:236-262) on the [E + N] token matrix:
+    tokens = norm_attention(tokens + attention(tokens)); tokens = norm_mlp(tokens + mlp(tokens))
+    for ALL tokens (edges and centre), then the node update from the centre token."""
+    N, E = topo.n_atoms, topo.n_edges
+    d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
+    scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec, pack=pw)
+    qkv = _empty((E + N, 3 * d), fc)
+    gemm(X, T["w_qkv_raw"], qkv, bias=T["b_qkv"], precision=prec, pack=pw)
+    o = _empty((E + N, d), fc)
+    lse = _empty((E + N, nh), fc)
+    call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,
+         scale, topo.max_row, prec, ptr(o), ptr(lse))
+    Z1 = _empty((E + N, d), fc)
+    gemm(o, T["w_o"], Z1, bias=T["b_o"], residual=X, precision=prec, pack=pw)
+    X1 = _empty((E + N, d), fc)
+    rstd1 = _rms_norm(Z1, T["g_attn"], X1)
+    dff = T["w_out"].shape[1]
+    ug = _empty((E + N, 2 * dff), fc)
+    s = _empty((E + N, dff), fc)
+    gemm(X1, T["w_in_raw"], s, bias=T["b_in"], epilogue=EPI_SWIGLU, aux_out=ug, precision=prec, pack=pw)
+    Z2 = _empty((E + N, d), fc)
+    gemm(s, T["w_out"], Z2, bias=T["b_out"], residual=X1, precision=prec, pack=pw)
+    del s
+    X2f = _empty((E + N + H, d), fc)
+    X2 = X2f[:E + N]
+    rstd2 = _rms_norm(Z2, T["g_mlp"], X2)
+    # node update from the centre token (as in the PreLN layer)
+    h1 = _empty((N, dn), fc)
+    gemm(X2[E:], T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec, pack=pw)
+    rstd3 = _rstd(h1)
+    ugc = _empty((N, 4 * dn), fc)
+    sc = _empty((N, 2 * dn), fc)
+    gemm(h1, T["wc_in"], sc, bias=T["bc_in"], row_scale=rstd3, epilogue=EPI_SWIGLU, aux_out=ugc,
+         precision=prec, pack=pw)
+    h2 = _empty((N, dn), fc)
+    gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec, pack=pw)
+    K = dict(X=X, qkv=qkv, o=o, lse=lse, Z1=Z1, rstd1=rstd1, X1=X1, ug=ug, Z2=Z2, rstd2=rstd2,
+             h1=h1, rstd3=rstd3, ugc=ugc)
+    return X2, X2f, h2, K
+
+
+def _tl_backward_postln(pw: PackedWeights, T: dict, K: dict, hyp, topo: Topology, fc, d_h, d_t, d_fc,
+                        h_grad_wanted: bool, prec):
+    """dgrad of :func:`_tl_forward_postln`: (d_h [N,d_node], d_t [E,d_pet]) of the layer outputs ->
+    (d_t, d_h) of its inputs; the key-bias gradient is accumulated into d_fc."""
+    N, E = topo.n_atoms, topo.n_edges
+    d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
+    scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    dff = T["w_out"].shape[1]
+    # ---- node update: h2 = h1 + Wc_out swiglu(Wc_in rms(h1)),  h1 = h + W_exp X2[E:]
+    d_ugc = _empty((N, 4 * dn), fc)
+    gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec, pack=pw)
+    d_xhc = _empty((N, dn), fc)
+    gemm(d_ugc, T["wc_in_t"], d_xhc, precision=prec, pack=pw)
+    d_h1 = _empty((N, dn), fc)
+    _rms_bwd(d_xhc, K["h1"], K["rstd3"], d_h, d_h1)
+    d_X2 = _empty((E + N, d), fc)
+    d_X2[:E].copy_(d_t)
+    gemm(d_h1, T["w_exp_t"], d_X2[E:], precision=prec, pack=pw)
+    # ---- X2 = norm_mlp(Z2),  Z2 = X1 + W_out swiglu(W_in X1 + b_in) + b_out
+    d_Z2 = _empty((E + N, d), fc)
+    call("rms_norm_bwd", ptr(d_X2), ptr(K["Z2"]), ptr(K["rstd2"]), ptr(T["g_mlp"]), None, E + N, d, ptr(d_Z2))
+    d_ug = _empty((E + N, 2 * dff), fc)
+    gemm(d_Z2, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec, pack=pw)
+    d_X1 = d_X2  # reuse
+    gemm(d_ug, T["w_in_raw_t"], d_X1, residual=d_Z2, precision=prec, pack=pw)
+    del d_ug
+    # ---- X1 = norm_attention(Z1),  Z1 = X + W_o attention(W_qkv X + b_qkv) + b_o
+    d_Z1 = d_Z2  # reuse
+    call("rms_norm_bwd", ptr(d_X1), ptr(K["Z1"]), ptr(K["rstd1"]), ptr(T["g_attn"]), None, E + N, d, ptr(d_Z1))
+    d_o = d_X1  # reuse
+    gemm(d_Z1, T["w_o_t"], d_o, precision=prec, pack=pw)
+    d_qkv = _empty((E + N, 3 * d), fc)
+    dsum = _empty((E + N, nh), fc)
+    call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o), ptr(topo.row_ptr), ptr(fc),
+         N, E, nh, d // nh, scale, topo.max_row, prec, ptr(d_qkv), ptr(d_fc), ptr(dsum))
+    d_X = _empty((E + N, d), fc)
+    gemm(d_qkv, T["w_qkv_raw_t"], d_X, residual=d_Z1, precision=prec, pack=pw)
+    del d_qkv
+    d_h_new = None
+    if h_grad_wanted:
+        d_h_new = _empty((N, dn), fc)
+        gemm(d_X[E:], T["w_con_t"], d_h_new, residual=d_h1, precision=prec, pack=pw)
+    return d_X[:E], (d_h_new if h_grad_wanted else d_h)
+
+
 def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc, h, m, prec):
     """One CartesianTransformer (transformer.py:463-562) on the CSR layout.  Returns the node
     features after its attention layers, the token matrix X ([E + N] rows; rows [:E] are the output
@@ -370,6 +474,10 @@ def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc,
     del a1
     S["c1"] = c1
     for T in L["tl"]:
+        if hyp["transformer_type"] == "PostLN":
+            X, Xf, h, K = _tl_forward_postln(pw, T, hyp, topo, fc, h, X, H, prec)
+            S["tl"].append(K)
+            continue
         K: dict = {}
         gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec, pack=pw)
         qkv = _empty((E + N, 3 * d), vec)
@@ -499,6 +607,9 @@ def _gnn_backward(pw: PackedWeights, L: dict, S: dict, hyp, topo: Topology, fc, 
     for k in range(len(L["tl"]) - 1, -1, -1):
         T, K = L["tl"][k], S["tl"][k]
         dff = T["w_out"].shape[1]
+        if hyp["transformer_type"] == "PostLN":
+            d_t, d_h = _tl_backward_postln(pw, T, K, hyp, topo, fc, d_h, d_t, d_fc, h_grad_wanted or k > 0, prec)
+            continue
         # ---- edge MLP: t'' = t' + W_out swiglu(W_in rms(t'))
         d_tp = _empty((E, d), ref)
         d_xh = _empty((E, d), ref)

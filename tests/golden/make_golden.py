@@ -146,6 +146,9 @@ def main():
     # residual featurizer (backend.py:589-649)
     make_case("qm9_5_residual", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=dict(featurizer_type="residual"))
     make_case("water_384_residual", [water], [1, 8], hypers=dict(featurizer_type="residual"), fp64=False)
+    # PostLN transformer layers (transformer.py:236-262)
+    make_case("qm9_5_postln", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=dict(transformer_type="PostLN"))
+    make_case("water_384_postln", [water], [1, 8], hypers=dict(transformer_type="PostLN"), fp64=False)
 
     carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
     make_case("carbon_5", carbon, [6], with_strain=False)

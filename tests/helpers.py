@@ -10,7 +10,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64",
                 "si_64_cosine", "co_periodic", "ragged_mix",
                 # residual featurizer (backend.py:589-649): one readout per GNN layer
-                "qm9_5_residual", "water_384_residual"]
+                "qm9_5_residual", "water_384_residual",
+                # PostLN transformer layers (transformer.py:236-262)
+                "qm9_5_postln", "water_384_postln"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(
