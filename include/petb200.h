@@ -277,6 +277,15 @@ PETB200_API int petb200_rms_norm_bwd(const float* d_y, const float* x, const flo
                          const float* base, int64_t n_rows, int d, float* out,
                          petb200_stream_t stream);
 
+/* torch.nn.LayerNorm(d) (eps 1e-5, affine) as a standalone op for normalization = "LayerNorm"
+ * (transformer.py:181-186): y = (x - mean) * rstd * gamma + beta; backward
+ * out = base + rstd * (g - mean(g) - xhat * mean(g * xhat)), g = d_y * gamma (base nullable).  */
+PETB200_API int petb200_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t n_rows,
+                           int d, float* y, float* mean, float* rstd, petb200_stream_t stream);
+PETB200_API int petb200_layer_norm_bwd(const float* d_y, const float* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* base, int64_t n_rows, int d, float* out,
+                           petb200_stream_t stream);
+
 /* ---------------------------------------------------------------------- attention
  * Per-atom multi-head attention over tokens {centre i} U {edges of row i} with the
  * key-only additive bias log(max(w_q, 1e-15)), w = 1 for the centre token and f_e for

@@ -15,9 +15,9 @@ may read from ``batch_data`` (``padding_mask``, ``cutoff_factors``, ``edge_dista
 keeps working unchanged.
 
 Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649); transformer types
-``PreLN`` (default) and ``PostLN`` (transformer.py:236-262).  Not built yet (raise
-``NotImplementedError``): adaptive cutoff, LayerNorm / SiLU variants, system conditioning, weight
-gradients (training).
+``PreLN`` (default) and ``PostLN`` (transformer.py:236-262); normalisation ``RMSNorm`` (default) or
+``LayerNorm``; activation ``SwiGLU`` (default) or ``SiLU``.  Not built yet (raise
+``NotImplementedError``): adaptive cutoff, system conditioning, weight gradients (training).
 """
 from typing import Dict, List, Optional, Tuple
 
@@ -203,10 +203,6 @@ class B200PETBackend(PETParameters):
             raise ValueError(f"Unknown cutoff function type: {hypers['cutoff_function']}. "
                              f"Supported types are 'Cosine' and 'Bump'.")
         unsupported = []
-        if hypers["normalization"] != "RMSNorm":
-            unsupported.append("normalization=" + hypers["normalization"])
-        if hypers["activation"] != "SwiGLU":
-            unsupported.append("activation=" + hypers["activation"])
         if hypers["featurizer_type"] not in ("feedforward", "residual"):
             raise ValueError(f"Unknown featurizer type: {hypers['featurizer_type']}")
         if hypers.get("num_neighbors_adaptive") is not None:
@@ -215,8 +211,8 @@ class B200PETBackend(PETParameters):
             unsupported.append("system_conditioning")
         if (hypers["d_pet"], hypers["d_node"], hypers["d_head"], hypers["num_heads"]) != (128, 256, 128, 8):
             unsupported.append("d_pet/d_node/d_head/num_heads other than 128/256/128/8")
-        if hypers["d_feedforward"] % 64 != 0:
-            unsupported.append("d_feedforward not a multiple of 64")
+        if hypers["d_feedforward"] % 128 != 0:
+            unsupported.append("d_feedforward not a multiple of 128")
         if unsupported:
             raise NotImplementedError(
                 "B200PETBackend: not built yet (SURVEY.md 8(f).4): " + ", ".join(unsupported))

@@ -242,6 +242,79 @@ __global__ void rms_bwd_kernel(const float* __restrict__ d_xhat, const float* __
   }
 }
 
+// ------------------------------------------------- LayerNorm as a standalone op
+// torch.nn.LayerNorm(d) (eps = 1e-5, affine) for the normalization = "LayerNorm" variant
+// (transformer.py:181-186): y = (x - mean) * rstd * gamma + beta; mean and rstd kept.
+template <int V>
+__global__ void layer_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int64_t n_rows,
+                                      float* __restrict__ y, float* __restrict__ mean,
+                                      float* __restrict__ rstd) {
+  int64_t row = global_warp();
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 t[V];
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    t[v] = __ldg(reinterpret_cast<const float4*>(x) + row * (32 * V) + v * 32 + lane);
+    s += t[v].x + t[v].y + t[v].z + t[v].w;
+  }
+  const float mu = warp_sum(s) / (float)(128 * V);
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    t[v] = make_float4(t[v].x - mu, t[v].y - mu, t[v].z - mu, t[v].w - mu);
+    ss += t[v].x * t[v].x + t[v].y * t[v].y + t[v].z * t[v].z + t[v].w * t[v].w;
+  }
+  const float rs = rsqrtf(warp_sum(ss) / (float)(128 * V) + 1e-5f);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + v * 32 + lane);
+    reinterpret_cast<float4*>(y)[row * (32 * V) + v * 32 + lane] =
+        make_float4(t[v].x * rs * g.x + b.x, t[v].y * rs * g.y + b.y, t[v].z * rs * g.z + b.z,
+                    t[v].w * rs * g.w + b.w);
+  }
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+}
+// out = base + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = d_y * gamma, xhat = (x - mean) * rstd
+template <int V>
+__global__ void layer_norm_bwd_kernel(const float* __restrict__ d_y, const float* __restrict__ x,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      const float* __restrict__ gamma, const float* __restrict__ base,
+                                      int64_t n_rows, float* __restrict__ out) {
+  int64_t row = global_warp();
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float mu = mean[row], rs = rstd[row];
+  float4 g[V], xh[V];
+  float sg = 0.f, dot = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    g[v] = __ldg(reinterpret_cast<const float4*>(d_y) + row * (32 * V) + v * 32 + lane);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(gamma) + v * 32 + lane);
+    g[v] = make_float4(g[v].x * w.x, g[v].y * w.y, g[v].z * w.z, g[v].w * w.w);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(x) + row * (32 * V) + v * 32 + lane);
+    xh[v] = make_float4((t.x - mu) * rs, (t.y - mu) * rs, (t.z - mu) * rs, (t.w - mu) * rs);
+    sg += g[v].x + g[v].y + g[v].z + g[v].w;
+    dot += g[v].x * xh[v].x + g[v].y * xh[v].y + g[v].z * xh[v].z + g[v].w * xh[v].w;
+  }
+  sg = warp_sum(sg) / (float)(128 * V);
+  dot = warp_sum(dot) / (float)(128 * V);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float4 b = base ? __ldg(reinterpret_cast<const float4*>(base) + row * (32 * V) + v * 32 + lane)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(out)[row * (32 * V) + v * 32 + lane] =
+        make_float4(b.x + rs * (g[v].x - sg - xh[v].x * dot), b.y + rs * (g[v].y - sg - xh[v].y * dot),
+                    b.z + rs * (g[v].z - sg - xh[v].z * dot), b.w + rs * (g[v].w - sg - xh[v].w * dot));
+  }
+}
+
 // ----------------------------------------------- message reversal + LayerNorm (d = 128)
 // backend.py:559-575: cc[e] = LayerNorm_256(cat[t_e, t_rev(e)]), eps = 1e-5, affine.
 // Algorithmic traffic per edge: read 2 x 512 B (t_e, gathered t_rev(e)) + 4 B (rev),
@@ -546,6 +619,34 @@ extern "C" PETB200_API int petb200_rms_norm_bwd(const float* d_y, const float* x
     return PETB200_ERR_UNSUPPORTED;
   }
   return check_launch("rms_norm_bwd");
+}
+
+extern "C" PETB200_API int petb200_layer_norm_fwd(const float* x, const float* gamma, const float* beta,
+                                      int64_t n_rows, int d, float* y, float* mean, float* rstd,
+                                      cudaStream_t stream) {
+  if (d == 128) {
+    LAUNCH_ROWS(layer_norm_fwd_kernel<1>, n_rows, x, gamma, beta, n_rows, y, mean, rstd);
+  } else if (d == 256) {
+    LAUNCH_ROWS(layer_norm_fwd_kernel<2>, n_rows, x, gamma, beta, n_rows, y, mean, rstd);
+  } else {
+    set_error("layer_norm_fwd: d must be 128 or 256 (got %d)", d);
+    return PETB200_ERR_UNSUPPORTED;
+  }
+  return check_launch("layer_norm_fwd");
+}
+
+extern "C" PETB200_API int petb200_layer_norm_bwd(const float* d_y, const float* x, const float* mean,
+                                      const float* rstd, const float* gamma, const float* base,
+                                      int64_t n_rows, int d, float* out, cudaStream_t stream) {
+  if (d == 128) {
+    LAUNCH_ROWS(layer_norm_bwd_kernel<1>, n_rows, d_y, x, mean, rstd, gamma, base, n_rows, out);
+  } else if (d == 256) {
+    LAUNCH_ROWS(layer_norm_bwd_kernel<2>, n_rows, d_y, x, mean, rstd, gamma, base, n_rows, out);
+  } else {
+    set_error("layer_norm_bwd: d must be 128 or 256 (got %d)", d);
+    return PETB200_ERR_UNSUPPORTED;
+  }
+  return check_launch("layer_norm_bwd");
 }
 
 extern "C" PETB200_API int petb200_combine_ln_fwd(const float* t, const int32_t* rev, const float* gamma,

@@ -189,7 +189,10 @@ class PackedWeights:
         self.signature = self._signature(module)
         self.split_cache: Dict[tuple, Tensor] = {}
         g = lambda t: t.detach()  # noqa: E731
-        post_ln = getattr(module, "hypers", {}).get("transformer_type", "PreLN") == "PostLN"
+        mh = getattr(module, "hypers", {})
+        generic = (mh.get("transformer_type", "PreLN"), mh.get("normalization", "RMSNorm"),
+                   mh.get("activation", "SwiGLU")) != ("PreLN", "RMSNorm", "SwiGLU")
+        nb = lambda n: (g(n.weight), g(n.bias) if getattr(n, "bias", None) is not None else None)  # noqa: E731
         self.gnn: List[dict] = []
         for layer in module.gnn_layers:
             L: dict = {}
@@ -219,12 +222,13 @@ class PackedWeights:
                     tl.attention.input_linear.weight, tl.norm_attention.weight, True)
                 T["b_qkv"] = g(tl.attention.input_linear.bias)
                 T["qkv_img"] = _linear_image(T["w_qkv"])   # fused RMSNorm + QKV projection
-                if post_ln:
-                    # PostLN normalises the residual stream itself: the Linears see un-normalised
-                    # inputs, so the norm weights are NOT folded (transformer.py:236-262)
+                if generic:
+                    # the generic layer path runs the normalisations as standalone ops: un-folded
+                    # weights and the norm parameters themselves
                     T["w_qkv_raw"] = g(tl.attention.input_linear.weight)
                     T["w_qkv_raw_t"], _ = _t_and_scaled(tl.attention.input_linear.weight)
-                    T["g_attn"], T["g_mlp"] = g(tl.norm_attention.weight), g(tl.norm_mlp.weight)
+                    T["n_attn"], T["n_mlp"] = nb(tl.norm_attention), nb(tl.norm_mlp)
+                    T["n_c"] = nb(tl.norm_center_features)
                 T["w_o"] = g(tl.attention.output_linear.weight)
                 T["b_o"] = g(tl.attention.output_linear.bias)
                 T["w_o_t"], _ = _t_and_scaled(tl.attention.output_linear.weight)
@@ -235,7 +239,7 @@ class PackedWeights:
                 T["w_out_t"], _ = _t_and_scaled(tl.mlp.w_out.weight)
                 # operand-tile images of the fused feed-forward kernels (petb200_mlp_fwd / _bwd)
                 T["mlp_img"] = _mlp_images(T["w_in"], T["w_out"])
-                if post_ln:
+                if generic:
                     T["w_in_raw"] = g(tl.mlp.w_in.weight)
                     T["w_in_raw_t"], _ = _t_and_scaled(tl.mlp.w_in.weight)
                 T["w_con"] = g(tl.center_contraction.weight)
@@ -250,6 +254,9 @@ class PackedWeights:
                 T["wc_out"] = g(tl.center_mlp.w_out.weight)
                 T["bc_out"] = g(tl.center_mlp.w_out.bias)
                 T["wc_out_t"], _ = _t_and_scaled(tl.center_mlp.w_out.weight)
+                if generic:
+                    T["wc_in_raw"] = g(tl.center_mlp.w_in.weight)
+                    T["wc_in_raw_t"], _ = _t_and_scaled(tl.center_mlp.w_in.weight)
                 L["tl"].append(T)
             self.gnn.append(L)
         self.combine: List[dict] = []
@@ -349,98 +356,171 @@ def _rms_bwd(d_xhat, x, rstd, base, out):
     return out
 
 
-def _rms_norm(x: Tensor, gamma: Tensor, out: Tensor):
-    rstd = _empty((x.shape[0],), x)
-    call("rms_norm_fwd", ptr(x), ptr(gamma), x.shape[0], x.shape[1], ptr(out), ptr(rstd))
-    return rstd
+def _is_generic(hyp) -> bool:
+    """True for every layer variant other than the default PreLN + RMSNorm + SwiGLU (which has its own
+    path with folded norm weights and fused kernels)."""
+    return (hyp["transformer_type"], hyp["normalization"], hyp["activation"]) != ("PreLN", "RMSNorm", "SwiGLU")
 
 
-def _tl_forward_postln(pw: PackedWeights, T: dict, hyp, topo: Topology, fc, h, X, H, prec):
-    """TransformerLayer._forward_post_ln_impl (transformer.py:236-262) on the [E + N] token matrix:
-    tokens = norm_attention(tokens + attention(tokens)); tokens = norm_mlp(tokens + mlp(tokens))
-    for ALL tokens (edges and centre), then the node update from the centre token."""
+def _norm_fwd(kind: str, x: Tensor, norm, out: Tensor):
+    """out = norm(x) as a standalone op; returns the statistics the backward needs."""
+    gamma, beta = norm
+    rows, d = x.shape
+    rstd = _empty((rows,), x)
+    if kind == "RMSNorm":
+        call("rms_norm_fwd", ptr(x), ptr(gamma), rows, d, ptr(out), ptr(rstd))
+        return None, rstd
+    mean = _empty((rows,), x)
+    call("layer_norm_fwd", ptr(x), ptr(gamma), ptr(beta), rows, d, ptr(out), ptr(mean), ptr(rstd))
+    return mean, rstd
+
+
+def _norm_bwd(kind: str, d_y: Tensor, x: Tensor, stats, norm, base, out: Tensor):
+    mean, rstd = stats
+    rows, d = x.shape
+    if kind == "RMSNorm":
+        call("rms_norm_bwd", ptr(d_y), ptr(x), ptr(rstd), ptr(norm[0]), ptr(base), rows, d, ptr(out))
+    else:
+        call("layer_norm_bwd", ptr(d_y), ptr(x), ptr(mean), ptr(rstd), ptr(norm[0]), ptr(base), rows, d, ptr(out))
+    return out
+
+
+def _ff_fwd(pw, act: str, xn: Tensor, w_in, b_in, w_out, b_out, residual, out: Tensor, prec):
+    """FeedForward (transformer.py:21-50) on already-normalised rows: out = residual + W_out act(W_in xn).
+    Returns the pre-activations ([rows, 2 d_ff] for SwiGLU, [rows, d_ff] for SiLU)."""
+    rows, dff = xn.shape[0], w_out.shape[1]
+    s = _empty((rows, dff), xn)
+    if act == "SwiGLU":
+        aux = _empty((rows, 2 * dff), xn)
+        gemm(xn, w_in, s, bias=b_in, epilogue=EPI_SWIGLU, aux_out=aux, precision=prec, pack=pw)
+    else:
+        aux = _empty((rows, dff), xn)
+        gemm(xn, w_in, s, bias=b_in, epilogue=EPI_SILU, aux_out=aux, precision=prec, pack=pw)
+    gemm(s, w_out, out, bias=b_out, residual=residual, precision=prec, pack=pw)
+    return aux
+
+
+def _ff_bwd(pw, act: str, d_out: Tensor, aux: Tensor, w_out_t, w_in_t, residual, out: Tensor, prec):
+    """out = residual + (d FeedForward / d xn)^T d_out."""
+    rows = d_out.shape[0]
+    d_pre = _empty((rows, aux.shape[1]), d_out)
+    gemm(d_out, w_out_t, d_pre, epilogue=EPI_SWIGLU_BWD if act == "SwiGLU" else EPI_MUL_DSILU, aux_in=aux,
+         precision=prec, pack=pw)
+    gemm(d_pre, w_in_t, out, residual=residual, precision=prec, pack=pw)
+    return out
+
+
+def _tl_forward_generic(pw: PackedWeights, T: dict, hyp, topo: Topology, fc, h, X, H, prec):
+    """TransformerLayer for every variant but the default one: PreLN (transformer.py:203-234) or
+    PostLN (:236-262), RMSNorm or LayerNorm, SwiGLU or SiLU — standalone normalisation ops and plain
+    GEMMs on the [E + N] token matrix."""
     N, E = topo.n_atoms, topo.n_edges
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
+    kind, act, post = hyp["normalization"], hyp["activation"], hyp["transformer_type"] == "PostLN"
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    K: dict = {"X": X}
     gemm(h, T["w_con"], X[E:], bias=T["b_con"], precision=prec, pack=pw)
+    if post:
+        qkv_in = X
+    else:
+        qkv_in = _empty((E + N, d), fc)
+        K["st_a"] = _norm_fwd(kind, X, T["n_attn"], qkv_in)
     qkv = _empty((E + N, 3 * d), fc)
-    gemm(X, T["w_qkv_raw"], qkv, bias=T["b_qkv"], precision=prec, pack=pw)
+    gemm(qkv_in, T["w_qkv_raw"], qkv, bias=T["b_qkv"], precision=prec, pack=pw)
+    del qkv_in
     o = _empty((E + N, d), fc)
     lse = _empty((E + N, nh), fc)
     call("attention_fwd", ptr(qkv), ptr(topo.row_ptr), ptr(fc), N, E, nh, d // nh,
          scale, topo.max_row, prec, ptr(o), ptr(lse))
-    Z1 = _empty((E + N, d), fc)
-    gemm(o, T["w_o"], Z1, bias=T["b_o"], residual=X, precision=prec, pack=pw)
-    X1 = _empty((E + N, d), fc)
-    rstd1 = _rms_norm(Z1, T["g_attn"], X1)
-    dff = T["w_out"].shape[1]
-    ug = _empty((E + N, 2 * dff), fc)
-    s = _empty((E + N, dff), fc)
-    gemm(X1, T["w_in_raw"], s, bias=T["b_in"], epilogue=EPI_SWIGLU, aux_out=ug, precision=prec, pack=pw)
-    Z2 = _empty((E + N, d), fc)
-    gemm(s, T["w_out"], Z2, bias=T["b_out"], residual=X1, precision=prec, pack=pw)
-    del s
-    X2f = _empty((E + N + H, d), fc)
-    X2 = X2f[:E + N]
-    rstd2 = _rms_norm(Z2, T["g_mlp"], X2)
-    # node update from the centre token (as in the PreLN layer)
+    K.update(qkv=qkv, o=o, lse=lse)
+    Xoutf = _empty((E + N + H, d), fc)
+    Xout = Xoutf[:E + N]
+    if post:
+        Z1 = _empty((E + N, d), fc)
+        gemm(o, T["w_o"], Z1, bias=T["b_o"], residual=X, precision=prec, pack=pw)
+        X1 = _empty((E + N, d), fc)
+        K["st_a"] = _norm_fwd(kind, Z1, T["n_attn"], X1)
+        Z2 = _empty((E + N, d), fc)
+        K["aux"] = _ff_fwd(pw, act, X1, T["w_in_raw"], T["b_in"], T["w_out"], T["b_out"], X1, Z2, prec)
+        K["st_m"] = _norm_fwd(kind, Z2, T["n_mlp"], Xout)
+        K.update(Z1=Z1, X1=X1, Z2=Z2)
+        centre = Xout[E:]
+    else:
+        tp = _empty((E, d), fc)
+        gemm(o[:E], T["w_o"], tp, bias=T["b_o"], residual=X[:E], precision=prec, pack=pw)
+        centre = _empty((N, d), fc)
+        gemm(o[E:], T["w_o"], centre, bias=T["b_o"], precision=prec, pack=pw)
+        tpn = _empty((E, d), fc)
+        K["st_m"] = _norm_fwd(kind, tp, T["n_mlp"], tpn)
+        K["aux"] = _ff_fwd(pw, act, tpn, T["w_in_raw"], T["b_in"], T["w_out"], T["b_out"], tp, Xout[:E], prec)
+        K["tp"] = tp
+    # node update: h1 = h + W_exp centre ; h2 = h1 + FF_c(norm_c(h1))
     h1 = _empty((N, dn), fc)
-    gemm(X2[E:], T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec, pack=pw)
-    rstd3 = _rstd(h1)
-    ugc = _empty((N, 4 * dn), fc)
-    sc = _empty((N, 2 * dn), fc)
-    gemm(h1, T["wc_in"], sc, bias=T["bc_in"], row_scale=rstd3, epilogue=EPI_SWIGLU, aux_out=ugc,
-         precision=prec, pack=pw)
+    gemm(centre, T["w_exp"], h1, bias=T["b_exp"], residual=h, precision=prec, pack=pw)
+    h1n = _empty((N, dn), fc)
+    K["st_c"] = _norm_fwd(kind, h1, T["n_c"], h1n)
     h2 = _empty((N, dn), fc)
-    gemm(sc, T["wc_out"], h2, bias=T["bc_out"], residual=h1, precision=prec, pack=pw)
-    K = dict(X=X, qkv=qkv, o=o, lse=lse, Z1=Z1, rstd1=rstd1, X1=X1, ug=ug, Z2=Z2, rstd2=rstd2,
-             h1=h1, rstd3=rstd3, ugc=ugc)
-    return X2, X2f, h2, K
+    K["auxc"] = _ff_fwd(pw, act, h1n, T["wc_in_raw"], T["bc_in"], T["wc_out"], T["bc_out"], h1, h2, prec)
+    K["h1"] = h1
+    return Xout, Xoutf, h2, K
 
 
-def _tl_backward_postln(pw: PackedWeights, T: dict, K: dict, hyp, topo: Topology, fc, d_h, d_t, d_fc,
-                        h_grad_wanted: bool, prec):
-    """dgrad of :func:`_tl_forward_postln`: (d_h [N,d_node], d_t [E,d_pet]) of the layer outputs ->
+def _tl_backward_generic(pw: PackedWeights, T: dict, K: dict, hyp, topo: Topology, fc, d_h, d_t, d_fc,
+                         h_grad_wanted: bool, prec):
+    """dgrad of :func:`_tl_forward_generic`: (d_h [N,d_node], d_t [E,d_pet]) of the layer outputs ->
     (d_t, d_h) of its inputs; the key-bias gradient is accumulated into d_fc."""
     N, E = topo.n_atoms, topo.n_edges
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
+    kind, act, post = hyp["normalization"], hyp["activation"], hyp["transformer_type"] == "PostLN"
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
-    dff = T["w_out"].shape[1]
-    # ---- node update: h2 = h1 + Wc_out swiglu(Wc_in rms(h1)),  h1 = h + W_exp X2[E:]
-    d_ugc = _empty((N, 4 * dn), fc)
-    gemm(d_h, T["wc_out_t"], d_ugc, epilogue=EPI_SWIGLU_BWD, aux_in=K["ugc"], precision=prec, pack=pw)
-    d_xhc = _empty((N, dn), fc)
-    gemm(d_ugc, T["wc_in_t"], d_xhc, precision=prec, pack=pw)
+    X = K["X"]
+    # ---- node update
+    d_h1n = _empty((N, dn), fc)
+    _ff_bwd(pw, act, d_h, K["auxc"], T["wc_out_t"], T["wc_in_raw_t"], None, d_h1n, prec)
     d_h1 = _empty((N, dn), fc)
-    _rms_bwd(d_xhc, K["h1"], K["rstd3"], d_h, d_h1)
-    d_X2 = _empty((E + N, d), fc)
-    d_X2[:E].copy_(d_t)
-    gemm(d_h1, T["w_exp_t"], d_X2[E:], precision=prec, pack=pw)
-    # ---- X2 = norm_mlp(Z2),  Z2 = X1 + W_out swiglu(W_in X1 + b_in) + b_out
-    d_Z2 = _empty((E + N, d), fc)
-    call("rms_norm_bwd", ptr(d_X2), ptr(K["Z2"]), ptr(K["rstd2"]), ptr(T["g_mlp"]), None, E + N, d, ptr(d_Z2))
-    d_ug = _empty((E + N, 2 * dff), fc)
-    gemm(d_Z2, T["w_out_t"], d_ug, epilogue=EPI_SWIGLU_BWD, aux_in=K["ug"], precision=prec, pack=pw)
-    d_X1 = d_X2  # reuse
-    gemm(d_ug, T["w_in_raw_t"], d_X1, residual=d_Z2, precision=prec, pack=pw)
-    del d_ug
-    # ---- X1 = norm_attention(Z1),  Z1 = X + W_o attention(W_qkv X + b_qkv) + b_o
-    d_Z1 = d_Z2  # reuse
-    call("rms_norm_bwd", ptr(d_X1), ptr(K["Z1"]), ptr(K["rstd1"]), ptr(T["g_attn"]), None, E + N, d, ptr(d_Z1))
-    d_o = d_X1  # reuse
-    gemm(d_Z1, T["w_o_t"], d_o, precision=prec, pack=pw)
+    _norm_bwd(kind, d_h1n, K["h1"], K["st_c"], T["n_c"], d_h, d_h1)
+    d_o = _empty((E + N, d), fc)
+    if post:
+        d_X2 = _empty((E + N, d), fc)
+        d_X2[:E].copy_(d_t)
+        gemm(d_h1, T["w_exp_t"], d_X2[E:], precision=prec, pack=pw)
+        d_Z2 = _empty((E + N, d), fc)
+        _norm_bwd(kind, d_X2, K["Z2"], K["st_m"], T["n_mlp"], None, d_Z2)
+        d_X1 = d_X2  # reuse
+        _ff_bwd(pw, act, d_Z2, K["aux"], T["w_out_t"], T["w_in_raw_t"], d_Z2, d_X1, prec)
+        d_Z1 = d_Z2  # reuse
+        _norm_bwd(kind, d_X1, K["Z1"], K["st_a"], T["n_attn"], None, d_Z1)
+        gemm(d_Z1, T["w_o_t"], d_o, precision=prec, pack=pw)
+    else:
+        d_centre = _empty((N, d), fc)
+        gemm(d_h1, T["w_exp_t"], d_centre, precision=prec, pack=pw)
+        d_tpn = _empty((E, d), fc)
+        _ff_bwd(pw, act, d_t, K["aux"], T["w_out_t"], T["w_in_raw_t"], None, d_tpn, prec)
+        d_tp = _empty((E, d), fc)
+        _norm_bwd(kind, d_tpn, K["tp"], K["st_m"], T["n_mlp"], d_t, d_tp)
+        gemm(d_tp, T["w_o_t"], d_o[:E], precision=prec, pack=pw)
+        gemm(d_centre, T["w_o_t"], d_o[E:], precision=prec, pack=pw)
     d_qkv = _empty((E + N, 3 * d), fc)
     dsum = _empty((E + N, nh), fc)
     call("attention_bwd", ptr(K["qkv"]), ptr(K["o"]), ptr(K["lse"]), ptr(d_o), ptr(topo.row_ptr), ptr(fc),
          N, E, nh, d // nh, scale, topo.max_row, prec, ptr(d_qkv), ptr(d_fc), ptr(dsum))
     d_X = _empty((E + N, d), fc)
-    gemm(d_qkv, T["w_qkv_raw_t"], d_X, residual=d_Z1, precision=prec, pack=pw)
+    if post:
+        gemm(d_qkv, T["w_qkv_raw_t"], d_X, residual=d_Z1, precision=prec, pack=pw)
+    else:
+        d_Xn = d_o  # reuse
+        gemm(d_qkv, T["w_qkv_raw_t"], d_Xn, precision=prec, pack=pw)
+        mean, rstd = K["st_a"]
+        st_e = (None if mean is None else mean[:E], rstd[:E])
+        st_c = (None if mean is None else mean[E:], rstd[E:])
+        _norm_bwd(kind, d_Xn[:E], X[:E], st_e, T["n_attn"], d_tp, d_X[:E])
+        _norm_bwd(kind, d_Xn[E:], X[E:], st_c, T["n_attn"], None, d_X[E:])
     del d_qkv
-    d_h_new = None
+    d_h_new = d_h
     if h_grad_wanted:
         d_h_new = _empty((N, dn), fc)
         gemm(d_X[E:], T["w_con_t"], d_h_new, residual=d_h1, precision=prec, pack=pw)
-    return d_X[:E], (d_h_new if h_grad_wanted else d_h)
+    return d_X[:E], d_h_new
 
 
 def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc, h, m, prec):
@@ -474,8 +554,8 @@ def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc,
     del a1
     S["c1"] = c1
     for T in L["tl"]:
-        if hyp["transformer_type"] == "PostLN":
-            X, Xf, h, K = _tl_forward_postln(pw, T, hyp, topo, fc, h, X, H, prec)
+        if _is_generic(hyp):
+            X, Xf, h, K = _tl_forward_generic(pw, T, hyp, topo, fc, h, X, H, prec)
             S["tl"].append(K)
             continue
         K: dict = {}
@@ -607,8 +687,8 @@ def _gnn_backward(pw: PackedWeights, L: dict, S: dict, hyp, topo: Topology, fc, 
     for k in range(len(L["tl"]) - 1, -1, -1):
         T, K = L["tl"][k], S["tl"][k]
         dff = T["w_out"].shape[1]
-        if hyp["transformer_type"] == "PostLN":
-            d_t, d_h = _tl_backward_postln(pw, T, K, hyp, topo, fc, d_h, d_t, d_fc, h_grad_wanted or k > 0, prec)
+        if _is_generic(hyp):
+            d_t, d_h = _tl_backward_generic(pw, T, K, hyp, topo, fc, d_h, d_t, d_fc, h_grad_wanted or k > 0, prec)
             continue
         # ---- edge MLP: t'' = t' + W_out swiglu(W_in rms(t'))
         d_tp = _empty((E, d), ref)

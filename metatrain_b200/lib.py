@@ -64,6 +64,8 @@ _SIGNATURES = {
     "petb200_avg_reverse_bwd": [_P, _P, _I64, _I, _P, _P, _P],
     "petb200_rms_rstd": [_P, _I64, _I, _P, _P],
     "petb200_rms_bwd": [_P, _P, _P, _P, _I64, _I, _P, _P],
+    "petb200_layer_norm_fwd": [_P, _P, _P, _I64, _I, _P, _P, _P, _P],
+    "petb200_layer_norm_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_rms_norm_fwd": [_P, _P, _I64, _I, _P, _P, _P],
     "petb200_rms_norm_bwd": [_P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_attention_fwd": [_P, _P, _P, _I64, _I64, _I, _I, _F, _I, _I, _P, _P, _P],

@@ -29,33 +29,37 @@ class _Holder(nn.Module):
         raise RuntimeError("parameter holder: arithmetic lives in the CUDA engine")
 
 
-def _swiglu_holder(d_model: int, d_ff: int) -> _Holder:
+def _ff_holder(d_model: int, d_ff: int, activation: str) -> _Holder:
+    """FeedForward (transformer.py:21-39): SwiGLU projects to value and gate, SiLU to d_ff."""
     h = _Holder()
-    h.w_in = nn.Linear(d_model, 2 * d_ff)
+    h.w_in = nn.Linear(d_model, 2 * d_ff if activation.lower() == "swiglu" else d_ff)
     h.w_out = nn.Linear(d_ff, d_model)
     return h
 
 
-def _transformer_layer_holder(d_pet: int, d_node: int, d_ff: int) -> _Holder:
+def _transformer_layer_holder(d_pet: int, d_node: int, d_ff: int, norm: str = "RMSNorm",
+                              activation: str = "SwiGLU") -> _Holder:
+    norm_class = getattr(nn, norm)  # transformer.py:181
     layer = _Holder()
     layer.attention = _Holder()
     layer.attention.input_linear = nn.Linear(d_pet, 3 * d_pet)
     layer.attention.output_linear = nn.Linear(d_pet, d_pet)
-    layer.norm_attention = nn.RMSNorm(d_pet)
-    layer.norm_mlp = nn.RMSNorm(d_pet)
-    layer.mlp = _swiglu_holder(d_pet, d_ff)
+    layer.norm_attention = norm_class(d_pet)
+    layer.norm_mlp = norm_class(d_pet)
+    layer.mlp = _ff_holder(d_pet, d_ff, activation)
     layer.center_contraction = nn.Linear(d_node, d_pet)
     layer.center_expansion = nn.Linear(d_pet, d_node)
-    layer.norm_center_features = nn.RMSNorm(d_node)
-    layer.center_mlp = _swiglu_holder(d_node, 2 * d_node)
+    layer.norm_center_features = norm_class(d_node)
+    layer.center_mlp = _ff_holder(d_node, 2 * d_node, activation)
     return layer
 
 
-def _gnn_layer_holder(d_pet, d_node, d_ff, n_attention, n_species, is_first) -> _Holder:
+def _gnn_layer_holder(d_pet, d_node, d_ff, n_attention, n_species, is_first, norm="RMSNorm",
+                      activation="SwiGLU") -> _Holder:
     g = _Holder()
     g.trans = _Holder()
     g.trans.layers = nn.ModuleList(
-        [_transformer_layer_holder(d_pet, d_node, d_ff) for _ in range(n_attention)]
+        [_transformer_layer_holder(d_pet, d_node, d_ff, norm, activation) for _ in range(n_attention)]
     )
     g.edge_embedder = nn.Linear(4, d_pet)
     n_merge = 2 if is_first else 3
@@ -95,7 +99,8 @@ class PETParameters(nn.Module):
         self.gnn_layers = nn.ModuleList(
             [
                 _gnn_layer_holder(self.d_pet, self.d_node, self.d_feedforward,
-                                  self.num_attention_layers, n_species, l == 0)
+                                  self.num_attention_layers, n_species, l == 0,
+                                  hypers.get("normalization", "RMSNorm"), hypers.get("activation", "SwiGLU"))
                 for l in range(self.num_gnn_layers)
             ]
         )

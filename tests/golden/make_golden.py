@@ -149,6 +149,13 @@ def main():
     # PostLN transformer layers (transformer.py:236-262)
     make_case("qm9_5_postln", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=dict(transformer_type="PostLN"))
     make_case("water_384_postln", [water], [1, 8], hypers=dict(transformer_type="PostLN"), fp64=False)
+    # the original PET layer: PostLN + LayerNorm + SiLU + residual featurizer; PreLN with LayerNorm + SiLU
+    classic = dict(transformer_type="PostLN", normalization="LayerNorm", activation="SiLU",
+                   featurizer_type="residual")
+    make_case("water_384_classic", [water], [1, 8], hypers=classic, fp64=False)
+    make_case("qm9_5_classic", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=classic)
+    make_case("water_384_preln_ln_silu", [water], [1, 8],
+              hypers=dict(normalization="LayerNorm", activation="SiLU"), fp64=False)
 
     carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
     make_case("carbon_5", carbon, [6], with_strain=False)

@@ -12,7 +12,10 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 # residual featurizer (backend.py:589-649): one readout per GNN layer
                 "qm9_5_residual", "water_384_residual",
                 # PostLN transformer layers (transformer.py:236-262)
-                "qm9_5_postln", "water_384_postln"]
+                "qm9_5_postln", "water_384_postln",
+                # the original PET layer (PostLN + LayerNorm + SiLU + residual featurizer) and the
+                # PreLN layer with LayerNorm + SiLU
+                "water_384_classic", "qm9_5_classic", "water_384_preln_ln_silu"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(

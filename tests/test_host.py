@@ -63,8 +63,7 @@ def test_hyper_validation_matches_reference_error_types():
     res = B200PETBackend(dict(DEFAULT_HYPERS, featurizer_type="residual"), [1])  # built: backend.py:589-649
     assert res.num_readout_layers == DEFAULT_HYPERS["num_gnn_layers"] and len(res.combination_mlps) == 0
     B200PETBackend(dict(DEFAULT_HYPERS, transformer_type="PostLN"), [1])  # built: transformer.py:236-262
-    with pytest.raises(NotImplementedError):
-        B200PETBackend(dict(DEFAULT_HYPERS, normalization="LayerNorm"), [1])
+    B200PETBackend(dict(DEFAULT_HYPERS, normalization="LayerNorm", activation="SiLU"), [1])  # built
     with pytest.raises(NotImplementedError):
         B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16), [1])
 
