@@ -172,6 +172,46 @@ PETB200_API int petb200_force_scatter(const float* edge_grad, const int32_t* row
                       const int32_t* system_of_atom, int64_t n_atoms, int64_t n_edges,
                       float* d_pos, float* d_cells, petb200_stream_t stream);
 
+/* ------------------------------------------------------------- adaptive cutoff (a4)
+ * get_adaptive_cutoffs_solver (src/metatrain/pet/modules/adaptive_cutoff.py:110-229) and its use in
+ * compute_batch_tensors (structures.py:222-262), on the CSR rows of the pairs within the maximum
+ * cutoff ("all" edges below); the pairs that survive the pair-cutoff mask form a second CSR
+ * ("kept" edges, built with petb200_csr_build from the keep mask returned here).
+ *   solve     : per atom r_root (root of n_total(r) = num_neighbors), dn_root = max(dn/dr, 1e-6)
+ *               there, atomic_cutoff = clamp(r_root - residual/dn_root, R/16, R), pass = 1 where
+ *               the clamp is inactive;
+ *   pair_mask : pair_cutoff[e] = mean of the two atoms' cutoffs, keep[e] = |r_e| + 1e-15 <=
+ *               pair_cutoff[e], counts[ctr] += keep (counts zeroed by the caller);
+ *   edges_fwd_rc / edges_bwd_rc : petb200_edges_fwd / _bwd with one cutoff per edge; the backward
+ *               also returns d_edge_cutoff[e] = -d_fc[e] * f'(|r_e|);
+ *   bwd       : coef[i] = pass * 0.5 * sum_{e in kept row i} (d_pair_cutoff[e] + d_pair_cutoff[rev e])
+ *               / dn_root[i];  d_dist_all[k] = coef[ctr k] * (d bump / d r)(d_k; r_root[ctr k]) —
+ *               feed it to petb200_edges_bwd on the "all" topology as d_dist.                   */
+PETB200_API int petb200_adaptive_cutoff_solve(const int32_t* row_ptr, const float* edge_dist, int64_t n_atoms,
+                                  float num_neighbors, float max_cutoff, float width, float* r_root,
+                                  float* dn_root, float* atomic_cutoff, float* pass,
+                                  petb200_stream_t stream);
+PETB200_API int petb200_adaptive_pair_mask(const int32_t* ctr, const int32_t* col, const float* edge_vec,
+                               const float* atomic_cutoff, int64_t n_edges, float* pair_cutoff,
+                               int32_t* keep, int32_t* counts, petb200_stream_t stream);
+PETB200_API int petb200_edges_fwd_rc(const float* positions, const float* cells,
+                         const int32_t* system_of_atom, const int32_t* ctr, const int32_t* col,
+                         const int32_t* shift_csr, int64_t n_edges, const float* edge_cutoff,
+                         float width, int cutoff_function, float* edge_vec, float* edge_dist,
+                         float* cutoff_factor, petb200_stream_t stream);
+PETB200_API int petb200_edges_bwd_rc(const float* d_vec, const float* d_dist, const float* d_fc,
+                         const float* edge_vec, const float* edge_dist, const int32_t* row_ptr,
+                         const int32_t* ctr, const int32_t* rev, const int32_t* shift_csr,
+                         const int32_t* system_of_atom, int64_t n_atoms, int64_t n_edges,
+                         const float* edge_cutoff, float width, int cutoff_function,
+                         float* edge_grad, float* d_pos, float* d_cells, float* d_edge_cutoff,
+                         petb200_stream_t stream);
+PETB200_API int petb200_adaptive_cutoff_bwd(const int32_t* row_ptr_kept, const int32_t* rev_kept,
+                                const float* d_pair_cutoff, const float* dn_root, const float* pass,
+                                int64_t n_atoms, const int32_t* ctr_all, const float* dist_all,
+                                const float* r_root, int64_t n_edges_all, float width, float* coef,
+                                float* d_dist_all, petb200_stream_t stream);
+
 /* --------------------------------------------------------------- dense contractions
  * C[M,N] = epilogue(row_scale * (A[M,K] . W[N,K]^T) + bias) (+ residual) — every
  * torch.nn.Linear of transformer.py / backend.py, and its dgrad with W^T.             */

@@ -16,8 +16,10 @@ keeps working unchanged.
 
 Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649); transformer types
 ``PreLN`` (default) and ``PostLN`` (transformer.py:236-262); normalisation ``RMSNorm`` (default) or
-``LayerNorm``; activation ``SwiGLU`` (default) or ``SiLU``.  Not built yet (raise
-``NotImplementedError``): adaptive cutoff, system conditioning, weight gradients (training).
+``LayerNorm``; activation ``SwiGLU`` (default) or ``SiLU``; fixed cutoff (default) or the adaptive
+cutoff with the ``solver`` method (adaptive_cutoff.py:110-229).  Not built yet (raise
+``NotImplementedError``): the ``grid`` adaptive-cutoff method, system conditioning, weight
+gradients (training).
 """
 from typing import Dict, List, Optional, Tuple
 
@@ -67,6 +69,36 @@ class _EdgeGeometry(torch.autograd.Function):
         if d_cells is not None:
             d_cells = d_cells.to(ctx.in_dtypes[1])
         return d_pos, d_cells, None, None, None, None
+
+
+class _AdaptiveEdgeGeometry(torch.autograd.Function):
+    """``_EdgeGeometry`` with per-pair cutoffs from the adaptive-cutoff solver: the backward adds
+    the gradient that reaches the positions through the per-atom cutoffs (the implicit-function
+    step, adaptive_cutoff.py:203-227)."""
+
+    @staticmethod
+    def forward(ctx, positions, cells, topo, adaptive, cutoff, width, func):
+        pos = positions.detach().to(torch.float32).contiguous()
+        cel = cells.detach().to(torch.float32).contiguous()
+        vec, dist, fc = engine.adaptive_edges_forward(topo, adaptive, pos, cel, width, func)
+        ctx.topo, ctx.adaptive, ctx.params = topo, adaptive, (cutoff, width, func)
+        ctx.in_dtypes = (positions.dtype, cells.dtype)
+        ctx.save_for_backward(vec, dist)
+        return vec, dist, fc
+
+    @staticmethod
+    def backward(ctx, d_vec, d_dist, d_fc):
+        vec, dist = ctx.saved_tensors
+        cutoff, width, func = ctx.params
+        need_cells = ctx.needs_input_grad[1]
+        c = lambda g: None if g is None else g.contiguous()  # noqa: E731
+        d_pos, d_cells = engine.adaptive_edges_backward(
+            ctx.topo, ctx.adaptive, vec, dist, c(d_vec), c(d_dist), c(d_fc), cutoff, width, func,
+            need_cells)
+        d_pos = d_pos.to(ctx.in_dtypes[0])
+        if d_cells is not None:
+            d_cells = d_cells.to(ctx.in_dtypes[1])
+        return d_pos, d_cells, None, None, None, None, None
 
 
 class _Features(torch.autograd.Function):
@@ -205,8 +237,12 @@ class B200PETBackend(PETParameters):
         unsupported = []
         if hypers["featurizer_type"] not in ("feedforward", "residual"):
             raise ValueError(f"Unknown featurizer type: {hypers['featurizer_type']}")
-        if hypers.get("num_neighbors_adaptive") is not None:
-            unsupported.append("num_neighbors_adaptive (adaptive cutoff)")
+        if (hypers.get("num_neighbors_adaptive") is not None
+                and hypers.get("adaptive_cutoff_method", "solver").lower() != "solver"):
+            if hypers["adaptive_cutoff_method"].lower() != "grid":  # structures.py:244-248
+                raise ValueError("adaptive_cutoff_method must be 'grid' or 'solver', got "
+                                 + hypers["adaptive_cutoff_method"])
+            unsupported.append("adaptive_cutoff_method 'grid' (the default 'solver' is built)")
         if hypers.get("system_conditioning"):
             unsupported.append("system_conditioning")
         if (hypers["d_pet"], hypers["d_node"], hypers["d_head"], hypers["num_heads"]) != (128, 256, 128, 8):
@@ -226,6 +262,9 @@ class B200PETBackend(PETParameters):
         self.cutoff_function = hypers["cutoff_function"]
         self.cutoff_width = float(hypers["cutoff_width"])
         self.num_heads = int(hypers["num_heads"])
+        self.num_neighbors_adaptive = (float(hypers["num_neighbors_adaptive"])
+                                       if hypers.get("num_neighbors_adaptive") is not None else None)
+        self.adaptive_cutoff_method = hypers.get("adaptive_cutoff_method", "solver")
         self.system_conditioning = None
         self._precision = _PRECISIONS[precision]
         self._cutoff_id = CUTOFF_BUMP if self.cutoff_function.lower() == "bump" else CUTOFF_COSINE
@@ -288,12 +327,25 @@ class B200PETBackend(PETParameters):
         z_nodes = self.species_to_species_index[species.long()]
         topo = engine.build_topology(positions, centers, neighbors, cell_shifts, cells,
                                      system_indices, z_nodes, self.cutoff)
-        vec, dist, fc = _EdgeGeometry.apply(positions, cells, topo, self.cutoff,
-                                            self.cutoff_width, self._cutoff_id)
+        atomic_cutoffs = None
+        if self.num_neighbors_adaptive is None:
+            vec, dist, fc = _EdgeGeometry.apply(positions, cells, topo, self.cutoff,
+                                                self.cutoff_width, self._cutoff_id)
+        else:
+            # per-atom cutoffs, then the topology of the pairs inside the pair cutoffs
+            topo, adaptive = engine.adaptive_topology(
+                topo, positions.detach().to(torch.float32).contiguous(),
+                cells.detach().to(torch.float32).contiguous(), self.cutoff,
+                self.num_neighbors_adaptive, float(cutoff_width_adaptive))
+            vec, dist, fc = _AdaptiveEdgeGeometry.apply(positions, cells, topo, adaptive, self.cutoff,
+                                                        self.cutoff_width, self._cutoff_id)
+            atomic_cutoffs = adaptive.atomic_cutoffs.to(positions.dtype)
         if not self.emit_nef:
             batch_data = {"element_indices_nodes": z_nodes}
         else:
             batch_data = self._nef_batch_data(topo, positions, z_nodes, vec, dist, fc)
+            if atomic_cutoffs is not None:
+                batch_data["atomic_cutoffs_stats"] = atomic_cutoffs
         # CSR handles consumed by calculate_features / predict (not part of the reference's
         # dictionary; plain tensors + one opaque python attribute)
         vec._petb200_topology = topo

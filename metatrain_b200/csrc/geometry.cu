@@ -42,6 +42,7 @@ __global__ void edges_fwd_kernel(const float* __restrict__ pos, const float* __r
                                  const int32_t* __restrict__ sys_of_atom,
                                  const int32_t* __restrict__ ctr, const int32_t* __restrict__ col,
                                  const int32_t* __restrict__ shift, int64_t n_edges, float cutoff,
+                                 const float* __restrict__ edge_cutoff /* nullable: per-edge cutoff */,
                                  float width, int func, float* __restrict__ vec,
                                  float* __restrict__ dist_out, float* __restrict__ fc_out) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,13 +59,15 @@ __global__ void edges_fwd_kernel(const float* __restrict__ pos, const float* __r
   vec[3 * e + 2] = rz;
   dist_out[e] = sqrtf(r2 + 1e-15f);  // structures.py:330 (embedder input)
   float f, df;
-  cutoff_eval(sqrtf(r2) + 1e-15f, cutoff, width, func, f, df);  // structures.py:221
+  cutoff_eval(sqrtf(r2) + 1e-15f, edge_cutoff ? edge_cutoff[e] : cutoff, width, func, f, df);  // structures.py:221
   fc_out[e] = f;
 }
 
 __global__ void edge_grad_kernel(const float* __restrict__ d_vec, const float* __restrict__ d_dist,
                                  const float* __restrict__ d_fc, const float* __restrict__ vec,
                                  const float* __restrict__ dist, int64_t n_edges, float cutoff,
+                                 const float* __restrict__ edge_cutoff /* nullable */,
+                                 float* __restrict__ d_edge_cutoff /* nullable: -d_fc * f'(d) */,
                                  float width, int func, float* __restrict__ G) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
@@ -75,14 +78,122 @@ __global__ void edge_grad_kernel(const float* __restrict__ d_vec, const float* _
         gz = d_vec ? d_vec[3 * e + 2] : 0.f;
   float coef = 0.f;
   if (d_dist) coef += d_dist[e] / dist[e];  // d sqrt(r.r+eps) / dr = r / sqrt(r.r+eps)
+  if (d_edge_cutoff) d_edge_cutoff[e] = 0.f;
   if (d_fc) {
     float f, df;
-    cutoff_eval(nrm + 1e-15f, cutoff, width, func, f, df);
+    cutoff_eval(nrm + 1e-15f, edge_cutoff ? edge_cutoff[e] : cutoff, width, func, f, df);
     if (nrm > 0.f) coef += d_fc[e] * df / nrm;  // d|r|/dr = r/|r| (0 at r = 0, as torch.norm)
+    // the cutoff functions depend on (d - cutoff) only: df/dcutoff = -df/dd
+    if (d_edge_cutoff) d_edge_cutoff[e] = -d_fc[e] * df;
   }
   G[3 * e + 0] = gx + coef * rx;
   G[3 * e + 1] = gy + coef * ry;
   G[3 * e + 2] = gz + coef * rz;
+}
+
+// ----------------------------------------------------------------- adaptive cutoff
+// Restates get_adaptive_cutoffs_solver (src/metatrain/pet/modules/adaptive_cutoff.py:110-229) and
+// its use in compute_batch_tensors (structures.py:222-262) on the CSR rows of the pairs within
+// the maximum cutoff R: per atom, solve  n_total(r) = sum_j bump(d_j; r, w) + n* (r/R)^3 = n*
+// with a bracketed Newton iteration, then one implicit-function step that carries the gradient.
+
+// smoothed step of a neighbour at distance d for probe cutoff r, and its derivative w.r.t. r
+// (adaptive_cutoff.py:74-95)
+__device__ __forceinline__ void probe_count(float d, float r, float w, float& f, float& df_dr) {
+  const float s = (d - (r - w)) / w;
+  const bool active = s > 0.f && s < 1.f;
+  const float safe = fminf(fmaxf(s, 1e-6f), 1.0f - 1e-6f);
+  float sn, cs;
+  sincosf(kPi * safe, &sn, &cs);
+  const float th = tanhf(cs / sn);
+  f = active ? 0.5f * (1.0f + th) : (s <= 0.f ? 1.f : 0.f);
+  df_dr = active ? (0.5f * kPi / w) * (1.0f - th * th) / (sn * sn) : 0.f;
+}
+
+// one warp per atom
+__global__ void adaptive_solve_kernel(const int32_t* __restrict__ row_ptr, const float* __restrict__ dist,
+                                      int64_t n_atoms, float n_target, float r_max, float width,
+                                      float* __restrict__ r_root, float* __restrict__ dn_root,
+                                      float* __restrict__ r_atom, float* __restrict__ pass) {
+  const int64_t atom = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (atom >= n_atoms) return;
+  const int lo = row_ptr[atom], hi = row_ptr[atom + 1];
+  const float inv_max = 1.0f / r_max;
+  auto totals = [&](float r, float& n, float& dn) {
+    float a = 0.f, b = 0.f;
+    for (int e = lo + lane; e < hi; e += 32) {
+      float f, df;
+      probe_count(dist[e], r, width, f, df);
+      a += f;
+      b += df;
+    }
+    const float x = r * inv_max;
+    n = warp_sum(a) + n_target * x * x * x;
+    dn = warp_sum(b) + 3.0f * n_target * x * x * inv_max;
+  };
+  float r_lo = 0.f, r_hi = r_max, r = 0.5f * r_max, n, dn;
+  for (int it = 0; it < 10; ++it) {  // adaptive_cutoff.py:171-188
+    totals(r, n, dn);
+    const float f = n - n_target;
+    if (f <= 0.f) r_lo = r; else r_hi = r;
+    const float r_newton = r - f / fmaxf(dn, 1e-6f);
+    r = (r_newton >= r_lo && r_newton <= r_hi) ? r_newton : 0.5f * (r_lo + r_hi);
+  }
+  totals(r, n, dn);
+  // implicit-function step (:203-227): r and dn are constants for the gradient
+  const float raw = r - (n - n_target) / fmaxf(dn, 1e-6f);
+  const float lo_c = r_max * (1.0f / 16.0f);
+  if (lane == 0) {
+    r_root[atom] = r;
+    dn_root[atom] = fmaxf(dn, 1e-6f);
+    r_atom[atom] = fminf(fmaxf(raw, lo_c), r_max);
+    pass[atom] = (raw >= lo_c && raw <= r_max) ? 1.f : 0.f;  // torch.clamp passes gradient on the closed range
+  }
+}
+
+// pair cutoffs (mean of the two atoms', structures.py:253-255) and the keep mask (:256-262)
+__global__ void adaptive_pair_kernel(const int32_t* __restrict__ ctr, const int32_t* __restrict__ col,
+                                     const float* __restrict__ vec, const float* __restrict__ r_atom,
+                                     int64_t n_edges, float* __restrict__ pair_cutoff,
+                                     int32_t* __restrict__ keep, int32_t* __restrict__ counts) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float rc = 0.5f * (r_atom[ctr[e]] + r_atom[col[e]]);
+  const float x = vec[3 * e], y = vec[3 * e + 1], z = vec[3 * e + 2];
+  const int k = sqrtf(x * x + y * y + z * z) + 1e-15f <= rc;
+  pair_cutoff[e] = rc;
+  keep[e] = k;
+  if (k) atomicAdd(&counts[ctr[e]], 1);
+}
+
+// backward, step 1 (one warp per atom, rows of the masked topology): the gradient of the atom's
+// cutoff is half the sum over its edges and their reverses (pair cutoffs are symmetric means);
+// coef[i] = pass * d_r_atom / dn_root is what every pre-mask neighbour distance of i receives
+__global__ void adaptive_atom_grad_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ rev,
+                                          const float* __restrict__ d_pair_cutoff,
+                                          const float* __restrict__ dn_root, const float* __restrict__ pass,
+                                          int64_t n_atoms, float* __restrict__ coef) {
+  const int64_t atom = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (atom >= n_atoms) return;
+  float acc = 0.f;
+  for (int e = row_ptr[atom] + lane; e < row_ptr[atom + 1]; e += 32)
+    acc += d_pair_cutoff[e] + d_pair_cutoff[rev[e]];
+  acc = warp_sum(acc);
+  if (lane == 0) coef[atom] = pass[atom] * 0.5f * acc / dn_root[atom];
+}
+
+// backward, step 2 (pre-mask edges): d r_atom / d d_k = (df/dr)(d_k; r_root) / dn_root
+__global__ void adaptive_dist_grad_kernel(const int32_t* __restrict__ ctr, const float* __restrict__ dist,
+                                          const float* __restrict__ r_root, const float* __restrict__ coef,
+                                          int64_t n_edges, float width, float* __restrict__ d_dist) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int i = ctr[e];
+  float f, df;
+  probe_count(dist[e], r_root[i], width, f, df);
+  d_dist[e] = coef[i] * df;
 }
 
 // one warp per atom: d_pos[i] = sum_{e in row i} (G[rev e] - G[e])
@@ -159,7 +270,7 @@ extern "C" PETB200_API int petb200_edges_fwd(const float* positions, const float
                   "edges_fwd: unknown cutoff function %d", cutoff_function);
   if (n_edges == 0) return PETB200_OK;
   edges_fwd_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
-      positions, cells, system_of_atom, ctr, col, shift_csr, n_edges, cutoff, width,
+      positions, cells, system_of_atom, ctr, col, shift_csr, n_edges, cutoff, nullptr, width,
       cutoff_function, edge_vec, edge_dist, cutoff_factor);
   return check_launch("edges_fwd");
 }
@@ -175,8 +286,8 @@ extern "C" PETB200_API int petb200_edges_bwd(const float* d_vec, const float* d_
                   "edges_bwd: unknown cutoff function %d", cutoff_function);
   if (n_edges > 0) {
     edge_grad_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
-        d_vec, d_dist, d_fc, edge_vec, edge_dist, n_edges, cutoff, width, cutoff_function,
-        edge_grad);
+        d_vec, d_dist, d_fc, edge_vec, edge_dist, n_edges, cutoff, nullptr, nullptr, width,
+        cutoff_function, edge_grad);
   }
   if (n_atoms > 0 && d_pos) {
     force_scatter_kernel<<<(unsigned)ceil_div(n_atoms * 32, 256), 256, 0, stream>>>(
@@ -200,7 +311,8 @@ extern "C" PETB200_API int petb200_edge_grad(const float* d_vec, const float* d_
                   "edge_grad: unknown cutoff function %d", cutoff_function);
   if (n_edges == 0) return PETB200_OK;
   edge_grad_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
-      d_vec, d_dist, d_fc, edge_vec, edge_dist, n_edges, cutoff, width, cutoff_function, edge_grad);
+      d_vec, d_dist, d_fc, edge_vec, edge_dist, n_edges, cutoff, nullptr, nullptr, width, cutoff_function,
+      edge_grad);
   return check_launch("edge_grad");
 }
 
@@ -219,4 +331,86 @@ extern "C" PETB200_API int petb200_force_scatter(const float* edge_grad, const i
         edge_grad, shift_csr, ctr, system_of_atom, n_edges, d_cells);
   }
   return check_launch("force_scatter");
+}
+
+// ---- per-edge cutoffs (adaptive cutoff): the same kernels with a cutoff array
+extern "C" PETB200_API int petb200_edges_fwd_rc(const float* positions, const float* cells,
+                                    const int32_t* system_of_atom, const int32_t* ctr,
+                                    const int32_t* col, const int32_t* shift_csr, int64_t n_edges,
+                                    const float* edge_cutoff, float width, int cutoff_function,
+                                    float* edge_vec, float* edge_dist, float* cutoff_factor,
+                                    cudaStream_t stream) {
+  PETB200_REQUIRE(cutoff_function == PETB200_CUTOFF_BUMP || cutoff_function == PETB200_CUTOFF_COSINE,
+                  "edges_fwd_rc: unknown cutoff function %d", cutoff_function);
+  PETB200_REQUIRE(edge_cutoff != nullptr, "edges_fwd_rc: edge_cutoff is null");
+  if (n_edges == 0) return PETB200_OK;
+  edges_fwd_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
+      positions, cells, system_of_atom, ctr, col, shift_csr, n_edges, 0.f, edge_cutoff, width,
+      cutoff_function, edge_vec, edge_dist, cutoff_factor);
+  return check_launch("edges_fwd_rc");
+}
+
+extern "C" PETB200_API int petb200_edges_bwd_rc(const float* d_vec, const float* d_dist, const float* d_fc,
+                                    const float* edge_vec, const float* edge_dist,
+                                    const int32_t* row_ptr, const int32_t* ctr, const int32_t* rev,
+                                    const int32_t* shift_csr, const int32_t* system_of_atom,
+                                    int64_t n_atoms, int64_t n_edges, const float* edge_cutoff,
+                                    float width, int cutoff_function, float* edge_grad, float* d_pos,
+                                    float* d_cells, float* d_edge_cutoff, cudaStream_t stream) {
+  PETB200_REQUIRE(cutoff_function == PETB200_CUTOFF_BUMP || cutoff_function == PETB200_CUTOFF_COSINE,
+                  "edges_bwd_rc: unknown cutoff function %d", cutoff_function);
+  PETB200_REQUIRE(edge_cutoff != nullptr, "edges_bwd_rc: edge_cutoff is null");
+  if (n_edges > 0) {
+    edge_grad_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
+        d_vec, d_dist, d_fc, edge_vec, edge_dist, n_edges, 0.f, edge_cutoff, d_edge_cutoff, width,
+        cutoff_function, edge_grad);
+  }
+  if (n_atoms > 0 && d_pos) {
+    force_scatter_kernel<<<(unsigned)ceil_div(n_atoms * 32, 256), 256, 0, stream>>>(
+        edge_grad, row_ptr, rev, n_atoms, d_pos);
+  }
+  if (n_edges > 0 && d_cells) {
+    cell_grad_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
+        edge_grad, shift_csr, ctr, system_of_atom, n_edges, d_cells);
+  }
+  return check_launch("edges_bwd_rc");
+}
+
+extern "C" PETB200_API int petb200_adaptive_cutoff_solve(const int32_t* row_ptr, const float* edge_dist,
+                                             int64_t n_atoms, float num_neighbors, float max_cutoff,
+                                             float width, float* r_root, float* dn_root,
+                                             float* atomic_cutoff, float* pass, cudaStream_t stream) {
+  PETB200_REQUIRE(max_cutoff > 0.f && width > 0.f && num_neighbors > 0.f,
+                  "adaptive_cutoff_solve: cutoff, width and neighbour target must be positive");
+  if (n_atoms == 0) return PETB200_OK;
+  adaptive_solve_kernel<<<(unsigned)ceil_div(n_atoms * 32, 256), 256, 0, stream>>>(
+      row_ptr, edge_dist, n_atoms, num_neighbors, max_cutoff, width, r_root, dn_root, atomic_cutoff, pass);
+  return check_launch("adaptive_cutoff_solve");
+}
+
+extern "C" PETB200_API int petb200_adaptive_pair_mask(const int32_t* ctr, const int32_t* col,
+                                          const float* edge_vec, const float* atomic_cutoff,
+                                          int64_t n_edges, float* pair_cutoff, int32_t* keep,
+                                          int32_t* counts, cudaStream_t stream) {
+  if (n_edges == 0) return PETB200_OK;
+  adaptive_pair_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
+      ctr, col, edge_vec, atomic_cutoff, n_edges, pair_cutoff, keep, counts);
+  return check_launch("adaptive_pair_mask");
+}
+
+extern "C" PETB200_API int petb200_adaptive_cutoff_bwd(const int32_t* row_ptr_kept, const int32_t* rev_kept,
+                                           const float* d_pair_cutoff, const float* dn_root,
+                                           const float* pass, int64_t n_atoms, const int32_t* ctr_all,
+                                           const float* dist_all, const float* r_root,
+                                           int64_t n_edges_all, float width, float* coef,
+                                           float* d_dist_all, cudaStream_t stream) {
+  if (n_atoms > 0) {
+    adaptive_atom_grad_kernel<<<(unsigned)ceil_div(n_atoms * 32, 256), 256, 0, stream>>>(
+        row_ptr_kept, rev_kept, d_pair_cutoff, dn_root, pass, n_atoms, coef);
+  }
+  if (n_edges_all > 0) {
+    adaptive_dist_grad_kernel<<<(unsigned)ceil_div(n_edges_all, 256), 256, 0, stream>>>(
+        ctr_all, dist_all, r_root, coef, n_edges_all, width, d_dist_all);
+  }
+  return check_launch("adaptive_cutoff_bwd");
 }

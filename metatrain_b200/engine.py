@@ -344,6 +344,104 @@ def edges_backward(topo: Topology, vec, dist, d_vec, d_dist, d_fc, cutoff, width
     return d_pos, d_cells
 
 
+# --------------------------------------------------------------------- adaptive cutoff
+@dataclass
+class AdaptiveCutoff:
+    """What the adaptive-cutoff backward needs from the forward solve (all on the device)."""
+    outer: Topology           # pairs within the maximum cutoff (rows the solver summed over)
+    vec_outer: Tensor         # [E_outer,3]
+    dist_outer: Tensor        # [E_outer]
+    r_root: Tensor            # [N] root of n_total(r) = num_neighbors
+    dn_root: Tensor           # [N] max(dn_total/dr, 1e-6) at the root
+    clamp_pass: Tensor        # [N] 1 where clamp(R/16, R) is inactive
+    atomic_cutoffs: Tensor    # [N]
+    pair_cutoffs: Tensor      # [E] of the kept edges
+    width: float
+
+
+def adaptive_topology(outer: Topology, positions: Tensor, cells: Tensor, max_cutoff: float,
+                      num_neighbors: float, width: float):
+    """a4 with ``num_neighbors_adaptive`` set (structures.py:222-262): per-atom cutoffs from the
+    solver (adaptive_cutoff.py:110-229), symmetrised pair cutoffs, and the CSR topology of the
+    pairs inside them.  Returns (kept topology, AdaptiveCutoff)."""
+    if outer.halo is not None:
+        raise NotImplementedError("adaptive cutoff is not built for atom-sharded runs")
+    dev = positions.device
+    N, EO = outer.n_atoms, outer.n_edges
+    i32 = torch.int32
+    vec_o, dist_o, _ = edges_forward(outer, positions, cells, max_cutoff, 1.0, lib.CUTOFF_COSINE)
+    r_root, dn_root, r_atom, cpass = (_empty((N,), positions) for _ in range(4))
+    call("adaptive_cutoff_solve", ptr(outer.row_ptr), ptr(dist_o), N, float(num_neighbors),
+         float(max_cutoff), float(width), ptr(r_root), ptr(dn_root), ptr(r_atom), ptr(cpass))
+    rc_o = _empty((max(EO, 1),), positions)
+    keep = torch.empty(max(EO, 1), device=dev, dtype=i32)
+    counts = torch.zeros(N + 1, device=dev, dtype=i32)
+    call("adaptive_pair_mask", ptr(outer.ctr), ptr(outer.col), ptr(vec_o), ptr(r_atom), EO,
+         ptr(rc_o), ptr(keep), ptr(counts))
+    ws_bytes = lib.load().petb200_csr_build_workspace(EO, N)
+    workspace = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    row_ptr = torch.empty(N + 1, device=dev, dtype=i32)
+    perm = torch.empty(max(EO, 1), device=dev, dtype=i32)
+    stats = torch.zeros(3, device=dev, dtype=i32)
+    call("csr_build", ptr(outer.ctr), ptr(keep), ptr(counts), EO, N, ptr(row_ptr), ptr(perm),
+         ptr(stats), ptr(workspace), ws_bytes)
+    n_edges, max_row = (int(v) for v in stats[:2].tolist())
+    ctr = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
+    col = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
+    shift = torch.empty((max(n_edges, 1), 3), device=dev, dtype=i32)[:n_edges]
+    rev = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
+    call("csr_gather", ptr(perm), ptr(outer.ctr), ptr(outer.col), ptr(outer.shift), n_edges,
+         ptr(ctr), ptr(col), ptr(shift))
+    # the pair cutoffs are symmetric, so the kept set is closed under edge reversal
+    call("reverse_map", ptr(row_ptr), ptr(ctr), ptr(col), ptr(shift), n_edges, N, ptr(rev),
+         ptr(stats[2:]))
+    sel = perm[:n_edges].long()
+    z_neighbors = (outer.z_nodes[col.long()] if n_edges > 0
+                   else torch.empty(0, device=dev, dtype=i32))
+    kept = Topology(N, n_edges, outer.n_structures, max_row, row_ptr, ctr, col, rev, shift,
+                    outer.system_of_atom, outer.z_nodes, z_neighbors.contiguous(),
+                    outer.perm[sel], n_positions=outer.n_positions)
+    return kept, AdaptiveCutoff(outer, vec_o, dist_o, r_root, dn_root, cpass, r_atom,
+                                rc_o[:EO][sel].contiguous(), float(width))
+
+
+def adaptive_edges_forward(topo: Topology, ad: AdaptiveCutoff, positions, cells, width, func):
+    E = topo.n_edges
+    vec, dist, fc = _empty((E, 3), positions), _empty((E,), positions), _empty((E,), positions)
+    call("edges_fwd_rc", ptr(positions), ptr(cells), ptr(topo.system_of_atom), ptr(topo.ctr),
+         ptr(topo.col), ptr(topo.shift), E, ptr(ad.pair_cutoffs), float(width), func,
+         ptr(vec), ptr(dist), ptr(fc))
+    return vec, dist, fc
+
+
+def adaptive_edges_backward(topo: Topology, ad: AdaptiveCutoff, vec, dist, d_vec, d_dist, d_fc,
+                            max_cutoff, width, func, need_cells: bool):
+    """Gradients through the kept edges (direct) and through the per-atom cutoffs (the
+    implicit-function step of the solver), summed."""
+    E, N = topo.n_edges, topo.n_atoms
+    outer = ad.outer
+    scratch = _empty((max(E, 1), 3), vec)
+    d_pos = _empty((N, 3), vec)
+    d_cells = torch.zeros((topo.n_structures, 3, 3), device=vec.device) if need_cells else None
+    d_rc = _empty((max(E, 1),), vec)
+    call("edges_bwd_rc", ptr(d_vec), ptr(d_dist), ptr(d_fc), ptr(vec), ptr(dist), ptr(topo.row_ptr),
+         ptr(topo.ctr), ptr(topo.rev), ptr(topo.shift), ptr(topo.system_of_atom), N, E,
+         ptr(ad.pair_cutoffs), float(width), func, ptr(scratch), ptr(d_pos), ptr(d_cells), ptr(d_rc))
+    if d_fc is None:
+        return d_pos, d_cells
+    coef = _empty((N,), vec)
+    d_dist_o = _empty((max(outer.n_edges, 1),), vec)
+    call("adaptive_cutoff_bwd", ptr(topo.row_ptr), ptr(topo.rev), ptr(d_rc), ptr(ad.dn_root),
+         ptr(ad.clamp_pass), N, ptr(outer.ctr), ptr(ad.dist_outer), ptr(ad.r_root), outer.n_edges,
+         ad.width, ptr(coef), ptr(d_dist_o))
+    d_pos_o, d_cells_o = edges_backward(outer, ad.vec_outer, ad.dist_outer, None, d_dist_o, None,
+                                        max_cutoff, 1.0, lib.CUTOFF_COSINE, need_cells)
+    d_pos += d_pos_o
+    if need_cells:
+        d_cells += d_cells_o
+    return d_pos, d_cells
+
+
 # ---------------------------------------------------------------------------- features
 def _rstd(x: Tensor) -> Tensor:
     out = _empty((x.shape[0],), x)

@@ -69,8 +69,10 @@ def evaluate(
         eps = torch.eye(3, device=pos.device, dtype=pos.dtype, requires_grad=True)
         pos_in = pos @ eps
         cells_in = cells @ eps
+    # PET.forward hands its cutoff_width_adaptive hyper to preprocess (model.py:417-426)
     batch = backend.preprocess(pos_in, centers, neighbors, species, cells_in, cell_shifts,
-                               system_indices, 1.0)
+                               system_indices,
+                               float(backend.hypers.get("cutoff_width_adaptive", 1.0)))
     nodes, edges = backend.calculate_features(batch)
     pred, _, _ = backend.predict(nodes, edges, batch, cells_in, system_indices, [target])
     atomic = torch.cat(pred[target], dim=1) if len(pred[target]) > 1 else pred[target][0]

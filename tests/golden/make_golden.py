@@ -91,14 +91,21 @@ def run_reference(backend, inp, target, dtype, with_strain):
         edge_features_sum=np.array([float((edges[0] * bd["padding_mask"][..., None]).double().sum()),
                                     float((edges[0] * bd["padding_mask"][..., None]).double().abs().sum())]),
         n_edges_kept=np.array(int(bd["padding_mask"].sum())),
+        atomic_cutoffs=bd["atomic_cutoffs_stats"].detach().numpy(),
     )
     if with_strain:
         out["dE_dstrain"] = grads[1].numpy()
     return out
 
 
+ONLY = set(sys.argv[1:])  # optional: regenerate just these cases
+
+
 def make_case(name, frames, atomic_types, target="energy", hypers=None, nl_cutoff=4.5,
               with_strain=False, fp64=True):
+    if ONLY and name not in ONLY:
+        path = os.path.join(HERE, name + ".npz")
+        return dict(np.load(path)) if os.path.exists(path) else None
     inp = batch_frames(frames, nl_cutoff)
     be32 = ref_loader.build_reference_backend(atomic_types, target, hypers).eval()
     fp = weight_fingerprint(be32.state_dict())
@@ -159,6 +166,11 @@ def main():
 
     carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
     make_case("carbon_5", carbon, [6], with_strain=False)
+
+    # adaptive cutoff, solver method (adaptive_cutoff.py:110-229, structures.py:222-262)
+    make_case("water_384_adaptive", [water], [1, 8], hypers=dict(num_neighbors_adaptive=16))
+    make_case("qm9_5_adaptive", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=dict(num_neighbors_adaptive=6))
+    make_case("carbon_5_adaptive", carbon, [6], hypers=dict(num_neighbors_adaptive=10), with_strain=True)
 
     si = silicon_box()
     make_case("si_64", [si], [14], with_strain=True)

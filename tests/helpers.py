@@ -15,7 +15,9 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 "qm9_5_postln", "water_384_postln",
                 # the original PET layer (PostLN + LayerNorm + SiLU + residual featurizer) and the
                 # PreLN layer with LayerNorm + SiLU
-                "water_384_classic", "qm9_5_classic", "water_384_preln_ln_silu"]
+                "water_384_classic", "qm9_5_classic", "water_384_preln_ln_silu",
+                # adaptive cutoff, solver method (adaptive_cutoff.py:110-229)
+                "water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(

@@ -71,7 +71,24 @@ def test_reference_hard_coded_energies():
     torch.testing.assert_close(out["energies"].cpu().ravel(), expected)
 
 
-@pytest.mark.parametrize("case", ["si_64", "ragged_mix", "carbon_5"])
+@pytest.mark.parametrize("case", ["water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive"])
+def test_adaptive_cutoffs_match_reference(case):
+    """Per-atom cutoffs of the solver (adaptive_cutoff.py:110-229) and the pairs kept by the
+    symmetrised pair cutoffs (structures.py:253-262), against the unmodified reference."""
+    g = load_golden(case)
+    be = make_backend(g)
+    inp = golden_inputs(g, DEV)
+    bd = be.preprocess(inp["positions"], inp["centers"], inp["neighbors"], inp["species"],
+                       inp["cells"], inp["cell_shifts"], inp["system_indices"], 1.0)
+    rc = bd["atomic_cutoffs_stats"].cpu().numpy()
+    assert rc.shape == g["ref32_atomic_cutoffs"].shape
+    assert np.abs(rc - g["ref32_atomic_cutoffs"]).max() <= 2e-5
+    assert int(bd["padding_mask"].sum()) == int(g["ref32_n_edges_kept"])
+    assert rc.min() >= g["hypers"]["cutoff"] / 16 and rc.max() <= g["hypers"]["cutoff"]
+
+
+@pytest.mark.parametrize("case", ["si_64", "ragged_mix", "carbon_5", "carbon_5_adaptive",
+                                  "water_384_adaptive"])
 def test_stages_match_oracle(case):
     """Stage-by-stage comparison with the oracle on identical weights and inputs."""
     g = load_golden(case)
