@@ -500,10 +500,15 @@ def run_petb200(args):
     # The contractions are tall-skinny (M = edges, N, K <= 1024): arithmetic intensity
     # 32..128 flop/B is below the ridge (~215), so the dominant kernel is HBM-bound; the
     # tensor-pipe view is reported next to it.
+    # DRAM traffic per launch from the committed ncu launch list of this command
+    # (profiles/r1_launches_final.md: dram__bytes_read + dram__bytes_write summed over the 624
+    # gemm_tc launches it holds, 179 946 MB); only quoted for the workload it was captured on
+    ncu_traffic = 179.946e9 / 624 if (args.precision == "bf16x3" and tuple(args.reps) == tuple(REPS)) else None
     roofline = {
         "kernel": "gemm (all dense contractions of the step: gemm_tc_kernel / gemm_simt_kernel)",
         "bound": "hbm", "achieved": gemm_gbs, "peak": hbm, "unit": "GB/s", "frac": gemm_gbs / hbm,
-        "traffic": None, "peak_source": which,
+        "traffic": ncu_traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1_launches_final.md)",
+        "algorithmic_bytes_per_launch": g_bytes / g_n, "peak_source": which,
         "algorithmic_bytes_per_step": g_bytes / 3, "launches_per_step": g_n // 3,
         "ms_per_step": g_t / 3 * 1e3, "share_of_step": (g_t / 3 * 1e3) / step_ms,
         "precision": args.precision,
@@ -513,7 +518,12 @@ def run_petb200(args):
     edge_scatter = {
         "kernel": "combine_ln_fwd (message reversal + LayerNorm)", "bound": "hbm",
         "achieved": scatter_gbs, "peak": hbm, "unit": "GB/s", "frac": scatter_gbs / hbm,
-        "traffic": None, "peak_source": which, "avg_launch_us": c_t / c_n * 1e6,
+        "traffic": ((3771e6 + 5577e6) / 16 if tuple(args.reps) == tuple(REPS) else None),
+        "traffic_unit": "bytes per launch (ncu, profiles/r1_launches_final.md)",
+        "algorithmic_bytes_per_launch": scatter_bytes / c_n,
+        "note": "DRAM traffic is below the algorithmic bytes: every `out` row is read twice (own edge + "
+                "as the reversed row of its partner) and the second read is served from L2",
+        "peak_source": which, "avg_launch_us": c_t / c_n * 1e6,
     }
     attn = {k: {"ms_per_step": tot[k][0] / 3 * 1e3, "launches_per_step": tot[k][2] // 3,
                 "bound": "hbm", "achieved": tot[k][3] / tot[k][0] * 1e-9, "peak": hbm, "unit": "GB/s",

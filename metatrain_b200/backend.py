@@ -324,9 +324,27 @@ class B200PETBackend(PETParameters):
     ) -> Dict[str, Tensor]:
         """Same signature and returned keys as ``PETBackend.preprocess`` (backend.py:238)."""
         _require_cuda(positions, "preprocess")
+        topo, z_nodes = self.build_topology(positions, centers, neighbors, species, cells,
+                                            cell_shifts, system_indices)
+        return self.preprocess_on_topology(positions, cells, topo, z_nodes, cutoff_width_adaptive)
+
+    def build_topology(self, positions, centers, neighbors, species, cells, cell_shifts,
+                       system_indices, keep_all_pairs: bool = False):
+        """The integer half of ``preprocess`` (a4-a6): CSR rows, reverse-edge map.  The one
+        device->host read of the stage (edge count) happens here.  ``keep_all_pairs`` keeps the
+        pairs of a skin list that are beyond the cutoff (their cutoff factor is 0); the topology
+        then stays valid while the list does — what ``md.GraphedEvaluator`` replays."""
+        _require_cuda(positions, "preprocess")
         z_nodes = self.species_to_species_index[species.long()]
         topo = engine.build_topology(positions, centers, neighbors, cell_shifts, cells,
-                                     system_indices, z_nodes, self.cutoff)
+                                     system_indices, z_nodes,
+                                     float("inf") if keep_all_pairs else self.cutoff)
+        return topo, z_nodes
+
+    def preprocess_on_topology(self, positions, cells, topo, z_nodes,
+                               cutoff_width_adaptive: float = 1.0) -> Dict[str, Tensor]:
+        """The floating-point half of ``preprocess`` on a given topology (no host
+        synchronisation with a fixed cutoff)."""
         atomic_cutoffs = None
         if self.num_neighbors_adaptive is None:
             vec, dist, fc = _EdgeGeometry.apply(positions, cells, topo, self.cutoff,

@@ -180,6 +180,37 @@ def _linear_image(w_folded: Tensor):
     return img
 
 
+def _w(mod) -> Tensor:
+    """Effective weight of a Linear / Embedding / norm module.  A LoRA-wrapped Linear
+    (``src/metatrain/pet/modules/finetuning.py:357-378``: ``y = linear(x) + scaling * B(A(x))``) is
+    merged: ``W + scaling * B A``."""
+    if hasattr(mod, "lora_A") and hasattr(mod, "lora_B"):
+        base = mod.linear.weight.detach()
+        return base + float(mod.scaling) * (mod.lora_B.weight.detach() @ mod.lora_A.weight.detach())
+    return mod.weight.detach()
+
+
+def _b(mod) -> Optional[Tensor]:
+    if hasattr(mod, "lora_A") and hasattr(mod, "lora_B"):
+        mod = mod.linear
+    bias = getattr(mod, "bias", None)
+    return bias.detach() if bias is not None else None
+
+
+# Bumped whenever ANY torch module registers a sub-module or a parameter (e.g. LoRA injection,
+# finetuning.py:326-353, swaps Linear attributes deep inside the backend): cached parameter lists
+# are re-walked after such an event.
+_STRUCTURE_EPOCH = [0]
+
+
+def _bump_structure_epoch(*_args):
+    _STRUCTURE_EPOCH[0] += 1
+
+
+torch.nn.modules.module.register_module_module_registration_hook(_bump_structure_epoch)
+torch.nn.modules.module.register_module_parameter_registration_hook(_bump_structure_epoch)
+
+
 class PackedWeights:
     """Device-side views/derivatives of the module parameters the kernels consume:
     RMSNorm weights folded into the following Linear (W.diag(gamma)), and W^T for every
@@ -188,23 +219,22 @@ class PackedWeights:
     def __init__(self, module: torch.nn.Module):
         self.signature = self._signature(module)
         self.split_cache: Dict[tuple, Tensor] = {}
-        g = lambda t: t.detach()  # noqa: E731
         mh = getattr(module, "hypers", {})
         generic = (mh.get("transformer_type", "PreLN"), mh.get("normalization", "RMSNorm"),
                    mh.get("activation", "SwiGLU")) != ("PreLN", "RMSNorm", "SwiGLU")
-        nb = lambda n: (g(n.weight), g(n.bias) if getattr(n, "bias", None) is not None else None)  # noqa: E731
+        nb = lambda n: (_w(n), _b(n) if getattr(n, "bias", None) is not None else None)  # noqa: E731
         self.gnn: List[dict] = []
         for layer in module.gnn_layers:
             L: dict = {}
-            L["w_geo"] = g(layer.edge_embedder.weight).contiguous()
-            L["b_geo"] = g(layer.edge_embedder.bias)
-            L["w1"] = g(layer.compress[0].weight)
-            L["b1"] = g(layer.compress[0].bias)
-            L["w1_t"], _ = _t_and_scaled(layer.compress[0].weight)
-            L["w2"] = g(layer.compress[2].weight)
-            L["b2"] = g(layer.compress[2].bias)
-            L["w2_t"], _ = _t_and_scaled(layer.compress[2].weight)
-            L["nbr"] = (g(layer.neighbor_embedder.weight).contiguous()
+            L["w_geo"] = _w(layer.edge_embedder).contiguous()
+            L["b_geo"] = _b(layer.edge_embedder)
+            L["w1"] = _w(layer.compress[0])
+            L["b1"] = _b(layer.compress[0])
+            L["w1_t"], _ = _t_and_scaled(_w(layer.compress[0]))
+            L["w2"] = _w(layer.compress[2])
+            L["b2"] = _b(layer.compress[2])
+            L["w2_t"], _ = _t_and_scaled(_w(layer.compress[2]))
+            L["nbr"] = (_w(layer.neighbor_embedder).contiguous()
                         if hasattr(layer, "neighbor_embedder") else None)
             # concatenation folded into the first Linear (petb200_compress_gemm):
             #   W_1 . cat[geo | nbr | m] + b_1 = W_1m . m + G . (r, d) + Tbl[z_j] + b'
@@ -218,59 +248,57 @@ class PackedWeights:
             L["tl"] = []
             for tl in layer.trans.layers:
                 T: dict = {}
-                T["w_qkv_t"], T["w_qkv"] = _t_and_scaled(
-                    tl.attention.input_linear.weight, tl.norm_attention.weight, True)
-                T["b_qkv"] = g(tl.attention.input_linear.bias)
+                T["w_qkv_t"], T["w_qkv"] = _t_and_scaled(_w(tl.attention.input_linear), tl.norm_attention.weight, True)
+                T["b_qkv"] = _b(tl.attention.input_linear)
                 T["qkv_img"] = _linear_image(T["w_qkv"])   # fused RMSNorm + QKV projection
                 if generic:
                     # the generic layer path runs the normalisations as standalone ops: un-folded
                     # weights and the norm parameters themselves
-                    T["w_qkv_raw"] = g(tl.attention.input_linear.weight)
-                    T["w_qkv_raw_t"], _ = _t_and_scaled(tl.attention.input_linear.weight)
+                    T["w_qkv_raw"] = _w(tl.attention.input_linear)
+                    T["w_qkv_raw_t"], _ = _t_and_scaled(_w(tl.attention.input_linear))
                     T["n_attn"], T["n_mlp"] = nb(tl.norm_attention), nb(tl.norm_mlp)
                     T["n_c"] = nb(tl.norm_center_features)
-                T["w_o"] = g(tl.attention.output_linear.weight)
-                T["b_o"] = g(tl.attention.output_linear.bias)
-                T["w_o_t"], _ = _t_and_scaled(tl.attention.output_linear.weight)
-                T["w_in_t"], T["w_in"] = _t_and_scaled(tl.mlp.w_in.weight, tl.norm_mlp.weight, True)
-                T["b_in"] = g(tl.mlp.w_in.bias)
-                T["w_out"] = g(tl.mlp.w_out.weight)
-                T["b_out"] = g(tl.mlp.w_out.bias)
-                T["w_out_t"], _ = _t_and_scaled(tl.mlp.w_out.weight)
+                T["w_o"] = _w(tl.attention.output_linear)
+                T["b_o"] = _b(tl.attention.output_linear)
+                T["w_o_t"], _ = _t_and_scaled(_w(tl.attention.output_linear))
+                T["w_in_t"], T["w_in"] = _t_and_scaled(_w(tl.mlp.w_in), tl.norm_mlp.weight, True)
+                T["b_in"] = _b(tl.mlp.w_in)
+                T["w_out"] = _w(tl.mlp.w_out)
+                T["b_out"] = _b(tl.mlp.w_out)
+                T["w_out_t"], _ = _t_and_scaled(_w(tl.mlp.w_out))
                 # operand-tile images of the fused feed-forward kernels (petb200_mlp_fwd / _bwd)
                 T["mlp_img"] = _mlp_images(T["w_in"], T["w_out"])
                 if generic:
-                    T["w_in_raw"] = g(tl.mlp.w_in.weight)
-                    T["w_in_raw_t"], _ = _t_and_scaled(tl.mlp.w_in.weight)
-                T["w_con"] = g(tl.center_contraction.weight)
-                T["b_con"] = g(tl.center_contraction.bias)
-                T["w_con_t"], _ = _t_and_scaled(tl.center_contraction.weight)
-                T["w_exp"] = g(tl.center_expansion.weight)
-                T["b_exp"] = g(tl.center_expansion.bias)
-                T["w_exp_t"], _ = _t_and_scaled(tl.center_expansion.weight)
-                T["wc_in_t"], T["wc_in"] = _t_and_scaled(
-                    tl.center_mlp.w_in.weight, tl.norm_center_features.weight, True)
-                T["bc_in"] = g(tl.center_mlp.w_in.bias)
-                T["wc_out"] = g(tl.center_mlp.w_out.weight)
-                T["bc_out"] = g(tl.center_mlp.w_out.bias)
-                T["wc_out_t"], _ = _t_and_scaled(tl.center_mlp.w_out.weight)
+                    T["w_in_raw"] = _w(tl.mlp.w_in)
+                    T["w_in_raw_t"], _ = _t_and_scaled(_w(tl.mlp.w_in))
+                T["w_con"] = _w(tl.center_contraction)
+                T["b_con"] = _b(tl.center_contraction)
+                T["w_con_t"], _ = _t_and_scaled(_w(tl.center_contraction))
+                T["w_exp"] = _w(tl.center_expansion)
+                T["b_exp"] = _b(tl.center_expansion)
+                T["w_exp_t"], _ = _t_and_scaled(_w(tl.center_expansion))
+                T["wc_in_t"], T["wc_in"] = _t_and_scaled(_w(tl.center_mlp.w_in), tl.norm_center_features.weight, True)
+                T["bc_in"] = _b(tl.center_mlp.w_in)
+                T["wc_out"] = _w(tl.center_mlp.w_out)
+                T["bc_out"] = _b(tl.center_mlp.w_out)
+                T["wc_out_t"], _ = _t_and_scaled(_w(tl.center_mlp.w_out))
                 if generic:
-                    T["wc_in_raw"] = g(tl.center_mlp.w_in.weight)
-                    T["wc_in_raw_t"], _ = _t_and_scaled(tl.center_mlp.w_in.weight)
+                    T["wc_in_raw"] = _w(tl.center_mlp.w_in)
+                    T["wc_in_raw_t"], _ = _t_and_scaled(_w(tl.center_mlp.w_in))
                 L["tl"].append(T)
             self.gnn.append(L)
         self.combine: List[dict] = []
         for norm, mlp in zip(module.combination_norms, module.combination_mlps):
             C: dict = {}
-            C["gamma"], C["beta"] = g(norm.weight), g(norm.bias)
-            C["w_a"], C["b_a"] = g(mlp[0].weight), g(mlp[0].bias)
-            C["w_b"], C["b_b"] = g(mlp[2].weight), g(mlp[2].bias)
-            C["w_a_t"], _ = _t_and_scaled(mlp[0].weight)
-            C["w_b_t"], _ = _t_and_scaled(mlp[2].weight)
+            C["gamma"], C["beta"] = _w(norm), _b(norm)
+            C["w_a"], C["b_a"] = _w(mlp[0]), _b(mlp[0])
+            C["w_b"], C["b_b"] = _w(mlp[2]), _b(mlp[2])
+            C["w_a_t"], _ = _t_and_scaled(_w(mlp[0]))
+            C["w_b_t"], _ = _t_and_scaled(_w(mlp[2]))
             self.combine.append(C)
         # one node embedding per readout layer (1 with the feedforward featurizer)
-        self.node_emb = [g(e.weight).contiguous() for e in module.node_embedders]
-        self.edge_emb = g(module.edge_embedder.weight).contiguous()
+        self.node_emb = [_w(e).contiguous() for e in module.node_embedders]
+        self.edge_emb = _w(module.edge_embedder).contiguous()
         self.heads: Dict[str, List[dict]] = {}   # target -> one entry per readout layer
         for name in module.node_heads.keys():
             per_layer = []
@@ -278,17 +306,17 @@ class PackedWeights:
                 H: dict = {}
                 nh, eh = module.node_heads[name][r], module.edge_heads[name][r]
                 for tag, head in (("n", nh), ("e", eh)):
-                    H[tag + "1"], H[tag + "1_b"] = g(head[0].weight), g(head[0].bias)
-                    H[tag + "2"], H[tag + "2_b"] = g(head[2].weight), g(head[2].bias)
-                    H[tag + "1_t"], _ = _t_and_scaled(head[0].weight)
-                    H[tag + "2_t"], _ = _t_and_scaled(head[2].weight)
+                    H[tag + "1"], H[tag + "1_b"] = _w(head[0]), _b(head[0])
+                    H[tag + "2"], H[tag + "2_b"] = _w(head[2]), _b(head[2])
+                    H[tag + "1_t"], _ = _t_and_scaled(_w(head[0]))
+                    H[tag + "2_t"], _ = _t_and_scaled(_w(head[2]))
                 keys = list(module.node_last_layers[name][r].keys())
                 H["block_keys"] = keys
                 H["block_sizes"] = [module.node_last_layers[name][r][k].weight.shape[0] for k in keys]
-                H["wn"] = torch.cat([g(module.node_last_layers[name][r][k].weight) for k in keys]).contiguous()
-                H["bn"] = torch.cat([g(module.node_last_layers[name][r][k].bias) for k in keys]).contiguous()
-                H["we"] = torch.cat([g(module.edge_last_layers[name][r][k].weight) for k in keys]).contiguous()
-                H["be"] = torch.cat([g(module.edge_last_layers[name][r][k].bias) for k in keys]).contiguous()
+                H["wn"] = torch.cat([_w(module.node_last_layers[name][r][k]) for k in keys]).contiguous()
+                H["bn"] = torch.cat([_b(module.node_last_layers[name][r][k]) for k in keys]).contiguous()
+                H["we"] = torch.cat([_w(module.edge_last_layers[name][r][k]) for k in keys]).contiguous()
+                H["be"] = torch.cat([_b(module.edge_last_layers[name][r][k]) for k in keys]).contiguous()
                 per_layer.append(H)
             self.heads[name] = per_layer
 
@@ -298,11 +326,11 @@ class PackedWeights:
         # costs ~0.5 ms and this runs in every stage of every step); B200PETBackend drops the cache
         # whenever its parameter SET can change (add_output / remove_output / _apply /
         # load_state_dict), in-place updates are caught by (data_ptr, _version)
-        params = module.__dict__.get("_petb200_param_list")
-        if params is None:
-            params = list(module.parameters())
-            module.__dict__["_petb200_param_list"] = params
-        return tuple((p.data_ptr(), p._version) for p in params)
+        cached = module.__dict__.get("_petb200_param_list")
+        if cached is None or cached[0] != _STRUCTURE_EPOCH[0]:
+            cached = (_STRUCTURE_EPOCH[0], list(module.parameters()))
+            module.__dict__["_petb200_param_list"] = cached
+        return tuple((p.data_ptr(), p._version) for p in cached[1])
 
     def is_current(self, module) -> bool:
         return self.signature == self._signature(module)

@@ -104,6 +104,21 @@ def load_reference_backend_class():
     return _LOADED
 
 
+def load_reference_finetuning():
+    """The reference's ``pet/modules/finetuning.py`` module (LoRA injection), unmodified."""
+    load_reference_backend_class()
+    full = "metatrain.pet.modules.finetuning"
+    if full not in sys.modules:
+        _stub("metatrain.utils")
+        _stub("metatrain.utils.data")
+        _stub("metatrain.utils.data.target_info", TargetInfo=_Dummy)
+        spec = importlib.util.spec_from_file_location(full, os.path.join(_PET_DIR, "modules", "finetuning.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[full] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules[full]
+
+
 def build_reference_backend(atomic_types, target="energy", hypers=None, seed=0,
                             dtype=None):
     """Seeded construction in the RNG order of pet/model.py:115,145-147."""
@@ -118,11 +133,16 @@ def build_reference_backend(atomic_types, target="energy", hypers=None, seed=0,
     torch.manual_seed(seed)
     h = dict(DEFAULT_HYPERS)
     if hypers:
-        h.update(hypers)
+        h.update({k: v for k, v in hypers.items() if not k.startswith("_")})
     be = cls(h, list(atomic_types))
     # key naming of pet/model.py:1045-1051: <target>_<keyname>_<keyvalue>; a scalar
     # target has the single key "_" = 0  -> "<target>___0"
     be.add_output(target, {f"{target}___0": [1]})
+    lora = (hypers or {}).get("_lora")
+    if lora:  # test-only pseudo hyper: LoRA adapters injected by the reference's own function
+        torch.manual_seed(lora["seed"])
+        load_reference_finetuning().inject_lora_layers(
+            be, tuple(lora["target_modules"]), rank=lora["rank"], alpha=lora["alpha"])
     if dtype is not None:
         be = be.to(dtype)
     return be

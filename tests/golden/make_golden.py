@@ -164,6 +164,15 @@ def main():
     make_case("water_384_preln_ln_silu", [water], [1, 8],
               hypers=dict(normalization="LayerNorm", activation="SiLU"), fp64=False)
 
+    # LoRA adapters (finetuning.py:322-378) on the attention projections (the reference default
+    # target modules) and on every feed-forward / compress Linear; adapters seeded with 1
+    make_case("water_384_lora", [water], [1, 8], fp64=False,
+              hypers=dict(_lora=dict(rank=4, alpha=8.0, seed=1, target_modules=["input_linear", "output_linear"])))
+    make_case("qm9_5_lora_wide", qm9, [1, 6, 7, 8], target="mtt::U0",
+              hypers=dict(_lora=dict(rank=8, alpha=4.0, seed=1,
+                                     target_modules=["input_linear", "output_linear", "w_in", "w_out",
+                                                     "center_contraction", "center_expansion"])))
+
     carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
     make_case("carbon_5", carbon, [6], with_strain=False)
 

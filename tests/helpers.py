@@ -17,7 +17,9 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 # PreLN layer with LayerNorm + SiLU
                 "water_384_classic", "qm9_5_classic", "water_384_preln_ln_silu",
                 # adaptive cutoff, solver method (adaptive_cutoff.py:110-229)
-                "water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive"]
+                "water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive",
+                # LoRA adapters (finetuning.py:322-378), merged into the packed weights
+                "water_384_lora", "qm9_5_lora_wide"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(
@@ -36,8 +38,21 @@ def load_golden(name):
     g["target"] = str(g["target"])
     g["hypers"] = dict(DEFAULT_HYPERS)
     g["hypers"].update(ast.literal_eval(str(g["hypers_override"])))
+    g["lora"] = g["hypers"].pop("_lora", None)  # test-only: LoRA adapters injected after construction
     g["atomic_types"] = [int(z) for z in g["atomic_types"]]
     return g
+
+
+def apply_lora(module, g):
+    """Inject the golden case's LoRA adapters (same seed and order as make_golden.py did on the
+    reference).  Returns the extra state-dict entry the oracle needs (the adapter scale)."""
+    if not g.get("lora"):
+        return {}
+    from metatrain_b200.finetuning import inject_lora_layers
+    lora = g["lora"]
+    torch.manual_seed(lora["seed"])
+    inject_lora_layers(module, tuple(lora["target_modules"]), rank=lora["rank"], alpha=lora["alpha"])
+    return {"lora.scaling": torch.tensor(lora["alpha"] / lora["rank"])}
 
 
 def seed_all(seed=0):

@@ -7,7 +7,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from helpers import GOLDEN_CASES, golden_inputs, load_golden, seed_all  # noqa: E402
+from helpers import GOLDEN_CASES, apply_lora, golden_inputs, load_golden, seed_all  # noqa: E402
 from metatrain_b200 import B200PETBackend, evaluate  # noqa: E402
 from metatrain_b200.systems import make_batch, replicate, water_384  # noqa: E402
 from oracle import pet_oracle  # noqa: E402
@@ -20,6 +20,7 @@ def make_backend(g, precision="fp32"):
     seed_all(0)
     be = B200PETBackend(g["hypers"], g["atomic_types"], precision=precision)
     be.add_output(g["target"], {g["target"] + "___0": [1]})
+    apply_lora(be, g)
     return be.to(DEV).eval()
 
 
@@ -60,6 +61,25 @@ def test_tensor_core_split_meets_force_tolerance(case):
     f1 = np.abs(out1["dE_dpos"].cpu().numpy() - g["ref32_dE_dpos"]).max()
     print(f"{case}: bf16 single-pass force max-abs-err {f1:.2e} eV/A")
     assert f1 <= 0.2
+
+
+def test_lora_adapters_are_merged_and_repacked_on_update():
+    """LoRA adapters (finetuning.py:357-378) are merged into the packed weights; zeroing every
+    lora_B in place must fall back to the base model's golden (the packed weights follow the
+    parameters' versions)."""
+    from metatrain_b200.finetuning import LoRALinear
+    g, base = load_golden("water_384_lora"), load_golden("water_384")
+    be = make_backend(g)
+    adapted = [m for m in be.modules() if isinstance(m, LoRALinear)]
+    assert len(adapted) == 2 * g["hypers"]["num_gnn_layers"] * g["hypers"]["num_attention_layers"]
+    out = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    assert np.abs(out["dE_dpos"].cpu().numpy() - g["ref32_dE_dpos"]).max() <= 2e-5
+    with torch.no_grad():
+        for m in adapted:
+            m.lora_B.weight.zero_()
+    out = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    assert np.abs(out["energies"].cpu().numpy() - base["ref32_energies"]).max() <= 1e-5 * abs(base["ref32_energies"]).max()
+    assert np.abs(out["dE_dpos"].cpu().numpy() - base["ref32_dE_dpos"]).max() <= 2e-5
 
 
 def test_reference_hard_coded_energies():
@@ -268,6 +288,34 @@ def test_verlet_list_reuse_matches_fresh_lists():
         assert (out["dE_dpos"] - ref["dE_dpos"]).abs().max() <= 2e-5
         pos = pos + 0.04 * torch.randn(pos.shape, generator=gen).to(DEV)
     assert vl.n_builds >= 1 and vl.n_reuses >= 2 and vl.n_builds + vl.n_reuses == 6
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_graphed_md_evaluator_matches_eager_steps(use_graph):
+    """md.GraphedEvaluator (device Verlet list + one CUDA graph per list) against evaluate() with
+    a fresh exact neighbor list, along a random walk that forces list rebuilds / re-captures."""
+    from metatrain_b200 import GraphedEvaluator
+    from metatrain_b200.neighbors_gpu import neighbor_list_gpu
+    g = load_golden("si_64")
+    be = make_backend(g, precision="bf16x3")
+    inp = golden_inputs(g, DEV)
+    cell = inp["cells"][0]
+    md = GraphedEvaluator(be, inp["species"], cell, periodic=True, skin=0.3, target=g["target"],
+                          use_graph=use_graph)
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    pos = inp["positions"].clone()
+    for step in range(12):
+        out = md(pos)
+        e, f = out["energies"].clone(), out["dE_dpos"].clone()
+        c, n, s = neighbor_list_gpu(pos, cell, True, be.cutoff)
+        ref = evaluate(be, pos, c.long(), n.long(), inp["species"], inp["cells"], s, inp["system_indices"],
+                       target=g["target"])
+        assert (e - ref["energies"]).abs().max() <= 2e-5 * max(1.0, float(ref["energies"].abs().max()))
+        assert (f - ref["dE_dpos"]).abs().max() <= 2e-5, f"step {step}"
+        pos = pos + 0.04 * torch.randn(pos.shape, generator=gen).to(DEV)
+    assert md.verlet.n_builds >= 2 and md.verlet.n_reuses >= 4
+    if use_graph:
+        assert md.n_captures == md.verlet.n_builds and md.n_replays == 12
 
 
 def test_neighbor_order_invariance():

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, golden_inputs, load_golden, seed_all, weight_fingerprint
+from helpers import GOLDEN_CASES, apply_lora, golden_inputs, load_golden, seed_all, weight_fingerprint
 from metatrain_b200.parameters import PETParameters
 from oracle import pet_oracle, ref_loader
 from oracle.structures import neighbor_list
@@ -23,13 +23,18 @@ def seeded_state_dict(g):
     seed_all(0)
     p = PETParameters(g["hypers"], g["atomic_types"])
     p.add_output(g["target"], {g["target"] + "___0": [1]})
-    return p.state_dict()
+    extra = apply_lora(p, g)
+    sd = p.state_dict()
+    sd.update(extra)
+    return sd
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_seeded_weights_equal_reference(case):
     g = load_golden(case)
-    fp = weight_fingerprint(seeded_state_dict(g))
+    sd = seeded_state_dict(g)
+    sd.pop("lora.scaling", None)
+    fp = weight_fingerprint(sd)
     assert fp.shape == g["weight_fingerprint"].shape
     np.testing.assert_array_equal(fp, g["weight_fingerprint"])
 

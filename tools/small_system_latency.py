@@ -31,3 +31,17 @@ for case in ("si_64", "water_384"):
     dt = (time.perf_counter() - t0) / n
     na = inp["positions"].shape[0]
     print(f"{case}: {na} atoms, {dt * 1e3:.2f} ms per step (host-synchronous) = {na / dt:,.0f} atom-steps/s")
+    # the same step through md.GraphedEvaluator: device Verlet list + one CUDA graph replay per step
+    from metatrain_b200 import GraphedEvaluator  # noqa: E402
+    md = GraphedEvaluator(be, inp["species"], inp["cells"][0], periodic=True, skin=0.3, target=g["target"])
+    pos = inp["positions"].clone()
+    for _ in range(3):
+        md(pos)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        pos = pos + 1e-3 * torch.randn_like(pos)
+        md(pos)["dE_dpos"].cpu()
+    dt = (time.perf_counter() - t0) / n
+    print(f"{case}: CUDA-graph MD step {dt * 1e3:.2f} ms = {na / dt:,.0f} atom-steps/s "
+          f"({md.n_captures} captures, {md.n_replays} replays, list builds {md.verlet.n_builds})")
