@@ -263,7 +263,8 @@ def run_petb200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PETB200_NCCL_DEBUG", "WARN")  # keep stdout = 1 JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("PETB200_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner off stdout (= 1 JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     seed_all(0)
