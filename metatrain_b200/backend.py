@@ -143,11 +143,13 @@ class _Predict(torch.autograd.Function):
     readout layer."""
 
     @staticmethod
-    def forward(ctx, h, m, fc, backend, topo, name, layer):
+    def forward(ctx, h, m, fc, backend, topo, name, layer, sink=None):
         pw = backend._packed()
         prec = backend._precision
         atomic, saved = engine.predict_forward(pw, topo, name, h.contiguous(), m.contiguous(),
                                                fc.contiguous(), prec, layer)
+        if sink is not None:  # last-layer features (outputs of the node / edge heads), no gradient
+            sink.append((saved["n2"], saved["e2"]))
         ctx.topo, ctx.pw, ctx.saved, ctx.fc, ctx.name, ctx.prec, ctx.layer = topo, pw, saved, fc, name, prec, layer
         return atomic
 
@@ -155,7 +157,7 @@ class _Predict(torch.autograd.Function):
     def backward(ctx, d_atomic):
         d_h, d_m, d_fc = engine.predict_backward(ctx.pw, ctx.topo, ctx.name, ctx.fc.contiguous(),
                                                  ctx.saved, d_atomic, ctx.prec, ctx.layer)
-        return d_h, d_m, d_fc, None, None, None, None
+        return d_h, d_m, d_fc, None, None, None, None, None
 
 
 class _CsrToNef(torch.autograd.Function):
@@ -448,8 +450,11 @@ class B200PETBackend(PETParameters):
         system_indices: Tensor,
         requested_output_names: List[str],
     ) -> Tuple[Dict[str, List[Tensor]], Dict[str, List[Tensor]], Dict[str, List[Tensor]]]:
-        """Same contract as ``PETBackend.predict`` (backend.py:420).  The last-layer
-        feature dictionaries are returned empty (only needed for ``mtt::aux`` outputs)."""
+        """Same contract as ``PETBackend.predict`` (backend.py:420).  The last-layer feature
+        dictionaries (outputs of the node / edge heads, backend.py:651-687; read by the wrapper for
+        the ``mtt::aux::{target}_last_layer_features`` outputs) hold, for every REQUESTED output,
+        one ``[N, d_head]`` node tensor and one edge tensor (``[N, M, d_head]`` zero-padded NEF, or
+        CSR ``[E, d_head]`` when ``emit_nef`` is off) per readout layer; they are detached."""
         self._check_inference()
         topo = self._topology_of(batch_data)
         fc = batch_data["_petb200_fc"]
@@ -462,6 +467,8 @@ class B200PETBackend(PETParameters):
                 m = m_in if m_in.dim() == 2 else _NefToCsr.apply(m_in, topo)
             edges_csr.append(m)
         atomic_predictions: Dict[str, List[Tensor]] = {}
+        node_ll: Dict[str, List[Tensor]] = {}
+        edge_ll: Dict[str, List[Tensor]] = {}
         for name in self.node_last_layers.keys():
             if name not in requested_output_names:
                 continue
@@ -469,9 +476,12 @@ class B200PETBackend(PETParameters):
                 raise NotImplementedError("B200PETBackend: non_conservative_stress is not built")
             # node + edge contributions summed over the readout layers (backend.py:469-481)
             atomic = None
+            sink: List[Tuple[Tensor, Tensor]] = []
             for layer, (h, m) in enumerate(zip(node_features_list, edges_csr)):
-                part = _Predict.apply(h, m, fc, self, topo, name, layer)
+                part = _Predict.apply(h, m, fc, self, topo, name, layer, sink)
                 atomic = part if atomic is None else atomic + part
             sizes = self._packed().heads[name][0]["block_sizes"]
             atomic_predictions[name] = list(torch.split(atomic, sizes, dim=1))
-        return atomic_predictions, {}, {}
+            node_ll[name] = [n for n, _ in sink]
+            edge_ll[name] = [_CsrToNef.apply(e, topo) if self.emit_nef else e for _, e in sink]
+        return atomic_predictions, node_ll, edge_ll

@@ -176,7 +176,7 @@ def evaluate_sharded(backend, shard: Shard, positions: Tensor, species: Tensor, 
     vec, dist_, fc = _EdgeGeometry.apply(pos_local, cells, topo, backend.cutoff,
                                          backend.cutoff_width, backend._cutoff_id)
     h, m = _Features.apply(vec, dist_, fc, backend, topo)
-    atomic = _Predict.apply(h, m, fc, backend, topo, target, 0)    # [n_own, P]
+    atomic = _Predict.apply(h, m, fc, backend, topo, target, 0, None)    # [n_own, P]
     energy = atomic.sum(dim=0, keepdim=True)
     total = energy.detach().clone()
     dist.all_reduce(total, group=group)

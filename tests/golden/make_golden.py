@@ -199,6 +199,10 @@ def main():
     pair = dict(Z=np.array([6, 6]), positions=np.array([[0.0, 0, 0], [0, 0, 100.0]]),
                 cell=np.zeros((3, 3)), pbc=False)
     make_case("ragged_mix", [h2o, lone, pair, qm9[0]], [1, 6, 7, 8])
+    # the same ragged batch through the adaptive cutoff: atoms without neighbours solve to the
+    # maximum cutoff, rows shorter than the target keep every pair
+    make_case("ragged_mix_adaptive", [h2o, lone, pair, qm9[0], carbon[0]], [1, 6, 7, 8],
+              hypers=dict(num_neighbors_adaptive=8))
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 # PreLN layer with LayerNorm + SiLU
                 "water_384_classic", "qm9_5_classic", "water_384_preln_ln_silu",
                 # adaptive cutoff, solver method (adaptive_cutoff.py:110-229)
-                "water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive",
+                "water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive", "ragged_mix_adaptive",
                 # LoRA adapters (finetuning.py:322-378), merged into the packed weights
                 "water_384_lora", "qm9_5_lora_wide"]
 

@@ -91,7 +91,8 @@ def test_reference_hard_coded_energies():
     torch.testing.assert_close(out["energies"].cpu().ravel(), expected)
 
 
-@pytest.mark.parametrize("case", ["water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive"])
+@pytest.mark.parametrize("case", ["water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive",
+                                  "ragged_mix_adaptive"])
 def test_adaptive_cutoffs_match_reference(case):
     """Per-atom cutoffs of the solver (adaptive_cutoff.py:110-229) and the pairs kept by the
     symmetrised pair cutoffs (structures.py:253-262), against the unmodified reference."""
@@ -137,8 +138,14 @@ def test_stages_match_oracle(case):
     torch.testing.assert_close(nodes[0].detach().cpu(), ref["node_features"], atol=2e-4, rtol=1e-4)
     m = rb["mask"][..., None]
     torch.testing.assert_close(edges[0].detach().cpu() * m, ref["edge_features"] * m, atol=2e-4, rtol=1e-4)
-    pred, _, _ = be.predict(nodes, edges, bd, inp["cells"], inp["system_indices"], [g["target"]])
+    pred, node_ll, edge_ll = be.predict(nodes, edges, bd, inp["cells"], inp["system_indices"], [g["target"]])
     torch.testing.assert_close(pred[g["target"]][0].detach().cpu(), ref["atomic"], atol=2e-5, rtol=1e-5)
+    # last-layer features (backend.py:651-687)
+    assert len(node_ll[g["target"]]) == len(ref["node_last_layer_features"]) == be.num_readout_layers
+    for ours, theirs in zip(node_ll[g["target"]], ref["node_last_layer_features"]):
+        torch.testing.assert_close(ours.cpu(), theirs, atol=2e-4, rtol=1e-4)
+    for ours, theirs in zip(edge_ll[g["target"]], ref["edge_last_layer_features"]):
+        torch.testing.assert_close(ours.cpu() * m, theirs * m, atol=2e-4, rtol=1e-4)
     (grad,) = torch.autograd.grad(pred[g["target"]][0].sum(), pos)
     assert (grad.cpu() - ref["dE_dpos"]).abs().max() <= 2e-5
 
