@@ -47,7 +47,7 @@ def _worker(rank, world, init_file, out_file, reps, precision):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,reps", [(2, (2, 1, 1)), (2, (1, 1, 1))])
+@pytest.mark.parametrize("world,reps", [(2, (2, 1, 1)), (2, (1, 1, 1)), (1, (1, 1, 1))])
 def test_sharded_matches_single_gpu(world, reps):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
