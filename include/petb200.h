@@ -267,6 +267,11 @@ PETB200_API int petb200_norm_linear(const float* x, int64_t ldx, const void* ima
 PETB200_API int petb200_embedding(const float* table, const int32_t* idx, int64_t n_rows, int d,
                       float* out, int64_t ld_out, petb200_stream_t stream);
 
+/* x[m,:] += table[idx[m],:]: per-system conditioning embedding added to the node features of the
+ * atoms of each system (backend.py:551-552; conditioning.py:97-100).                              */
+PETB200_API int petb200_add_gathered_rows(const float* table, const int32_t* idx, int64_t n_rows, int d,
+                              float* x, int64_t ld_x, petb200_stream_t stream);
+
 /* out[k][n] = in[n][k] * (col_scale ? col_scale[k] : 1): weight preparation
  * (dgrad operand W^T; RMSNorm weight folded into the following Linear).                */
 PETB200_API int petb200_transpose_scale(const float* in, int rows, int cols, const float* col_scale,

@@ -18,8 +18,8 @@ Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649); tr
 ``PreLN`` (default) and ``PostLN`` (transformer.py:236-262); normalisation ``RMSNorm`` (default) or
 ``LayerNorm``; activation ``SwiGLU`` (default) or ``SiLU``; fixed cutoff (default) or the adaptive
 cutoff with the ``solver`` method (adaptive_cutoff.py:110-229).  Not built yet (raise
-``NotImplementedError``): the ``grid`` adaptive-cutoff method, system conditioning, weight
-gradients (training).
+``NotImplementedError``): the ``grid`` adaptive-cutoff method, weight gradients (training).
+System conditioning (charge / spin embeddings, conditioning.py) is built.
 """
 from typing import Dict, List, Optional, Tuple
 
@@ -107,12 +107,14 @@ class _Features(torch.autograd.Function):
     features of every GNN layer (2 L tensors)."""
 
     @staticmethod
-    def forward(ctx, vec, dist, fc, backend, topo):
+    def forward(ctx, vec, dist, fc, backend, topo, charge=None, spin_multiplicity=None):
         pw = backend._packed()
         prec = backend._precision
+        cond = (engine.conditioning_table(pw, charge, spin_multiplicity)
+                if backend.system_conditioning is not None else None)
         ctx.backend, ctx.topo, ctx.pw, ctx.fc, ctx.prec = backend, topo, pw, fc, prec
         ctx.residual = backend.featurizer_type == "residual"
-        args = (pw, backend.hypers, topo, vec.contiguous(), dist.contiguous(), fc.contiguous(), prec)
+        args = (pw, backend.hypers, topo, vec.contiguous(), dist.contiguous(), fc.contiguous(), prec, cond)
         if ctx.residual:
             nodes, edges, ctx.saved = engine.features_forward_residual(*args)
             return tuple(nodes) + tuple(edges)
@@ -127,7 +129,7 @@ class _Features(torch.autograd.Function):
             d_vec, d_dist, d_fc = engine.features_backward_residual(
                 ctx.pw, ctx.backend.hypers, topo, ctx.fc.contiguous(), ctx.saved,
                 list(grads[:n_layers]), list(grads[n_layers:]), ctx.prec)
-            return d_vec, d_dist, d_fc, None, None
+            return d_vec, d_dist, d_fc, None, None, None, None
         d_h, d_m = grads
         if d_h is None:
             d_h = torch.zeros((topo.n_atoms, ctx.backend.d_node), device=ctx.fc.device)
@@ -135,7 +137,7 @@ class _Features(torch.autograd.Function):
             d_m = torch.zeros((topo.n_edges, ctx.backend.d_pet), device=ctx.fc.device)
         d_vec, d_dist, d_fc = engine.features_backward(
             ctx.pw, ctx.backend.hypers, topo, ctx.fc.contiguous(), ctx.saved, d_h, d_m, ctx.prec)
-        return d_vec, d_dist, d_fc, None, None
+        return d_vec, d_dist, d_fc, None, None, None, None
 
 
 class _Predict(torch.autograd.Function):
@@ -245,8 +247,6 @@ class B200PETBackend(PETParameters):
                 raise ValueError("adaptive_cutoff_method must be 'grid' or 'solver', got "
                                  + hypers["adaptive_cutoff_method"])
             unsupported.append("adaptive_cutoff_method 'grid' (the default 'solver' is built)")
-        if hypers.get("system_conditioning"):
-            unsupported.append("system_conditioning")
         if (hypers["d_pet"], hypers["d_node"], hypers["d_head"], hypers["num_heads"]) != (128, 256, 128, 8):
             unsupported.append("d_pet/d_node/d_head/num_heads other than 128/256/128/8")
         if hypers["d_feedforward"] % 128 != 0:
@@ -267,7 +267,6 @@ class B200PETBackend(PETParameters):
         self.num_neighbors_adaptive = (float(hypers["num_neighbors_adaptive"])
                                        if hypers.get("num_neighbors_adaptive") is not None else None)
         self.adaptive_cutoff_method = hypers.get("adaptive_cutoff_method", "solver")
-        self.system_conditioning = None
         self._precision = _PRECISIONS[precision]
         self._cutoff_id = CUTOFF_BUMP if self.cutoff_function.lower() == "bump" else CUTOFF_COSINE
         self._pw: Optional[engine.PackedWeights] = None
@@ -427,8 +426,14 @@ class B200PETBackend(PETParameters):
             raise NotImplementedError("B200PETBackend: diagnostic feature capture is not built")
         self._check_inference()
         topo = self._topology_of(batch_data)
+        charge = spin = None
+        if self.system_conditioning is not None:
+            # set by the wrapper after preprocess (pet/model.py:464-471; backend.py:375-378)
+            charge, spin = batch_data["charge"], batch_data["spin_multiplicity"]
+            if charge.shape[0] != topo.n_structures or spin.shape[0] != topo.n_structures:
+                raise ValueError("calculate_features: one charge and one spin multiplicity per system expected")
         outs = _Features.apply(batch_data["_petb200_vec"], batch_data["_petb200_dist"],
-                               batch_data["_petb200_fc"], self, topo)
+                               batch_data["_petb200_fc"], self, topo, charge, spin)
         n_layers = len(outs) // 2   # 1 (feedforward) or num_gnn_layers (residual featurizer)
         nodes, edges = list(outs[:n_layers]), list(outs[n_layers:])
         if not self.emit_nef:

@@ -28,6 +28,19 @@ __global__ void embedding_kernel(const float* __restrict__ table, const int32_t*
   for (int c = threadIdx.x & 31; c < d4; c += 32) out[row * ld4 + c] = __ldg(src + c);
 }
 
+// x[row,:] += table[idx[row],:]: the per-system conditioning embedding broadcast to the atoms of each
+// system and added to the node features (backend.py:551-552, conditioning.py:97-100)
+__global__ void add_gathered_rows_kernel(const float* __restrict__ table, const int32_t* __restrict__ idx,
+                                         int64_t n_rows, int d4, float4* __restrict__ x, int64_t ld4) {
+  int64_t row = global_warp();
+  if (row >= n_rows) return;
+  const float4* src = reinterpret_cast<const float4*>(table) + (int64_t)idx[row] * d4;
+  for (int c = threadIdx.x & 31; c < d4; c += 32) {
+    const float4 a = x[row * ld4 + c], b = __ldg(src + c);
+    x[row * ld4 + c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
 // ------------------------------------------------------------------ weight preparation
 __global__ void transpose_scale_kernel(const float* __restrict__ in, int rows, int cols,
                                        const float* __restrict__ col_scale,
@@ -515,6 +528,14 @@ extern "C" PETB200_API int petb200_embedding(const float* table, const int32_t* 
   LAUNCH_ROWS(embedding_kernel, n_rows, table, idx, n_rows, d / 4, reinterpret_cast<float4*>(out),
               ld_out / 4);
   return check_launch("embedding");
+}
+
+extern "C" PETB200_API int petb200_add_gathered_rows(const float* table, const int32_t* idx, int64_t n_rows,
+                                         int d, float* x, int64_t ld_x, cudaStream_t stream) {
+  PETB200_REQUIRE(d % 4 == 0 && ld_x % 4 == 0, "add_gathered_rows: d and ld_x must be multiples of 4");
+  LAUNCH_ROWS(add_gathered_rows_kernel, n_rows, table, idx, n_rows, d / 4, reinterpret_cast<float4*>(x),
+              ld_x / 4);
+  return check_launch("add_gathered_rows");
 }
 
 extern "C" PETB200_API int petb200_transpose_scale(const float* in, int rows, int cols,

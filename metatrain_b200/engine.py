@@ -299,6 +299,14 @@ class PackedWeights:
         # one node embedding per readout layer (1 with the feedforward featurizer)
         self.node_emb = [_w(e).contiguous() for e in module.node_embedders]
         self.edge_emb = _w(module.edge_embedder).contiguous()
+        # system conditioning (conditioning.py:8-100): two embedding tables and a 2-layer projection
+        sc = getattr(module, "system_conditioning", None)
+        self.cond: Optional[dict] = None
+        if sc is not None:
+            self.cond = dict(charge=_w(sc.charge_embedding).contiguous(),
+                             spin=_w(sc.spin_multiplicity_embedding).contiguous(),
+                             w1=_w(sc.project[0]), b1=_b(sc.project[0]),
+                             w2=_w(sc.project[2]), b2=_b(sc.project[2]), max_charge=int(sc.max_charge))
         self.heads: Dict[str, List[dict]] = {}   # target -> one entry per readout layer
         for name in module.node_heads.keys():
             per_layer = []
@@ -739,7 +747,34 @@ def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc,
     return h, X, Xf, S
 
 
-def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32):
+def conditioning_table(pw: PackedWeights, charge: Tensor, spin_multiplicity: Tensor) -> Tensor:
+    """Per-system conditioning embedding [B, d_node] (conditioning.py:97-99): charge and spin
+    embeddings, concatenated, Linear -> SiLU -> Linear.  B rows only: fp32 path."""
+    C = pw.cond
+    dev = C["w1"].device
+    B, dn = charge.shape[0], C["w2"].shape[0]
+    cat = torch.empty((B, 2 * dn), device=dev)
+    ci = (charge.to(dev) + C["max_charge"]).to(torch.int32).contiguous()
+    si = (spin_multiplicity.to(dev) - 1).to(torch.int32).contiguous()
+    call("embedding", ptr(C["charge"]), ptr(ci), B, dn, ptr(cat), 2 * dn)
+    call("embedding", ptr(C["spin"]), ptr(si), B, dn, ptr(cat[:, dn:]), 2 * dn)
+    hid, pre = torch.empty((B, dn), device=dev), torch.empty((B, dn), device=dev)
+    gemm(cat, C["w1"], hid, bias=C["b1"], epilogue=EPI_SILU, aux_out=pre, precision=PREC_FP32)
+    table = torch.empty((B, dn), device=dev)
+    gemm(hid, C["w2"], table, bias=C["b2"], precision=PREC_FP32)
+    return table
+
+
+def _add_conditioning(h: Tensor, cond_table: Optional[Tensor], topo: Topology) -> None:
+    """h[i] += table[system of atom i], in place (backend.py:551-552, :632-633); the table does not
+    depend on the positions, so the backward passes d_h through unchanged."""
+    if cond_table is not None:
+        call("add_gathered_rows", ptr(cond_table), ptr(topo.system_of_atom), topo.n_atoms, h.shape[1],
+             ptr(h), h.stride(0))
+
+
+def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32,
+                     cond_table: Optional[Tensor] = None):
     """Feedforward featurizer, backend.py:496-587 (+ transformer.py:463-562,203-234) on the CSR
     layout.  Returns (node features [N,d_node], edge messages [E,d_pet], saved-for-backward)."""
     N, E = topo.n_atoms, topo.n_edges
@@ -752,6 +787,7 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
     saved = []
     for l, (L, C) in enumerate(zip(pw.gnn, pw.combine)):
         h, X, Xf, S = _gnn_forward(pw, L, hyp, topo, vec, dist, fc, h, m, prec)
+        _add_conditioning(h, cond_table, topo)
         t = X[:E]
         if halo is not None:
             # reversed messages of halo edges live on the peers: all-to-all-v into the ghost rows
@@ -773,7 +809,8 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
 
 
 
-def features_forward_residual(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32):
+def features_forward_residual(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32,
+                              cond_table: Optional[Tensor] = None):
     """Residual featurizer, backend.py:589-649: every GNN layer starts from its own node embedding,
     its node / edge outputs are kept for a readout of their own, and the next layer's input
     messages are 0.5 * (m + out[reversed edge]).  Returns (list of node features, list of edge
@@ -789,6 +826,7 @@ def features_forward_residual(pw: PackedWeights, hyp, topo: Topology, vec, dist,
         h0 = _empty((N, dn), vec)
         call("embedding", ptr(pw.node_emb[l]), ptr(topo.z_nodes), N, dn, ptr(h0), dn)
         h, X, _, S = _gnn_forward(pw, L, hyp, topo, vec, dist, fc, h0, m, prec)
+        _add_conditioning(h, cond_table, topo)
         t = X[:E]
         nodes.append(h)
         edges.append(t)

@@ -56,6 +56,8 @@ def evaluate(
     target: str = "energy",
     gradients: bool = True,
     strain: bool = False,
+    charge: Optional[Tensor] = None,
+    spin_multiplicity: Optional[Tensor] = None,
 ) -> Dict[str, Tensor]:
     """One energy(+forces, +strain gradient) evaluation of a batch of structures.
 
@@ -73,6 +75,16 @@ def evaluate(
     batch = backend.preprocess(pos_in, centers, neighbors, species, cells_in, cell_shifts,
                                system_indices,
                                float(backend.hypers.get("cutoff_width_adaptive", 1.0)))
+    if backend.system_conditioning is not None:
+        # what PET.forward does between the stages (pet/model.py:464-471): systems without the data
+        # default to charge 0 / spin multiplicity 1 (:1173-1174)
+        n_sys = cells.shape[0]
+        charge = torch.zeros(n_sys, dtype=torch.long, device=pos.device) if charge is None else charge
+        spin_multiplicity = (torch.ones(n_sys, dtype=torch.long, device=pos.device)
+                             if spin_multiplicity is None else spin_multiplicity)
+        backend.system_conditioning.validate(charge, spin_multiplicity)
+        batch["charge"], batch["spin_multiplicity"] = charge, spin_multiplicity
+        batch["system_indices"] = system_indices
     nodes, edges = backend.calculate_features(batch)
     pred, _, _ = backend.predict(nodes, edges, batch, cells_in, system_indices, [target])
     atomic = torch.cat(pred[target], dim=1) if len(pred[target]) > 1 else pred[target][0]

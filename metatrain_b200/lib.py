@@ -63,6 +63,7 @@ _SIGNATURES = {
     "petb200_mlp_fwd": [_P, _I64, _P, _P, _P, _I64, _I, _I, _P, _I64, _P],
     "petb200_mlp_bwd": [_P, _I64, _P, _I64, _P, _P, _I64, _I, _I, _P, _I64, _P],
     "petb200_embedding": [_P, _P, _I64, _I, _P, _I64, _P],
+    "petb200_add_gathered_rows": [_P, _P, _I64, _I, _P, _I64, _P],
     "petb200_transpose_scale": [_P, _I, _I, _P, _P, _P, _P],
     "petb200_compress_input": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_geom_embed_bwd": [_P, _I64, _P, _I64, _I, _I, _P, _P, _P],

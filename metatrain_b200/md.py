@@ -34,7 +34,8 @@ class GraphedEvaluator:
     """
 
     def __init__(self, backend: B200PETBackend, species: Tensor, cell: Tensor, periodic: bool = True,
-                 skin: float = 0.3, target: str = "energy", use_graph: bool = True):
+                 skin: float = 0.3, target: str = "energy", use_graph: bool = True,
+                 charge: int = 0, spin_multiplicity: int = 1):
         if backend.num_neighbors_adaptive is not None:
             raise NotImplementedError("GraphedEvaluator: the adaptive cutoff re-derives the topology "
                                       "from the positions every step; use evaluate()")
@@ -46,6 +47,10 @@ class GraphedEvaluator:
         self.cell = cell.to(dev, torch.float32).contiguous()
         self.cells = self.cell.reshape(1, 3, 3)
         self.system_indices = torch.zeros(self.species.shape[0], dtype=torch.long, device=dev)
+        self._charge = torch.tensor([charge], dtype=torch.long, device=dev)
+        self._spin = torch.tensor([spin_multiplicity], dtype=torch.long, device=dev)
+        if backend.system_conditioning is not None:
+            backend.system_conditioning.validate(self._charge, self._spin)
         self.verlet = VerletNeighborList(backend.cutoff, skin, periodic)
         self._pos = torch.zeros((self.species.shape[0], 3), device=dev, requires_grad=True)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -62,6 +67,8 @@ class GraphedEvaluator:
         emit, be.emit_nef = be.emit_nef, False
         try:
             batch = be.preprocess_on_topology(self._pos, self.cells, self._topo, self._z_nodes)
+            if be.system_conditioning is not None:
+                batch["charge"], batch["spin_multiplicity"] = self._charge, self._spin
             nodes, edges = be.calculate_features(batch)
             pred, _, _ = be.predict(nodes, edges, batch, self.cells, self.system_indices, [self.target])
         finally:

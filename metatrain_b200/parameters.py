@@ -16,7 +16,7 @@ MLP, centre contraction/expansion/MLP), ``transformer.py:446-461`` (geometry emb
 compress, neighbour embedder), ``backend.py:171-217`` (heads + last layers per target).
 """
 from math import prod
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import torch
 from torch import nn
@@ -77,6 +77,39 @@ def _head_holder(d_in: int, d_head: int) -> nn.Sequential:
     )
 
 
+class SystemConditioning(_Holder):
+    """Parameters of ``SystemConditioningEmbedding`` (``src/metatrain/pet/modules/conditioning.py:8-100``)
+    under the reference's names: per-system charge and spin-multiplicity embeddings, concatenated
+    and projected to ``d_out`` by Linear -> SiLU -> Linear (the last one zero-initialised, :40-48).
+    ``validate`` mirrors the reference's range check (:53-79); the wrapper calls it
+    (``pet/model.py:468``)."""
+
+    required_data_keys: List[str] = ["charge", "spin_multiplicity"]
+
+    def __init__(self, d_out: int, max_charge: int = 10, max_spin_multiplicity: int = 10) -> None:
+        super().__init__()
+        self.max_charge = max_charge
+        self.max_spin_multiplicity = max_spin_multiplicity
+        self.charge_embedding = nn.Embedding(2 * max_charge + 1, d_out)
+        self.spin_multiplicity_embedding = nn.Embedding(max_spin_multiplicity, d_out)
+        gate = nn.Linear(d_out, d_out)
+        nn.init.zeros_(gate.weight)
+        nn.init.zeros_(gate.bias)
+        self.project = nn.Sequential(nn.Linear(2 * d_out, d_out), nn.SiLU(), gate)
+
+    def validate(self, charge: torch.Tensor, spin_multiplicity: torch.Tensor) -> None:
+        if (charge < -self.max_charge).any() or (charge > self.max_charge).any():
+            raise ValueError(
+                f"charge values must be in [{-self.max_charge}, {self.max_charge}], got "
+                f"min={charge.min().item()}, max={charge.max().item()}. Increase max_charge in "
+                f"model hypers to support wider charge ranges.")
+        if (spin_multiplicity < 1).any() or (spin_multiplicity > self.max_spin_multiplicity).any():
+            raise ValueError(
+                f"spin_multiplicity values must be in [1, {self.max_spin_multiplicity}], got "
+                f"min={spin_multiplicity.min().item()}, max={spin_multiplicity.max().item()}. Increase "
+                f"max_spin_multiplicity in model hypers to support higher spin multiplicities.")
+
+
 class PETParameters(nn.Module):
     """Owns every learnable tensor of the PET backend under the reference's names."""
 
@@ -124,6 +157,11 @@ class PETParameters(nn.Module):
             [nn.Embedding(n_species, self.d_node) for _ in range(self.num_readout_layers)]
         )
         self.edge_embedder = nn.Embedding(n_species, self.d_pet)
+        if hypers.get("system_conditioning"):  # backend.py:121-130
+            self.system_conditioning: Optional[SystemConditioning] = SystemConditioning(
+                self.d_node, int(hypers["max_charge"]), int(hypers["max_spin_multiplicity"]))
+        else:
+            self.system_conditioning = None
         self.node_heads = nn.ModuleDict()
         self.edge_heads = nn.ModuleDict()
         self.node_last_layers = nn.ModuleDict()

@@ -169,13 +169,16 @@ def evaluate_sharded(backend, shard: Shard, positions: Tensor, species: Tensor, 
     cells = cell.reshape(1, 3, 3)
     sysidx = torch.zeros(len(shard.local_ids), dtype=torch.int64, device=dev)
     backend._check_inference()
+    if backend.num_neighbors_adaptive is not None or backend.system_conditioning is not None:
+        raise NotImplementedError("evaluate_sharded: adaptive cutoff / system conditioning are not built "
+                                  "for atom-sharded runs")
     topo = engine.build_topology(pos_local, centers, neighbors, shifts, cells, sysidx, z_nodes,
                                  backend.cutoff, check_symmetric=False,
                                  n_rows=len(shard.own_ids))
     attach_halo(topo, shard, dev, group)
     vec, dist_, fc = _EdgeGeometry.apply(pos_local, cells, topo, backend.cutoff,
                                          backend.cutoff_width, backend._cutoff_id)
-    h, m = _Features.apply(vec, dist_, fc, backend, topo)
+    h, m = _Features.apply(vec, dist_, fc, backend, topo, None, None)
     atomic = _Predict.apply(h, m, fc, backend, topo, target, 0, None)    # [n_own, P]
     energy = atomic.sum(dim=0, keepdim=True)
     total = energy.detach().clone()

@@ -138,6 +138,13 @@ def build_reference_backend(atomic_types, target="energy", hypers=None, seed=0,
     # key naming of pet/model.py:1045-1051: <target>_<keyname>_<keyvalue>; a scalar
     # target has the single key "_" = 0  -> "<target>___0"
     be.add_output(target, {f"{target}___0": [1]})
+    gate_seed = (hypers or {}).get("_gate_seed")
+    if gate_seed is not None:  # test-only pseudo hyper: activate the zero-initialised conditioning gate
+        torch.manual_seed(gate_seed)
+        gate = be.system_conditioning.project[2]
+        with torch.no_grad():
+            gate.weight.normal_(0.0, 0.05)
+            gate.bias.normal_(0.0, 0.05)
     lora = (hypers or {}).get("_lora")
     if lora:  # test-only pseudo hyper: LoRA adapters injected by the reference's own function
         torch.manual_seed(lora["seed"])

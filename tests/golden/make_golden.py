@@ -77,6 +77,9 @@ def run_reference(backend, inp, target, dtype, with_strain):
     sysi = t(inp["system_indices"])
     bd = backend.preprocess(pos_in, t(inp["centers"]), t(inp["neighbors"]), t(inp["species"]),
                             cells_in, t(inp["cell_shifts"]), sysi, 1.0)
+    if "charge" in inp:  # what PET.forward adds for system conditioning (pet/model.py:464-471)
+        bd["charge"], bd["spin_multiplicity"] = t(inp["charge"]), t(inp["spin_multiplicity"])
+        bd["system_indices"] = sysi
     nodes, edges = backend.calculate_features(bd)
     pred, _, _ = backend.predict(nodes, edges, bd, cells_in, sysi, [target])
     atomic = pred[target][0]
@@ -102,11 +105,14 @@ ONLY = set(sys.argv[1:])  # optional: regenerate just these cases
 
 
 def make_case(name, frames, atomic_types, target="energy", hypers=None, nl_cutoff=4.5,
-              with_strain=False, fp64=True):
+              with_strain=False, fp64=True, charge=None, spin_multiplicity=None):
     if ONLY and name not in ONLY:
         path = os.path.join(HERE, name + ".npz")
         return dict(np.load(path)) if os.path.exists(path) else None
     inp = batch_frames(frames, nl_cutoff)
+    if charge is not None:
+        inp["charge"] = np.asarray(charge, dtype=np.int64)
+        inp["spin_multiplicity"] = np.asarray(spin_multiplicity, dtype=np.int64)
     be32 = ref_loader.build_reference_backend(atomic_types, target, hypers).eval()
     fp = weight_fingerprint(be32.state_dict())
     ref32 = run_reference(be32, inp, target, torch.float32, with_strain)
@@ -163,6 +169,16 @@ def main():
     make_case("qm9_5_classic", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=classic)
     make_case("water_384_preln_ln_silu", [water], [1, 8],
               hypers=dict(normalization="LayerNorm", activation="SiLU"), fp64=False)
+
+    # system conditioning (conditioning.py): per-system charge / spin embeddings added to the node
+    # features after every GNN layer; the zero-initialised gate is re-drawn (seed 2) so that the
+    # branch is active ("_gate_seed" is a test-only pseudo hyper, see oracle/ref_loader.py)
+    make_case("qm9_5_conditioned", qm9, [1, 6, 7, 8], target="mtt::U0",
+              hypers=dict(system_conditioning=True, _gate_seed=2),
+              charge=[-1, 0, 1, 2, 0], spin_multiplicity=[1, 2, 3, 1, 2])
+    make_case("qm9_5_conditioned_residual", qm9, [1, 6, 7, 8], target="mtt::U0", fp64=False,
+              hypers=dict(system_conditioning=True, featurizer_type="residual", _gate_seed=2),
+              charge=[3, -2, 0, 1, -10], spin_multiplicity=[10, 1, 2, 4, 3])
 
     # LoRA adapters (finetuning.py:322-378) on the attention projections (the reference default
     # target modules) and on every feed-forward / compress Linear; adapters seeded with 1

@@ -19,7 +19,9 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 # adaptive cutoff, solver method (adaptive_cutoff.py:110-229)
                 "water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive", "ragged_mix_adaptive",
                 # LoRA adapters (finetuning.py:322-378), merged into the packed weights
-                "water_384_lora", "qm9_5_lora_wide"]
+                "water_384_lora", "qm9_5_lora_wide",
+                # system conditioning (conditioning.py:8-100)
+                "qm9_5_conditioned", "qm9_5_conditioned_residual"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(
@@ -39,6 +41,7 @@ def load_golden(name):
     g["hypers"] = dict(DEFAULT_HYPERS)
     g["hypers"].update(ast.literal_eval(str(g["hypers_override"])))
     g["lora"] = g["hypers"].pop("_lora", None)  # test-only: LoRA adapters injected after construction
+    g["gate_seed"] = g["hypers"].pop("_gate_seed", None)  # test-only: conditioning gate re-drawn
     g["atomic_types"] = [int(z) for z in g["atomic_types"]]
     return g
 
@@ -46,6 +49,12 @@ def load_golden(name):
 def apply_lora(module, g):
     """Inject the golden case's LoRA adapters (same seed and order as make_golden.py did on the
     reference).  Returns the extra state-dict entry the oracle needs (the adapter scale)."""
+    if g.get("gate_seed") is not None:  # same draw as oracle/ref_loader.build_reference_backend
+        torch.manual_seed(g["gate_seed"])
+        gate = module.system_conditioning.project[2]
+        with torch.no_grad():
+            gate.weight.normal_(0.0, 0.05)
+            gate.bias.normal_(0.0, 0.05)
     if not g.get("lora"):
         return {}
     from metatrain_b200.finetuning import inject_lora_layers
@@ -63,11 +72,14 @@ def seed_all(seed=0):
 
 def golden_inputs(g, device="cpu", dtype=torch.float32):
     t = lambda k: torch.tensor(g[k]).to(device)  # noqa: E731
-    return dict(
+    out = dict(
         positions=t("positions").to(dtype), centers=t("centers"), neighbors=t("neighbors"),
         species=t("species"), cells=t("cells").to(dtype), cell_shifts=t("cell_shifts"),
         system_indices=t("system_indices"),
     )
+    if "charge" in g:  # system conditioning inputs
+        out.update(charge=t("charge"), spin_multiplicity=t("spin_multiplicity"))
+    return out
 
 
 def weight_fingerprint(state_dict):

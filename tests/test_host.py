@@ -69,8 +69,12 @@ def test_hyper_validation_matches_reference_error_types():
         B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16, adaptive_cutoff_method="grid"), [1])
     with pytest.raises(ValueError, match="must be 'grid' or 'solver'"):
         B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16, adaptive_cutoff_method="x"), [1])
-    with pytest.raises(NotImplementedError):
-        B200PETBackend(dict(DEFAULT_HYPERS, system_conditioning=True), [1])
+    cond = B200PETBackend(dict(DEFAULT_HYPERS, system_conditioning=True), [1])  # built: conditioning.py
+    assert "system_conditioning.project.2.weight" in cond.state_dict()
+    with pytest.raises(ValueError, match="charge values must be in"):
+        cond.system_conditioning.validate(torch.tensor([11]), torch.tensor([1]))
+    with pytest.raises(ValueError, match="spin_multiplicity values must be in"):
+        cond.system_conditioning.validate(torch.tensor([0]), torch.tensor([0]))
 
 
 def test_no_cpu_fallback():
