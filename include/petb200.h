@@ -212,6 +212,20 @@ PETB200_API int petb200_adaptive_cutoff_bwd(const int32_t* row_ptr_kept, const i
                                 const float* r_root, int64_t n_edges_all, float width, float* coef,
                                 float* d_dist_all, petb200_stream_t stream);
 
+/* The legacy "grid" method (adaptive_cutoff.py:232-395): cutoff_i = sum_p c_p w_ip with Gaussian
+ * weights on how far the smoothed neighbour count at probe c_p = min_cutoff + p * spacing is from
+ * the target.  solve also returns grad_d[i][q] = d cutoff_i / d D_q; bwd turns the gradient of the
+ * pair cutoffs into d_dist_all on the "all" topology (`ones`: n_atoms floats equal to 1).          */
+PETB200_API int petb200_adaptive_grid_solve(const int32_t* row_ptr, const float* edge_dist, int64_t n_atoms,
+                                float num_neighbors, float width, float min_cutoff, float spacing,
+                                int n_probes, float* atomic_cutoff, float* grad_d,
+                                petb200_stream_t stream);
+PETB200_API int petb200_adaptive_grid_bwd(const int32_t* row_ptr_kept, const int32_t* rev_kept,
+                              const float* d_pair_cutoff, const float* ones, int64_t n_atoms,
+                              const int32_t* ctr_all, const float* dist_all, const float* grad_d,
+                              int64_t n_edges_all, float width, float min_cutoff, float spacing,
+                              int n_probes, float* coef, float* d_dist_all, petb200_stream_t stream);
+
 /* --------------------------------------------------------------- dense contractions
  * C[M,N] = epilogue(row_scale * (A[M,K] . W[N,K]^T) + bias) (+ residual) — every
  * torch.nn.Linear of transformer.py / backend.py, and its dgrad with W^T.             */

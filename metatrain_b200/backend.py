@@ -17,8 +17,8 @@ keeps working unchanged.
 Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649); transformer types
 ``PreLN`` (default) and ``PostLN`` (transformer.py:236-262); normalisation ``RMSNorm`` (default) or
 ``LayerNorm``; activation ``SwiGLU`` (default) or ``SiLU``; fixed cutoff (default) or the adaptive
-cutoff with the ``solver`` method (adaptive_cutoff.py:110-229).  Not built yet (raise
-``NotImplementedError``): the ``grid`` adaptive-cutoff method, weight gradients (training).
+cutoff with the ``solver`` (adaptive_cutoff.py:110-229) or ``grid`` (:232-395) method.  Not built
+yet (raise ``NotImplementedError``): weight gradients (training), diagnostic capture.
 System conditioning (charge / spin embeddings, conditioning.py) is built.
 """
 from typing import Dict, List, Optional, Tuple
@@ -209,6 +209,18 @@ class _NefToCsr(torch.autograd.Function):
         return out, None
 
 
+def _process_non_conservative_stress(tensor: Tensor, cells: Tensor, system_indices: Tensor,
+                                     num_properties: int) -> Tensor:
+    """[N, 9 P] direct stress predictions -> [N, 3, 3, P], divided by the cell volume (infinite
+    for the zero cells of non-periodic systems) and symmetrised (backend.py:780-813).  O(N)
+    bookkeeping on the readout's output, done with tensor ops."""
+    t = tensor.reshape(-1, 3, 3, num_properties)
+    volumes = torch.abs(torch.det(cells.to(tensor.dtype)))
+    volumes = torch.where(volumes == 0.0, torch.full_like(volumes, float("inf")), volumes)
+    t = t / volumes[system_indices.long()].reshape(-1, 1, 1, 1)
+    return 0.5 * (t + t.transpose(1, 2))
+
+
 # ------------------------------------------------------------------------ the module
 class B200PETBackend(PETParameters):
     """CUDA (sm_100a) implementation of the PET tensor backend.
@@ -242,11 +254,9 @@ class B200PETBackend(PETParameters):
         if hypers["featurizer_type"] not in ("feedforward", "residual"):
             raise ValueError(f"Unknown featurizer type: {hypers['featurizer_type']}")
         if (hypers.get("num_neighbors_adaptive") is not None
-                and hypers.get("adaptive_cutoff_method", "solver").lower() != "solver"):
-            if hypers["adaptive_cutoff_method"].lower() != "grid":  # structures.py:244-248
-                raise ValueError("adaptive_cutoff_method must be 'grid' or 'solver', got "
-                                 + hypers["adaptive_cutoff_method"])
-            unsupported.append("adaptive_cutoff_method 'grid' (the default 'solver' is built)")
+                and hypers.get("adaptive_cutoff_method", "solver").lower() not in ("solver", "grid")):
+            raise ValueError("adaptive_cutoff_method must be 'grid' or 'solver', got "
+                             + hypers["adaptive_cutoff_method"])  # structures.py:244-248
         if (hypers["d_pet"], hypers["d_node"], hypers["d_head"], hypers["num_heads"]) != (128, 256, 128, 8):
             unsupported.append("d_pet/d_node/d_head/num_heads other than 128/256/128/8")
         if hypers["d_feedforward"] % 128 != 0:
@@ -355,7 +365,8 @@ class B200PETBackend(PETParameters):
             topo, adaptive = engine.adaptive_topology(
                 topo, positions.detach().to(torch.float32).contiguous(),
                 cells.detach().to(torch.float32).contiguous(), self.cutoff,
-                self.num_neighbors_adaptive, float(cutoff_width_adaptive))
+                self.num_neighbors_adaptive, float(cutoff_width_adaptive),
+                self.adaptive_cutoff_method.lower())
             vec, dist, fc = _AdaptiveEdgeGeometry.apply(positions, cells, topo, adaptive, self.cutoff,
                                                         self.cutoff_width, self._cutoff_id)
             atomic_cutoffs = adaptive.atomic_cutoffs.to(positions.dtype)
@@ -477,8 +488,6 @@ class B200PETBackend(PETParameters):
         for name in self.node_last_layers.keys():
             if name not in requested_output_names:
                 continue
-            if name == "non_conservative_stress":
-                raise NotImplementedError("B200PETBackend: non_conservative_stress is not built")
             # node + edge contributions summed over the readout layers (backend.py:469-481)
             atomic = None
             sink: List[Tuple[Tensor, Tensor]] = []
@@ -486,7 +495,11 @@ class B200PETBackend(PETParameters):
                 part = _Predict.apply(h, m, fc, self, topo, name, layer, sink)
                 atomic = part if atomic is None else atomic + part
             sizes = self._packed().heads[name][0]["block_sizes"]
-            atomic_predictions[name] = list(torch.split(atomic, sizes, dim=1))
+            blocks = list(torch.split(atomic, sizes, dim=1))
+            if name == "non_conservative_stress":  # backend.py:483-490
+                blocks[0] = _process_non_conservative_stress(blocks[0], cells, system_indices,
+                                                             blocks[0].shape[1] // 9)
+            atomic_predictions[name] = blocks
             node_ll[name] = [n for n, _ in sink]
             edge_ll[name] = [_CsrToNef.apply(e, topo) if self.emit_nef else e for _, e in sink]
         return atomic_predictions, node_ll, edge_ll

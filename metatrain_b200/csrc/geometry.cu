@@ -196,6 +196,97 @@ __global__ void adaptive_dist_grad_kernel(const int32_t* __restrict__ ctr, const
   d_dist[e] = coef[i] * df;
 }
 
+// ---- the legacy "grid" method (adaptive_cutoff.py:232-395): smoothed neighbour counts n_p at P
+// probe cutoffs c_p = min_cutoff + p * spacing, D_p = n_p - n* + n* x_p^3 (x_p = p / (P - 1)),
+// widths W_p = max(|torch.gradient(D)_p|, 1e-12), weights e_p = exp(-(D_p / W_p)^2 / 2) normalised
+// over p, cutoff = sum_p c_p e_p.  One warp per atom, lane p owns probe p (P <= 32).  Besides the
+// cutoff the kernel stores G[i][q] = d cutoff_i / d D_q, which is all the backward needs.
+// (The reference subtracts the batch-wide max of the log-weights before exp(); it cancels in
+// the normalisation — the per-atom max is used here.)
+constexpr int kMaxProbes = 32;
+
+__global__ void adaptive_grid_kernel(const int32_t* __restrict__ row_ptr, const float* __restrict__ dist,
+                                     int64_t n_atoms, float n_target, float width, float min_cutoff,
+                                     float spacing, int n_probes, float* __restrict__ r_atom,
+                                     float* __restrict__ grad_d /* [n_atoms, n_probes] */) {
+  const int64_t atom = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (atom >= n_atoms) return;
+  const int lo = row_ptr[atom], hi = row_ptr[atom + 1];
+  const int P = n_probes;
+  // n_p for every probe: lanes stride over the row, then P warp reductions; lane p keeps n_p
+  float mine = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float c = min_cutoff + p * spacing;
+    float acc = 0.f;
+    for (int e = lo + lane; e < hi; e += 32) {
+      float f, df;
+      probe_count(dist[e], c, width, f, df);
+      acc += f;
+    }
+    acc = warp_sum(acc);
+    if (lane == p) mine = acc;
+  }
+  const bool on = lane < P;
+  const float c_p = min_cutoff + lane * spacing;
+  if (P == 1) {  // a single probe: the weighted mean is that probe, whatever the counts
+    if (lane == 0) {
+      r_atom[atom] = c_p;
+      grad_d[atom] = 0.f;
+    }
+    return;
+  }
+  const float x = (float)lane / (float)(P - 1);
+  const float D = on ? mine - n_target + n_target * x * x * x : 0.f;
+  // torch.gradient, unit spacing: centred differences inside, one-sided at the two ends
+  const float D_up = __shfl_down_sync(0xffffffffu, D, 1), D_dn = __shfl_up_sync(0xffffffffu, D, 1);
+  float g;
+  if (lane == 0) g = D_up - D;
+  else if (lane == P - 1) g = D - D_dn;
+  else g = 0.5f * (D_up - D_dn);
+  const float W = fmaxf(fabsf(g), 1e-12f);
+  const float L = on ? -0.5f * (D / W) * (D / W) : -INFINITY;
+  float Lmax = L;
+  for (int o = 16; o > 0; o >>= 1) Lmax = fmaxf(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, o));
+  const float e = on ? expf(L - Lmax) : 0.f;
+  const float S = warp_sum(e);
+  const float rbar = warp_sum(c_p * e) / S;
+  // backward coefficients
+  const float A = on ? e * (c_p - rbar) / S : 0.f;                        // d rbar / d L_p
+  const float dL_dD = -D / (W * W);
+  const float sgn = g > 0.f ? 1.f : (g < 0.f ? -1.f : 0.f);
+  const float B = (on && fabsf(g) > 1e-12f) ? A * (D * D / (W * W * W)) * sgn : 0.f;  // d rbar / d g_p
+  const float B_dn = __shfl_up_sync(0xffffffffu, B, 1);    // B_{q-1}
+  const float B_up = __shfl_down_sync(0xffffffffu, B, 1);  // B_{q+1}
+  float G = A * dL_dD;
+  // g_{q-1} depends on D_q with +1/2 (interior q-1) or +1 (q-1 = 0)
+  if (lane >= 1) G += (lane - 1 == 0 ? 1.f : 0.5f) * B_dn;
+  // g_{q+1} depends on D_q with -1/2 (interior q+1) or -1 (q+1 = P-1)
+  if (lane + 1 <= P - 1) G -= (lane + 1 == P - 1 ? 1.f : 0.5f) * B_up;
+  if (lane == 0) G -= B;
+  if (lane == P - 1) G += B;
+  if (on) grad_d[atom * P + lane] = G;
+  if (lane == 0) r_atom[atom] = rbar;
+}
+
+// backward through the grid method: d cutoff_i / d d_k = sum_q G[i][q] * d bump(d_k; c_q) / d d_k
+__global__ void adaptive_grid_dist_grad_kernel(const int32_t* __restrict__ ctr, const float* __restrict__ dist,
+                                               const float* __restrict__ grad_d, const float* __restrict__ coef,
+                                               int64_t n_edges, float width, float min_cutoff, float spacing,
+                                               int n_probes, float* __restrict__ d_dist) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int i = ctr[e];
+  const float d = dist[e];
+  float acc = 0.f;
+  for (int q = 0; q < n_probes; ++q) {
+    float f, df_dr;
+    probe_count(d, min_cutoff + q * spacing, width, f, df_dr);
+    acc -= grad_d[(int64_t)i * n_probes + q] * df_dr;  // d bump / d d = - d bump / d r
+  }
+  d_dist[e] = coef[i] * acc;
+}
+
 // one warp per atom: d_pos[i] = sum_{e in row i} (G[rev e] - G[e])
 __global__ void force_scatter_kernel(const float* __restrict__ G, const int32_t* __restrict__ row_ptr,
                                      const int32_t* __restrict__ rev, int64_t n_atoms,
@@ -413,4 +504,38 @@ extern "C" PETB200_API int petb200_adaptive_cutoff_bwd(const int32_t* row_ptr_ke
         ctr_all, dist_all, r_root, coef, n_edges_all, width, d_dist_all);
   }
   return check_launch("adaptive_cutoff_bwd");
+}
+
+extern "C" PETB200_API int petb200_adaptive_grid_solve(const int32_t* row_ptr, const float* edge_dist,
+                                           int64_t n_atoms, float num_neighbors, float width,
+                                           float min_cutoff, float spacing, int n_probes,
+                                           float* atomic_cutoff, float* grad_d, cudaStream_t stream) {
+  PETB200_REQUIRE(width > 0.f && spacing > 0.f && num_neighbors > 0.f,
+                  "adaptive_grid_solve: width, spacing and neighbour target must be positive");
+  if (n_probes < 1 || n_probes > kMaxProbes) {
+    set_error("adaptive_grid_solve: %d probe cutoffs; 1..%d are built", n_probes, kMaxProbes);
+    return PETB200_ERR_UNSUPPORTED;
+  }
+  if (n_atoms == 0) return PETB200_OK;
+  adaptive_grid_kernel<<<(unsigned)ceil_div(n_atoms * 32, 256), 256, 0, stream>>>(
+      row_ptr, edge_dist, n_atoms, num_neighbors, width, min_cutoff, spacing, n_probes, atomic_cutoff,
+      grad_d);
+  return check_launch("adaptive_grid_solve");
+}
+
+extern "C" PETB200_API int petb200_adaptive_grid_bwd(const int32_t* row_ptr_kept, const int32_t* rev_kept,
+                                         const float* d_pair_cutoff, const float* ones,
+                                         int64_t n_atoms, const int32_t* ctr_all, const float* dist_all,
+                                         const float* grad_d, int64_t n_edges_all, float width,
+                                         float min_cutoff, float spacing, int n_probes, float* coef,
+                                         float* d_dist_all, cudaStream_t stream) {
+  if (n_atoms > 0) {
+    adaptive_atom_grad_kernel<<<(unsigned)ceil_div(n_atoms * 32, 256), 256, 0, stream>>>(
+        row_ptr_kept, rev_kept, d_pair_cutoff, ones, ones, n_atoms, coef);
+  }
+  if (n_edges_all > 0) {
+    adaptive_grid_dist_grad_kernel<<<(unsigned)ceil_div(n_edges_all, 256), 256, 0, stream>>>(
+        ctr_all, dist_all, grad_d, coef, n_edges_all, width, min_cutoff, spacing, n_probes, d_dist_all);
+  }
+  return check_launch("adaptive_grid_bwd");
 }

@@ -11,6 +11,7 @@ keeps working unchanged.
 
 Equations: SURVEY.md Appendix A (derived from the cited reference lines).
 """
+import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -393,10 +394,16 @@ class AdaptiveCutoff:
     atomic_cutoffs: Tensor    # [N]
     pair_cutoffs: Tensor      # [E] of the kept edges
     width: float
+    method: str = "solver"
+    grid: Optional[tuple] = None       # grid method: (min_cutoff, spacing, n_probes)
+    grad_d: Optional[Tensor] = None    # grid method: d cutoff_i / d D_q  [N, n_probes]
+
+# minimum probe cutoff of the grid method (adaptive_cutoff.py:9-11)
+DEFAULT_MIN_PROBE_CUTOFF = 0.5
 
 
 def adaptive_topology(outer: Topology, positions: Tensor, cells: Tensor, max_cutoff: float,
-                      num_neighbors: float, width: float):
+                      num_neighbors: float, width: float, method: str = "solver"):
     """a4 with ``num_neighbors_adaptive`` set (structures.py:222-262): per-atom cutoffs from the
     solver (adaptive_cutoff.py:110-229), symmetrised pair cutoffs, and the CSR topology of the
     pairs inside them.  Returns (kept topology, AdaptiveCutoff)."""
@@ -407,8 +414,18 @@ def adaptive_topology(outer: Topology, positions: Tensor, cells: Tensor, max_cut
     i32 = torch.int32
     vec_o, dist_o, _ = edges_forward(outer, positions, cells, max_cutoff, 1.0, lib.CUTOFF_COSINE)
     r_root, dn_root, r_atom, cpass = (_empty((N,), positions) for _ in range(4))
-    call("adaptive_cutoff_solve", ptr(outer.row_ptr), ptr(dist_o), N, float(num_neighbors),
-         float(max_cutoff), float(width), ptr(r_root), ptr(dn_root), ptr(r_atom), ptr(cpass))
+    grid = grad_d = None
+    if method == "solver":
+        call("adaptive_cutoff_solve", ptr(outer.row_ptr), ptr(dist_o), N, float(num_neighbors),
+             float(max_cutoff), float(width), ptr(r_root), ptr(dn_root), ptr(r_atom), ptr(cpass))
+    else:
+        # probe cutoffs = torch.arange(min_cutoff, max_cutoff, width / 4) (adaptive_cutoff.py:267-276)
+        spacing = float(width) / 4.0
+        n_probes = max(int(math.ceil((float(max_cutoff) - DEFAULT_MIN_PROBE_CUTOFF) / spacing)), 0)
+        grid = (DEFAULT_MIN_PROBE_CUTOFF, spacing, n_probes)
+        grad_d = _empty((N, max(n_probes, 1)), positions)
+        call("adaptive_grid_solve", ptr(outer.row_ptr), ptr(dist_o), N, float(num_neighbors),
+             float(width), grid[0], spacing, n_probes, ptr(r_atom), ptr(grad_d))
     rc_o = _empty((max(EO, 1),), positions)
     keep = torch.empty(max(EO, 1), device=dev, dtype=i32)
     counts = torch.zeros(N + 1, device=dev, dtype=i32)
@@ -438,7 +455,7 @@ def adaptive_topology(outer: Topology, positions: Tensor, cells: Tensor, max_cut
                     outer.system_of_atom, outer.z_nodes, z_neighbors.contiguous(),
                     outer.perm[sel], n_positions=outer.n_positions)
     return kept, AdaptiveCutoff(outer, vec_o, dist_o, r_root, dn_root, cpass, r_atom,
-                                rc_o[:EO][sel].contiguous(), float(width))
+                                rc_o[:EO][sel].contiguous(), float(width), method, grid, grad_d)
 
 
 def adaptive_edges_forward(topo: Topology, ad: AdaptiveCutoff, positions, cells, width, func):
@@ -467,9 +484,15 @@ def adaptive_edges_backward(topo: Topology, ad: AdaptiveCutoff, vec, dist, d_vec
         return d_pos, d_cells
     coef = _empty((N,), vec)
     d_dist_o = _empty((max(outer.n_edges, 1),), vec)
-    call("adaptive_cutoff_bwd", ptr(topo.row_ptr), ptr(topo.rev), ptr(d_rc), ptr(ad.dn_root),
-         ptr(ad.clamp_pass), N, ptr(outer.ctr), ptr(ad.dist_outer), ptr(ad.r_root), outer.n_edges,
-         ad.width, ptr(coef), ptr(d_dist_o))
+    if ad.method == "solver":
+        call("adaptive_cutoff_bwd", ptr(topo.row_ptr), ptr(topo.rev), ptr(d_rc), ptr(ad.dn_root),
+             ptr(ad.clamp_pass), N, ptr(outer.ctr), ptr(ad.dist_outer), ptr(ad.r_root), outer.n_edges,
+             ad.width, ptr(coef), ptr(d_dist_o))
+    else:
+        ones = torch.ones((max(N, 1),), device=vec.device)
+        call("adaptive_grid_bwd", ptr(topo.row_ptr), ptr(topo.rev), ptr(d_rc), ptr(ones), N,
+             ptr(outer.ctr), ptr(ad.dist_outer), ptr(ad.grad_d), outer.n_edges, ad.width,
+             ad.grid[0], ad.grid[1], ad.grid[2], ptr(coef), ptr(d_dist_o))
     d_pos_o, d_cells_o = edges_backward(outer, ad.vec_outer, ad.dist_outer, None, d_dist_o, None,
                                         max_cutoff, 1.0, lib.CUTOFF_COSINE, need_cells)
     d_pos += d_pos_o

@@ -88,7 +88,11 @@ def evaluate(
     nodes, edges = backend.calculate_features(batch)
     pred, _, _ = backend.predict(nodes, edges, batch, cells_in, system_indices, [target])
     atomic = torch.cat(pred[target], dim=1) if len(pred[target]) > 1 else pred[target][0]
-    energies = sum_over_atoms(atomic, system_indices, cells.shape[0])
+    if atomic.dim() > 2:  # tensorial per-atom outputs (non_conservative_stress: [N, 3, 3, P])
+        energies = sum_over_atoms(atomic.reshape(atomic.shape[0], -1), system_indices,
+                                  cells.shape[0]).reshape((cells.shape[0],) + tuple(atomic.shape[1:]))
+    else:
+        energies = sum_over_atoms(atomic, system_indices, cells.shape[0])
     out = {"energies": energies.detach(), "atomic": atomic.detach()}
     if gradients:
         wrt = [pos] + ([eps] if strain else [])

@@ -45,6 +45,8 @@ _SIGNATURES = {
                           _P, _P, _P, _P],
     "petb200_edge_grad": [_P, _P, _P, _P, _P, _I64, _F, _F, _I, _P, _P],
     "petb200_adaptive_cutoff_solve": [_P, _P, _I64, _F, _F, _F, _P, _P, _P, _P, _P],
+    "petb200_adaptive_grid_solve": [_P, _P, _I64, _F, _F, _F, _F, _I, _P, _P, _P],
+    "petb200_adaptive_grid_bwd": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _F, _F, _F, _I, _P, _P, _P],
     "petb200_adaptive_pair_mask": [_P, _P, _P, _P, _I64, _P, _P, _P, _P],
     "petb200_edges_fwd_rc": [_P, _P, _P, _P, _P, _P, _I64, _P, _F, _I, _P, _P, _P, _P],
     "petb200_edges_bwd_rc": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _F, _I, _P, _P, _P,
@@ -140,7 +142,7 @@ def stream_ptr() -> int:
 
 
 # kernels launched by each entry point (for bench.py's ``gpu_launches`` claim)
-_KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "edges_bwd_rc": 3, "adaptive_cutoff_bwd": 2, "csr_build": 6, "readout_bwd": 2,
+_KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "edges_bwd_rc": 3, "adaptive_cutoff_bwd": 2, "adaptive_grid_bwd": 2, "csr_build": 6, "readout_bwd": 2,
                      "force_scatter": 2, "mlp_pack": 2}
 launch_count = 0
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call

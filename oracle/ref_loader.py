@@ -120,7 +120,7 @@ def load_reference_finetuning():
 
 
 def build_reference_backend(atomic_types, target="energy", hypers=None, seed=0,
-                            dtype=None):
+                            dtype=None, out_shape=(1,)):
     """Seeded construction in the RNG order of pet/model.py:115,145-147."""
     import random
 
@@ -137,7 +137,7 @@ def build_reference_backend(atomic_types, target="energy", hypers=None, seed=0,
     be = cls(h, list(atomic_types))
     # key naming of pet/model.py:1045-1051: <target>_<keyname>_<keyvalue>; a scalar
     # target has the single key "_" = 0  -> "<target>___0"
-    be.add_output(target, {f"{target}___0": [1]})
+    be.add_output(target, {f"{target}___0": list(out_shape)})
     gate_seed = (hypers or {}).get("_gate_seed")
     if gate_seed is not None:  # test-only pseudo hyper: activate the zero-initialised conditioning gate
         torch.manual_seed(gate_seed)

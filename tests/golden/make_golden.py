@@ -83,7 +83,7 @@ def run_reference(backend, inp, target, dtype, with_strain):
     nodes, edges = backend.calculate_features(bd)
     pred, _, _ = backend.predict(nodes, edges, bd, cells_in, sysi, [target])
     atomic = pred[target][0]
-    energies = torch.zeros(cells.shape[0], atomic.shape[1], dtype=dtype).index_add_(0, sysi, atomic)
+    energies = torch.zeros((cells.shape[0],) + tuple(atomic.shape[1:]), dtype=dtype).index_add_(0, sysi, atomic)
     wrt = [pos] + ([strain] if with_strain else [])
     grads = torch.autograd.grad(energies.sum(), wrt)
     out = dict(
@@ -105,7 +105,7 @@ ONLY = set(sys.argv[1:])  # optional: regenerate just these cases
 
 
 def make_case(name, frames, atomic_types, target="energy", hypers=None, nl_cutoff=4.5,
-              with_strain=False, fp64=True, charge=None, spin_multiplicity=None):
+              with_strain=False, fp64=True, charge=None, spin_multiplicity=None, out_shape=(1,)):
     if ONLY and name not in ONLY:
         path = os.path.join(HERE, name + ".npz")
         return dict(np.load(path)) if os.path.exists(path) else None
@@ -113,18 +113,20 @@ def make_case(name, frames, atomic_types, target="energy", hypers=None, nl_cutof
     if charge is not None:
         inp["charge"] = np.asarray(charge, dtype=np.int64)
         inp["spin_multiplicity"] = np.asarray(spin_multiplicity, dtype=np.int64)
-    be32 = ref_loader.build_reference_backend(atomic_types, target, hypers).eval()
+    be32 = ref_loader.build_reference_backend(atomic_types, target, hypers, out_shape=out_shape).eval()
     fp = weight_fingerprint(be32.state_dict())
     ref32 = run_reference(be32, inp, target, torch.float32, with_strain)
     payload = dict(inp)
     payload["atomic_types"] = np.array(atomic_types, dtype=np.int64)
     payload["target"] = np.array(target)
     payload["hypers_override"] = np.array(repr(hypers or {}))
+    payload["out_shape"] = np.array(out_shape, dtype=np.int64)
     payload["weight_fingerprint"] = fp
     for k, v in ref32.items():
         payload["ref32_" + k] = v
     if fp64:
-        be64 = ref_loader.build_reference_backend(atomic_types, target, hypers, dtype=torch.float64).eval()
+        be64 = ref_loader.build_reference_backend(atomic_types, target, hypers, dtype=torch.float64,
+                                                  out_shape=out_shape).eval()
         ref64 = run_reference(be64, inp, target, torch.float64, with_strain)
         for k in ("energies", "atomic", "dE_dpos", "dE_dstrain"):
             if k in ref64:
@@ -147,6 +149,7 @@ def main():
     print("qm9_5 vs reference's hard-coded goldens: max abs diff", err)
     assert err < 1e-5
 
+    carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
     water = read_lammps_atomic(os.path.join(RES, "periodic_water.data"), {1: 1, 2: 8})
     make_case("water_384", [water], [1, 8])
     # seed box of the 10k / 100k water benchmarks (positions only)
@@ -180,6 +183,11 @@ def main():
               hypers=dict(system_conditioning=True, featurizer_type="residual", _gate_seed=2),
               charge=[3, -2, 0, 1, -10], spin_multiplicity=[10, 1, 2, 4, 3])
 
+    # direct (non-conservative) stress head: [N, 9] -> [N, 3, 3, 1], / volume, symmetrised
+    # (backend.py:483-490, 780-813); periodic boxes and a zero-cell molecule (volume -> inf)
+    make_case("stress_head_mix", [carbon[0], carbon[1], qm9[0]], [1, 6, 7, 8], target="non_conservative_stress",
+              out_shape=(3, 3), fp64=False)
+
     # LoRA adapters (finetuning.py:322-378) on the attention projections (the reference default
     # target modules) and on every feed-forward / compress Linear; adapters seeded with 1
     make_case("water_384_lora", [water], [1, 8], fp64=False,
@@ -189,13 +197,17 @@ def main():
                                      target_modules=["input_linear", "output_linear", "w_in", "w_out",
                                                      "center_contraction", "center_expansion"])))
 
-    carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
     make_case("carbon_5", carbon, [6], with_strain=False)
 
     # adaptive cutoff, solver method (adaptive_cutoff.py:110-229, structures.py:222-262)
     make_case("water_384_adaptive", [water], [1, 8], hypers=dict(num_neighbors_adaptive=16))
     make_case("qm9_5_adaptive", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=dict(num_neighbors_adaptive=6))
     make_case("carbon_5_adaptive", carbon, [6], hypers=dict(num_neighbors_adaptive=10), with_strain=True)
+    # the legacy grid method (adaptive_cutoff.py:232-395)
+    grid = dict(adaptive_cutoff_method="grid")
+    make_case("water_384_adaptive_grid", [water], [1, 8], hypers=dict(num_neighbors_adaptive=16, **grid))
+    make_case("carbon_5_adaptive_grid", carbon, [6], hypers=dict(num_neighbors_adaptive=10, **grid),
+              with_strain=True)
 
     si = silicon_box()
     make_case("si_64", [si], [14], with_strain=True)
@@ -219,6 +231,8 @@ def main():
     # maximum cutoff, rows shorter than the target keep every pair
     make_case("ragged_mix_adaptive", [h2o, lone, pair, qm9[0], carbon[0]], [1, 6, 7, 8],
               hypers=dict(num_neighbors_adaptive=8))
+    make_case("ragged_mix_adaptive_grid", [h2o, lone, pair, qm9[0], carbon[0]], [1, 6, 7, 8],
+              hypers=dict(num_neighbors_adaptive=8, adaptive_cutoff_method="grid"))
 
 
 if __name__ == "__main__":

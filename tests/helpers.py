@@ -18,10 +18,13 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 "water_384_classic", "qm9_5_classic", "water_384_preln_ln_silu",
                 # adaptive cutoff, solver method (adaptive_cutoff.py:110-229)
                 "water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive", "ragged_mix_adaptive",
+                "water_384_adaptive_grid", "carbon_5_adaptive_grid", "ragged_mix_adaptive_grid",
                 # LoRA adapters (finetuning.py:322-378), merged into the packed weights
                 "water_384_lora", "qm9_5_lora_wide",
                 # system conditioning (conditioning.py:8-100)
-                "qm9_5_conditioned", "qm9_5_conditioned_residual"]
+                "qm9_5_conditioned", "qm9_5_conditioned_residual",
+                # direct stress head (backend.py:780-813)
+                "stress_head_mix"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(
@@ -43,6 +46,7 @@ def load_golden(name):
     g["lora"] = g["hypers"].pop("_lora", None)  # test-only: LoRA adapters injected after construction
     g["gate_seed"] = g["hypers"].pop("_gate_seed", None)  # test-only: conditioning gate re-drawn
     g["atomic_types"] = [int(z) for z in g["atomic_types"]]
+    g["out_shape"] = [int(v) for v in g["out_shape"]] if "out_shape" in g else [1]
     return g
 
 

@@ -19,7 +19,7 @@ FORCE_TOL = 1e-4  # eV/A, BASELINE.json north_star ("forces within 1e-4 eV/A of 
 def make_backend(g, precision="fp32"):
     seed_all(0)
     be = B200PETBackend(g["hypers"], g["atomic_types"], precision=precision)
-    be.add_output(g["target"], {g["target"] + "___0": [1]})
+    be.add_output(g["target"], {g["target"] + "___0": g["out_shape"]})
     apply_lora(be, g)
     return be.to(DEV).eval()
 
@@ -92,7 +92,8 @@ def test_reference_hard_coded_energies():
 
 
 @pytest.mark.parametrize("case", ["water_384_adaptive", "qm9_5_adaptive", "carbon_5_adaptive",
-                                  "ragged_mix_adaptive"])
+                                  "ragged_mix_adaptive", "water_384_adaptive_grid",
+                                  "carbon_5_adaptive_grid", "ragged_mix_adaptive_grid"])
 def test_adaptive_cutoffs_match_reference(case):
     """Per-atom cutoffs of the solver (adaptive_cutoff.py:110-229) and the pairs kept by the
     symmetrised pair cutoffs (structures.py:253-262), against the unmodified reference."""
@@ -109,7 +110,7 @@ def test_adaptive_cutoffs_match_reference(case):
 
 
 @pytest.mark.parametrize("case", ["si_64", "ragged_mix", "carbon_5", "carbon_5_adaptive",
-                                  "water_384_adaptive"])
+                                  "water_384_adaptive", "carbon_5_adaptive_grid"])
 def test_stages_match_oracle(case):
     """Stage-by-stage comparison with the oracle on identical weights and inputs."""
     g = load_golden(case)

@@ -65,8 +65,7 @@ def test_hyper_validation_matches_reference_error_types():
     B200PETBackend(dict(DEFAULT_HYPERS, transformer_type="PostLN"), [1])  # built: transformer.py:236-262
     B200PETBackend(dict(DEFAULT_HYPERS, normalization="LayerNorm", activation="SiLU"), [1])  # built
     B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16), [1])  # built: adaptive_cutoff.py:110-229
-    with pytest.raises(NotImplementedError):
-        B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16, adaptive_cutoff_method="grid"), [1])
+    B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16, adaptive_cutoff_method="grid"), [1])  # :232-395
     with pytest.raises(ValueError, match="must be 'grid' or 'solver'"):
         B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=16, adaptive_cutoff_method="x"), [1])
     cond = B200PETBackend(dict(DEFAULT_HYPERS, system_conditioning=True), [1])  # built: conditioning.py

@@ -22,7 +22,7 @@ REFERENCE_HARD_CODED = np.array(  # test_regression.py:66-74
 def seeded_state_dict(g):
     seed_all(0)
     p = PETParameters(g["hypers"], g["atomic_types"])
-    p.add_output(g["target"], {g["target"] + "___0": [1]})
+    p.add_output(g["target"], {g["target"] + "___0": g["out_shape"]})
     extra = apply_lora(p, g)
     sd = p.state_dict()
     sd.update(extra)
