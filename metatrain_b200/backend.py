@@ -18,7 +18,8 @@ Featurizers: ``feedforward`` (default) and ``residual`` (backend.py:589-649); tr
 ``PreLN`` (default) and ``PostLN`` (transformer.py:236-262); normalisation ``RMSNorm`` (default) or
 ``LayerNorm``; activation ``SwiGLU`` (default) or ``SiLU``; fixed cutoff (default) or the adaptive
 cutoff with the ``solver`` (adaptive_cutoff.py:110-229) or ``grid`` (:232-395) method.  Not built
-yet (raise ``NotImplementedError``): weight gradients (training), diagnostic capture.
+yet (raise ``NotImplementedError``): weight gradients (training).  Diagnostic capture fires the
+``node_backbone`` / ``edge_backbone`` hook points only.
 System conditioning (charge / spin embeddings, conditioning.py) is built.
 """
 from typing import Dict, List, Optional, Tuple
@@ -432,9 +433,10 @@ class B200PETBackend(PETParameters):
         self, batch_data: Dict[str, Tensor], capture_diagnostics: bool = False
     ) -> Tuple[List[Tensor], List[Tensor]]:
         """Same contract as ``PETBackend.calculate_features`` (backend.py:344): returns
-        ``([node features [N, d_node]], [edge features [N, M, d_pet]])``."""
-        if capture_diagnostics:
-            raise NotImplementedError("B200PETBackend: diagnostic feature capture is not built")
+        ``([node features [N, d_node]], [edge features [N, M, d_pet]])``.  With
+        ``capture_diagnostics`` the outputs pass through the ``node_backbone`` / ``edge_backbone``
+        identity modules so that forward hooks registered on them fire (the hook points inside the
+        featurizer do not exist in the fused implementation)."""
         self._check_inference()
         topo = self._topology_of(batch_data)
         charge = spin = None
@@ -454,6 +456,14 @@ class B200PETBackend(PETParameters):
             m_nef = _CsrToNef.apply(m, topo)
             m_nef._petb200_csr = m  # lets predict() skip the NEF round trip
             nef.append(m_nef)
+        if capture_diagnostics and not torch.jit.is_scripting() and not torch.jit.is_tracing():
+            # backend.py:396-415: hooks on node_backbone[i] / edge_backbone[i] see the raw backbone
+            # features.  Hooks on modules INSIDE the featurizer never fire here: the GNN layers run
+            # as fused kernels, their sub-modules only hold parameters.
+            nodes = [self.node_backbone[i](h) for i, h in enumerate(nodes)]
+            # (a hook that replaces the tensor drops the CSR shortcut attribute: predict() then
+            # gathers the NEF tensor back to CSR)
+            nef = [self.edge_backbone[i](m_nef) for i, m_nef in enumerate(nef)]
         return nodes, nef
 
     # ------------------------------------------------------------------ stage 3

@@ -166,6 +166,12 @@ class PETParameters(nn.Module):
         self.edge_heads = nn.ModuleDict()
         self.node_last_layers = nn.ModuleDict()
         self.edge_last_layers = nn.ModuleDict()
+        # parameter-free hook points for diagnostic outputs (backend.py:138-155)
+        ident = lambda n: nn.ModuleList([nn.Identity() for _ in range(n)])  # noqa: E731
+        self.gnn_layers_post_mp_node = ident(self.num_gnn_layers)
+        self.gnn_layers_post_mp_edge = ident(self.num_gnn_layers)
+        self.node_backbone = ident(self.num_readout_layers)
+        self.edge_backbone = ident(self.num_readout_layers)
 
     def add_output(self, target_name: str, output_shapes: Dict[str, List[int]]) -> None:
         r = range(self.num_readout_layers)

@@ -170,6 +170,26 @@ def test_predict_accepts_plain_nef_tensor():
     torch.testing.assert_close(ga, gb, atol=1e-6, rtol=1e-6)
 
 
+def test_capture_diagnostics_fires_backbone_hooks():
+    """backend.py:396-415: with capture_diagnostics the raw backbone features pass through the
+    node_backbone / edge_backbone identity modules, where the wrapper hangs its forward hooks."""
+    g = load_golden("si_64")
+    be = make_backend(g)
+    inp = golden_inputs(g, DEV)
+    bd = be.preprocess(inp["positions"], inp["centers"], inp["neighbors"], inp["species"],
+                       inp["cells"], inp["cell_shifts"], inp["system_indices"], 1.0)
+    seen = {}
+    hooks = [be.node_backbone[0].register_forward_hook(lambda m, i, o: seen.__setitem__("node", o)),
+             be.edge_backbone[0].register_forward_hook(lambda m, i, o: seen.__setitem__("edge", o))]
+    nodes, edges = be.calculate_features(bd, capture_diagnostics=True)
+    for h in hooks:
+        h.remove()
+    assert seen["node"] is nodes[0] and seen["edge"] is edges[0]
+    assert seen["edge"].shape == (bd["padding_mask"].shape[0], bd["padding_mask"].shape[1], be.d_pet)
+    plain_nodes, plain_edges = be.calculate_features(bd)
+    assert torch.equal(plain_nodes[0], nodes[0]) and torch.equal(plain_edges[0], edges[0])
+
+
 def test_csr_only_mode_equals_default():
     g = load_golden("water_384")
     be = make_backend(g)
