@@ -32,6 +32,7 @@ extern "C" PETB200_API int petb200_gemm(const float* A, int64_t lda, const float
   PETB200_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
   PETB200_REQUIRE(N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
   PETB200_REQUIRE(K % 16 == 0, "gemm: K=%d must be a multiple of 16", K);
+  if (M == 0) return PETB200_OK;  // empty operands carry null pointers
   PETB200_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0, "gemm: leading dims must be x4");
   PETB200_REQUIRE(aligned16(A) && aligned16(W) && aligned16(C), "gemm: pointers must be 16 B aligned");
   PETB200_REQUIRE(!residual || (ldr % 4 == 0 && aligned16(residual)), "gemm: residual alignment");
@@ -69,6 +70,7 @@ extern "C" PETB200_API int petb200_compress_gemm(const float* messages, int64_t 
   PETB200_REQUIRE(d == 128, "compress_gemm: only d_pet = 128 is built (got %d)", d);
   PETB200_REQUIRE(precision == PETB200_PREC_BF16X3 || precision == PETB200_PREC_BF16,
                   "compress_gemm: tensor-core precisions only (the fp32 path uses compress_input + gemm)");
+  if (n_edges == 0) return PETB200_OK;
   PETB200_REQUIRE(messages && w1m_split && geo_w && edge_vec && edge_dist && pre && out,
                   "compress_gemm: null argument");
   PETB200_REQUIRE(!nbr_table || z_neighbor, "compress_gemm: a table needs its row index");

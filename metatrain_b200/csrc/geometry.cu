@@ -433,8 +433,8 @@ extern "C" PETB200_API int petb200_edges_fwd_rc(const float* positions, const fl
                                     cudaStream_t stream) {
   PETB200_REQUIRE(cutoff_function == PETB200_CUTOFF_BUMP || cutoff_function == PETB200_CUTOFF_COSINE,
                   "edges_fwd_rc: unknown cutoff function %d", cutoff_function);
-  PETB200_REQUIRE(edge_cutoff != nullptr, "edges_fwd_rc: edge_cutoff is null");
   if (n_edges == 0) return PETB200_OK;
+  PETB200_REQUIRE(edge_cutoff != nullptr, "edges_fwd_rc: edge_cutoff is null");
   edges_fwd_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
       positions, cells, system_of_atom, ctr, col, shift_csr, n_edges, 0.f, edge_cutoff, width,
       cutoff_function, edge_vec, edge_dist, cutoff_factor);
@@ -450,7 +450,7 @@ extern "C" PETB200_API int petb200_edges_bwd_rc(const float* d_vec, const float*
                                     float* d_cells, float* d_edge_cutoff, cudaStream_t stream) {
   PETB200_REQUIRE(cutoff_function == PETB200_CUTOFF_BUMP || cutoff_function == PETB200_CUTOFF_COSINE,
                   "edges_bwd_rc: unknown cutoff function %d", cutoff_function);
-  PETB200_REQUIRE(edge_cutoff != nullptr, "edges_bwd_rc: edge_cutoff is null");
+  PETB200_REQUIRE(n_edges == 0 || edge_cutoff != nullptr, "edges_bwd_rc: edge_cutoff is null");
   if (n_edges > 0) {
     edge_grad_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(
         d_vec, d_dist, d_fc, edge_vec, edge_dist, n_edges, 0.f, edge_cutoff, d_edge_cutoff, width,

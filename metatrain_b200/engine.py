@@ -47,6 +47,15 @@ def split_weight(w: Tensor, pack=None) -> Tensor:
     return torch.as_strided(base, w.shape, w.stride(), w.storage_offset())
 
 
+def _split_weight_ptr(w: Tensor, pack) -> int:
+    """Device address of ``split_weight(w, pack)`` without building the view tensor (the split
+    buffer has the byte layout of the fp32 source: same offsets)."""
+    base = pack.split_cache.get((w.untyped_storage().data_ptr(), w._version)) if pack is not None else None
+    if base is None:
+        return split_weight(w, pack).data_ptr()
+    return base.data_ptr() + 4 * w.storage_offset()
+
+
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, bias=None, row_scale=None, residual=None,
          aux_in=None, aux_out=None, epilogue=EPI_NONE, accumulate=False,
          precision=PREC_FP32, pack=None) -> Tensor:
@@ -56,11 +65,10 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, bias=None, row_scale=None, residu
     m, k = a.shape
     n = w.shape[0]
     assert w.shape[1] == k and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
-    if precision != PREC_FP32:
-        w = split_weight(w, pack)
+    w_ptr = w.data_ptr() if precision == PREC_FP32 else _split_weight_ptr(w, pack)
     aux = aux_in if aux_in is not None else aux_out
     call(
-        "gemm", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), m, n, k,
+        "gemm", ptr(a), a.stride(0), w_ptr, w.stride(0), ptr(out), out.stride(0), m, n, k,
         ptr(bias), ptr(row_scale), ptr(residual),
         residual.stride(0) if residual is not None else 0,
         ptr(aux_in), ptr(aux_out), aux.stride(0) if aux is not None else 0,

@@ -149,19 +149,24 @@ launch_count = 0
 profile_hook = None
 
 
+_ENTRY = {}  # name -> bound ctypes function (saves a string build + getattr per launch)
+
+
 def call(name: str, *args) -> None:
     """Invoke ``petb200_<name>`` on torch's current stream; raise on a non-zero status."""
     global launch_count
-    lib = load()
+    fn = _ENTRY.get(name)
+    if fn is None:
+        fn = _ENTRY[name] = getattr(load(), "petb200_" + name)
     n_kernels = _KERNELS_PER_CALL.get(name, 1)
     if name == "attention_bwd" and args[12] != PREC_FP32 and args[11] + 1 <= 64:
         n_kernels = 1  # single tensor-core kernel (attention_tc.cu) instead of dQ + dKdV
     launch_count += n_kernels
     if profile_hook is not None:
         with profile_hook(name, args):
-            status = getattr(lib, "petb200_" + name)(*args, stream_ptr())
+            status = fn(*args, stream_ptr())
     else:
-        status = getattr(lib, "petb200_" + name)(*args, stream_ptr())
+        status = fn(*args, stream_ptr())
     if status != 0:
-        msg = lib.petb200_last_error().decode("utf-8", "replace")
+        msg = load().petb200_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"petb200_{name} failed ({status}): {msg}")

@@ -212,6 +212,9 @@ def main():
     si = silicon_box()
     make_case("si_64", [si], [14], with_strain=True)
     make_case("si_64_cosine", [si], [14], hypers=dict(cutoff_function="Cosine"), fp64=False)
+    # 70 neighbours per atom (cutoff 7 A): rows longer than the 64 tokens the tensor-core attention
+    # kernels hold, i.e. the long-row fallback of the bf16x3 path
+    make_case("si_64_cutoff7", [si], [14], hypers=dict(cutoff=7.0), nl_cutoff=7.0, fp64=False)
 
     # the periodic 2-atom system of pet/tests/test_backend.py:68-80 (strain gradient)
     co = dict(Z=np.array([6, 8]), positions=np.array([[0.0, 0.0, 0.0], [1.5, 1.5, 1.5]]),

@@ -8,7 +8,7 @@ import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64",
-                "si_64_cosine", "co_periodic", "ragged_mix",
+                "si_64_cosine", "si_64_cutoff7", "co_periodic", "ragged_mix",
                 # residual featurizer (backend.py:589-649): one readout per GNN layer
                 "qm9_5_residual", "water_384_residual",
                 # PostLN transformer layers (transformer.py:236-262)

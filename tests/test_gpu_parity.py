@@ -232,6 +232,26 @@ def test_empty_and_errors():
         evaluate(be, **inp, target=g["target"])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("adaptive", [None, 4])
+def test_atoms_without_any_neighbour(adaptive, precision):
+    """A batch whose neighbor list is empty (every atom isolated): zero-length rows everywhere,
+    with the fixed and with the adaptive cutoff; compared with the oracle on the same weights."""
+    g = load_golden("qm9_5")
+    g["hypers"] = dict(g["hypers"], num_neighbors_adaptive=adaptive)
+    be = make_backend(g, precision=precision)
+    sd = {k: v.detach().cpu() for k, v in be.state_dict().items()}
+    pos = torch.tensor([[0.0, 0, 0], [20.0, 0, 0], [0, 30.0, 0], [5.0, 5.0, 50.0]])
+    inp = dict(positions=pos, centers=torch.zeros(0, dtype=torch.long), neighbors=torch.zeros(0, dtype=torch.long),
+               species=torch.tensor([1, 6, 8, 7]), cells=torch.zeros(2, 3, 3),
+               cell_shifts=torch.zeros(0, 3, dtype=torch.long), system_indices=torch.tensor([0, 0, 1, 1]))
+    ref = pet_oracle.energy_and_gradients(sd, g["hypers"], **inp, target=g["target"])
+    out = evaluate(be, **{k: v.to(DEV) for k, v in inp.items()}, target=g["target"])
+    torch.testing.assert_close(out["energies"].cpu(), ref["energies"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(out["atomic"].cpu(), ref["atomic"], atol=1e-5, rtol=1e-5)
+    assert float(out["dE_dpos"].abs().max()) == 0.0 and float(ref["dE_dpos"].abs().max()) == 0.0
+
+
 def test_evaluator_loop_matches_reference_semantics():
     """eval_targets mirrors cli/eval.py:_eval_targets: batching (last batch smaller), per-atom
     energy metrics, force metrics, predictions equal to direct evaluation."""
