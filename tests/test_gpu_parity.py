@@ -252,6 +252,31 @@ def test_atoms_without_any_neighbour(adaptive, precision):
     assert float(out["dE_dpos"].abs().max()) == 0.0 and float(ref["dE_dpos"].abs().max()) == 0.0
 
 
+def test_float64_inputs_and_empty_structure_in_a_batch():
+    """fp64 positions / cells are accepted (computed in fp32, gradients returned in the input dtype,
+    like a float32 model fed by an fp64 MD engine), and a structure without atoms in the middle of a
+    batch gets a zero energy row (sum_over_atoms.py:31 semantics)."""
+    g = load_golden("carbon_5")
+    be = make_backend(g)
+    inp = golden_inputs(g, DEV)
+    ref = evaluate(be, **inp, target=g["target"], strain=True)
+    inp64 = dict(inp, positions=inp["positions"].double(), cells=inp["cells"].double())
+    out = evaluate(be, **inp64, target=g["target"], strain=True)
+    assert out["dE_dpos"].dtype == torch.float64 and out["dE_dstrain"].dtype == torch.float64
+    assert (out["dE_dpos"].float() - ref["dE_dpos"]).abs().max() <= 1e-6
+    assert (out["dE_dstrain"].float() - ref["dE_dstrain"]).abs().max() <= 1e-5
+    assert (out["energies"] - ref["energies"]).abs().max() <= 1e-6
+    # insert an empty structure as system 2: later systems shift up by one
+    sysi = inp["system_indices"].clone()
+    sysi[sysi >= 2] += 1
+    cells = torch.cat([inp["cells"][:2], torch.eye(3, device=DEV)[None] * 7.0, inp["cells"][2:]])
+    out = evaluate(be, **dict(inp, system_indices=sysi, cells=cells), target=g["target"])
+    assert out["energies"].shape[0] == 6 and float(out["energies"][2].abs().sum()) == 0.0
+    keep = [0, 1, 3, 4, 5]
+    assert (out["energies"][keep] - ref["energies"]).abs().max() <= 1e-6
+    assert (out["dE_dpos"] - ref["dE_dpos"]).abs().max() <= 1e-6
+
+
 def test_evaluator_loop_matches_reference_semantics():
     """eval_targets mirrors cli/eval.py:_eval_targets: batching (last batch smaller), per-atom
     energy metrics, force metrics, predictions equal to direct evaluation."""
@@ -336,6 +361,27 @@ def test_verlet_list_reuse_matches_fresh_lists():
         assert (out["dE_dpos"] - ref["dE_dpos"]).abs().max() <= 2e-5
         pos = pos + 0.04 * torch.randn(pos.shape, generator=gen).to(DEV)
     assert vl.n_builds >= 1 and vl.n_reuses >= 2 and vl.n_builds + vl.n_reuses == 6
+
+
+def test_graphed_md_evaluator_on_a_molecule():
+    """Non-periodic system (zero cell): the bounding-box neighbor list path of the MD evaluator."""
+    from metatrain_b200 import GraphedEvaluator
+    from metatrain_b200.neighbors_gpu import neighbor_list_gpu
+    g = load_golden("qm9_5")
+    be = make_backend(g, precision="bf16x3")
+    inp = golden_inputs(g, DEV)
+    sel = inp["system_indices"] == 3
+    pos, species, cell = inp["positions"][sel].clone(), inp["species"][sel], torch.zeros(3, 3, device=DEV)
+    md = GraphedEvaluator(be, species, cell, periodic=False, skin=0.4, target=g["target"])
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    for _ in range(6):
+        out = md(pos)
+        e, f = out["energies"].clone(), out["dE_dpos"].clone()
+        c, n, s = neighbor_list_gpu(pos, cell, False, be.cutoff)
+        ref = evaluate(be, pos, c.long(), n.long(), species, cell[None], s,
+                       torch.zeros(len(species), dtype=torch.long, device=DEV), target=g["target"])
+        assert (e - ref["energies"]).abs().max() <= 2e-5 and (f - ref["dE_dpos"]).abs().max() <= 2e-5
+        pos = pos + 0.05 * torch.randn(pos.shape, generator=gen).to(DEV)
 
 
 @pytest.mark.parametrize("use_graph", [True, False])
