@@ -34,6 +34,33 @@ def test_library_exports_every_declared_symbol():
     assert handle.petb200_version() >= 1
 
 
+def declared_prototypes():
+    """name -> list of C parameter declarations, parsed from include/petb200.h."""
+    text = open(os.path.join(ROOT, "include", "petb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"PETB200_API\s+[\w\s\*]+?\b(petb200_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every hand-written ctypes argument list in lib._SIGNATURES must agree, position by position,
+    with the C prototype (a drifted list corrupts the call silently)."""
+    def ctype_of(param):
+        if "*" in param or "petb200_stream_t" in param:
+            return ctypes.c_void_p
+        base = param.replace("const", "").split()[0]
+        return {"int64_t": ctypes.c_int64, "int": ctypes.c_int, "float": ctypes.c_float,
+                "size_t": ctypes.c_size_t}[base]
+    protos = declared_prototypes()
+    assert set(protos) == set(lib._SIGNATURES)
+    for name, params in protos.items():
+        expected = [ctype_of(p) for p in params]
+        assert lib._SIGNATURES[name] == expected, f"{name}: ctypes {lib._SIGNATURES[name]} vs header {params}"
+
+
 def test_state_dict_contract():
     g = load_golden("qm9_5")
     seed_all(0)
