@@ -234,6 +234,15 @@ def main():
     # maximum cutoff, rows shorter than the target keep every pair
     make_case("ragged_mix_adaptive", [h2o, lone, pair, qm9[0], carbon[0]], [1, 6, 7, 8],
               hypers=dict(num_neighbors_adaptive=8))
+    # everything at once: original PET layer (PostLN + LayerNorm + SiLU), residual featurizer, adaptive
+    # cutoff, system conditioning, LoRA adapters on every Linear of the transformer layers, Cosine
+    # cutoff function, periodic and non-periodic structures in one batch, strain gradient
+    make_case("kitchen_sink", [h2o, lone, pair, qm9[0], carbon[0], carbon[3]], [1, 6, 7, 8],
+              hypers=dict(classic, num_neighbors_adaptive=8, system_conditioning=True, _gate_seed=2,
+                          cutoff_function="Cosine",
+                          _lora=dict(rank=4, alpha=8.0, seed=1,
+                                     target_modules=["input_linear", "output_linear", "w_in", "w_out"])),
+              charge=[0, 1, -1, 0, 2, 0], spin_multiplicity=[1, 2, 1, 3, 1, 2], with_strain=True, fp64=False)
     make_case("ragged_mix_adaptive_grid", [h2o, lone, pair, qm9[0], carbon[0]], [1, 6, 7, 8],
               hypers=dict(num_neighbors_adaptive=8, adaptive_cutoff_method="grid"))
 

@@ -24,7 +24,9 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 # system conditioning (conditioning.py:8-100)
                 "qm9_5_conditioned", "qm9_5_conditioned_residual",
                 # direct stress head (backend.py:780-813)
-                "stress_head_mix"]
+                "stress_head_mix",
+                # all variants combined in one model / one ragged batch
+                "kitchen_sink"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(
