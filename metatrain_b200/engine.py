@@ -838,8 +838,6 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
     return h, m, saved
 
 
-
-
 def features_forward_residual(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec=PREC_FP32,
                               cond_table: Optional[Tensor] = None):
     """Residual featurizer, backend.py:589-649: every GNN layer starts from its own node embedding,

@@ -7,7 +7,6 @@ weights are packed (``engine.PackedWeights``) every adapted layer is merged into
 """
 from typing import Sequence
 
-import torch
 from torch import nn
 
 

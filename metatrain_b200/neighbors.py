@@ -8,7 +8,6 @@ linked-cell search in numpy that returns every ordered pair ``(i, j, S)`` with
 and triclinic cells of any size (several periodic images per pair when the cell is
 smaller than the cutoff).  A CUDA cell-list builder is the next row of SURVEY.md 8(f).
 """
-import math
 from typing import Tuple
 
 import numpy as np
