@@ -252,6 +252,38 @@ def test_atoms_without_any_neighbour(adaptive, precision):
     assert float(out["dE_dpos"].abs().max()) == 0.0 and float(ref["dE_dpos"].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("variant", ["fixed", "adaptive_solver", "adaptive_grid"])
+def test_reference_autograd_system_against_fp64_oracle(variant, precision):
+    """The system of the reference's autograd test (utils/testing/autograd.py:24-43): two carbon atoms
+    in a 2 A cubic cell — ~95 periodic images per atom inside the cutoff, i.e. rows longer than the
+    tensor-core attention tile and shifts up to +-3.  Forces against the oracle evaluated in fp64
+    (whose own gradient is gradcheck-ed in tests/test_oracle.py)."""
+    from helpers import DEFAULT_HYPERS
+    from oracle.structures import neighbor_list
+    hyp = dict(DEFAULT_HYPERS)
+    if variant != "fixed":
+        hyp.update(num_neighbors_adaptive=20.0, adaptive_cutoff_method=variant.split("_")[1])
+    seed_all(0)
+    be = B200PETBackend(hyp, [6], precision=precision)
+    be.add_output("energy", {"energy___0": [1]})
+    be = be.to(DEV).eval()
+    sd64 = {k: (v.detach().cpu().double() if v.is_floating_point() else v.detach().cpu())
+            for k, v in be.state_dict().items()}
+    pos0 = np.array([[0.0, 0.0, 0.0], [0.9, 0.9, 0.9]])
+    cell = 2.0 * np.eye(3)
+    i, j, S = neighbor_list(pos0, cell, True, 4.5)
+    inp = dict(positions=torch.tensor(pos0), centers=torch.tensor(i), neighbors=torch.tensor(j),
+               species=torch.tensor([6, 6]), cells=torch.tensor(cell)[None], cell_shifts=torch.tensor(S),
+               system_indices=torch.zeros(2, dtype=torch.long))
+    ref = pet_oracle.energy_and_gradients(sd64, hyp, **inp, target="energy", with_strain=True)
+    dev_inp = {k: (v.float() if v.is_floating_point() else v).to(DEV) for k, v in inp.items()}
+    out = evaluate(be, **dev_inp, target="energy", strain=True)
+    assert abs(float(out["energies"]) - float(ref["energies"])) <= 2e-5 * max(1.0, abs(float(ref["energies"])))
+    assert (out["dE_dpos"].cpu().double() - ref["dE_dpos"]).abs().max() <= FORCE_TOL
+    assert (out["dE_dstrain"].cpu().double() - ref["dE_dstrain"]).abs().max() <= 5e-4
+
+
 def test_float64_inputs_and_empty_structure_in_a_batch():
     """fp64 positions / cells are accepted (computed in fp32, gradients returned in the input dtype,
     like a float32 model fed by an fp64 MD engine), and a structure without atoms in the middle of a

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, apply_lora, golden_inputs, load_golden, seed_all, weight_fingerprint
+from helpers import DEFAULT_HYPERS, GOLDEN_CASES, apply_lora, golden_inputs, load_golden, seed_all, weight_fingerprint
 from metatrain_b200.parameters import PETParameters
 from oracle import pet_oracle, ref_loader
 from oracle.structures import neighbor_list
@@ -91,6 +91,41 @@ def test_manual_attention_equals_sdpa():
     b = pet_oracle.energy_and_gradients(sd, g["hypers"], **golden_inputs(g), manual_attention=True)
     torch.testing.assert_close(a["atomic"], b["atomic"], atol=1e-5, rtol=1e-5)
     torch.testing.assert_close(a["dE_dpos"], b["dE_dpos"], atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("variant", ["fixed", "adaptive_solver", "adaptive_grid"])
+def test_oracle_gradcheck_on_the_reference_autograd_system(variant):
+    """The reference's autograd test (src/metatrain/utils/testing/autograd.py:24-94): two carbon
+    atoms at (0,0,0) and (0.9,0.9,0.9) in a 2 A cubic cell, fp64, torch.autograd.gradcheck of the
+    summed energy w.r.t. the positions — restated on the oracle, also through both adaptive-cutoff
+    methods (whose gradient comes from the implicit-function step / the probe weights)."""
+    hyp = dict(DEFAULT_HYPERS)
+    if variant != "fixed":
+        hyp.update(num_neighbors_adaptive=20.0, adaptive_cutoff_method=variant.split("_")[1])
+    seed_all(0)
+    p = PETParameters(hyp, [6])
+    p.add_output("energy", {"energy___0": [1]})
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in p.state_dict().items()}
+    pos0 = np.array([[0.0, 0.0, 0.0], [0.9, 0.9, 0.9]])
+    cell = 2.0 * np.eye(3)
+    i, j, S = neighbor_list(pos0, cell, True, 4.5)
+    fixed = dict(centers=torch.tensor(i), neighbors=torch.tensor(j), species=torch.tensor([6, 6]),
+                 cells=torch.tensor(cell)[None], cell_shifts=torch.tensor(S),
+                 system_indices=torch.zeros(2, dtype=torch.long))
+
+    def energy(positions):
+        batch = pet_oracle.build_batch(positions, fixed["centers"], fixed["neighbors"], fixed["species"],
+                                       fixed["cells"], fixed["cell_shifts"], fixed["system_indices"],
+                                       sd["species_to_species_index"], hyp["cutoff"], hyp["cutoff_function"],
+                                       hyp["cutoff_width"], False, hyp["num_neighbors_adaptive"],
+                                       hyp["cutoff_width_adaptive"], hyp["adaptive_cutoff_method"])
+        node, msg = pet_oracle.features(sd, hyp, batch)
+        return pet_oracle.predict(sd, hyp, node, msg, batch, "energy").sum()
+
+    positions = torch.tensor(pos0, dtype=torch.float64, requires_grad=True)
+    # the solver's gradient is exact at the converged root only: 10 Newton steps leave ~1e-9
+    tol = dict(atol=1e-6, rtol=1e-4) if variant == "adaptive_solver" else {}
+    assert torch.autograd.gradcheck(energy, positions, fast_mode=True, **tol)
 
 
 def test_oracle_neighbor_list_definition():
