@@ -139,6 +139,40 @@ def make_case(name, frames, atomic_types, target="energy", hypers=None, nl_cutof
     return payload
 
 
+def make_training_case(name, frames, atomic_types, target="energy", hypers=None, nl_cutoff=4.5):
+    """Pins what a training step differentiates (not built on the GPU yet):
+    the reference backend in train mode, fp64, loss = sum(E) + 0.1 * sum(|dE/dr|^2) with the force
+    term built by ``create_graph=True`` (src/metatrain/utils/output_gradient.py:34-40), gradient
+    w.r.t. every parameter.  Stored: the loss and (sum, sum of squares) of every parameter gradient,
+    in state-dict order."""
+    if ONLY and name not in ONLY:
+        return
+    inp = batch_frames(frames, nl_cutoff)
+    be = ref_loader.build_reference_backend(atomic_types, target, hypers, dtype=torch.float64).train()
+    t = lambda a: torch.tensor(a)  # noqa: E731
+    pos = t(inp["positions"]).double().requires_grad_(True)
+    cells, sysi = t(inp["cells"]).double(), t(inp["system_indices"])
+    bd = be.preprocess(pos, t(inp["centers"]), t(inp["neighbors"]), t(inp["species"]), cells,
+                       t(inp["cell_shifts"]), sysi, 1.0)
+    nodes, edges = be.calculate_features(bd)
+    pred, _, _ = be.predict(nodes, edges, bd, cells, sysi, [target])
+    atomic = pred[target][0]
+    energies = torch.zeros(cells.shape[0], atomic.shape[1], dtype=torch.float64).index_add_(0, sysi, atomic)
+    (de_dr,) = torch.autograd.grad(energies.sum(), pos, create_graph=True)
+    loss = energies.sum() + 0.1 * (de_dr ** 2).sum()
+    names = [n for n, _ in be.named_parameters()]
+    grads = torch.autograd.grad(loss, list(be.parameters()), allow_unused=True)
+    rows = [[0.0, 0.0] if gr is None else [float(gr.sum()), float((gr * gr).sum())] for gr in grads]
+    payload = dict(inp)
+    payload.update(atomic_types=np.array(atomic_types, dtype=np.int64), target=np.array(target),
+                   hypers_override=np.array(repr(hypers or {})), out_shape=np.array([1], dtype=np.int64),
+                   train_loss=np.array(float(loss)), train_grad_fingerprint=np.array(rows),
+                   train_param_names=np.array(names))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **payload)
+    print(f"{name}: loss {float(loss):.9f}, {len(names)} parameter gradients -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     torch.set_num_threads(8)
     qm9 = read_xyz_frames(os.path.join(RES, "qm9_reduced_100.xyz"), 5)
@@ -150,6 +184,8 @@ def main():
     assert err < 1e-5
 
     carbon = read_xyz_frames(os.path.join(RES, "carbon_reduced_100.xyz"), 5)
+    make_training_case("train_qm9_2", qm9[:2], [1, 6, 7, 8], target="mtt::U0")
+    make_training_case("train_carbon_1", carbon[:1], [6])
     water = read_lammps_atomic(os.path.join(RES, "periodic_water.data"), {1: 1, 2: 8})
     make_case("water_384", [water], [1, 8])
     # seed box of the 10k / 100k water benchmarks (positions only)

@@ -128,6 +128,40 @@ def test_oracle_gradcheck_on_the_reference_autograd_system(variant):
     assert torch.autograd.gradcheck(energy, positions, fast_mode=True, **tol)
 
 
+@pytest.mark.parametrize("case", ["train_qm9_2", "train_carbon_1"])
+def test_oracle_parameter_gradients_match_reference_training_goldens(case):
+    """What a training step differentiates (the CUDA path does not build
+    weight gradients yet): loss = sum(E) + 0.1 sum |dE/dr|^2 with the force term from
+    create_graph=True (output_gradient.py:34-40), manual attention as the reference uses when
+    training (backend.py:380-384), fp64.  Pins the oracle's gradient w.r.t. EVERY parameter to the
+    unmodified reference, so that the wgrad / double-backward kernels have a checker."""
+    g = load_golden(case)
+    seed_all(0)
+    p = PETParameters(g["hypers"], g["atomic_types"])
+    p.add_output(g["target"], {g["target"] + "___0": [1]})
+    names = [n for n, _ in p.named_parameters()]
+    assert names == [str(n) for n in g["train_param_names"]]
+    w = {k: (v.double() if v.is_floating_point() else v) for k, v in p.state_dict().items()}
+    for n in names:
+        w[n] = w[n].clone().requires_grad_(True)
+    inp = golden_inputs(g, dtype=torch.float64)
+    pos = inp["positions"].clone().requires_grad_(True)
+    batch = pet_oracle.build_batch(pos, inp["centers"], inp["neighbors"], inp["species"], inp["cells"],
+                                   inp["cell_shifts"], inp["system_indices"], w["species_to_species_index"],
+                                   g["hypers"]["cutoff"], g["hypers"]["cutoff_function"],
+                                   g["hypers"]["cutoff_width"])
+    node, msg = pet_oracle.features(w, g["hypers"], batch, manual_attention=True)
+    atomic = pet_oracle.predict(w, g["hypers"], node, msg, batch, g["target"])
+    energies = torch.zeros(inp["cells"].shape[0], atomic.shape[1], dtype=torch.float64).index_add_(
+        0, inp["system_indices"], atomic)
+    (de_dr,) = torch.autograd.grad(energies.sum(), pos, create_graph=True)
+    loss = energies.sum() + 0.1 * (de_dr ** 2).sum()
+    grads = torch.autograd.grad(loss, [w[n] for n in names], allow_unused=True)
+    np.testing.assert_allclose(float(loss.detach()), float(g["train_loss"]), rtol=1e-10)
+    rows = np.array([[0.0, 0.0] if gr is None else [float(gr.sum()), float((gr * gr).sum())] for gr in grads])
+    np.testing.assert_allclose(rows, g["train_grad_fingerprint"], rtol=1e-7, atol=1e-12)
+
+
 def test_oracle_neighbor_list_definition():
     """All ordered (i, j, S) with |r_j + S.cell - r_i| <= rc, no (i, i, 0) — checked
     against an O(N^2 * images) enumeration on the triclinic multi-image carbon cell."""
