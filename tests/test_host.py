@@ -103,6 +103,36 @@ def test_hyper_validation_matches_reference_error_types():
         cond.system_conditioning.validate(torch.tensor([0]), torch.tensor([0]))
 
 
+def test_lora_injection_mirrors_reference_state_dict_keys():
+    """finetuning.py:322-378: wrapped Linears keep the reference's sub-module names, so the keys
+    of a LoRA-finetuned checkpoint (`...input_linear.linear.weight`, `...lora_A.weight`) load."""
+    from metatrain_b200.finetuning import LoRALinear, inject_lora_layers
+    be = B200PETBackend(DEFAULT_HYPERS, [1, 8])
+    be.add_output("energy", {"energy___0": [1]})
+    before = set(be.state_dict())
+    inject_lora_layers(be, ("input_linear", "output_linear"), rank=4, alpha=8.0)
+    after = set(be.state_dict())
+    stem = "gnn_layers.0.trans.layers.0.attention.input_linear"
+    assert stem + ".weight" in before and stem + ".weight" not in after
+    assert {stem + ".linear.weight", stem + ".linear.bias", stem + ".lora_A.weight", stem + ".lora_B.weight"} <= after
+    n_wrapped = sum(isinstance(m, LoRALinear) for m in be.modules())
+    assert n_wrapped == 2 * DEFAULT_HYPERS["num_gnn_layers"] * DEFAULT_HYPERS["num_attention_layers"]
+    assert len(after) == len(before) + 3 * n_wrapped - n_wrapped  # +A, +B per wrapped layer; weight/bias renamed
+    inject_lora_layers(be, ("input_linear",))  # already wrapped: not an nn.Linear any more, left alone
+    assert sum(isinstance(m, LoRALinear) for m in be.modules()) == n_wrapped
+
+
+def test_graphed_evaluator_needs_a_cuda_backend():
+    from metatrain_b200 import GraphedEvaluator
+    be = B200PETBackend(DEFAULT_HYPERS, [1, 8])
+    be.add_output("energy", {"energy___0": [1]})
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        GraphedEvaluator(be, torch.tensor([1, 8]), torch.eye(3))
+    ad = B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=8), [1, 8])
+    with pytest.raises(NotImplementedError, match="adaptive cutoff"):
+        GraphedEvaluator(ad, torch.tensor([1, 8]), torch.eye(3))
+
+
 def test_no_cpu_fallback():
     be = B200PETBackend(DEFAULT_HYPERS, [1, 8])
     be.add_output("energy", {"energy___0": [1]})
