@@ -2,6 +2,7 @@
 neighbor list, hyper-parameter validation (no GPU compute)."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -131,6 +132,22 @@ def test_graphed_evaluator_needs_a_cuda_backend():
     ad = B200PETBackend(dict(DEFAULT_HYPERS, num_neighbors_adaptive=8), [1, 8])
     with pytest.raises(NotImplementedError, match="adaptive cutoff"):
         GraphedEvaluator(ad, torch.tensor([1, 8]), torch.eye(3))
+
+
+def test_bench_reads_measured_peaks_tolerantly(tmp_path, monkeypatch):
+    """bench.py's roofline denominators come from the driver-written MEASURED_PEAKS.json; whatever
+    its key names, a malformed or missing file must fall back instead of killing the bench."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.peaks() == (6650.0, 1590.0, 1400.0, "fallback")
+    for content in ({"hbm_gbs": 6556.8, "bf16_tflops": 1651, "bf16_tflops_sustained": 1403.7},
+                    {"hbm": {"copy_GBs": 6556.8}, "bf16": {"burst_tflops": 1651.0, "sustained_tflops": 1403.7}}):
+        (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps(content))
+        assert bench.peaks() == (6556.8, 1651.0, 1403.7, "measured")
+    (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
+    assert bench.peaks()[3] == "fallback"
 
 
 def test_no_cpu_fallback():
