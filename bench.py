@@ -57,7 +57,23 @@ def parse():
     ap.add_argument("--reps", type=int, nargs=3, default=list(REPS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "independent"])
+    ap.add_argument("--config4", action="store_true",
+                    help="also time the 96 768-atom box of BASELINE.json configs[3] (always on at 8 GPUs)")
     return ap.parse_args()
+
+
+def workload_config(reps, world, multi):
+    """The `config` object, identical in the petb200 and the reference arm."""
+    n = 384 * reps[0] * reps[1] * reps[2]
+    return {"workload": f"PET default hypers, periodic water box {reps[0]}x{reps[1]}x{reps[2]} tiling "
+                        f"of the 384-atom fixture ({n} atoms per GPU), cutoff 4.5 A, energy + forces "
+                        "(BASELINE.json configs[1])",
+            "atoms_per_gpu": n, "n_gpus": world,
+            "parallelism": ("1 GPU" if world == 1 else
+                            f"one {n * world}-atom box sharded by atoms over {world} GPUs, halo "
+                            "all-to-all-v + all-reduce over NCCL" if multi == "sharded" else
+                            f"{world} independent boxes (1 per GPU)"),
+            "cache": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"}
 
 
 def hypers():
@@ -97,30 +113,22 @@ def time_oracle(reps, steps, warmup):
     return n_atoms / dt, dt, n_atoms
 
 
-def pick_reference_sample(steps, warmup, budget_s=150.0):
-    """Largest tiling of the workload whose (steps + warmup) CPU passes fit the budget."""
-    _, t1, _ = time_oracle((1, 1, 1), 1, 1)
-    for reps, n in (((3, 3, 3), 27), ((2, 2, 2), 8)):
-        if (steps + warmup) * n * 1.4 * t1 <= budget_s:
-            return reps
-    return (1, 1, 1)
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    reps = pick_reference_sample(args.steps, args.warmup)
+    # always the full BASELINE configs[1] box (same config as the GPU arm): ~6 s per step on the
+    # GPU box's host cores
+    reps = tuple(args.reps)
     value, dt, n_atoms = time_oracle(reps, args.steps, max(args.warmup, 1))
-    sample = (f"water {reps[0]}x{reps[1]}x{reps[2]} tiling ({n_atoms} atoms) of the 10 368-atom "
-              f"workload, {args.steps} steps after {max(args.warmup, 1)} warm-up")
+    sample = (f"the full per-GPU box: water {reps[0]}x{reps[1]}x{reps[2]} tiling ({n_atoms} atoms), "
+              f"{args.steps} steps after {max(args.warmup, 1)} warm-up, oracle port on all host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PET default hypers, periodic water box tiled from the 384-atom "
-                               "fixture, cutoff 4.5 A, energy + forces", "atoms": n_atoms},
+        "config": workload_config(reps, int(os.environ.get("WORLD_SIZE", "1")), args.multi),
         "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": os.cpu_count(),
                          "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0,
@@ -293,8 +301,11 @@ def run_petb200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PETB200_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner off stdout (= 1 JSON line)
+        # NCCL's own logging is left exactly as the caller configured it (the driver reads the
+        # communicator sizes from NCCL_DEBUG=INFO output); only when nothing is configured is the
+        # version banner kept off stdout (= 1 JSON line)
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     seed_all(0)
@@ -304,41 +315,66 @@ def run_petb200(args):
     be.emit_nef = False  # energies + forces only need the CSR handles
 
     sharded = world > 1 and args.multi == "sharded"
-    if sharded:
+
+    def sharded_case(box):
+        """One box sharded by atoms over all ranks: (resident step, e2e step, H2D tensors, edges)."""
         from metatrain_b200.neighbors import neighbor_list
         from metatrain_b200.sharded import (build_shard, evaluate_sharded, shard_to_device,
                                             shard_to_host_tensors)
-        reps = (args.reps[0], args.reps[1], args.reps[2] * world)
-        box = replicate(water_384(), reps)
-        nl = neighbor_list(box["positions"], box["cell"], True, CUTOFF)
+        nl = box.get("nl") or neighbor_list(box["positions"], box["cell"], True, CUTOFF)
         shard = build_shard(box["positions"], box["cell"], nl, rank, world)
-        host = shard_to_host_tensors(shard, pin_memory=True)
+        host_l = shard_to_host_tensors(shard, pin_memory=True)
         host_pos = torch.tensor(box["positions"], dtype=torch.float32).pin_memory()
         host_z = torch.tensor(box["Z"], dtype=torch.int32).pin_memory()
         host_cell = torch.tensor(box["cell"], dtype=torch.float32).pin_memory()
-        lists = shard_to_device(shard, dev, host)
+        lists = shard_to_device(shard, dev, host_l)
         pos_d, z_d, cell_d = host_pos.to(dev), host_z.to(dev), host_cell.to(dev)
-        n_atoms = len(box["Z"]) // world          # per-GPU share of the one big box
-        n_edges = len(shard.centers)
-        n_total = len(box["Z"])
+        n_all = len(box["Z"])
+        e_h = torch.empty((1, 1), dtype=torch.float32).pin_memory()
+        f_h = torch.empty((n_all, 3), dtype=torch.float32).pin_memory()
 
-        def step_resident():
+        def resident():
             return evaluate_sharded(be, shard, pos_d, z_d, cell_d, target=TARGET, device_lists=lists)
 
-        e_host = torch.empty((1, 1), dtype=torch.float32).pin_memory()
-        f_host = torch.empty((n_total, 3), dtype=torch.float32).pin_memory()
-
-        def step_e2e():
-            lists_in = shard_to_device(shard, dev, host)
-            out = evaluate_sharded(be, shard, host_pos.to(dev, non_blocking=True),
-                                   host_z.to(dev, non_blocking=True),
-                                   host_cell.to(dev, non_blocking=True), target=TARGET,
-                                   device_lists=lists_in)
-            e_host.copy_(out["energies"], non_blocking=True)
-            f_host.copy_(out["dE_dpos"], non_blocking=True)
+        def e2e():
+            lists_in = shard_to_device(shard, dev, host_l)
+            o = evaluate_sharded(be, shard, host_pos.to(dev, non_blocking=True),
+                                 host_z.to(dev, non_blocking=True),
+                                 host_cell.to(dev, non_blocking=True), target=TARGET,
+                                 device_lists=lists_in)
+            e_h.copy_(o["energies"], non_blocking=True)
+            f_h.copy_(o["dE_dpos"], non_blocking=True)
             torch.cuda.synchronize()
 
-        h2d_tensors = list(host.values()) + [host_pos, host_z, host_cell]
+        return dict(resident=resident, e2e=e2e, h2d=list(host_l.values()) + [host_pos, host_z, host_cell],
+                    d2h=e_h.numel() * 4 + f_h.numel() * 4, n_edges=len(shard.centers), n_total=n_all,
+                    halo_edges=int(sum(len(a) for a in shard.halo_recv)))
+
+    def timed(fn, steps, warm=2):
+        """ms per step of `fn`, CUDA events, max over ranks."""
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    if sharded:
+        reps = (args.reps[0], args.reps[1], args.reps[2] * world)
+        box = replicate(water_384(), reps)
+        case = sharded_case(box)
+        step_resident, step_e2e, h2d_tensors = case["resident"], case["e2e"], case["h2d"]
+        n_total, n_edges, d2h = case["n_total"], case["n_edges"], case["d2h"]
+        n_atoms = n_total // world          # per-GPU share of the one big box
     else:
         box = replicate(water_384(), tuple(args.reps))
         host = make_batch([box], CUTOFF, pin_memory=True)
@@ -352,6 +388,7 @@ def run_petb200(args):
 
         e_host = torch.empty((1, 1), dtype=torch.float32).pin_memory()
         f_host = torch.empty((n_atoms, 3), dtype=torch.float32).pin_memory()
+        d2h = e_host.numel() * 4 + f_host.numel() * 4
 
         def step_e2e():
             dev_in = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -369,42 +406,54 @@ def run_petb200(args):
 
     for _ in range(max(args.warmup, 3)):
         out = step_resident()
-    # accuracy next to the throughput: tiled forces vs the reference's golden for the seed box
-    from helpers import load_golden
+
+    # ---- accuracy next to the throughput (any failure makes the run exit non-zero)
+    from helpers import load_golden, load_long_box
+    failures = []
     g = load_golden("water_384")
     tiles = n_total // 384
     f = out["dE_dpos"].cpu().numpy().reshape(tiles, 384, 3)
-    # tiles far from the origin see differently rounded fp32 positions than the seed box (the
-    # golden), so the golden check uses the first 27 tiles (the single-GPU box); sharded runs
-    # are additionally compared with a single-GPU evaluation of the SAME big box
-    force_err = float(np.abs(f[:27] - g["ref32_dE_dpos"][None]).max())
-    energy_err = float(abs(float(out["energies"]) / tiles - float(g["ref32_energies"].ravel()[0])) / 384)
-    force_err_single, golden_note = None, None
-    if sharded and rank == 0:
-        whole = {k: v.to(dev) for k, v in make_batch([box], CUTOFF).items()}
-        ref_out = evaluate(be, **whole, target=TARGET)
-        force_err_single = float((ref_out["dE_dpos"] - out["dE_dpos"]).abs().max())
-        del whole, ref_out
-        # The sharded box is several times longer than the seed box: its fp32 coordinates (up to
-        # ~400 A) round ~1e-5 A differently from the golden's inputs, which alone moves forces by
-        # ~3e-4 eV/A.  Parity with the reference is therefore established on the standard
-        # single-GPU box (same engine, same kernels) and carried over by the sharded-vs-single
-        # comparison above, which is exact.
-        small = {k: v.to(dev) for k, v in make_batch([replicate(water_384(), tuple(args.reps))], CUTOFF).items()}
-        out_small = evaluate(be, **small, target=TARGET)
-        t_small = small["positions"].shape[0] // 384
-        f_small = out_small["dE_dpos"].cpu().numpy().reshape(t_small, 384, 3)
-        golden_note = {"sharded_box_first_27_tiles_vs_seed_golden_eV_per_A": force_err,
-                       "why": "fp32 rounding of the larger box's coordinates (inputs differ from the golden's)"}
-        force_err = float(np.abs(f_small - g["ref32_dE_dpos"][None]).max())
-        energy_err = float(abs(float(out_small["energies"]) / t_small - float(g["ref32_energies"].ravel()[0])) / 384)
-        del small, out_small
+    accuracy = {}
+    if not sharded:
+        # 27 periodic copies of the seed box: every tile must reproduce the unmodified
+        # reference's forces for the seed box (tests/golden/water_384.npz)
+        force_err = float(np.abs(f - g["ref32_dE_dpos"][None]).max())
+        energy_err = float(abs(float(out["energies"]) / tiles - float(g["ref32_energies"].ravel()[0])) / 384)
+    else:
+        # (1) the sharded evaluation against a single-GPU evaluation of the SAME box
+        force_err_single = None
+        if rank == 0:
+            whole = {k: v.to(dev) for k, v in make_batch([box], CUTOFF).items()}
+            ref_out = evaluate(be, **whole, target=TARGET)
+            force_err_single = float((ref_out["dE_dpos"] - out["dE_dpos"]).abs().max())
+            del whole, ref_out
+            torch.cuda.empty_cache()
+            if not force_err_single <= 1e-6:
+                failures.append(f"sharded vs single-GPU forces differ by {force_err_single:.3e}")
+        accuracy["force_max_abs_err_vs_single_gpu_eV_per_A"] = force_err_single
+        # (2) the sharded path against the UNMODIFIED reference on an elongated box fed with the
+        # same fp32-rounded coordinates (tests/golden/water_long_1x1x24.npz: 9 216 atoms, z to
+        # 376 A; reference fp32 and fp64)
+        lg = load_long_box("water_long_1x1x24")
+        long_box = dict(positions=lg["positions"].astype(np.float64), cell=lg["cells"][0].astype(np.float64),
+                        Z=lg["species"], nl=lg["nl"])
+        lo = sharded_case(long_box)["resident"]()
+        fl = lo["dE_dpos"].cpu().numpy()
+        force_err = float(np.abs(fl - lg["ref64_dE_dpos"]).max())
+        accuracy["long_box_1x1x24_force_err_vs_reference_fp64"] = force_err
+        accuracy["long_box_1x1x24_force_err_vs_reference_fp32"] = float(np.abs(fl - lg["ref32_dE_dpos"]).max())
+        accuracy["long_box_1x1x24_reference_fp32_vs_fp64"] = float(np.abs(lg["ref32_dE_dpos"] - lg["ref64_dE_dpos"]).max())
+        energy_err = float(abs(float(lo["energies"]) - float(lg["ref64_energies"].ravel()[0])) / len(fl))
+        # (3) the timed box itself: all tiles against the seed golden; coordinates up to
+        # ~47 * world A from the origin are rounded differently from the golden's inputs, which
+        # alone moves forces by ~1e-4 (see (2) for the like-for-like check)
+        accuracy["timed_box_all_tiles_vs_seed_golden"] = float(np.abs(f - g["ref32_dE_dpos"][None]).max())
+        del lo
         torch.cuda.empty_cache()
-    if sharded:
-        # the comparison above released the allocator cache on rank 0: warm it up again so the
-        # timed region does not pay cudaMalloc
-        for _ in range(2):
+        for _ in range(2):   # the checks released the allocator cache: warm it up again
             step_resident()
+    if not force_err <= 1e-4:
+        failures.append(f"force max-abs-err {force_err:.3e} eV/A exceeds 1e-4")
 
     sampler = ClockSampler(local)
     barrier()
@@ -441,7 +490,30 @@ def run_petb200(args):
         e2e_sec = float(t)
     e2e_value = world * n_atoms * args.steps / e2e_sec
     h2d = sum(v.numel() * v.element_size() for v in h2d_tensors)
-    d2h = e_host.numel() * 4 + f_host.numel() * 4
+
+    # ---- BASELINE.json's other multi-GPU readings of the metric (extra keys, fewer steps)
+    strong, config4 = None, None
+    if sharded:
+        # strong scaling: the SAME 10 368-atom box over all GPUs ("10k-atom box @1/2/4/8")
+        sbox = replicate(water_384(), tuple(args.reps))
+        sc = sharded_case(sbox)
+        ms = timed(sc["resident"], args.steps)
+        strong = {"atoms": sc["n_total"], "n_gpus": world, "ms_per_step": ms,
+                  "value": sc["n_total"] / ms * 1e3, "unit": "atom-steps/s", "scaling": "strong",
+                  "edges_per_gpu": sc["n_edges"], "halo_edges_per_gpu": sc["halo_edges"]}
+        del sc
+        torch.cuda.empty_cache()
+        if world == 8 or args.config4:
+            # BASELINE.json configs[3]: the 6x6x7 tiling = 96 768 atoms over the GPUs of the box
+            cbox = replicate(water_384(), (6, 6, 7))
+            cc = sharded_case(cbox)
+            ms = timed(cc["resident"], max(args.steps // 2, 3))
+            config4 = {"workload": "water 6x6x7 tiling, 96 768 atoms (BASELINE.json configs[3])",
+                       "atoms": cc["n_total"], "n_gpus": world, "ms_per_step": ms,
+                       "value": cc["n_total"] / ms * 1e3, "unit": "atom-steps/s",
+                       "edges_per_gpu": cc["n_edges"], "halo_edges_per_gpu": cc["halo_edges"]}
+            del cc
+            torch.cuda.empty_cache()
 
     # MD-engine style step: only positions go host->device, the neighbor list is rebuilt on
     # the GPU every step (petb200_nl_count / nl_fill), energies + forces come back
@@ -521,52 +593,82 @@ def run_petb200(args):
                   f"{n_l // 3:3d} launches/step {t_s / 3 * 1e3:8.3f} ms/step  {by / t_s * 1e-9:7.0f} GB/s",
                   file=sys.stderr)
     hbm, tf_burst, tf_sust, which = peaks()
-    g_t, g_flops, g_n, g_bytes = tot["gemm"]
-    c_t, c_edges, c_n, _ = tot["combine_ln_fwd"]
-    gemm_tflops = g_flops / g_t * 1e-12
-    gemm_gbs = g_bytes / g_t * 1e-9
-    scatter_bytes = 2060.0 * c_edges  # 2x512 B read + 4 B rev + 1024 B write + 8 B stats per edge
-    scatter_gbs = scatter_bytes / c_t * 1e-9
     step_ms = sec / args.steps * 1e3
-    # The contractions are tall-skinny (M = edges, N, K <= 1024): arithmetic intensity
-    # 32..128 flop/B is below the ridge (~215), so the dominant kernel is HBM-bound; the
-    # tensor-pipe view is reported next to it.
-    # DRAM traffic per launch from the committed ncu launch list of this command
-    # (profiles/r1_launches_final.md: dram__bytes_read + dram__bytes_write summed over the 624
-    # gemm_tc launches it holds, 179 946 MB); only quoted for the workload it was captured on
-    ncu_traffic = 179.946e9 / 624 if (args.precision == "bf16x3" and tuple(args.reps) == tuple(REPS)) else None
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel family,
+    # written by tools/summarize_launches.py --json from the committed ncu launch list of this
+    # command; only quoted for the workload it was captured on
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.precision == "bf16x3" and tuple(args.reps) == tuple(REPS) and not sharded:
+            traffic = tj.get("bytes_per_launch", {})
+            traffic_src = tj.get("source")
+    except (OSError, ValueError):
+        pass
+
+    def traffic_of(prefix):
+        hits = [(k, v) for k, v in traffic.items() if k.startswith(prefix)]
+        if not hits:
+            return None
+        n = sum(v["launches"] for _, v in hits)
+        return sum(v["bytes_per_launch"] * v["launches"] for _, v in hits) / n
+
+    # per C-ABI entry point: time, algorithmic flops / bytes, both roofline views
+    kernels = {}
+    for k, (t_s, work, n_l, byt) in tot.items():
+        entry = {"ms_per_step": t_s / 3 * 1e3, "launches_per_step": n_l // 3,
+                 "share_of_step": (t_s / 3 * 1e3) / step_ms}
+        if byt:
+            entry.update(achieved_gbs=byt / t_s * 1e-9, hbm_frac=byt / t_s * 1e-9 / hbm,
+                         algorithmic_bytes_per_launch=byt / n_l)
+        if work and k != "combine_ln_fwd":
+            entry.update(achieved_tflops=work / t_s * 1e-12, tensor_frac=work / t_s * 1e-12 / tf_sust,
+                         flops_per_launch=work / n_l)
+        kernels[k] = entry
+    # the dominant kernel family of the step: the dense contractions (gemm_tc_kernel).  SURVEY 8(d)
+    # classifies them as tensor work: headline = algorithmic flops vs the measured sustained bf16
+    # peak; the HBM view (they are tall-skinny, 32..128 flop/B) is the sub-key.
+    g_t, g_flops, g_n, g_bytes = tot["gemm"]
+    gemm_tflops = g_flops / g_t * 1e-12
     roofline = {
-        "kernel": "gemm (all dense contractions of the step: gemm_tc_kernel / gemm_simt_kernel)",
-        "bound": "hbm", "achieved": gemm_gbs, "peak": hbm, "unit": "GB/s", "frac": gemm_gbs / hbm,
-        "traffic": ncu_traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1_launches_final.md)",
-        "algorithmic_bytes_per_launch": g_bytes / g_n, "peak_source": which,
-        "algorithmic_bytes_per_step": g_bytes / 3, "launches_per_step": g_n // 3,
+        "kernel": "gemm (all dense contractions of the step that are not inside a fused kernel: "
+                  "gemm_tc_kernel)",
+        "bound": "tensor", "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
+        "frac": gemm_tflops / tf_sust, "traffic": traffic_of("gemm_tc_kernel"),
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)",
+        "flops_per_launch": g_flops / g_n, "launches_per_step": g_n // 3,
         "ms_per_step": g_t / 3 * 1e3, "share_of_step": (g_t / 3 * 1e3) / step_ms,
-        "precision": args.precision,
-        "tensor_view": {"achieved_tflops": gemm_tflops, "peak_tflops": tf_sust,
-                        "frac": gemm_tflops / tf_sust, "flops_per_step": g_flops / 3},
+        "precision": args.precision + " (3 MMAs per product: the issued-MMA ceiling is peak / 3)",
+        "peak_source": which + " (MEASURED_PEAKS.json bf16_tflops_sustained)" if which == "measured" else which,
+        "hbm_view": {"achieved": g_bytes / g_t * 1e-9, "peak": hbm, "unit": "GB/s",
+                     "frac": g_bytes / g_t * 1e-9 / hbm, "algorithmic_bytes_per_launch": g_bytes / g_n},
     }
-    edge_scatter = {
-        "kernel": "combine_ln_fwd (message reversal + LayerNorm)", "bound": "hbm",
-        "achieved": scatter_gbs, "peak": hbm, "unit": "GB/s", "frac": scatter_gbs / hbm,
-        "traffic": ((3771e6 + 5577e6) / 16 if tuple(args.reps) == tuple(REPS) else None),
-        "traffic_unit": "bytes per launch (ncu, profiles/r1_launches_final.md)",
-        "algorithmic_bytes_per_launch": scatter_bytes / c_n,
-        "note": "DRAM traffic is below the algorithmic bytes: every `out` row is read twice (own edge + "
-                "as the reversed row of its partner) and the second read is served from L2",
-        "peak_source": which, "avg_launch_us": c_t / c_n * 1e6,
-    }
-    attn = {k: {"ms_per_step": tot[k][0] / 3 * 1e3, "launches_per_step": tot[k][2] // 3,
-                "bound": "hbm", "achieved": tot[k][3] / tot[k][0] * 1e-9, "peak": hbm, "unit": "GB/s",
-                "frac": tot[k][3] / tot[k][0] * 1e-9 / hbm, "peak_source": which}
-            for k in ("attention_fwd", "attention_bwd") if k in tot}
-    # fused feed-forward kernels (mlp_fused.cu): HBM view on the algorithmic MINIMUM bytes and the
-    # tensor view on algorithmic flops (the 2-term split issues 3x as many MMAs)
-    fused = {k: {"ms_per_step": tot[k][0] / 3 * 1e3, "launches_per_step": tot[k][2] // 3,
-                 "achieved_gbs": tot[k][3] / tot[k][0] * 1e-9, "hbm_frac": tot[k][3] / tot[k][0] * 1e-9 / hbm,
-                 "achieved_tflops": tot[k][1] / tot[k][0] * 1e-12,
-                 "tensor_frac": tot[k][1] / tot[k][0] * 1e-12 / tf_sust, "peak_source": which}
-             for k in ("mlp_fwd", "mlp_bwd") if k in tot}
+    # whole step: SURVEY 8(d) algorithmic flops (2.046 x forward) over the measured step time
+    deg = np.bincount(resident["centers"].cpu().numpy(), minlength=n_atoms) if not sharded else None
+    whole = None
+    if deg is not None:
+        f_fwd = 2001152.0 * n_edges + 4292864.0 * n_atoms + 2048.0 * float(((deg + 1.0) ** 2).sum())
+        f_step = 2.046 * f_fwd
+        whole = {"flops_per_step": f_step, "achieved_tflops": f_step / (step_ms * 1e-3) * 1e-12,
+                 "peak_tflops": tf_sust, "frac": f_step / (step_ms * 1e-3) * 1e-12 / tf_sust}
+    edge_scatter = None
+    if "combine_ln_fwd" in tot:
+        c_t, c_edges, c_n, _ = tot["combine_ln_fwd"]
+        scatter_bytes = 2060.0 * c_edges  # 2x512 B read + 4 B rev + 1024 B write + 8 B stats per edge
+        edge_scatter = {
+            "kernel": "combine_ln_fwd (message reversal + LayerNorm)", "bound": "hbm",
+            "achieved": scatter_bytes / c_t * 1e-9, "peak": hbm, "unit": "GB/s",
+            "frac": scatter_bytes / c_t * 1e-9 / hbm, "traffic": traffic_of("combine_ln_fwd_kernel"),
+            "algorithmic_bytes_per_launch": scatter_bytes / c_n, "peak_source": which,
+            "avg_launch_us": c_t / c_n * 1e6}
+    if "edge_exchange" in tot:
+        c_t, c_edges, c_n, byt = tot["edge_exchange"]
+        edge_scatter = {
+            "kernel": "edge_exchange (the edge scatter: message reversal gather + per-row LayerNorm "
+                      "statistics, no intermediate written)", "bound": "hbm",
+            "achieved": byt / c_t * 1e-9, "peak": hbm, "unit": "GB/s", "frac": byt / c_t * 1e-9 / hbm,
+            "traffic": traffic_of("edge_exchange_kernel"),
+            "algorithmic_bytes_per_launch": byt / c_n, "peak_source": which, "avg_launch_us": c_t / c_n * 1e6}
 
     if world > 1:
         dist.barrier()
@@ -580,24 +682,16 @@ def run_petb200(args):
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (2-term split, fp32 accumulate)",
                   "bf16": "bf16"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"PET default hypers, periodic water box {args.reps[0]}x{args.reps[1]}x"
-                               f"{args.reps[2]} tiling of the 384-atom fixture, cutoff 4.5 A, "
-                               "energy + forces (BASELINE.json configs[1])",
-                   "atoms_per_gpu": n_atoms, "edges_per_gpu": n_edges,
-                   "parallelism": ("1 GPU" if world == 1 else
-                                   f"one {n_total}-atom box sharded by atoms over {world} GPUs, halo "
-                                   "all-to-all-v + all-reduce over NCCL" if sharded else
-                                   f"{world} independent boxes (1 per GPU)"),
-                   "cache": "per-step working set (~8 GB of activations) >> 126 MB L2; no explicit flush"},
+        "config": workload_config(tuple(args.reps), world, args.multi),
+        "details": {"atoms_total": n_total, "edges_per_gpu": n_edges},
         "force_max_abs_err_eV_per_A": force_err, "energy_abs_err_eV_per_atom": energy_err,
-        "force_max_abs_err_vs_single_gpu_eV_per_A": force_err_single,
-        "force_err_note": golden_note,
+        "accuracy": accuracy, "parity_failures": failures,
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec / args.steps * 1e3},
         "e2e_device_neighbor_list": md,
+        "strong_scaling": strong, "config4": config4,
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": roofline, "edge_scatter": edge_scatter, "attention": attn,
-        "fused_feed_forward": fused,
+        "roofline": roofline, "whole_step": whole, "edge_scatter": edge_scatter, "kernels": kernels,
     }
     if not args.no_cpu_baseline and world == 1:
         v, dt, n = time_oracle((2, 2, 2), 3, 1)  # ~10-15 s of CPU work on 16 cores
@@ -606,6 +700,9 @@ def run_petb200(args):
             "sample": f"water 2x2x2 tiling ({n} atoms) of the workload, 3 steps after 1 warm-up "
                       f"({dt:.2f} s/step)"}
     print(json.dumps(line))
+    if failures:
+        print("PARITY FAILURE: " + "; ".join(failures), file=sys.stderr)
+        sys.exit(3)
 
 
 def main():

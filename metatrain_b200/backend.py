@@ -42,6 +42,13 @@ def _require_cuda(t: Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
             f"B200PETBackend.{what}: expected CUDA tensors; this backend has no CPU path")
+    # every kernel is launched on the CURRENT device's current stream (lib.call): tensors living
+    # on another device would be touched from the wrong context / an unordered stream
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f"B200PETBackend.{what}: tensors live on {t.device} but the current CUDA device is "
+            f"cuda:{torch.cuda.current_device()}; wrap the call in `with torch.cuda.device(...)` "
+            "or call torch.cuda.set_device first")
 
 
 # ------------------------------------------------------------------ autograd stages
@@ -133,9 +140,9 @@ class _Features(torch.autograd.Function):
             return d_vec, d_dist, d_fc, None, None, None, None
         d_h, d_m = grads
         if d_h is None:
-            d_h = torch.zeros((topo.n_atoms, ctx.backend.d_node), device=ctx.fc.device)
+            d_h = torch.zeros((topo.n_atoms, ctx.backend.d_node), device=ctx.fc.device, dtype=torch.float32)
         if d_m is None:
-            d_m = torch.zeros((topo.n_edges, ctx.backend.d_pet), device=ctx.fc.device)
+            d_m = torch.zeros((topo.n_edges, ctx.backend.d_pet), device=ctx.fc.device, dtype=torch.float32)
         d_vec, d_dist, d_fc = engine.features_backward(
             ctx.pw, ctx.backend.hypers, topo, ctx.fc.contiguous(), ctx.saved, d_h, d_m, ctx.prec)
         return d_vec, d_dist, d_fc, None, None, None, None
@@ -171,7 +178,7 @@ class _CsrToNef(torch.autograd.Function):
         d = 1
         for s in x.shape[1:]:
             d *= s
-        out = torch.empty((topo.n_atoms, topo.max_row) + tuple(x.shape[1:]), device=x.device)
+        out = torch.empty((topo.n_atoms, topo.max_row) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
         call("csr_to_nef", ptr(x.contiguous()), ptr(topo.row_ptr), topo.n_atoms, topo.n_edges,
              topo.max_row, d, ptr(out))
         ctx.topo, ctx.d, ctx.tail = topo, d, tuple(x.shape[1:])
@@ -180,7 +187,7 @@ class _CsrToNef(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         topo = ctx.topo
-        out = torch.empty((topo.n_edges,) + ctx.tail, device=g.device)
+        out = torch.empty((topo.n_edges,) + ctx.tail, device=g.device, dtype=torch.float32)
         call("nef_to_csr", ptr(g.contiguous()), ptr(topo.row_ptr), ptr(topo.ctr), topo.n_atoms,
              topo.n_edges, topo.max_row, ctx.d, ptr(out))
         return out, None
@@ -195,7 +202,7 @@ class _NefToCsr(torch.autograd.Function):
         d = 1
         for s in tail:
             d *= s
-        out = torch.empty((topo.n_edges,) + tail, device=x.device)
+        out = torch.empty((topo.n_edges,) + tail, device=x.device, dtype=torch.float32)
         call("nef_to_csr", ptr(x.contiguous()), ptr(topo.row_ptr), ptr(topo.ctr), topo.n_atoms,
              topo.n_edges, topo.max_row, d, ptr(out))
         ctx.topo, ctx.d, ctx.tail = topo, d, tail
@@ -204,7 +211,7 @@ class _NefToCsr(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         topo = ctx.topo
-        out = torch.empty((topo.n_atoms, topo.max_row) + ctx.tail, device=g.device)
+        out = torch.empty((topo.n_atoms, topo.max_row) + ctx.tail, device=g.device, dtype=torch.float32)
         call("csr_to_nef", ptr(g.contiguous()), ptr(topo.row_ptr), topo.n_atoms, topo.n_edges,
              topo.max_row, ctx.d, ptr(out))
         return out, None
@@ -341,16 +348,29 @@ class B200PETBackend(PETParameters):
         return self.preprocess_on_topology(positions, cells, topo, z_nodes, cutoff_width_adaptive)
 
     def build_topology(self, positions, centers, neighbors, species, cells, cell_shifts,
-                       system_indices, keep_all_pairs: bool = False):
+                       system_indices, list_cutoff: Optional[float] = None):
         """The integer half of ``preprocess`` (a4-a6): CSR rows, reverse-edge map.  The one
-        device->host read of the stage (edge count) happens here.  ``keep_all_pairs`` keeps the
-        pairs of a skin list that are beyond the cutoff (their cutoff factor is 0); the topology
-        then stays valid while the list does — what ``md.GraphedEvaluator`` replays."""
+        device->host read of the stage (edge count) happens here.  ``list_cutoff`` (> the model
+        cutoff) keeps the pairs of a skin list out to that radius (beyond the model cutoff their
+        cutoff factor is 0); the topology then stays valid while the list does — what
+        ``md.GraphedEvaluator`` replays.  The pairs are always selected by the symmetric filter
+        (``petb200_nl_filter_count``), never taken from the caller's list unfiltered: a device
+        neighbor list may accept a pair at its radius in one direction only."""
         _require_cuda(positions, "preprocess")
-        z_nodes = self.species_to_species_index[species.long()]
+        table = self.species_to_species_index
+        if table.device != positions.device:
+            raise RuntimeError(f"B200PETBackend.preprocess: inputs on {positions.device}, parameters on "
+                               f"{table.device}")
+        z = species.long()
+        # atomic numbers outside the table or not in atomic_types: the reference fails in
+        # nn.Embedding (index out of range); here the flag travels with the stage's one
+        # device->host read and raises a ValueError
+        outside = (z < 0) | (z >= table.shape[0])
+        z_nodes = torch.where(outside, torch.full_like(z, -1), table[z.clamp(0, table.shape[0] - 1)])
         topo = engine.build_topology(positions, centers, neighbors, cell_shifts, cells,
                                      system_indices, z_nodes,
-                                     float("inf") if keep_all_pairs else self.cutoff)
+                                     self.cutoff if list_cutoff is None else float(list_cutoff),
+                                     species_for_error=species)
         return topo, z_nodes
 
     def preprocess_on_topology(self, positions, cells, topo, z_nodes,

@@ -101,7 +101,8 @@ class Topology:
 
 def build_topology(positions: Tensor, centers: Tensor, neighbors: Tensor, cell_shifts: Tensor,
                    cells: Tensor, system_indices: Tensor, z_nodes: Tensor, cutoff: float,
-                   check_symmetric: bool = True, n_rows: Optional[int] = None) -> Topology:
+                   check_symmetric: bool = True, n_rows: Optional[int] = None,
+                   species_for_error: Optional[Tensor] = None) -> Topology:
     """a4-a6 of SURVEY.md 8(a): filter pairs beyond the cutoff, CSR by centre (stable),
     reverse-edge map.  One device->host read of (E, max neighbours, missing reverses) —
     the reference syncs at the same place (structures.py:292-294)."""
@@ -125,11 +126,17 @@ def build_topology(positions: Tensor, centers: Tensor, neighbors: Tensor, cell_s
     workspace = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     row_ptr = torch.empty(n_atoms + 1, device=dev, dtype=i32)
     perm = torch.empty(max(n_pairs, 1), device=dev, dtype=i32)
-    stats = torch.zeros(3, device=dev, dtype=i32)  # E_kept, max row, missing reverses
+    stats = torch.zeros(4, device=dev, dtype=i32)  # E_kept, max row, missing reverses, bad species
     call("csr_build", ptr(centers), ptr(keep), ptr(counts), n_pairs, n_atoms, ptr(row_ptr),
          ptr(perm), ptr(stats), ptr(workspace), ws_bytes)
+    stats[3] = (z_nodes < 0).any()
     # the edge count sizes every later buffer: one small D2H read
-    n_edges, max_row = (int(v) for v in stats[:2].tolist())
+    n_edges, max_row, _, bad_species = (int(v) for v in stats.tolist())
+    if bad_species:
+        bad = (species_for_error if species_for_error is not None else z_nodes)[z_nodes < 0]
+        raise ValueError("atomic types " + str(sorted(set(int(v) for v in bad.tolist())))
+                         + " are not in the model's atomic_types (the species embedding has no row "
+                         "for them; the reference raises an index error in nn.Embedding here)")
     ctr = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
     col = torch.empty(max(n_edges, 1), device=dev, dtype=i32)[:n_edges]
     shift = torch.empty((max(n_edges, 1), 3), device=dev, dtype=i32)[:n_edges]
@@ -137,7 +144,7 @@ def build_topology(positions: Tensor, centers: Tensor, neighbors: Tensor, cell_s
     call("csr_gather", ptr(perm), ptr(centers), ptr(neighbors), ptr(cell_shifts), n_edges,
          ptr(ctr), ptr(col), ptr(shift))
     call("reverse_map", ptr(row_ptr), ptr(ctr), ptr(col), ptr(shift), n_edges, n_atoms, ptr(rev),
-         ptr(stats[2:]))
+         ptr(stats[2:3]))
     if check_symmetric and n_edges > 0:
         missing = int(stats[2].item())
         if missing:
@@ -371,9 +378,9 @@ def edges_backward(topo: Topology, vec, dist, d_vec, d_dist, d_fc, cutoff, width
     halo = topo.halo
     H = halo.n_ghost if halo is not None else 0
     scratch = _empty((max(E + H, 1), 3), vec)
-    d_pos = (torch.zeros((topo.n_positions, 3), device=vec.device) if topo.n_positions > N
+    d_pos = (torch.zeros((topo.n_positions, 3), device=vec.device, dtype=torch.float32) if topo.n_positions > N
              else _empty((N, 3), vec))
-    d_cells = torch.zeros((topo.n_structures, 3, 3), device=vec.device) if need_cells else None
+    d_cells = torch.zeros((topo.n_structures, 3, 3), device=vec.device, dtype=torch.float32) if need_cells else None
     if halo is None:
         call("edges_bwd", ptr(d_vec), ptr(d_dist), ptr(d_fc), ptr(vec), ptr(dist),
              ptr(topo.row_ptr), ptr(topo.ctr), ptr(topo.rev), ptr(topo.shift),
@@ -483,7 +490,7 @@ def adaptive_edges_backward(topo: Topology, ad: AdaptiveCutoff, vec, dist, d_vec
     outer = ad.outer
     scratch = _empty((max(E, 1), 3), vec)
     d_pos = _empty((N, 3), vec)
-    d_cells = torch.zeros((topo.n_structures, 3, 3), device=vec.device) if need_cells else None
+    d_cells = torch.zeros((topo.n_structures, 3, 3), device=vec.device, dtype=torch.float32) if need_cells else None
     d_rc = _empty((max(E, 1),), vec)
     call("edges_bwd_rc", ptr(d_vec), ptr(d_dist), ptr(d_fc), ptr(vec), ptr(dist), ptr(topo.row_ptr),
          ptr(topo.ctr), ptr(topo.rev), ptr(topo.shift), ptr(topo.system_of_atom), N, E,
@@ -497,7 +504,7 @@ def adaptive_edges_backward(topo: Topology, ad: AdaptiveCutoff, vec, dist, d_vec
              ptr(ad.clamp_pass), N, ptr(outer.ctr), ptr(ad.dist_outer), ptr(ad.r_root), outer.n_edges,
              ad.width, ptr(coef), ptr(d_dist_o))
     else:
-        ones = torch.ones((max(N, 1),), device=vec.device)
+        ones = torch.ones((max(N, 1),), device=vec.device, dtype=torch.float32)
         call("adaptive_grid_bwd", ptr(topo.row_ptr), ptr(topo.rev), ptr(d_rc), ptr(ones), N,
              ptr(outer.ctr), ptr(ad.dist_outer), ptr(ad.grad_d), outer.n_edges, ad.width,
              ad.grid[0], ad.grid[1], ad.grid[2], ptr(coef), ptr(d_dist_o))
@@ -784,14 +791,19 @@ def conditioning_table(pw: PackedWeights, charge: Tensor, spin_multiplicity: Ten
     C = pw.cond
     dev = C["w1"].device
     B, dn = charge.shape[0], C["w2"].shape[0]
-    cat = torch.empty((B, 2 * dn), device=dev)
+    cat = torch.empty((B, 2 * dn), device=dev, dtype=torch.float32)
     ci = (charge.to(dev) + C["max_charge"]).to(torch.int32).contiguous()
     si = (spin_multiplicity.to(dev) - 1).to(torch.int32).contiguous()
+    # the embedding kernel does not bounds-check: same limits as SystemConditioning.validate
+    # (conditioning.py:58-79), enforced here too for callers that skipped it (B values)
+    if B and bool(((ci < 0) | (ci >= C["charge"].shape[0]) | (si < 0) | (si >= C["spin"].shape[0])).any()):
+        raise ValueError("system conditioning: charge / spin multiplicity outside the embedding tables "
+                         f"(|charge| <= {C['max_charge']}, 1 <= spin multiplicity <= {C['spin'].shape[0]})")
     call("embedding", ptr(C["charge"]), ptr(ci), B, dn, ptr(cat), 2 * dn)
     call("embedding", ptr(C["spin"]), ptr(si), B, dn, ptr(cat[:, dn:]), 2 * dn)
-    hid, pre = torch.empty((B, dn), device=dev), torch.empty((B, dn), device=dev)
+    hid, pre = (torch.empty((B, dn), device=dev, dtype=torch.float32) for _ in range(2))
     gemm(cat, C["w1"], hid, bias=C["b1"], epilogue=EPI_SILU, aux_out=pre, precision=PREC_FP32)
-    table = torch.empty((B, dn), device=dev)
+    table = torch.empty((B, dn), device=dev, dtype=torch.float32)
     gemm(hid, C["w2"], table, bias=C["b2"], precision=PREC_FP32)
     return table
 
@@ -961,9 +973,9 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
     ref = fc
-    d_vec = torch.zeros((E, 3), device=ref.device)
-    d_dist = torch.zeros((E,), device=ref.device)
-    d_fc = torch.zeros((E,), device=ref.device)
+    d_vec = torch.zeros((E, 3), device=ref.device, dtype=torch.float32)
+    d_dist = torch.zeros((E,), device=ref.device, dtype=torch.float32)
+    d_fc = torch.zeros((E,), device=ref.device, dtype=torch.float32)
     d_m = d_m.contiguous().clone()  # accumulated in place below
     d_h = d_h.contiguous()
     n_layers = len(pw.gnn)
@@ -998,20 +1010,20 @@ def features_backward_residual(pw: PackedWeights, hyp, topo: Topology, fc, saved
     None).  Returns (d_vec [E,3], d_dist [E], d_fc [E])."""
     N, E = topo.n_atoms, topo.n_edges
     d, dn = hyp["d_pet"], hyp["d_node"]
-    d_vec = torch.zeros((E, 3), device=fc.device)
-    d_dist = torch.zeros((E,), device=fc.device)
-    d_fc = torch.zeros((E,), device=fc.device)
+    d_vec = torch.zeros((E, 3), device=fc.device, dtype=torch.float32)
+    d_dist = torch.zeros((E,), device=fc.device, dtype=torch.float32)
+    d_fc = torch.zeros((E,), device=fc.device, dtype=torch.float32)
     d_m_next = None  # gradient w.r.t. the input messages of layer l + 1
     for l in range(len(pw.gnn) - 1, -1, -1):
-        d_h = d_nodes[l].contiguous() if d_nodes[l] is not None else torch.zeros((N, dn), device=fc.device)
-        d_t = d_edges[l].contiguous().clone() if d_edges[l] is not None else torch.zeros((E, d), device=fc.device)
+        d_h = d_nodes[l].contiguous() if d_nodes[l] is not None else torch.zeros((N, dn), device=fc.device, dtype=torch.float32)
+        d_t = d_edges[l].contiguous().clone() if d_edges[l] is not None else torch.zeros((E, d), device=fc.device, dtype=torch.float32)
         d_m = None
         if d_m_next is not None:
             # m_{l+1} = 0.5 (m_l + t_l[rev]):  d_t[e] += 0.5 d_m_next[rev[e]],  d_m_l = 0.5 d_m_next
             d_m = _empty((E, d), fc)
             call("avg_reverse_bwd", ptr(d_m_next), ptr(topo.rev), E, d, ptr(d_t), ptr(d_m))
         elif l > 0:
-            d_m = torch.zeros((E, d), device=fc.device)
+            d_m = torch.zeros((E, d), device=fc.device, dtype=torch.float32)
         _gnn_backward(pw, pw.gnn[l], saved[l], hyp, topo, fc, d_h, d_t, d_m if l > 0 else None, d_vec, d_dist,
                       d_fc, False, prec)
         d_m_next = d_m if l > 0 else None
@@ -1049,7 +1061,7 @@ def predict_backward(pw: PackedWeights, topo: Topology, name: str, fc, saved, d_
     n_out = H["wn"].shape[0]
     d_atomic = d_atomic.contiguous()
     d_n2p, d_e2p = _empty((N, dh), fc), _empty((E, dh), fc)
-    d_fc = torch.zeros((E,), device=fc.device)
+    d_fc = torch.zeros((E,), device=fc.device, dtype=torch.float32)
     call("readout_bwd", ptr(d_atomic), ptr(saved["pe"]), ptr(H["wn"]), ptr(H["we"]), ptr(fc),
          ptr(topo.ctr), ptr(saved["n2p"]), ptr(saved["e2p"]), N, E, dh, n_out, ptr(d_n2p),
          ptr(d_e2p), ptr(d_fc))

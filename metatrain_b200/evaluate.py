@@ -21,7 +21,7 @@ class _SumOverAtoms(torch.autograd.Function):
     @staticmethod
     def forward(ctx, atomic, struct_ptr, system_indices):
         n_struct = struct_ptr.shape[0] - 1
-        out = torch.empty((n_struct, atomic.shape[1]), device=atomic.device)
+        out = torch.empty((n_struct, atomic.shape[1]), device=atomic.device, dtype=torch.float32)
         call("sum_over_atoms", ptr(atomic.contiguous()), ptr(struct_ptr), n_struct,
              atomic.shape[1], ptr(out))
         ctx.save_for_backward(system_indices)

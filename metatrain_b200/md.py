@@ -101,9 +101,12 @@ class GraphedEvaluator:
             self._pos.copy_(pos)
         if rebuilt:
             self._list_id = self.verlet.n_builds
+            # the skin list is filtered by the model's exactly symmetric pair test at the list
+            # radius (the device list's own acceptance test is not bitwise symmetric for pairs that
+            # cross a periodic boundary; its 2e-6 margin makes it a superset of this selection)
             self._topo, self._z_nodes = self.backend.build_topology(
                 pos, centers, neighbors, self.species, self.cells, shifts, self.system_indices,
-                keep_all_pairs=True)
+                list_cutoff=self.backend.cutoff + self.verlet.skin)
             self._graph = None
             if self.use_graph:
                 self._capture()

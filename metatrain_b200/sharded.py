@@ -7,7 +7,8 @@ independent; the only cross-atom dataflow is the reversed-message gather
 and, in the force path, the scatter of edge gradients onto the neighbour atom
 (autograd of ``structures.py:220``).  So:
 
-* atoms are split into ``world`` spatial slabs (equal atom counts along the longest cell axis);
+* atoms are split into ``world`` spatial bricks (recursive equal-count bisection along the cell
+  axes, ``brick_owner``; or slabs along the longest axis, ``slab_owner``);
   a rank owns its atoms and **all edges centred on them** (full CSR rows -> attention stays local);
 * a *halo edge* is an owned edge ``(i -> j, S)`` whose neighbour ``j`` lives on a peer ``p``.  Its
   reversed edge ``(j -> i, -S)`` is one of ``p``'s halo edges towards us — the two sets are
@@ -63,6 +64,47 @@ def slab_owner(positions: np.ndarray, cell: np.ndarray, world: int) -> np.ndarra
     return owner
 
 
+def _grid_factors(world: int, lengths: np.ndarray):
+    """(pa, pb, pc) with pa pb pc = world minimising the cut surface of bricks in a cell with the
+    given edge lengths."""
+    best, best_cost = (1, 1, world), None
+    for pa in range(1, world + 1):
+        if world % pa:
+            continue
+        for pb in range(1, world // pa + 1):
+            if (world // pa) % pb:
+                continue
+            pc = world // (pa * pb)
+            # cut planes per axis x area of one plane
+            cost = ((pa > 1) * pa * lengths[1] * lengths[2] + (pb > 1) * pb * lengths[0] * lengths[2]
+                    + (pc > 1) * pc * lengths[0] * lengths[1])
+            if best_cost is None or cost < best_cost - 1e-9:
+                best, best_cost = (pa, pb, pc), cost
+    return best
+
+
+def brick_owner(positions: np.ndarray, cell: np.ndarray, world: int) -> np.ndarray:
+    """Owner rank of every atom: ``pa x pb x pc`` bricks (recursive equal-count bisection along
+    the three cell axes), which cut ~(pa + pb + pc) planes instead of the ``world`` planes of
+    slabs: at 8 ranks a cubic box loses 3 x 2 half-planes of halo instead of 8."""
+    frac = positions @ np.linalg.inv(cell)
+    frac -= np.floor(frac)
+    grid = _grid_factors(world, np.linalg.norm(cell, axis=1))
+    owner = np.zeros(len(positions), dtype=np.int64)
+    groups = [np.arange(len(positions))]
+    for axis, parts in enumerate(grid):
+        nxt = []
+        for ids in groups:
+            order = ids[np.argsort(frac[ids, axis], kind="stable")]
+            split = (np.arange(len(order)) * parts) // max(len(order), 1)
+            for q in range(parts):
+                nxt.append(order[split == q])
+        groups = nxt
+    for r, ids in enumerate(groups):
+        owner[ids] = r
+    return owner
+
+
 @dataclass
 class Shard:
     """One rank's part of a structure, host side (numpy) + halo description."""
@@ -80,12 +122,14 @@ class Shard:
     halo_send: List[np.ndarray]  # per peer: local input-edge ids in send order
 
 
-def build_shard(positions: np.ndarray, cell: np.ndarray, nl, rank: int, world: int) -> Shard:
+def build_shard(positions: np.ndarray, cell: np.ndarray, nl, rank: int, world: int,
+                partition: str = "bricks") -> Shard:
     """Partition a periodic structure.  ``nl = (i, j, S)`` is its full neighbor list sorted by
-    centre (``metatrain_b200.neighbors.neighbor_list``)."""
+    centre (``metatrain_b200.neighbors.neighbor_list``); ``partition`` = "bricks" or "slabs"."""
     gi, gj, gs = nl
     n = len(positions)
-    owner = slab_owner(np.asarray(positions, dtype=np.float64), np.asarray(cell, dtype=np.float64), world)
+    split = {"bricks": brick_owner, "slabs": slab_owner}[partition]
+    owner = split(np.asarray(positions, dtype=np.float64), np.asarray(cell, dtype=np.float64), world)
     own_ids = np.nonzero(owner == rank)[0]
     mine = np.nonzero(owner[gi] == rank)[0]          # local edges, still sorted by centre
     li, lj, ls = gi[mine], gj[mine], gs[mine]

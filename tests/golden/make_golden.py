@@ -173,6 +173,39 @@ def make_training_case(name, frames, atomic_types, target="energy", hypers=None,
     print(f"{name}: loss {float(loss):.9f}, {len(names)} parameter gradients -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def make_long_box_case(name, frame, reps, atomic_types, fp64=True):
+    """Elongated periodic boxes for the atom-sharded path (BASELINE.json configs[3] is a slab-sharded
+    box ~8x longer than the seed box): the reference is run on the SAME fp32-rounded coordinates the
+    GPU path sees (up to ~375 A at 1x1x24), fp32 and fp64.  Compact file: positions + outputs only;
+    the tests rebuild the (deterministic) neighbor list themselves."""
+    if ONLY and name not in ONLY:
+        return
+    from oracle.structures import replicate
+    box = replicate(frame, reps)
+    box["positions"] = box["positions"].astype(np.float32).astype(np.float64)  # what both sides are fed
+    inp = batch_frames([box], 4.5)
+    payload = dict(positions=inp["positions"], cells=inp["cells"], species=inp["species"],
+                   reps=np.array(reps, dtype=np.int64), n_edges=np.array(len(inp["centers"])),
+                   atomic_types=np.array(atomic_types, dtype=np.int64), target=np.array("energy"),
+                   hypers_override=np.array(repr({})), out_shape=np.array([1], dtype=np.int64))
+    be32 = ref_loader.build_reference_backend(atomic_types, "energy", None).eval()
+    payload["weight_fingerprint"] = weight_fingerprint(be32.state_dict())
+    ref32 = run_reference(be32, inp, "energy", torch.float32, False)
+    for k in ("energies", "dE_dpos"):
+        payload["ref32_" + k] = ref32[k]
+    if fp64:
+        be64 = ref_loader.build_reference_backend(atomic_types, "energy", None, dtype=torch.float64).eval()
+        ref64 = run_reference(be64, inp, "energy", torch.float64, False)
+        for k in ("energies", "dE_dpos"):
+            payload["ref64_" + k] = ref64[k]
+        print(f"{name}: reference fp32 vs fp64 force max-abs diff "
+              f"{np.abs(ref32['dE_dpos'] - ref64['dE_dpos']).max():.3e}")
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **payload)
+    print(f"{name}: N={len(inp['species'])} E={len(inp['centers'])} E={ref32['energies'].ravel()} "
+          f"-> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     torch.set_num_threads(8)
     qm9 = read_xyz_frames(os.path.join(RES, "qm9_reduced_100.xyz"), 5)
@@ -188,6 +221,10 @@ def main():
     make_training_case("train_carbon_1", carbon[:1], [6])
     water = read_lammps_atomic(os.path.join(RES, "periodic_water.data"), {1: 1, 2: 8})
     make_case("water_384", [water], [1, 8])
+    # elongated boxes of the atom-sharded runs: 1x1x8 (3 072 atoms, z to 125 A) and 1x1x24
+    # (9 216 atoms, z to 376 A), same fp32-rounded coordinates on both sides
+    make_long_box_case("water_long_1x1x8", water, (1, 1, 8), [1, 8])
+    make_long_box_case("water_long_1x1x24", water, (1, 1, 24), [1, 8])
     # seed box of the 10k / 100k water benchmarks (positions only)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(HERE)), "metatrain_b200",
                                      "data", "water_384.npz"),

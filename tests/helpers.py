@@ -94,3 +94,25 @@ def weight_fingerprint(state_dict):
         v64 = v.detach().to(torch.float64).cpu()
         rows.append([float(v64.sum()), float((v64 * v64).sum())])
     return np.array(rows, dtype=np.float64)
+
+
+LONG_BOX_CASES = ["water_long_1x1x8", "water_long_1x1x24"]
+
+
+def load_long_box(name):
+    """Compact goldens of the elongated water boxes (make_golden.make_long_box_case): fp32 positions,
+    cell and species plus the unmodified reference's fp32 / fp64 outputs on exactly those inputs.
+    The (deterministic) neighbor list is rebuilt here."""
+    from metatrain_b200.neighbors import neighbor_list
+    g = load_golden(name)
+    pos = g["positions"].astype(np.float64)
+    cell = g["cells"][0].astype(np.float64)
+    i, j, S = neighbor_list(pos, cell, True, g["hypers"]["cutoff"])
+    assert len(i) == int(g["n_edges"]), "neighbor list differs from the one the golden was made with"
+    g["nl"] = (i, j, S)
+    g["batch"] = dict(
+        positions=torch.from_numpy(g["positions"]), centers=torch.from_numpy(i.astype(np.int32)),
+        neighbors=torch.from_numpy(j.astype(np.int32)), species=torch.from_numpy(g["species"].astype(np.int32)),
+        cells=torch.from_numpy(g["cells"]), cell_shifts=torch.from_numpy(S.astype(np.int32).reshape(-1, 3)),
+        system_indices=torch.zeros(len(pos), dtype=torch.int64))
+    return g

@@ -7,7 +7,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from helpers import GOLDEN_CASES, apply_lora, golden_inputs, load_golden, seed_all  # noqa: E402
+from helpers import (GOLDEN_CASES, LONG_BOX_CASES, apply_lora, golden_inputs, load_golden,  # noqa: E402
+                     load_long_box, seed_all)
 from metatrain_b200 import B200PETBackend, evaluate  # noqa: E402
 from metatrain_b200.systems import make_batch, replicate, water_384  # noqa: E402
 from oracle import pet_oracle  # noqa: E402
@@ -61,6 +62,29 @@ def test_tensor_core_split_meets_force_tolerance(case):
     f1 = np.abs(out1["dE_dpos"].cpu().numpy() - g["ref32_dE_dpos"]).max()
     print(f"{case}: bf16 single-pass force max-abs-err {f1:.2e} eV/A")
     assert f1 <= 0.2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("case", LONG_BOX_CASES)
+def test_elongated_boxes_match_reference(case, precision):
+    """The boxes of the atom-sharded runs are up to 24x longer than the seed box (z to 376 A): fp32
+    coordinates there carry ~3e-5 A of rounding.  The unmodified reference was run on exactly these
+    fp32-rounded coordinates (fp32 and fp64); its own fp32-vs-fp64 force difference is the floor
+    (2.5e-5 at 1x1x8, 7.7e-5 at 1x1x24)."""
+    g = load_long_box(case)
+    be = make_backend(g, precision=precision)
+    be.emit_nef = False
+    out = evaluate(be, **{k: v.to(DEV) for k, v in g["batch"].items()}, target=g["target"])
+    f = out["dE_dpos"].cpu().numpy()
+    err32 = np.abs(f - g["ref32_dE_dpos"]).max()
+    err64 = np.abs(f - g["ref64_dE_dpos"]).max()
+    floor = np.abs(g["ref32_dE_dpos"] - g["ref64_dE_dpos"]).max()
+    print(f"{case} {precision}: force err vs ref fp32 {err32:.2e}, vs ref fp64 {err64:.2e} "
+          f"(reference fp32 vs fp64: {floor:.2e})")
+    assert err64 <= FORCE_TOL, f"force max-abs-err vs the fp64 reference {err64:.2e}"
+    assert err32 <= FORCE_TOL + floor
+    e_ref = float(g["ref64_energies"].ravel()[0])
+    assert abs(float(out["energies"]) - e_ref) <= 2e-6 * abs(e_ref)
 
 
 def test_lora_adapters_are_merged_and_repacked_on_update():
@@ -309,6 +333,38 @@ def test_float64_inputs_and_empty_structure_in_a_batch():
     assert (out["dE_dpos"] - ref["dE_dpos"]).abs().max() <= 1e-6
 
 
+def test_default_dtype_float64_does_not_leak_into_work_buffers():
+    """Atomistic test suites often run under torch.set_default_dtype(torch.float64): every buffer
+    handed to the C ABI must still be fp32."""
+    g = load_golden("si_64")
+    ref = evaluate(make_backend(g, "bf16x3"), **golden_inputs(g, DEV), target=g["target"], strain=True)
+    torch.set_default_dtype(torch.float64)
+    try:
+        be = make_backend(g, "bf16x3").float()
+        out = evaluate(be, **golden_inputs(g, DEV), target=g["target"], strain=True)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    for k in ("energies", "dE_dpos", "dE_dstrain"):
+        assert torch.equal(out[k].float(), ref[k]), k
+
+
+def test_unsupported_atomic_type_and_foreign_device_raise():
+    g = load_golden("qm9_5")            # atomic_types [1, 6, 7, 8]
+    be = make_backend(g)
+    inp = golden_inputs(g, DEV)
+    inp["species"] = inp["species"].clone()
+    inp["species"][3] = 5               # inside the lookup table, not a model type
+    with pytest.raises(ValueError, match="atomic types .*5"):
+        evaluate(be, **inp, target=g["target"])
+    inp["species"][3] = 117             # beyond the lookup table
+    with pytest.raises(ValueError, match="atomic types"):
+        evaluate(be, **inp, target=g["target"])
+    if torch.cuda.device_count() > 1:
+        with pytest.raises(RuntimeError, match="current CUDA device"):
+            evaluate(be, **golden_inputs(g, "cuda:1"), target=g["target"])
+        torch.cuda.synchronize()
+
+
 def test_evaluator_loop_matches_reference_semantics():
     """eval_targets mirrors cli/eval.py:_eval_targets: batching (last batch smaller), per-atom
     energy metrics, force metrics, predictions equal to direct evaluation."""
@@ -442,6 +498,24 @@ def test_graphed_md_evaluator_matches_eager_steps(use_graph):
     assert md.verlet.n_builds >= 2 and md.verlet.n_reuses >= 4
     if use_graph:
         assert md.n_captures == md.verlet.n_builds and md.n_replays == 12
+
+
+def test_graphed_md_evaluator_survives_many_list_rebuilds_on_a_small_periodic_box():
+    """Small periodic box = most pairs cross a boundary: the device list's acceptance test is not
+    bitwise symmetric there, the topology must come from the symmetric filter (no sporadic
+    'neighbor list is not symmetric')."""
+    from metatrain_b200.md import GraphedEvaluator
+    g = load_golden("si_64")
+    be = make_backend(g, "bf16x3")
+    inp = golden_inputs(g, DEV)
+    ev = GraphedEvaluator(be, inp["species"], inp["cells"][0], skin=0.05, target=g["target"], use_graph=False)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    pos = inp["positions"].clone()
+    for _ in range(60):
+        pos = pos + 0.03 * torch.randn(pos.shape, generator=gen, device=DEV)
+        out = ev(pos)
+        assert torch.isfinite(out["dE_dpos"]).all()
+    assert ev.verlet.n_builds >= 20
 
 
 def test_neighbor_order_invariance():

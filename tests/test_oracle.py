@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import DEFAULT_HYPERS, GOLDEN_CASES, apply_lora, golden_inputs, load_golden, seed_all, weight_fingerprint
+from helpers import (DEFAULT_HYPERS, GOLDEN_CASES, apply_lora, golden_inputs, load_golden, load_long_box, seed_all,
+                     weight_fingerprint)
 from metatrain_b200.parameters import PETParameters
 from oracle import pet_oracle, ref_loader
 from oracle.structures import neighbor_list
@@ -63,6 +64,20 @@ def test_oracle_matches_golden(case):
     if strain:
         assert np.abs(out["dE_dstrain"].numpy() - g["ref32_dE_dstrain"]).max() <= 2e-5
     assert int(out["batch"]["mask"].sum()) == int(g["ref32_n_edges_kept"])
+
+
+def test_oracle_matches_reference_on_elongated_box():
+    """Elongated box of the atom-sharded runs (1x1x8 tiling, z to 125 A), fp32 coordinates: the oracle
+    reproduces the unmodified reference's fp32 outputs, and the reference's own fp32-vs-fp64 force
+    difference there (the accuracy floor of fp32 coordinates this far from the origin) is recorded."""
+    g = load_long_box("water_long_1x1x8")
+    np.testing.assert_array_equal(weight_fingerprint(seeded_state_dict(g)), g["weight_fingerprint"])
+    batch = {k: (v.long() if not v.is_floating_point() else v) for k, v in g["batch"].items()}
+    out = pet_oracle.energy_and_gradients(seeded_state_dict(g), g["hypers"], **batch, target=g["target"])
+    assert abs(float(out["energies"]) - float(g["ref32_energies"].ravel()[0])) <= 2e-6 * abs(float(g["ref32_energies"].ravel()[0]))
+    assert np.abs(out["dE_dpos"].numpy() - g["ref32_dE_dpos"]).max() <= 2e-5
+    floor = np.abs(g["ref32_dE_dpos"] - g["ref64_dE_dpos"]).max()
+    assert floor <= 1e-4
 
 
 def test_oracle_fp64_matches_reference_fp64():

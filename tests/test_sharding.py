@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from metatrain_b200.neighbors import neighbor_list
-from metatrain_b200.sharded import Halo, build_shard, slab_owner
+from metatrain_b200.sharded import Halo, brick_owner, build_shard, slab_owner
 from metatrain_b200.systems import replicate, water_384
 from oracle.pet_oracle import reverse_edge_map_sorted
 
@@ -23,7 +23,7 @@ def _worker(rank, world, init_file, result_file):
     n_edges = len(gi)
     rev_global = reverse_edge_map_sorted(torch.from_numpy(gi), torch.from_numpy(gj),
                                          torch.from_numpy(gs)).numpy()
-    shard = build_shard(box["positions"], box["cell"], nl, rank, world)
+    shard = build_shard(box["positions"], box["cell"], nl, rank, world, partition="slabs")
     owner = slab_owner(box["positions"], box["cell"], world)
     ok = True
     # every atom has exactly one owner, equal counts
@@ -74,3 +74,20 @@ def test_slab_owner_balanced_for_eight_ranks():
     owner = slab_owner(box["positions"], box["cell"], 8)
     counts = np.bincount(owner, minlength=8)
     assert counts.sum() == len(owner) and counts.max() - counts.min() <= 1
+
+
+def test_brick_owner_balanced_and_compact():
+    box = replicate(water_384(), (2, 2, 2))
+    nl = neighbor_list(box["positions"], box["cell"], True, 4.5)
+    for world in (2, 4, 8):
+        owner = brick_owner(box["positions"], box["cell"], world)
+        counts = np.bincount(owner, minlength=world)
+        assert counts.sum() == len(owner) and counts.max() - counts.min() <= world
+    # 8 bricks cut fewer edges than 8 slabs of the same cubic box
+    cut = lambda own: int((own[nl[0]] != own[nl[1]]).sum())  # noqa: E731
+    assert cut(brick_owner(box["positions"], box["cell"], 8)) < cut(slab_owner(box["positions"], box["cell"], 8))
+    # every shard sees mirror-image halo sets with every peer
+    shards = [build_shard(box["positions"], box["cell"], nl, r, 4) for r in range(4)]
+    for a in range(4):
+        for b in range(4):
+            assert len(shards[a].halo_send[b]) == len(shards[b].halo_recv[a])

@@ -2,16 +2,21 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_*] --csv` launch list.
 
     python tools/summarize_launches.py gpurun_out/launches.csv > profiles/rNN_launches.md
+    python tools/summarize_launches.py gpurun_out/launches.csv --json profiles/traffic.json
+
+The JSON form (DRAM bytes per launch of every kernel) is what bench.py quotes as
+`roofline.traffic`.
 """
 import collections
 import csv
+import json
 import re
 import sys
 
 SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def main(path):
+def main(path, json_out=None):
     with open(path) as fh:
         lines = [ln for ln in fh if ln.startswith('"')]
     tot = collections.defaultdict(lambda: collections.defaultdict(float))
@@ -22,6 +27,16 @@ def main(path):
         v = float(row["Metric Value"].replace(",", "")) * SCALE.get(row["Metric Unit"], 1.0)
         tot[name][row["Metric Name"]] += v
         ids[name].add(row["ID"])
+    if json_out:
+        table = {}
+        for k, v in tot.items():
+            if "dram__bytes_read.sum" not in v:
+                continue
+            n = len(ids[k])
+            table[k] = {"launches": n, "avg_us": v["gpu__time_duration.sum"] / n,
+                        "bytes_per_launch": (v["dram__bytes_read.sum"] + v.get("dram__bytes_write.sum", 0.0)) / n}
+        with open(json_out, "w") as fh:
+            json.dump({"source": path, "bytes_per_launch": table}, fh, indent=1, sort_keys=True)
     total = sum(v["gpu__time_duration.sum"] for v in tot.values())
     has_dram = any("dram__bytes_read.sum" in v for v in tot.values())
     print(f"# ncu launch list summary: {path}\n")
@@ -43,4 +58,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[3] if len(sys.argv) > 3 and sys.argv[2] == "--json" else None)
