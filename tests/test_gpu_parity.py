@@ -337,10 +337,11 @@ def test_default_dtype_float64_does_not_leak_into_work_buffers():
     """Atomistic test suites often run under torch.set_default_dtype(torch.float64): every buffer
     handed to the C ABI must still be fp32."""
     g = load_golden("si_64")
-    ref = evaluate(make_backend(g, "bf16x3"), **golden_inputs(g, DEV), target=g["target"], strain=True)
+    be = make_backend(g, "bf16x3")    # fp32 parameters (seeded init under the fp32 default)
+    ref = evaluate(be, **golden_inputs(g, DEV), target=g["target"], strain=True)
     torch.set_default_dtype(torch.float64)
     try:
-        be = make_backend(g, "bf16x3").float()
+        be._invalidate_packed()       # weights are re-packed under the fp64 default as well
         out = evaluate(be, **golden_inputs(g, DEV), target=g["target"], strain=True)
     finally:
         torch.set_default_dtype(torch.float32)
