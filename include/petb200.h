@@ -376,6 +376,32 @@ PETB200_API int petb200_combine_ln_fwd(const float* t, const int32_t* rev, const
 PETB200_API int petb200_combine_ln_bwd(const float* d_cc, const float* t, const int32_t* rev,
                            const float* gamma, const float* mean, const float* rstd,
                            int64_t n_edges, int d, float* d_cat, petb200_stream_t stream);
+/* The same block as ONE persistent tcgen05 kernel per direction (combine_fused.cu): the message
+ * reversal gather ("edge scatter"), the LayerNorm, both Linears of the combine MLP and the
+ * residual update
+ *   fwd:  m_io[e] += t[e] + W_b . silu(W_a . LN(cat[t[e], t[rev[e]]]) + b_a) + b_b
+ * with the LayerNorm folded into the first contraction:  W_a . LN(c) + b_a = r (W' c - mu s) + b',
+ * W' = W_a diag(gamma) (`w_a_folded`, [2d, 2d]), s = row sums of W' (`s_vec`), b' = W_a beta + b_a
+ * (`b_fold`).  Side outputs for the backward: the pre-activations p [E, 2d] and (mu, r) per edge
+ * (`stats`, [E, 2]).  `t` may hold ghost rows behind its first n_edges rows (atom-sharded runs):
+ * rev indexes rows of `t`.
+ *   bwd:  d_cat[e] = LN'(cat_e)^T W_a^T silu'(p_e) W_b^T g[e]   ([E, 2d]; finish with
+ *         petb200_combine_scatter_bwd).
+ * petb200_combine_pack builds the bf16 hi/lo operand-tile images (petb200_combine_image_bytes bytes
+ * each) from w_a_folded and w_b [d, 2d].  Built for d = 128; PETB200_ERR_UNSUPPORTED otherwise.
+ * Replaces, per GNN layer: backend.py:559-575 (reference), and the unfused sequence
+ * combine_ln_fwd + 2 x petb200_gemm (forward) / 2 x petb200_gemm + combine_ln_bwd (backward).      */
+PETB200_API size_t petb200_combine_image_bytes(int d, int backward);
+PETB200_API int petb200_combine_pack(const float* w_a_folded, const float* w_b, int d, void* image_fwd,
+                         void* image_bwd, petb200_stream_t stream);
+PETB200_API int petb200_combine_fwd(const float* t, int64_t ld_t, const int32_t* rev, const void* image_fwd,
+                        const float* s_vec, const float* b_fold, const float* b_out, int64_t n_edges,
+                        int d, float* m_io, int64_t ld_m, float* p_out, float* stats_out,
+                        petb200_stream_t stream);
+PETB200_API int petb200_combine_bwd(const float* g, int64_t ld_g, const float* p, const float* t, int64_t ld_t,
+                        const int32_t* rev, const float* stats, const void* image_bwd,
+                        const float* s_vec, const float* b_fold, int64_t n_edges, int d, float* d_cat,
+                        petb200_stream_t stream);
 /* out[e] = base[e] + d_cat[e, :d] + d_cat[rev[e], d:]  (rev is an involution, so the
  * scatter of the reversed half is a gather: no atomics).                               */
 PETB200_API int petb200_combine_scatter_bwd(const float* d_cat, const float* base, const int32_t* rev,

@@ -311,6 +311,18 @@ class PackedWeights:
             C["w_b"], C["b_b"] = _w(mlp[2]), _b(mlp[2])
             C["w_a_t"], _ = _t_and_scaled(_w(mlp[0]))
             C["w_b_t"], _ = _t_and_scaled(_w(mlp[2]))
+            # fused combine kernels (petb200_combine_fwd / _bwd): LayerNorm folded into the first Linear,
+            #   W_a . LN(c) + b_a = r (W' c - mu s) + b',  W' = W_a diag(gamma), s = W' 1, b' = W_a beta + b_a
+            C["img"] = None
+            if C["w_b"].shape[0] == 128 and tuple(C["w_a"].shape) == (256, 256):
+                wa64 = C["w_a"].double()
+                C["wa_fold"] = (wa64 * C["gamma"].double()[None, :]).float().contiguous()
+                C["s_vec"] = C["wa_fold"].double().sum(dim=1).float().contiguous()
+                C["b_fold"] = (wa64 @ C["beta"].double() + C["b_a"].double()).float().contiguous()
+                nbytes = lib.load().petb200_combine_image_bytes(128, 0)
+                C["img"] = [torch.empty(nbytes, device=C["w_a"].device, dtype=torch.uint8) for _ in range(2)]
+                call("combine_pack", ptr(C["wa_fold"]), ptr(C["w_b"].contiguous()), 128, ptr(C["img"][0]),
+                     ptr(C["img"][1]))
             self.combine.append(C)
         # one node embedding per readout layer (1 with the feedforward featurizer)
         self.node_emb = [_w(e).contiguous() for e in module.node_embedders]
@@ -835,6 +847,15 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
         if halo is not None:
             # reversed messages of halo edges live on the peers: all-to-all-v into the ghost rows
             halo.exchange(t.index_select(0, halo.send_idx), out=Xf[E + N:])
+        if prec != PREC_FP32 and C["img"] is not None:
+            # gather of the reversed messages, LayerNorm, both Linears and the residual update in one
+            # kernel; m <- m + t + W_b silu(...) + b_b in place on our own message buffer
+            p1, cstats = _empty((E, 2 * d), vec), _empty((E, 2), vec)
+            call("combine_fwd", ptr(t), t.stride(0), ptr(topo.rev), ptr(C["img"][0]), ptr(C["s_vec"]),
+                 ptr(C["b_fold"]), ptr(C["b_b"]), E, d, ptr(m), m.stride(0), ptr(p1), ptr(cstats))
+            S.update(t=t, p1=p1, cstats=cstats)
+            saved.append(S)
+            continue
         cc = _empty((E, 2 * d), vec)
         mean, rstd = _empty((E,), vec), _empty((E,), vec)
         call("combine_ln_fwd", ptr(t), ptr(topo.rev), ptr(C["gamma"]), ptr(C["beta"]), E, d,
@@ -984,12 +1005,20 @@ def features_backward(pw: PackedWeights, hyp, topo: Topology, fc, saved, d_h, d_
         # ---- message update:  m_out = m_in + t + W_b silu(W_a LN(cat[t, t_rev]) + b_a) + b_b
         d_p1f = _empty((E + H, 2 * d), ref)
         d_p1 = d_p1f[:E]
-        gemm(d_m, C["w_b_t"], d_p1, epilogue=EPI_MUL_DSILU, aux_in=S["p1"], precision=prec, pack=pw)
-        d_cc = _empty((E, 2 * d), ref)
-        gemm(d_p1, C["w_a_t"], d_cc, precision=prec, pack=pw)
-        d_cat = d_p1  # reuse
-        call("combine_ln_bwd", ptr(d_cc), ptr(S["t"]), ptr(topo.rev), ptr(C["gamma"]),
-             ptr(S["mean"]), ptr(S["rstd"]), E, d, ptr(d_cat))
+        d_cc = None
+        if "cstats" in S:
+            # both dgrad contractions, silu' and the LayerNorm backward in one kernel
+            d_cat = d_p1
+            call("combine_bwd", ptr(d_m), d_m.stride(0), ptr(S["p1"]), ptr(S["t"]), S["t"].stride(0),
+                 ptr(topo.rev), ptr(S["cstats"]), ptr(C["img"][1]), ptr(C["s_vec"]), ptr(C["b_fold"]), E, d,
+                 ptr(d_cat))
+        else:
+            gemm(d_m, C["w_b_t"], d_p1, epilogue=EPI_MUL_DSILU, aux_in=S["p1"], precision=prec, pack=pw)
+            d_cc = _empty((E, 2 * d), ref)
+            gemm(d_p1, C["w_a_t"], d_cc, precision=prec, pack=pw)
+            d_cat = d_p1  # reuse
+            call("combine_ln_bwd", ptr(d_cc), ptr(S["t"]), ptr(topo.rev), ptr(C["gamma"]),
+                 ptr(S["mean"]), ptr(S["rstd"]), E, d, ptr(d_cat))
         if halo is not None:
             # the "reversed half" gradients of our halo edges were computed by the peers
             got = halo.exchange(d_cat.index_select(0, halo.send_idx)[:, d:])

@@ -82,13 +82,17 @@ _SIGNATURES = {
     "petb200_combine_ln_fwd": [_P, _P, _P, _P, _I64, _I, _P, _P, _P, _P],
     "petb200_combine_ln_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_combine_scatter_bwd": [_P, _P, _P, _I64, _I, _P, _P],
+    "petb200_combine_image_bytes": [_I, _I],
+    "petb200_combine_pack": [_P, _P, _I, _P, _P, _P],
+    "petb200_combine_fwd": [_P, _I64, _P, _P, _P, _P, _P, _I64, _I, _P, _I64, _P, _P, _P],
+    "petb200_combine_bwd": [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_readout_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P],
     "petb200_readout_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P, _P],
     "petb200_sum_over_atoms": [_P, _P, _I64, _I, _P, _P],
     "petb200_last_error": [],
     "petb200_version": [],
 }
-_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_norm_linear_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
+_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_combine_image_bytes": _SZ, "petb200_norm_linear_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
             "petb200_nl_num_bins": _I64, "petb200_nl_workspace": _SZ}
 
 

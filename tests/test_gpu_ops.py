@@ -240,6 +240,54 @@ def test_combine_ln_fwd_bwd_scatter():
     assert_close(out, tt.grad + base.double(), 5e-5, 1e-5, "combine bwd")
 
 
+@pytest.mark.parametrize("E,ghosts", [(999, 0), (128, 0), (5, 0), (40000, 0), (3000, 77), (0, 0)])
+def test_combine_fused_fwd_bwd(E, ghosts):
+    """petb200_combine_fwd / _bwd (one tcgen05 kernel each: reversed-message gather, LayerNorm, both
+    Linears, residual) against fp64 autograd of backend.py:559-575.  ``ghosts`` rows behind the E own
+    rows play the halo rows of atom-sharded runs (some reversed edges point at them)."""
+    d = 128
+    t_all = rnd(E + ghosts, d, seed=1)
+    if E > 20:
+        t_all[:5] *= 20.0
+        t_all[5:10] += 3.0           # rows with a large mean
+    m0, g = rnd(E, d, seed=2), rnd(E, d, seed=3)
+    gamma, beta = rnd(2 * d, seed=4).abs() + 0.5, rnd(2 * d, seed=5, scale=0.3)
+    w_a, b_a = rnd(2 * d, 2 * d, seed=6, scale=(2 * d) ** -0.5), rnd(2 * d, seed=7, scale=0.1)
+    w_b, b_b = rnd(d, 2 * d, seed=8, scale=(2 * d) ** -0.5), rnd(d, seed=9, scale=0.1)
+    rev = _random_involution(E) if E > 0 else torch.zeros(0, dtype=torch.int32, device=DEV)
+    if ghosts:
+        rev = rev.clone()
+        rev[:ghosts] = torch.arange(E, E + ghosts, dtype=torch.int32, device=DEV)
+    wa_fold = (w_a.double() * gamma.double()[None, :]).float().contiguous()
+    s_vec = wa_fold.double().sum(1).float().contiguous()
+    b_fold = (w_a.double() @ beta.double() + b_a.double()).float().contiguous()
+    handle = lib.load()
+    imgs = [torch.empty(handle.petb200_combine_image_bytes(d, b), device=DEV, dtype=torch.uint8) for b in (0, 1)]
+    call("combine_pack", ptr(wa_fold), ptr(w_b), d, ptr(imgs[0]), ptr(imgs[1]))
+    m = m0.clone()
+    p1, stats = torch.empty(E, 2 * d, device=DEV), torch.empty(E, 2, device=DEV)
+    call("combine_fwd", ptr(t_all), d, ptr(rev), ptr(imgs[0]), ptr(s_vec), ptr(b_fold), ptr(b_b), E, d, ptr(m), d,
+         ptr(p1), ptr(stats))
+    if E == 0:
+        return
+    tt = t_all.double().cpu().requires_grad_(True)
+    rv = rev.long().cpu()
+    cat = torch.cat([tt[:E], tt[rv]], dim=-1)
+    pre = F.layer_norm(cat, (2 * d,), gamma.double().cpu(), beta.double().cpu(), 1e-5) @ w_a.double().cpu().T + b_a.double().cpu()
+    out = m0.double().cpu() + tt[:E] + F.silu(pre) @ w_b.double().cpu().T + b_b.double().cpu()
+    assert_close(p1, pre.detach(), 2e-4, 2e-5, "combine_fwd pre-activations")
+    assert_close(m, out.detach(), 2e-4, 2e-5, "combine_fwd output")
+    assert_close(stats[:, 0], cat.detach().mean(1), 1e-5, 1e-5, "combine_fwd mean")
+    assert_close(stats[:, 1], (cat.detach().var(1, unbiased=False) + 1e-5).rsqrt(), 1e-5, 2e-5, "combine_fwd rstd")
+    # backward: gradient w.r.t. cat (before the scatter of the reversed half)
+    cat.retain_grad()
+    (out - tt[:E]).backward(g.double().cpu())
+    d_cat = torch.empty(E, 2 * d, device=DEV)
+    call("combine_bwd", ptr(g), d, ptr(p1), ptr(t_all), d, ptr(rev), ptr(stats), ptr(imgs[1]), ptr(s_vec),
+         ptr(b_fold), E, d, ptr(d_cat))
+    assert_close(d_cat, cat.grad, 3e-4, 3e-5, "combine_bwd")
+
+
 def test_embedding_transpose_compress_geom():
     E, d = 777, 128
     table = rnd(5, d)
