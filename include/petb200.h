@@ -382,8 +382,11 @@ PETB200_API int petb200_combine_ln_bwd(const float* d_cc, const float* t, const 
  *   fwd:  m_io[e] += t[e] + W_b . silu(W_a . LN(cat[t[e], t[rev[e]]]) + b_a) + b_b
  * with the LayerNorm folded into the first contraction:  W_a . LN(c) + b_a = r (W' c - mu s) + b',
  * W' = W_a diag(gamma) (`w_a_folded`, [2d, 2d]), s = row sums of W' (`s_vec`), b' = W_a beta + b_a
- * (`b_fold`).  Side outputs for the backward: the pre-activations p [E, 2d] and (mu, r) per edge
- * (`stats`, [E, 2]).  `t` may hold ghost rows behind its first n_edges rows (atom-sharded runs):
+ * (`b_fold`).  Side outputs for the backward: the pre-activations `p` and (mu, r) per edge (`stats`,
+ * [E, 2]).  `p` is an opaque buffer of ceil(E / 128) * 128 * 2d floats in the kernels' private layout
+ * [128-edge tile][32-unit chunk][unit][edge of the tile] (the row-per-thread epilogues of both kernels
+ * then read / write whole 128 B lines); element (e, n) lives at
+ * ((e / 128 * 8 + n / 32) * 32 + n % 32) * 128 + e % 128.  `t` may hold ghost rows behind its first n_edges rows (atom-sharded runs):
  * rev indexes rows of `t`.
  *   bwd:  d_cat[e] = LN'(cat_e)^T W_a^T silu'(p_e) W_b^T g[e]   ([E, 2d]; finish with
  *         petb200_combine_scatter_bwd).

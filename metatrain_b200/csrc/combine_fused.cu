@@ -41,6 +41,18 @@ constexpr int XPITCH = D + 4;                                // floats per stage
 constexpr int CB_STAGING_BYTES = BM * XPITCH * 4;            // 67 584
 constexpr float kLnEps = 1e-5f;                              // torch.nn.LayerNorm default
 
+// Optional in-kernel timeline (tools/combine_trace.py; build with -DPETB200_COMBINE_TRACE): CTA 0
+// records clock64() at pipeline events of its first tiles.  Compiled out otherwise.
+#ifdef PETB200_COMBINE_TRACE
+__device__ long long* g_ctrace = nullptr;
+__device__ __forceinline__ void ctrace(int role, int tile, int chunk, int ev) {
+  if (g_ctrace != nullptr && blockIdx.x == 0 && tile >= 2 && tile < 6)
+    g_ctrace[((role * 4 + (tile - 2)) * 16 + chunk) * 8 + ev] = clock64();
+}
+#else
+__device__ __forceinline__ void ctrace(int, int, int, int) {}
+#endif
+
 __host__ __device__ constexpr int cf_stages() { return (HID / 64) * 6; }   // forward image
 __host__ __device__ constexpr int cb_stages() { return (HID / 64) * 6; }   // backward image
 
@@ -95,36 +107,25 @@ __global__ void combine_pack_kernel(const float* __restrict__ w_a, const float* 
   image[idx] = pack8(v, lo);
 }
 
-// fp32 row (32 floats at `row`) -> 16 packed bf16 hi columns + 16 lo columns
-__device__ __forceinline__ void split_part(const float* row, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+// fp32 row (32 floats at `row`) -> 16 packed bf16 hi columns + 16 lo columns; s1 / s2 accumulate the
+// sum and the sum of squares of (x - shift) (shifted data: no cancellation for rows with a large mean)
+template <bool STATS>
+__device__ __forceinline__ void split_part(const float* row, uint32_t (&hi)[16], uint32_t (&lo)[16],
+                                           float shift, float& s1, float& s2) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 v = *reinterpret_cast<const float4*>(row + 4 * q);
+    if (STATS) {
+      const float a = v.x - shift, b = v.y - shift, c = v.z - shift, d = v.w - shift;
+      s1 += (a + b) + (c + d);
+      s2 = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, s2))));
+    }
     hi[2 * q] = pack_bf16(v.x, v.y);
     hi[2 * q + 1] = pack_bf16(v.z, v.w);
     lo[2 * q] = pack_bf16(v.x - __uint_as_float(hi[2 * q] << 16), v.y - __uint_as_float(hi[2 * q] & 0xffff0000u));
     lo[2 * q + 1] = pack_bf16(v.z - __uint_as_float(hi[2 * q + 1] << 16),
                               v.w - __uint_as_float(hi[2 * q + 1] & 0xffff0000u));
   }
-}
-
-// mean and sum of squared deviations of the 128 floats at `row`
-__device__ __forceinline__ void row_moments(const float* row, float& mean, float& m2) {
-  float s = 0.f;
-#pragma unroll 8
-  for (int q = 0; q < 32; ++q) {
-    const float4 v = *reinterpret_cast<const float4*>(row + 4 * q);
-    s += (v.x + v.y) + (v.z + v.w);
-  }
-  mean = s * (1.0f / D);
-  float a = 0.f;
-#pragma unroll 8
-  for (int q = 0; q < 32; ++q) {
-    const float4 v = *reinterpret_cast<const float4*>(row + 4 * q);
-    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-    a += dx * dx + dy * dy + dz * dz + dw * dw;
-  }
-  m2 = a;
 }
 
 // ======================================================================== forward
@@ -210,34 +211,52 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
       cp_async_commit();
     };
     const float* row = reinterpret_cast<const float*>(smem + CF_XS_OFF) + (quarter * 32 + lane) * XPITCH;
-    auto park = [&](int half) {   // staged fp32 row -> bf16 hi / lo columns of the half in TMEM
+    // staged fp32 row -> bf16 hi / lo columns of the half in TMEM; returns the row's mean and sum of
+    // squared deviations (one pass, data shifted by the row's first element)
+    auto park = [&](int half, float& mean, float& m2) {
+      const float shift = row[0];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int part = 0; part < 4; ++part) {
         uint32_t hi[16], lo[16];
-        split_part(row + part * 32, hi, lo);
+        split_part<true>(row + part * 32, hi, lo, shift, s1, s2);
         tmem_st16(tmem_base + lane_base + half * 64 + part * 16, hi);
         tmem_st16(tmem_base + lane_base + CF_XLO_COL + half * 64 + part * 16, lo);
       }
+      mean = shift + s1 * (1.0f / D);
+      m2 = fmaxf(s2 - s1 * s1 * (1.0f / D), 0.f);
     };
-    if (sched.count > 0) issue_own(0);
+    // the gathered rows of a tile are pulled into L2 one tile ahead (one 512 B row per lane), so the
+    // gather in the middle of the tile's critical path is served from L2, not DRAM
+    auto prefetch_rev = [&](int i) {
+      const int64_t mine = sched.m0(i) + quarter * 32 + lane;
+      if (mine < M) prefetch_l2_bulk(t + (int64_t)__ldg(rev + mine) * ld_t, D * 4);
+    };
+    if (sched.count > 0) {
+      issue_own(0);
+      prefetch_rev(0);
+    }
     for (int i = 0; i < sched.count; ++i) {
+      if (i + 1 < sched.count) prefetch_rev(i + 1);
       cp_async_wait_group<0>();
       __syncwarp();
+      if (lane == 0 && quarter == 0) ctrace(3, i, 0, 0);
       mbar_wait(bar.x_empty(0), (i & 1) ^ 1);   // GEMM1 of the previous tile has consumed c
       tc_fence_after();
+      if (lane == 0 && quarter == 0) ctrace(3, i, 0, 1);
       float mean1, m2_1;
-      row_moments(row, mean1, m2_1);
-      park(0);
+      park(0, mean1, m2_1);
       __syncwarp();            // the warp's rows of the staging buffer are consumed
       issue_rev(i);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar.x_full(0));
+      if (lane == 0 && quarter == 0) ctrace(3, i, 0, 2);
       cp_async_wait_group<0>();
       __syncwarp();
+      if (lane == 0 && quarter == 0) ctrace(3, i, 0, 3);
       float mean2, m2_2;
-      row_moments(row, mean2, m2_2);
-      park(1);
+      park(1, mean2, m2_2);
       // LayerNorm statistics of the 256 gathered values (pairwise combination of the two halves)
       const float mu = 0.5f * (mean1 + mean2), dm = mean1 - mean2;
       const float var = (m2_1 + m2_2 + dm * dm * (0.25f * HID)) * (1.0f / HID);
@@ -250,6 +269,7 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar.x_full(1));
+      if (lane == 0 && quarter == 0) ctrace(3, i, 0, 4);
     }
   } else if (warp == TMA_WARP) {
     // ============================================================ weight-stage producer
@@ -279,8 +299,10 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
         for (int c = 0; c < NCH; ++c) {
           const uint32_t n = (uint32_t)(i * NCH + c);
           const int b = c & 1;
+          ctrace(0, i, c, 0);
           mbar_wait(bar.acc1_empty(b), ((n >> 1) & 1) ^ 1);
           tc_fence_after();
+          ctrace(0, i, c, 1);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (c == 0 && j == 1) {
@@ -288,6 +310,7 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
               tc_fence_after();
             }
             mbar_wait(bar.w_full(ring.stage), ring.phase);
+            ctrace(0, i, c, 2 + j);
             const uint32_t st = ring_u32 + ring.stage * STAGE;
 #pragma unroll
             for (int kq = 0; kq < 2; ++kq)
@@ -301,6 +324,7 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
             ring.advance(CF_RING_A);
           }
           tc_commit(bar.acc1_full(b));
+          ctrace(0, i, c, 4);
           if (c == NCH - 1) tc_commit(bar.x_empty(0));
         }
       }
@@ -324,9 +348,12 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
             w2_lo = ring.stage;
             ring.advance(CF_RING_B);
           }
+          ctrace(4, i, c, 0);
           mbar_wait(bar.a2_full(b), u & 1);
+          ctrace(4, i, c, 1);
           if (c == 0) mbar_wait(bar.acc2_empty(0), (i & 1) ^ 1);
           tc_fence_after();
+          ctrace(4, i, c, 2);
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             const uint32_t koff = (uint32_t)(b * 64 + kk * 32);
@@ -335,6 +362,7 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
                     ring_u32 + w2_lo * STAGE + koff, idesc2, (c | kk) != 0);
           }
           tc_commit(bar.a2_empty(b));
+          ctrace(4, i, c, 3);
           if (b == 1) {
             tc_commit(bar.w_empty(CF_RING_A + w2_hi));
             tc_commit(bar.w_empty(CF_RING_A + w2_lo));
@@ -358,18 +386,22 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
       for (int c = half; c < NCH; c += 2) {
         const int b = half;
         const uint32_t u = (uint32_t)(i * NCH + c) >> 1;
+        if (lane == 0 && quarter == 0) ctrace(1 + half, i, c, 0);
         mbar_wait(bar.acc1_full(b), u & 1);
         tc_fence_after();
+        if (lane == 0 && quarter == 0) ctrace(1 + half, i, c, 1);
         float v[32];
         tmem_ld32(tmem_base + lane_base + CF_ACC1_COL + b * CH, v);
         tc_fence_before();
         mbar_arrive(bar.acc1_empty(b));
+        if (lane == 0 && quarter == 0) ctrace(1 + half, i, c, 2);
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = rs * (v[k] - mu * s_s[c * CH + k]) + bf_s[c * CH + k];
-        if (m < M) {
-          float4* dst = reinterpret_cast<float4*>(p_out + m * HID + c * CH);
+        {   // saved for the backward in the kernels' private layout [tile][chunk][unit][row]: the 32
+            // lanes (= rows) of a warp write one 128 B line per unit
+          float* dst = p_out + ((int64_t)(sched.first + i * sched.stride) * NCH + c) * (CH * BM) + quarter * 32 + lane;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int k = 0; k < 32; ++k) dst[k * BM] = v[k];
         }
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -378,14 +410,17 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
           hi[q] = pack_bf16(a0, a1);
           lo[q] = pack_bf16(a0 - __uint_as_float(hi[q] << 16), a1 - __uint_as_float(hi[q] & 0xffff0000u));
         }
+        if (lane == 0 && quarter == 0) ctrace(1 + half, i, c, 3);
         mbar_wait(bar.a2_empty(b), (u & 1) ^ 1);
         tc_fence_after();
+        if (lane == 0 && quarter == 0) ctrace(1 + half, i, c, 4);
         const uint32_t a2 = tmem_base + lane_base + CF_A2_COL + b * 32;
         tmem_st16(a2, hi);
         tmem_st16(a2 + 16, lo);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar.a2_full(b));
+        if (lane == 0 && quarter == 0) ctrace(1 + half, i, c, 5);
       }
     }
   } else if (warp >= CB_STORE_WARP0 && warp < CB_STORE_WARP0 + 4) {
@@ -397,6 +432,13 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
     const float* bo_s = const_s + 2 * HID;
     for (int i = 0; i < sched.count; ++i) {
       const int64_t m_base = sched.m0(i) + quarter * 32;
+      // the tile's rows of m are first touched here: pull them into L2 while the chunk loop runs
+      if (ld_m == D) {
+        if (lane == 0 && m_base < M)
+          prefetch_l2_bulk(m_io + m_base * ld_m, (uint32_t)((M - m_base < 32 ? M - m_base : 32) * D * 4));
+      } else if (m_base + lane < M) {
+        prefetch_l2_bulk(m_io + (m_base + lane) * ld_m, D * 4);
+      }
       float4 rt[2][4], rm[2][4];
       auto fetch = [&](int sl) {
 #pragma unroll
@@ -409,8 +451,10 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
         }
       };
       fetch(0);
+      if (lane == 0 && sw == 0) ctrace(5, i, 0, 0);
       mbar_wait(bar.acc2_full(0), i & 1);
       tc_fence_after();
+      if (lane == 0 && sw == 0) ctrace(5, i, 0, 1);
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl) {
         if (sl + 1 < 8) fetch(sl + 1);
@@ -431,6 +475,7 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
                           a.w + b4.w + x.w + y.w);
         }
       }
+      if (lane == 0 && sw == 0) ctrace(5, i, 0, 2);
     }
   }
 
@@ -522,7 +567,8 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
 #pragma unroll
       for (int part = 0; part < 4; ++part) {
         uint32_t hi[16], lo[16];
-        split_part(row + part * 32, hi, lo);
+        float unused1 = 0.f, unused2 = 0.f;
+        split_part<false>(row + part * 32, hi, lo, 0.f, unused1, unused2);
         tmem_st16(tmem_base + lane_base + part * 16, hi);
         tmem_st16(tmem_base + lane_base + CBW_GLO_COL + part * 16, lo);
       }
@@ -623,15 +669,23 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
     const int half = warp >> 2;
     const float* s_s = const_s;
     const float* bf_s = const_s + HID;
+    // the pre-activation block of a tile (128 KB, contiguous) is pulled into L2 one tile ahead
+    auto prefetch_p = [&](int i) {
+      if (warp == 0 && lane < 8)
+        prefetch_l2_bulk(p + (int64_t)(sched.first + i * sched.stride) * (HID * BM) + lane * (HID * BM / 8),
+                         HID * BM * 4 / 8);
+    };
+    if (sched.count > 0) prefetch_p(0);
     for (int i = 0; i < sched.count; ++i) {
       const int64_t m = sched.m0(i) + quarter * 32 + lane;
       const bool ok = m < M;
-      const float4* prow = reinterpret_cast<const float4*>(p + (ok ? m : 0) * HID);
+      if (i + 1 < sched.count) prefetch_p(i + 1);
+      const float* ptile = p + (int64_t)(sched.first + i * sched.stride) * (HID * BM) + quarter * 32 + lane;
       float s1 = 0.f, s2 = 0.f;
-      float4 pv[8];
-      auto fetch_p = [&](int c) {
+      float pv[32];
+      auto fetch_p = [&](int c) {   // [tile][chunk][unit][row]: one 128 B line per warp and unit
 #pragma unroll
-        for (int q = 0; q < 8; ++q) pv[q] = ok ? __ldg(prow + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 32; ++k) pv[k] = __ldg(ptile + (c * CH + k) * BM);
       };
       fetch_p(half);
       for (int c = half; c < NCH; c += 2) {
@@ -646,13 +700,13 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float pe[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
+          const float pe[4] = {pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]};
           float dp[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int k = 4 * q + e;
             const float sg = fsigmoid(pe[e]);
-            dp[e] = v[k] * sg * (1.0f + pe[e] * (1.0f - sg));
+            dp[e] = ok ? v[k] * sg * (1.0f + pe[e] * (1.0f - sg)) : 0.f;
             s1 = fmaf(dp[e], s_s[c * CH + k], s1);
             s2 = fmaf(dp[e], pe[e] - bf_s[c * CH + k], s2);
           }
@@ -686,6 +740,13 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
                       (lane >> 3) + 4 * ((lane >> 2) & 1)};
     for (int i = 0; i < sched.count; ++i) {
       const int64_t m_base = sched.m0(i) + quarter * 32;
+      {   // rows of t this warp will need at the END of the tile: into L2 now (one row pair per lane)
+        const int64_t mp = m_base + lane;
+        if (mp < M) {
+          prefetch_l2_bulk(t + mp * ld_t, D * 4);
+          prefetch_l2_bulk(t + (int64_t)__ldg(rev + mp) * ld_t, D * 4);
+        }
+      }
       int64_t own[4], other[4];
       float mu[4], rs[4];
 #pragma unroll
@@ -761,6 +822,19 @@ int check_dims(const char* what, int d) {
 }  // namespace petb200
 
 using namespace petb200;
+
+// debugging aid, not part of the documented ABI: buffer of 6 roles x 4 tiles x 16 chunks x 8 int64
+// slots that CTA 0 of petb200_combine_fwd fills with clock64() stamps (NULL switches it off)
+extern "C" PETB200_API int petb200_debug_combine_trace(void* buffer) {
+#ifdef PETB200_COMBINE_TRACE
+  cudaMemcpyToSymbol(g_ctrace, &buffer, sizeof(void*));
+  return check_launch("debug_combine_trace");
+#else
+  (void)buffer;
+  set_error("debug_combine_trace: rebuild with -DPETB200_COMBINE_TRACE");
+  return PETB200_ERR_UNSUPPORTED;
+#endif
+}
 
 extern "C" PETB200_API size_t petb200_combine_image_bytes(int d, int backward) {
   (void)backward;

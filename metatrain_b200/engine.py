@@ -850,7 +850,8 @@ def features_forward(pw: PackedWeights, hyp, topo: Topology, vec, dist, fc, prec
         if prec != PREC_FP32 and C["img"] is not None:
             # gather of the reversed messages, LayerNorm, both Linears and the residual update in one
             # kernel; m <- m + t + W_b silu(...) + b_b in place on our own message buffer
-            p1, cstats = _empty((E, 2 * d), vec), _empty((E, 2), vec)
+            # (p1: pre-activations in the kernels' private tile layout, rows padded to whole 128-edge tiles)
+            p1, cstats = _empty((-(-E // 128) * 128, 2 * d), vec), _empty((E, 2), vec)
             call("combine_fwd", ptr(t), t.stride(0), ptr(topo.rev), ptr(C["img"][0]), ptr(C["s_vec"]),
                  ptr(C["b_fold"]), ptr(C["b_b"]), E, d, ptr(m), m.stride(0), ptr(p1), ptr(cstats))
             S.update(t=t, p1=p1, cstats=cstats)

@@ -265,7 +265,8 @@ def test_combine_fused_fwd_bwd(E, ghosts):
     imgs = [torch.empty(handle.petb200_combine_image_bytes(d, b), device=DEV, dtype=torch.uint8) for b in (0, 1)]
     call("combine_pack", ptr(wa_fold), ptr(w_b), d, ptr(imgs[0]), ptr(imgs[1]))
     m = m0.clone()
-    p1, stats = torch.empty(E, 2 * d, device=DEV), torch.empty(E, 2, device=DEV)
+    tiles = -(-E // 128)
+    p1, stats = torch.empty(tiles * 128, 2 * d, device=DEV), torch.empty(E, 2, device=DEV)
     call("combine_fwd", ptr(t_all), d, ptr(rev), ptr(imgs[0]), ptr(s_vec), ptr(b_fold), ptr(b_b), E, d, ptr(m), d,
          ptr(p1), ptr(stats))
     if E == 0:
@@ -275,7 +276,9 @@ def test_combine_fused_fwd_bwd(E, ghosts):
     cat = torch.cat([tt[:E], tt[rv]], dim=-1)
     pre = F.layer_norm(cat, (2 * d,), gamma.double().cpu(), beta.double().cpu(), 1e-5) @ w_a.double().cpu().T + b_a.double().cpu()
     out = m0.double().cpu() + tt[:E] + F.silu(pre) @ w_b.double().cpu().T + b_b.double().cpu()
-    assert_close(p1, pre.detach(), 2e-4, 2e-5, "combine_fwd pre-activations")
+    # private layout of the saved pre-activations: [tile][chunk of 32 units][unit][edge of the tile]
+    p_rows = p1.view(tiles, 8, 32, 128).permute(0, 3, 1, 2).reshape(tiles * 128, 2 * d)[:E]
+    assert_close(p_rows, pre.detach(), 2e-4, 2e-5, "combine_fwd pre-activations")
     assert_close(m, out.detach(), 2e-4, 2e-5, "combine_fwd output")
     assert_close(stats[:, 0], cat.detach().mean(1), 1e-5, 1e-5, "combine_fwd mean")
     assert_close(stats[:, 1], (cat.detach().var(1, unbiased=False) + 1e-5).rsqrt(), 1e-5, 2e-5, "combine_fwd rstd")
