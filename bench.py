@@ -584,10 +584,15 @@ def run_petb200(args):
                                 "max displacement < skin/2 -> energy+forces -> D2H"}
 
     # per-kernel roofline: instrumented extra steps (not part of the timed regions above)
+    # (the per-op Python schedule issues the same kernels as the C++ stage schedule, one entry point
+    # per kernel, so that each can be bracketed by events)
+    from metatrain_b200 import engine as _engine
     timer = KernelTimer()
     lib.profile_hook = timer
+    _engine.USE_STAGE_SCHEDULE = False
     for _ in range(3):
         step_resident()
+    _engine.USE_STAGE_SCHEDULE = True
     lib.profile_hook = None
     tot = timer.totals()
     if os.environ.get("PETB200_GEMM_SHAPES") and rank == 0:

@@ -437,6 +437,79 @@ PETB200_API int petb200_readout_bwd(const float* d_atomic, const float* edge_pre
                         int64_t n_atoms, int64_t n_edges, int d, int n_out, float* d_node_feat,
                         float* d_edge_feat, float* d_fc, petb200_stream_t stream);
 
+/* ------------------------------------------------------ stage-level schedule (schedule.cu)
+ * One call enqueues the whole kernel sequence of a stage on the stream, from C++, with caller-owned
+ * buffers: what the Python host would otherwise issue as ~30 separate entry-point calls per GNN
+ * layer and direction.  Built for the default layer (PreLN + RMSNorm + SwiGLU, d_pet = 128,
+ * tensor-core precisions); every other variant keeps the per-op schedule of the host.
+ *
+ * petb200_gnn_fwd / _bwd = one CartesianTransformer (transformer.py:463-562 with its
+ * TransformerLayers :203-234) on the [E + N] token layout: token builder, and per attention layer
+ * centre contraction, RMSNorm + QKV, attention, output projection, centre expansion + centre
+ * feed-forward, edge feed-forward.  Weight matrices are passed in the bf16 hi/lo split format of
+ * petb200_split_bf16 (`w` = device pointer, `ld` = leading dimension in floats).                  */
+typedef struct petb200_mat {
+  const float* w;
+  int64_t ld;
+} petb200_mat;
+
+typedef struct petb200_tl_weights {   /* one TransformerLayer (transformer.py:155-262) */
+  const void* qkv_image;              /* petb200_norm_linear_pack of W_qkv diag(gamma_attention) */
+  const float* b_qkv;
+  petb200_mat w_qkv_t;                /* [d, 3d]: (W_qkv diag(gamma_attention))^T */
+  petb200_mat w_o, w_o_t;             /* attention.output_linear [d, d] and its transpose */
+  const float* b_o;
+  const void* mlp_image_fwd;          /* petb200_mlp_pack images of the edge feed-forward */
+  const void* mlp_image_bwd;
+  const float* b_in;
+  const float* b_out;
+  int d_ff;                           /* hidden width of the edge feed-forward (after SwiGLU) */
+  petb200_mat w_con, w_con_t;         /* center_contraction [d, d_node] */
+  const float* b_con;
+  petb200_mat w_exp, w_exp_t;         /* center_expansion [d_node, d] */
+  const float* b_exp;
+  petb200_mat wc_in, wc_in_t;         /* center_mlp.w_in diag(gamma_center) [4 d_node, d_node] */
+  const float* bc_in;
+  petb200_mat wc_out, wc_out_t;       /* center_mlp.w_out [d_node, 2 d_node] */
+  const float* bc_out;
+} petb200_tl_weights;
+
+typedef struct petb200_gnn_weights {  /* one CartesianTransformer */
+  petb200_mat w1m;                    /* compress[0][:, -d:] (message columns), split */
+  petb200_mat w1m_t;                  /* its transpose [d, d], split */
+  const float* b_fold;                /* b_1 + W_1geo b_geo */
+  const float* geo_fold;              /* W_1geo W_geo [d, 4] */
+  const float* nbr_fold;              /* NbrEmb W_1nbr^T [S, d] or NULL (first GNN layer) */
+  petb200_mat w2, w2_t;               /* compress[2] [d, d] */
+  const float* b2;
+  int n_tl;
+  const petb200_tl_weights* tl;       /* HOST array of n_tl entries */
+} petb200_gnn_weights;
+
+typedef struct petb200_dims {
+  int64_t n_atoms, n_edges, n_ghost;  /* ghost rows follow the [E | N] token rows (atom-sharded runs) */
+  int d, d_node, num_heads, max_row, precision;
+  float scale;                        /* 1 / (sqrt(head_dim) * attention_temperature) */
+} petb200_dims;
+
+/* bytes of the forward's saved-for-backward buffer and of the scratch either direction needs */
+PETB200_API size_t petb200_gnn_saved_bytes(const petb200_gnn_weights* w, const petb200_dims* dims);
+PETB200_API size_t petb200_gnn_scratch_bytes(const petb200_gnn_weights* w, const petb200_dims* dims);
+/* x_out: [(E + N + n_ghost), d] token matrix after the last attention layer (rows [0, E) = the
+ * layer's output edge tokens); h_out [N, d_node].                                               */
+PETB200_API int petb200_gnn_fwd(const petb200_gnn_weights* w, const petb200_dims* dims, const int32_t* row_ptr,
+                    const int32_t* z_neighbors, const float* edge_vec, const float* edge_dist,
+                    const float* cutoff_factor, const float* h_in, const float* m_in, int64_t ld_m,
+                    float* x_out, float* h_out, void* saved, size_t saved_bytes, void* scratch,
+                    size_t scratch_bytes, petb200_stream_t stream);
+/* d_h [N, d_node] and d_t [E, d]: gradients of h_out and of the output edge tokens.  Accumulates
+ * into d_vec [E, 3], d_dist [E], d_fc [E]; adds the gradient w.r.t. m_in to d_m when d_m is not
+ * NULL; writes the gradient w.r.t. h_in to d_h_in when it is not NULL.                           */
+PETB200_API int petb200_gnn_bwd(const petb200_gnn_weights* w, const petb200_dims* dims, const int32_t* row_ptr,
+                    const float* cutoff_factor, const void* saved, const float* d_h, const float* d_t,
+                    float* d_m, int64_t ld_dm, float* d_vec, float* d_dist, float* d_fc, float* d_h_in,
+                    void* scratch, size_t scratch_bytes, petb200_stream_t stream);
+
 /* per-structure sums, src/metatrain/utils/sum_over_atoms.py:31 (deterministic: atoms of a
  * structure are contiguous; one warp per structure).                                    */
 PETB200_API int petb200_sum_over_atoms(const float* atomic, const int32_t* struct_ptr,

@@ -11,6 +11,7 @@ keeps working unchanged.
 
 Equations: SURVEY.md Appendix A (derived from the cited reference lines).
 """
+import ctypes
 import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
@@ -707,6 +708,60 @@ def _tl_backward_generic(pw: PackedWeights, T: dict, K: dict, hyp, topo: Topolog
     return d_X[:E], d_h_new
 
 
+def _mat(w: Tensor, pw) -> "lib.Mat":
+    """(device pointer of the bf16 hi/lo split of w, leading dimension) for the C++ schedule."""
+    assert w.dim() == 2 and w.stride(1) == 1
+    return lib.Mat(_split_weight_ptr(w, pw), w.stride(0))
+
+
+def _stage_structs(pw: PackedWeights, L: dict):
+    """ctypes mirror (petb200_gnn_weights) of one GNN layer's packed weights for petb200_gnn_fwd / _bwd,
+    or None when the layer is outside what the C++ schedule is built for.  Cached on the layer dict;
+    the packed tensors it points at live in ``pw`` (same lifetime)."""
+    if "_stage" in L:
+        return L["_stage"]
+    ok = all(T.get("qkv_img") is not None and T.get("mlp_img") is not None and "w_qkv_raw" not in T for T in L["tl"])
+    ok = ok and 1 <= len(L["tl"]) <= 16 and L["w_geo"].shape[0] == 128
+    if not ok:
+        L["_stage"] = None
+        return None
+    d = L["w_geo"].shape[0]
+    tls = (lib.TLWeights * len(L["tl"]))()
+    for k, T in enumerate(L["tl"]):
+        t = tls[k]
+        t.qkv_image, t.b_qkv, t.w_qkv_t = ptr(T["qkv_img"]), ptr(T["b_qkv"]), _mat(T["w_qkv_t"], pw)
+        t.w_o, t.w_o_t, t.b_o = _mat(T["w_o"], pw), _mat(T["w_o_t"], pw), ptr(T["b_o"])
+        t.mlp_image_fwd, t.mlp_image_bwd = ptr(T["mlp_img"][0]), ptr(T["mlp_img"][1])
+        t.b_in, t.b_out, t.d_ff = ptr(T["b_in"]), ptr(T["b_out"]), T["w_out"].shape[1]
+        t.w_con, t.w_con_t, t.b_con = _mat(T["w_con"], pw), _mat(T["w_con_t"], pw), ptr(T["b_con"])
+        t.w_exp, t.w_exp_t, t.b_exp = _mat(T["w_exp"], pw), _mat(T["w_exp_t"], pw), ptr(T["b_exp"])
+        t.wc_in, t.wc_in_t, t.bc_in = _mat(T["wc_in"], pw), _mat(T["wc_in_t"], pw), ptr(T["bc_in"])
+        t.wc_out, t.wc_out_t, t.bc_out = _mat(T["wc_out"], pw), _mat(T["wc_out_t"], pw), ptr(T["bc_out"])
+    g = lib.GNNWeights()
+    width = L["w1_t"].shape[0]
+    g.w1m, g.w1m_t = _mat(L["w1m"], pw), _mat(L["w1_t"][width - d:], pw)
+    g.b_fold, g.geo_fold, g.nbr_fold = ptr(L["b_fold"]), ptr(L["geo_fold"]), ptr(L["nbr_fold"])
+    g.w2, g.w2_t, g.b2 = _mat(L["w2"], pw), _mat(L["w2_t"], pw), ptr(L["b2"])
+    g.n_tl, g.tl = len(L["tl"]), tls
+    L["_stage"] = (g, tls)
+    return L["_stage"]
+
+
+def _dims(topo: Topology, hyp, H: int, prec: int) -> "lib.Dims":
+    d, nh = hyp["d_pet"], hyp["num_heads"]
+    return lib.Dims(topo.n_atoms, topo.n_edges, H, d, hyp["d_node"], nh, topo.max_row, prec,
+                    1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"]))
+
+
+def _bytes(n: int, like: Tensor) -> Tensor:
+    return torch.empty(max(int(n), 16), device=like.device, dtype=torch.uint8)
+
+
+#: use the C++ stage-level schedule (petb200_gnn_fwd / _bwd) where it applies; the per-op schedule
+#: below is the same sequence issued from Python (kept for the layer variants and as a cross-check)
+USE_STAGE_SCHEDULE = True
+
+
 def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc, h, m, prec):
     """One CartesianTransformer (transformer.py:463-562) on the CSR layout.  Returns the node
     features after its attention layers, the token matrix X ([E + N] rows; rows [:E] are the output
@@ -717,6 +772,20 @@ def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc,
     H = halo.n_ghost if halo is not None else 0  # ghost rows behind the [E | N] token rows
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
+    stage = (_stage_structs(pw, L) if USE_STAGE_SCHEDULE and prec != PREC_FP32 and not _is_generic(hyp)
+             and topo.max_row + 1 <= 64 and E > 0 else None)
+    if stage is not None:
+        # the whole CartesianTransformer enqueued by one C++ call (csrc/schedule.cu)
+        gw, dims = stage[0], _dims(topo, hyp, H, prec)
+        handle = lib.load()
+        saved = _bytes(handle.petb200_gnn_saved_bytes(ctypes.addressof(gw), ctypes.addressof(dims)), vec)
+        scratch = _bytes(handle.petb200_gnn_scratch_bytes(ctypes.addressof(gw), ctypes.addressof(dims)), vec)
+        Xf, h_out = _empty((E + N + H, d), vec), _empty((N, dn), vec)
+        lib.launch_count += lib.GNN_KERNELS["gnn_fwd"][0] + lib.GNN_KERNELS["gnn_fwd"][1] * len(L["tl"]) - 1
+        call("gnn_fwd", ctypes.addressof(gw), ctypes.addressof(dims), ptr(topo.row_ptr), ptr(topo.z_neighbors),
+             ptr(vec), ptr(dist), ptr(fc), ptr(h), ptr(m), m.stride(0), ptr(Xf), ptr(h_out), ptr(saved),
+             saved.numel(), ptr(scratch), scratch.numel())
+        return h_out, Xf[:E + N], Xf, {"stage": (gw, dims, saved), "tl": []}
     S: dict = {"tl": []}
     c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
     if prec != PREC_FP32 and d == 128:
@@ -911,6 +980,16 @@ def _gnn_backward(pw: PackedWeights, L: dict, S: dict, hyp, topo: Topology, fc, 
     d, dn, nh = hyp["d_pet"], hyp["d_node"], hyp["num_heads"]
     scale = 1.0 / ((d // nh) ** 0.5 * hyp["attention_temperature"])
     ref = fc
+    if "stage" in S:
+        gw, dims, saved = S["stage"]
+        scratch = _bytes(lib.load().petb200_gnn_scratch_bytes(ctypes.addressof(gw), ctypes.addressof(dims)), fc)
+        d_h_in = _empty((N, dn), ref) if h_grad_wanted else None
+        d_t = d_t.contiguous()
+        lib.launch_count += lib.GNN_KERNELS["gnn_bwd"][0] + lib.GNN_KERNELS["gnn_bwd"][1] * len(L["tl"]) - 1
+        call("gnn_bwd", ctypes.addressof(gw), ctypes.addressof(dims), ptr(topo.row_ptr), ptr(fc), ptr(saved),
+             ptr(d_h), ptr(d_t), ptr(d_m), d_m.stride(0) if d_m is not None else 0, ptr(d_vec), ptr(d_dist),
+             ptr(d_fc), ptr(d_h_in), ptr(scratch), scratch.numel())
+        return d_h_in
     for k in range(len(L["tl"]) - 1, -1, -1):
         T, K = L["tl"][k], S["tl"][k]
         dff = T["w_out"].shape[1]

@@ -88,12 +88,38 @@ _SIGNATURES = {
     "petb200_combine_bwd": [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_readout_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P],
     "petb200_readout_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P, _P],
+    "petb200_gnn_saved_bytes": [_P, _P],
+    "petb200_gnn_scratch_bytes": [_P, _P],
+    "petb200_gnn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _SZ, _P, _SZ, _P],
+    "petb200_gnn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P],
     "petb200_sum_over_atoms": [_P, _P, _I64, _I, _P, _P],
     "petb200_last_error": [],
     "petb200_version": [],
 }
-_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_combine_image_bytes": _SZ, "petb200_norm_linear_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
+_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_combine_image_bytes": _SZ, "petb200_gnn_saved_bytes": _SZ, "petb200_gnn_scratch_bytes": _SZ, "petb200_norm_linear_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
             "petb200_nl_num_bins": _I64, "petb200_nl_workspace": _SZ}
+
+
+# ---- structs of the stage-level schedule (include/petb200.h, "stage-level schedule")
+class Mat(ctypes.Structure):
+    _fields_ = [("w", _P), ("ld", _I64)]
+
+
+class TLWeights(ctypes.Structure):
+    _fields_ = [("qkv_image", _P), ("b_qkv", _P), ("w_qkv_t", Mat), ("w_o", Mat), ("w_o_t", Mat), ("b_o", _P),
+                ("mlp_image_fwd", _P), ("mlp_image_bwd", _P), ("b_in", _P), ("b_out", _P), ("d_ff", _I),
+                ("w_con", Mat), ("w_con_t", Mat), ("b_con", _P), ("w_exp", Mat), ("w_exp_t", Mat), ("b_exp", _P),
+                ("wc_in", Mat), ("wc_in_t", Mat), ("bc_in", _P), ("wc_out", Mat), ("wc_out_t", Mat), ("bc_out", _P)]
+
+
+class GNNWeights(ctypes.Structure):
+    _fields_ = [("w1m", Mat), ("w1m_t", Mat), ("b_fold", _P), ("geo_fold", _P), ("nbr_fold", _P), ("w2", Mat),
+                ("w2_t", Mat), ("b2", _P), ("n_tl", _I), ("tl", ctypes.POINTER(TLWeights))]
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [("n_atoms", _I64), ("n_edges", _I64), ("n_ghost", _I64), ("d", _I), ("d_node", _I),
+                ("num_heads", _I), ("max_row", _I), ("precision", _I), ("scale", _F)]
 
 
 def library_path() -> str:
@@ -149,6 +175,8 @@ def stream_ptr() -> int:
 _KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "edges_bwd_rc": 3, "adaptive_cutoff_bwd": 2, "adaptive_grid_bwd": 2, "csr_build": 6, "readout_bwd": 2,
                      "force_scatter": 2, "mlp_pack": 2}
 launch_count = 0
+#: kernels enqueued by one petb200_gnn_fwd / _bwd call: (fixed part, per attention layer)
+GNN_KERNELS = {"gnn_fwd": (2, 10), "gnn_bwd": (3, 11)}
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
 profile_hook = None
 

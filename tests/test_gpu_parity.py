@@ -214,6 +214,25 @@ def test_capture_diagnostics_fires_backbone_hooks():
     assert torch.equal(plain_nodes[0], nodes[0]) and torch.equal(plain_edges[0], edges[0])
 
 
+@pytest.mark.parametrize("case", ["water_384", "ragged_mix", "qm9_5_residual", "carbon_5"])
+def test_cxx_stage_schedule_equals_python_schedule(case):
+    """petb200_gnn_fwd / _bwd (the C++ stage-level schedule, csrc/schedule.cu) enqueue the same kernels
+    in the same order as the per-op Python schedule: results must be bit-identical."""
+    from metatrain_b200 import engine
+    g = load_golden(case)
+    be = make_backend(g, "bf16x3")
+    outs = {}
+    for flag in (True, False):
+        engine.USE_STAGE_SCHEDULE = flag
+        try:
+            outs[flag] = evaluate(be, **golden_inputs(g, DEV), target=g["target"], strain=True)
+        finally:
+            engine.USE_STAGE_SCHEDULE = True
+    for k in ("energies", "atomic", "dE_dpos"):
+        assert torch.equal(outs[True][k], outs[False][k]), k
+    assert np.abs(outs[True]["dE_dpos"].cpu().numpy() - g["ref32_dE_dpos"]).max() <= FORCE_TOL
+
+
 def test_csr_only_mode_equals_default():
     g = load_golden("water_384")
     be = make_backend(g)
