@@ -62,6 +62,23 @@ def test_ctypes_signatures_match_the_header():
         assert lib._SIGNATURES[name] == expected, f"{name}: ctypes {lib._SIGNATURES[name]} vs header {params}"
 
 
+def test_torchscript_operator_library_loads_and_registers_its_schemas():
+    """B3: csrc/libpetb200_torch.so (TORCH_LIBRARY(petb200, ...)) loads without a GPU and registers the
+    operators a scripted model calls; no compute here."""
+    import torch
+    from metatrain_b200 import export
+    export.build_torch_ops()
+    export.load_torch_ops()
+    topo, atomic = torch.ops.petb200.topology.default, torch.ops.petb200.pet_atomic.default
+    assert "Tensor[]" in str(topo._schema) and "float cutoff" in str(topo._schema)
+    assert str(atomic._schema).endswith("-> Tensor")
+    assert all(os.path.isfile(p) for p in export.extension_libraries())
+    with pytest.raises((RuntimeError, NotImplementedError)):   # no CPU path
+        torch.ops.petb200.topology(torch.zeros(2, 3), torch.zeros(1, 3, 3), torch.zeros(0, dtype=torch.int64),
+                                   torch.zeros(0, dtype=torch.int64), torch.zeros(0, 3, dtype=torch.int64),
+                                   torch.zeros(2, dtype=torch.int64), torch.zeros(2, dtype=torch.int64), 4.5)
+
+
 def test_state_dict_contract():
     g = load_golden("qm9_5")
     seed_all(0)
