@@ -44,6 +44,31 @@ def sum_over_atoms(atomic: Tensor, system_indices: Tensor, n_structures: int) ->
     return _SumOverAtoms.apply(atomic, struct_ptr, idx)
 
 
+def selection_mask(selected_atoms: Tensor, system_indices: Tensor) -> Tensor:
+    """Boolean mask ``[N]`` of the selected atoms of a batch.  ``selected_atoms``: a boolean mask
+    (returned as is) or ``[n, 2]`` integer ``(system, atom-within-system)`` pairs."""
+    if selected_atoms.dtype == torch.bool:
+        if selected_atoms.shape != system_indices.shape:
+            raise ValueError("selected_atoms mask must have one entry per atom")
+        return selected_atoms.to(system_indices.device)
+    sel = selected_atoms.to(system_indices.device).long()
+    if sel.dim() != 2 or sel.shape[1] != 2:
+        raise ValueError("selected_atoms must be a boolean mask [N] or (system, atom) pairs [n, 2]")
+    idx = system_indices.long()
+    n = idx.shape[0]
+    # atoms of a system are contiguous: first atom of every system by binary search
+    n_sys = int(idx[-1].item()) + 1 if n else 0
+    first = torch.searchsorted(idx, torch.arange(n_sys + 1, device=idx.device))
+    mask = torch.zeros(n, dtype=torch.bool, device=idx.device)
+    if sel.shape[0]:
+        sys_ok = (sel[:, 0] >= 0) & (sel[:, 0] < n_sys)
+        sys_c = sel[:, 0].clamp(0, max(n_sys - 1, 0))
+        glob = first[sys_c] + sel[:, 1]
+        ok = sys_ok & (sel[:, 1] >= 0) & (glob < first[sys_c + 1])
+        mask[glob[ok]] = True   # pairs that are not in the batch select nothing (mts.slice semantics)
+    return mask
+
+
 def evaluate(
     backend,
     positions: Tensor,
@@ -58,11 +83,21 @@ def evaluate(
     strain: bool = False,
     charge: Optional[Tensor] = None,
     spin_multiplicity: Optional[Tensor] = None,
+    selected_atoms: Optional[Tensor] = None,
 ) -> Dict[str, Tensor]:
     """One energy(+forces, +strain gradient) evaluation of a batch of structures.
 
     Returns ``energies [B, P]``, ``atomic [N, P]`` and, if requested, ``dE_dpos [N, 3]``
     and ``dE_dstrain [3, 3]`` (a single strain shared by the batch).
+
+    ``selected_atoms`` mirrors the argument of ``PET.forward``
+    (``src/metatrain/pet/model.py:282``; applied at ``:724`` / ``:921-925`` by slicing the per-atom
+    predictions before the sum over atoms): either a boolean mask ``[N]`` or ``[n, 2]`` integer
+    ``(system, atom)`` pairs (the values of the reference's ``Labels``).  Energies are then summed
+    over the selected atoms only, ``atomic`` holds their rows (in batch order), and the position
+    gradient is that of the selected atoms' energies w.r.t. ALL positions — what an MD engine with
+    domain decomposition needs: ghost atoms out to ``interaction_range = num_gnn_layers * cutoff``
+    (``model.py:1004``) take part in the message passing but are not summed.
     """
     pos = positions.detach().clone().requires_grad_(gradients)
     pos_in, cells_in = pos, cells
@@ -88,12 +123,16 @@ def evaluate(
     nodes, edges = backend.calculate_features(batch)
     pred, _, _ = backend.predict(nodes, edges, batch, cells_in, system_indices, [target])
     atomic = torch.cat(pred[target], dim=1) if len(pred[target]) > 1 else pred[target][0]
+    mask: Optional[Tensor] = None
+    if selected_atoms is not None:
+        mask = selection_mask(selected_atoms, system_indices)
+        atomic = atomic * mask.reshape((-1,) + (1,) * (atomic.dim() - 1)).to(atomic.dtype)
     if atomic.dim() > 2:  # tensorial per-atom outputs (non_conservative_stress: [N, 3, 3, P])
         energies = sum_over_atoms(atomic.reshape(atomic.shape[0], -1), system_indices,
                                   cells.shape[0]).reshape((cells.shape[0],) + tuple(atomic.shape[1:]))
     else:
         energies = sum_over_atoms(atomic, system_indices, cells.shape[0])
-    out = {"energies": energies.detach(), "atomic": atomic.detach()}
+    out = {"energies": energies.detach(), "atomic": atomic.detach() if mask is None else atomic.detach()[mask]}
     if gradients:
         wrt = [pos] + ([eps] if strain else [])
         grads = torch.autograd.grad(

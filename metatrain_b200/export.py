@@ -19,7 +19,7 @@ fixed cutoff, no system conditioning, one readout layer) on a tensor-core precis
 configuration the C++ stage schedule (``csrc/schedule.cu``) is built for.
 """
 import os
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 
@@ -126,8 +126,10 @@ def export_weights(backend, target: str) -> Tuple[List[Tensor], List[int], List[
 class ExportedPET(torch.nn.Module):
     """Scriptable energy model over the ``petb200::`` operators.
 
-    ``forward(positions, centers, neighbors, species, cells, cell_shifts, system_indices)`` returns
-    ``(energies [B, P], atomic [N, P])``; forces are ``-autograd.grad(energies.sum(), positions)``
+    ``forward(positions, centers, neighbors, species, cells, cell_shifts, system_indices,
+    selected_atoms=None)`` returns ``(energies [B, P], atomic [N, P])`` (``selected_atoms``: optional
+    boolean mask of the atoms to sum, the rest — e.g. ghost atoms within ``interaction_range`` of a
+    domain — only take part in the message passing); forces are ``-autograd.grad(energies.sum(), positions)``
     exactly as an MD engine computes them from the reference's exported model
     (``src/metatrain/utils/evaluate_model.py:21-160``)."""
 
@@ -140,10 +142,14 @@ class ExportedPET(torch.nn.Module):
         self.fmeta: List[float] = fmeta
         self.cutoff: float = float(backend.cutoff)
         self.interaction_range: float = float(backend.cutoff) * len(backend.gnn_layers)  # model.py:1004
+        # what an atom's energy really depends on with the feedforward featurizer: the last message
+        # update (backend.py:559-575) still mixes in the reversed token of the last GNN layer
+        self.receptive_range: float = float(backend.cutoff) * (len(backend.gnn_layers) + 1)
         self.register_buffer("species_to_species_index", backend.species_to_species_index.detach().clone())
 
     def forward(self, positions: Tensor, centers: Tensor, neighbors: Tensor, species: Tensor, cells: Tensor,
-                cell_shifts: Tensor, system_indices: Tensor) -> Tuple[Tensor, Tensor]:
+                cell_shifts: Tensor, system_indices: Tensor,
+                selected_atoms: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         z = species.to(torch.int64)
         table = self.species_to_species_index
         outside = (z < 0) | (z >= table.shape[0])
@@ -151,6 +157,8 @@ class ExportedPET(torch.nn.Module):
         topo = torch.ops.petb200.topology(positions, cells, centers, neighbors, cell_shifts, system_indices,
                                           z_nodes, self.cutoff)
         atomic = torch.ops.petb200.pet_atomic(positions, cells, topo, self.weights, self.meta, self.fmeta)
+        if selected_atoms is not None:   # boolean mask [N] (pet/model.py:282,921-925): ghosts are not summed
+            atomic = atomic * selected_atoms.to(atomic.dtype).unsqueeze(1)
         energies = torch.zeros((cells.shape[0], atomic.shape[1]), dtype=atomic.dtype, device=atomic.device)
         energies = energies.index_add(0, system_indices.to(torch.int64), atomic)
         return energies, atomic

@@ -60,6 +60,14 @@ def test_scripted_module_round_trips_and_matches_reference(case):
         if strain:
             assert np.abs(grads[1].cpu().numpy() - g["ref32_dE_dstrain"]).max() <= 1e-4
     assert loaded.interaction_range == pytest.approx(be.cutoff * len(be.gnn_layers))
+    # selected_atoms: only the selected atoms are summed, all of them take part in the message passing
+    mask = torch.zeros(inp["positions"].shape[0], dtype=torch.bool, device=DEV)
+    mask[::3] = True
+    e_sel, a_sel = loaded(inp["positions"], inp["centers"], inp["neighbors"], inp["species"], inp["cells"],
+                          inp["cell_shifts"], inp["system_indices"], mask)
+    ref_sel = evaluate(be, **inp, target=g["target"], selected_atoms=mask, gradients=False)
+    torch.testing.assert_close(e_sel, ref_sel["energies"], rtol=2e-6, atol=1e-5)
+    assert torch.equal(a_sel[mask], ref_sel["atomic"])
 
 
 def test_export_rejects_what_is_not_packaged_and_lists_its_extensions():

@@ -233,6 +233,54 @@ def test_cxx_stage_schedule_equals_python_schedule(case):
     assert np.abs(outs[True]["dE_dpos"].cpu().numpy() - g["ref32_dE_dpos"]).max() <= FORCE_TOL
 
 
+def test_selected_atoms_domain_decomposition_reproduces_the_periodic_box():
+    """``selected_atoms`` (pet/model.py:282,724): cut the periodic water box into two open clusters
+    (own atoms + ghost images), evaluate each with only its own atoms selected: per-atom energies
+    and the summed position gradients must reproduce the periodic evaluation — what LAMMPS domain
+    decomposition relies on.  Ghosts are taken out to (num_gnn_layers + 1) * cutoff: the feedforward
+    featurizer's last message update (backend.py:559-575) mixes in the reversed token of the LAST
+    GNN layer, so an atom's energy depends on atoms up to 3 cutoffs away, one more than the
+    ``interaction_range = num_gnn_layers * cutoff`` the reference declares (model.py:1004)."""
+    from metatrain_b200.neighbors import neighbor_list
+    g = load_golden("water_384")
+    be = make_backend(g, "fp32")
+    full = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    box = water_384()
+    pos, cell, Z = box["positions"], box["cell"], box["Z"]
+    n = len(Z)
+    rng_cut = be.cutoff * (len(be.gnn_layers) + 1)
+    frac = (pos @ np.linalg.inv(cell)) % 1.0
+    images = np.array([[a, b, c] for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)])
+    all_pos = (pos[None] + (images @ cell)[:, None]).reshape(-1, 3)
+    all_id = np.tile(np.arange(n), len(images))
+    home = np.repeat((images == 0).all(1), n)
+    e_atomic = np.zeros(n)
+    grad = np.zeros((n, 3))
+    for side in (0, 1):
+        own = np.nonzero((frac[:, 0] < 0.5) == (side == 0))[0]
+        d2 = ((all_pos[:, None, :] - pos[own][None, :, :]) ** 2).sum(-1).min(1)
+        keep = np.nonzero(d2 <= rng_cut ** 2)[0]
+        is_own = home[keep] & np.isin(all_id[keep], own)
+        cp, cz, cid = all_pos[keep], Z[all_id[keep]], all_id[keep]
+        i, j, S = neighbor_list(cp, np.eye(3), False, be.cutoff)
+        batch = dict(positions=torch.tensor(cp, dtype=torch.float32), centers=torch.tensor(i), neighbors=torch.tensor(j),
+                     species=torch.tensor(cz), cells=torch.zeros(1, 3, 3), cell_shifts=torch.tensor(S).reshape(-1, 3),
+                     system_indices=torch.zeros(len(cp), dtype=torch.long))
+        out = evaluate(be, **{k: v.to(DEV) for k, v in batch.items()}, target=g["target"],
+                       selected_atoms=torch.tensor(is_own))
+        assert out["atomic"].shape[0] == int(is_own.sum())
+        e_atomic[cid[is_own]] = out["atomic"].cpu().numpy()[:, 0]
+        np.add.at(grad, cid, out["dE_dpos"].cpu().numpy())
+        assert abs(float(out["energies"]) - float(out["atomic"].sum())) <= 1e-3
+    assert np.abs(e_atomic - full["atomic"].cpu().numpy()[:, 0]).max() <= 2e-5
+    assert np.abs(grad - full["dE_dpos"].cpu().numpy()).max() <= 5e-5
+    # (system, atom) pairs select the same atoms as the mask
+    pairs = torch.tensor([[0, 0], [0, 5], [0, 383], [3, 1]])
+    sel = evaluate(be, **golden_inputs(g, DEV), target=g["target"], selected_atoms=pairs)
+    assert torch.equal(sel["atomic"], full["atomic"][[0, 5, 383]])
+    assert abs(float(sel["energies"]) - float(full["atomic"][[0, 5, 383]].sum())) <= 1e-4
+
+
 def test_csr_only_mode_equals_default():
     g = load_golden("water_384")
     be = make_backend(g)
