@@ -336,7 +336,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
     // the rare "residual AND accumulate" case adds the old C late, unprefetched
     const float* pre_src = g.residual ? g.residual : (g.accumulate ? g.C : nullptr);
     const int64_t pre_ld = g.residual ? g.ldr : g.ldc;
+    // the residual applies to rows [0, residual_rows) only (edge rows of an [edges | atoms] token matrix)
+    const int64_t res_rows = (g.residual && g.residual_rows >= 0) ? g.residual_rows : g.M;
     const bool late_acc = g.residual && g.accumulate;
+    // SILU_GEO (petb200_compress_gemm, N = BN): the 4 geometry weights of each of this lane's 16 output
+    // columns stay in registers for the CTA's life (they were 4 L1 loads per output float4 before)
+    float4 gw[EPI == PETB200_EPI_SILU_GEO ? NCH : 1][4];
+    if (EPI == PETB200_EPI_SILU_GEO) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gw[ch][q] = ld4(g.geo_w + (64 * half + EPI_COLS * ch + 4 * c4 + q) * 4);
+    }
     for (int j = 0; j < sched.count; ++j) {
       int64_t m0;
       int n0;
@@ -366,9 +377,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
       }
       // Global operands of the whole item are requested BEFORE waiting for the MMA, so
       // their latency hides behind the main loop of this item.
-      float4 pre[NCH][4];
+      float4 pre[EPI == PETB200_EPI_SILU_GEO ? 1 : NCH][4];   // (SILU_GEO has no additive operand)
       if (EPI == PETB200_EPI_NONE || EPI == PETB200_EPI_SILU || EPI == PETB200_EPI_MUL_DSILU ||
-          EPI == PETB200_EPI_RMS_BWD || EPI == PETB200_EPI_SILU_GEO) {
+          EPI == PETB200_EPI_RMS_BWD) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -379,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
             if (!ok[it]) continue;
             if (EPI == PETB200_EPI_MUL_DSILU || EPI == PETB200_EPI_RMS_BWD) {
               pre[ch][it] = ld4(g.aux_in + m * g.ld_aux + c0);
-            } else if (pre_src) {
+            } else if (pre_src && m < res_rows) {
               pre[ch][it] = ld4(pre_src + m * pre_ld + c0);
             }
           }
@@ -474,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
             const float4 v = staged(it), x4 = pre[ch][it];
             float4 o = make_float4(rs[it] * v.x - x4.x * kap[it], rs[it] * v.y - x4.y * kap[it],
                                    rs[it] * v.z - x4.z * kap[it], rs[it] * v.w - x4.w * kap[it]);
-            if (g.residual) {
+            if (g.residual && m < res_rows) {
               const float4 r4 = ld4(g.residual + m * g.ldr + c0);
               o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
             }
@@ -535,7 +546,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
               const float4 gv = geo[it];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 w = ld4(g.geo_w + (c0 + q) * 4);
+                const float4 w = gw[EPI == PETB200_EPI_SILU_GEO ? ch : 0][q];
                 (&v.x)[q] += w.x * gv.x + w.y * gv.y + w.z * gv.z + w.w * gv.w;
               }
               if (g.row_table) {
@@ -556,7 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, GemmArgs g) {
                 const float4 r = ld4(pre_src + m * pre_ld + c0);
                 v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
               }
-            } else {
+            } else if (EPI != PETB200_EPI_SILU_GEO) {
               v.x += pre[ch][it].x;
               v.y += pre[ch][it].y;
               v.z += pre[ch][it].z;

@@ -18,6 +18,7 @@ struct GemmArgs {
   const float* row_scale;  // [M] or null
   const float* residual;   // [M, N] or null
   int64_t ldr;
+  int64_t residual_rows = -1;  // >= 0: the residual applies to rows [0, residual_rows) only (tensor-core path)
   const float* aux_in;  // MUL_DSILU: pre-activation [M, N]; SWIGLU_BWD: [u | g] [M, 2N]
   float* aux_out;       // SILU: pre-activation [M, N]; SWIGLU: [u | g] [M, N]
   int64_t ld_aux;

@@ -99,42 +99,54 @@ __global__ void compress_input_kernel(const float* __restrict__ vec, const float
 
 // backward of the geometry embedder: d_(r,d)[e] (+)= W_geo^T d_geo[e]
 // Eight lanes per edge (four edges per warp): 3 shuffle steps on 4 values per 4 rows instead of
-// 5 steps per row; every load is a coalesced 128-byte segment.  Requires d = 128.
+// 5 steps per row; every load is a coalesced 128-byte segment.  Grid-stride over edge groups with
+// the geometry weights of this lane's 16 columns in registers (they were one L1 load per 4 FMAs).
+// Requires d = 128.
 __global__ void geom_embed_bwd_kernel(const float* __restrict__ d_geo, int64_t ld,
                                       const float* __restrict__ w_geo, int64_t n_edges,
                                       int accumulate, float* __restrict__ d_vec,
                                       float* __restrict__ d_dist) {
   const int lane = threadIdx.x & 31, sub = lane & 7;
-  const int64_t e = global_warp() * 4 + (lane >> 3);
-  const bool ok = e < n_edges;
-  float ax = 0.f, ay = 0.f, az = 0.f, ad = 0.f;
+  float4 w[4][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k4 = sub + 8 * j;  // float4 column
-    const float4 gv = ok ? __ldg(reinterpret_cast<const float4*>(d_geo + e * ld) + k4)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(w_geo) + k4 * 4 + c);
-      ax = fmaf(gg[c], w.x, ax);
-      ay = fmaf(gg[c], w.y, ay);
-      az = fmaf(gg[c], w.z, az);
-      ad = fmaf(gg[c], w.w, ad);
+    for (int c = 0; c < 4; ++c) w[j][c] = __ldg(reinterpret_cast<const float4*>(w_geo) + (sub + 8 * j) * 4 + c);
+  const int64_t n_groups = ceil_div(n_edges, 4);
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t grp = global_warp(); grp < n_groups; grp += stride) {
+    const int64_t e = grp * 4 + (lane >> 3);
+    const bool ok = e < n_edges;
+    float4 gv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      gv[j] = ok ? __ldg(reinterpret_cast<const float4*>(d_geo + e * ld) + sub + 8 * j)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    float ax = 0.f, ay = 0.f, az = 0.f, ad = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gg[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ax = fmaf(gg[c], w[j][c].x, ax);
+        ay = fmaf(gg[c], w[j][c].y, ay);
+        az = fmaf(gg[c], w[j][c].z, az);
+        ad = fmaf(gg[c], w[j][c].w, ad);
+      }
     }
-  }
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    ax += __shfl_xor_sync(0xffffffffu, ax, o);
-    ay += __shfl_xor_sync(0xffffffffu, ay, o);
-    az += __shfl_xor_sync(0xffffffffu, az, o);
-    ad += __shfl_xor_sync(0xffffffffu, ad, o);
-  }
-  if (ok && sub == 0) {
-    if (accumulate) {
-      d_vec[3 * e] += ax; d_vec[3 * e + 1] += ay; d_vec[3 * e + 2] += az; d_dist[e] += ad;
-    } else {
-      d_vec[3 * e] = ax; d_vec[3 * e + 1] = ay; d_vec[3 * e + 2] = az; d_dist[e] = ad;
+    for (int o = 1; o < 8; o <<= 1) {
+      ax += __shfl_xor_sync(0xffffffffu, ax, o);
+      ay += __shfl_xor_sync(0xffffffffu, ay, o);
+      az += __shfl_xor_sync(0xffffffffu, az, o);
+      ad += __shfl_xor_sync(0xffffffffu, ad, o);
+    }
+    if (ok && sub == 0) {
+      if (accumulate) {
+        d_vec[3 * e] += ax; d_vec[3 * e + 1] += ay; d_vec[3 * e + 2] += az; d_dist[e] += ad;
+      } else {
+        d_vec[3 * e] = ax; d_vec[3 * e + 1] = ay; d_vec[3 * e + 2] = az; d_dist[e] = ad;
+      }
     }
   }
 }
@@ -570,7 +582,12 @@ extern "C" PETB200_API int petb200_geom_embed_bwd(const float* d_geo, int64_t ld
     return PETB200_ERR_UNSUPPORTED;
   }
   PETB200_REQUIRE(ld % 4 == 0, "geom_embed_bwd: ld must be a multiple of 4");
-  LAUNCH_ROWS(geom_embed_bwd_kernel, ceil_div(n_edges, 4), d_geo, ld, w_geo, n_edges, accumulate, d_vec, d_dist);
+  if (n_edges > 0) {
+    const int64_t blocks = ceil_div(ceil_div(n_edges, 4), kWarpsPerBlock);
+    const int64_t cap = 16 * kNumSMs;   // persistent: the weights are loaded once per thread
+    geom_embed_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kWarpsPerBlock * 32, 0, stream>>>(
+        d_geo, ld, w_geo, n_edges, accumulate, d_vec, d_dist);
+  }
   return check_launch("geom_embed_bwd");
 }
 

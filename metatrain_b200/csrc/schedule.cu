@@ -6,6 +6,7 @@
 // CartesianTransformer.forward (src/metatrain/pet/modules/transformer.py:463-562) and
 // TransformerLayer._forward_pre_ln_impl (:203-234) on the CSR token layout.
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace petb200 {
 namespace {
@@ -45,7 +46,7 @@ Saved carve_saved(Arena& a, const petb200_gnn_weights& w, const petb200_dims& g)
     L.qkv = a.f32(T, 3 * g.d);
     L.o = a.f32(T, g.d);
     L.lse = a.f32(T, g.num_heads);
-    L.tp = a.f32(E, g.d);
+    L.tp = a.f32(T, g.d);   // rows [0, E): t' (edge tokens after attention); rows [E, T): y_c (centre rows)
     L.h1 = a.f32(N, g.d_node);
     L.rstd3 = a.f32(N);
     L.ugc = a.f32(N, 4 * g.d_node);
@@ -63,6 +64,23 @@ int gemm(const float* A, int64_t lda, const petb200_mat& W, float* C, int64_t ld
          float* aux_out, int64_t ld_aux, int epilogue, int accumulate, int precision, cudaStream_t stream) {
   return petb200_gemm(A, lda, W.w, W.ld, C, ldc, M, N, K, bias, row_scale, residual, ldr, aux_in, aux_out, ld_aux,
                       epilogue, accumulate, precision, stream);
+}
+
+// One contraction over ALL token rows [edges | atoms] whose residual applies to the edge rows only:
+// the edge-row and the centre-row GEMM of the per-op schedule share their weights, so they are one launch
+int gemm_tokens(const float* A, int64_t lda, const petb200_mat& W, float* C, int64_t ldc, int64_t rows, int64_t edge_rows,
+                int N, int K, const float* bias, const float* row_scale, const float* residual, int64_t ldr,
+                const float* aux_in, int64_t ld_aux, int epilogue, int precision, cudaStream_t stream) {
+  if (rows == 0) return PETB200_OK;
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.W = W.w; g.ldw = W.ld; g.C = C; g.ldc = ldc; g.M = rows; g.N = N; g.K = K;
+  g.bias = bias; g.row_scale = row_scale; g.residual = residual; g.ldr = ldr; g.residual_rows = edge_rows;
+  g.aux_in = aux_in; g.aux_out = nullptr; g.ld_aux = ld_aux; g.epilogue = epilogue; g.accumulate = 0;
+  if (!gemm_tc_supports(g)) {
+    set_error("gnn schedule: contraction shape outside the tensor-core kernel (N %% 128, K %% 64)");
+    return PETB200_ERR_UNSUPPORTED;
+  }
+  return launch_gemm_tc(g, precision, stream);
 }
 
 int check(const petb200_gnn_weights* w, const petb200_dims* g, const char* what) {
@@ -88,11 +106,11 @@ extern "C" PETB200_API size_t petb200_gnn_scratch_bytes(const petb200_gnn_weight
   if (!w || !g) return 0;
   const int64_t E = g->n_edges, N = g->n_atoms, T = E + N;
   Arena f(nullptr), b(nullptr);
-  // forward: a1, yc, sc, two node-feature buffers
+  // forward: a1, (spare), sc, two node-feature buffers
   f.f32(E, g->d); f.f32(N, g->d); f.f32(N, 2 * g->d_node); f.f32(N, g->d_node); f.f32(N, g->d_node);
-  // backward: d_tp, two d_t buffers, d_ugc, d_xhc, d_h1, d_yc, d_o, d_qkv, dsum, two d_h buffers, d_c1
-  b.f32(E, g->d); b.f32(E, g->d); b.f32(E, g->d); b.f32(N, 4 * g->d_node); b.f32(N, g->d_node);
-  b.f32(N, g->d_node); b.f32(N, g->d); b.f32(T, g->d); b.f32(T, 3 * g->d); b.f32(T, g->num_heads);
+  // backward: d_tp | d_yc, two (d_t | d_c) buffers, d_ugc, d_xhc, d_h1, d_o, d_qkv, dsum, two d_h buffers, d_c1
+  b.f32(T, g->d); b.f32(T, g->d); b.f32(T, g->d); b.f32(N, 4 * g->d_node); b.f32(N, g->d_node);
+  b.f32(N, g->d_node); b.f32(T, g->d); b.f32(T, 3 * g->d); b.f32(T, g->num_heads);
   b.f32(N, g->d_node); b.f32(N, g->d_node); b.f32(E, g->d);
   return (f.used > b.used ? f.used : b.used) + kAlign;
 }
@@ -112,7 +130,7 @@ extern "C" PETB200_API int petb200_gnn_fwd(const petb200_gnn_weights* w, const p
   Arena sa(saved), sc(scratch);
   Saved S = carve_saved(sa, *w, *g);
   float* a1 = sc.f32(E, d);
-  float* yc = sc.f32(N, d);
+  sc.f32(N, d);
   float* swi = sc.f32(N, 2 * dn);
   float* hbuf[2] = {sc.f32(N, dn), sc.f32(N, dn)};
 
@@ -134,11 +152,10 @@ extern "C" PETB200_API int petb200_gnn_fwd(const petb200_gnn_weights* w, const p
     // RMSNorm + QKV projection, attention
     CHECK(petb200_norm_linear(L.x, d, t.qkv_image, t.b_qkv, T, d, 3 * d, L.qkv, 3 * d, L.rstd1, stream));
     CHECK(petb200_attention_fwd(L.qkv, row_ptr, fc, N, E, nh, d / nh, g->scale, g->max_row, prec, L.o, L.lse, stream));
-    // output projection: edge rows with the residual, centre rows without
-    CHECK(gemm(L.o, d, t.w_o, L.tp, d, E, d, d, t.b_o, nullptr, L.x, d, nullptr, nullptr, 0, PETB200_EPI_NONE, 0, prec,
-               stream));
-    CHECK(gemm(L.o + E * d, d, t.w_o, yc, d, N, d, d, t.b_o, nullptr, nullptr, 0, nullptr, nullptr, 0, PETB200_EPI_NONE,
-               0, prec, stream));
+    // output projection of all token rows in one launch: edge rows with the residual, centre rows without
+    float* yc = L.tp + E * d;
+    CHECK(gemm_tokens(L.o, d, t.w_o, L.tp, d, T, E, d, d, t.b_o, nullptr, L.x, d, nullptr, 0, PETB200_EPI_NONE, prec,
+                      stream));
     // node update: h1 = h + W_exp y_c ; h2 = h1 + W_out swiglu(W_in rms(h1))
     CHECK(gemm(yc, d, t.w_exp, L.h1, dn, N, dn, d, t.b_exp, nullptr, h, dn, nullptr, nullptr, 0, PETB200_EPI_NONE, 0,
                prec, stream));
@@ -167,12 +184,12 @@ extern "C" PETB200_API int petb200_gnn_bwd(const petb200_gnn_weights* w, const p
   const int d = g->d, dn = g->d_node, nh = g->num_heads, prec = g->precision;
   Arena sa(const_cast<void*>(saved)), sc(scratch);
   const Saved S = carve_saved(sa, *w, *g);
-  float* d_tp = sc.f32(E, d);
-  float* d_tbuf[2] = {sc.f32(E, d), sc.f32(E, d)};
+  float* d_tp = sc.f32(T, d);          // rows [0, E): d t' ; rows [E, T): d y_c
+  float* d_tbuf[2] = {sc.f32(T, d), sc.f32(T, d)};   // rows [0, E): d t ; rows [E, T): d (centre token)
   float* d_ugc = sc.f32(N, 4 * dn);
   float* d_xhc = sc.f32(N, dn);
   float* d_h1 = sc.f32(N, dn);
-  float* d_yc = sc.f32(N, d);
+  float* d_yc = d_tp + E * d;
   float* d_o = sc.f32(T, d);
   float* d_qkv = sc.f32(T, 3 * d);
   float* dsum = sc.f32(T, nh);
@@ -195,19 +212,15 @@ extern "C" PETB200_API int petb200_gnn_bwd(const petb200_gnn_weights* w, const p
     // h1 = h + W_exp y_c ; t' = t + y_e ; y = W_o o
     CHECK(gemm(d_h1, dn, t.w_exp_t, d_yc, d, N, d, dn, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0,
                PETB200_EPI_NONE, 0, prec, stream));
-    CHECK(gemm(d_tp, d, t.w_o_t, d_o, d, E, d, d, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, PETB200_EPI_NONE, 0,
-               prec, stream));
-    CHECK(gemm(d_yc, d, t.w_o_t, d_o + E * d, d, N, d, d, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0,
-               PETB200_EPI_NONE, 0, prec, stream));
+    CHECK(gemm_tokens(d_tp, d, t.w_o_t, d_o, d, T, T, d, d, nullptr, nullptr, nullptr, 0, nullptr, 0, PETB200_EPI_NONE,
+                      prec, stream));
     CHECK(petb200_attention_bwd(L.qkv, L.o, L.lse, d_o, row_ptr, fc, N, E, nh, d / nh, g->scale, g->max_row, prec, d_qkv,
                                 d_fc, dsum, stream));
     // dgrad through the QKV projection and the RMSNorm in front of it (RMSNorm backward in the epilogue)
     float* d_t_new = d_tbuf[k & 1];
-    float* d_c = d_yc;
-    CHECK(gemm(d_qkv, 3 * d, t.w_qkv_t, d_t_new, d, E, d, 3 * d, nullptr, L.rstd1, d_tp, d, L.x, nullptr, d,
-               PETB200_EPI_RMS_BWD, 0, prec, stream));
-    CHECK(gemm(d_qkv + E * 3 * d, 3 * d, t.w_qkv_t, d_c, d, N, d, 3 * d, nullptr, L.rstd1 + E, nullptr, 0, L.x + E * d,
-               nullptr, d, PETB200_EPI_RMS_BWD, 0, prec, stream));
+    float* d_c = d_t_new + E * d;
+    CHECK(gemm_tokens(d_qkv, 3 * d, t.w_qkv_t, d_t_new, d, T, E, d, 3 * d, nullptr, L.rstd1, d_tp, d, L.x, d,
+                      PETB200_EPI_RMS_BWD, prec, stream));
     if (k > 0 || d_h_in != nullptr) {
       float* d_h_new = k > 0 ? d_hbuf[k & 1] : d_h_in;
       CHECK(gemm(d_c, d, t.w_con_t, d_h_new, dn, N, dn, d, nullptr, nullptr, d_h1, dn, nullptr, nullptr, 0,

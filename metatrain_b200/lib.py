@@ -176,7 +176,7 @@ _KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "edges_b
                      "force_scatter": 2, "mlp_pack": 2}
 launch_count = 0
 #: kernels enqueued by one petb200_gnn_fwd / _bwd call: (fixed part, per attention layer)
-GNN_KERNELS = {"gnn_fwd": (2, 10), "gnn_bwd": (3, 11)}
+GNN_KERNELS = {"gnn_fwd": (2, 9), "gnn_bwd": (3, 9)}
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
 profile_hook = None
 
