@@ -359,7 +359,9 @@ PETB200_API int petb200_attention_fwd(const float* qkv, const int32_t* row_ptr,
                           int num_heads, int head_dim, float scale, int max_row,
                           int precision, float* out, float* lse, petb200_stream_t stream);
 /* d_qkv from d_out; d_fc[e] += (sum_{heads,queries} dS[.,e]) / f_e  (f_e > 1e-15).
- * dsum is [E+N, num_heads] scratch (row sums dO.O, passed between the two kernels).     */
+ * dsum: (E+N) * num_heads floats of scratch (fp32 path: row sums dO.O passed between its two
+ * kernels; tensor-core path: per-head key-bias gradients [num_heads, E+N], reduced over the heads
+ * by a second small kernel so that the heads of an atom never synchronise).                     */
 PETB200_API int petb200_attention_bwd(const float* qkv, const float* out, const float* lse,
                           const float* d_out, const int32_t* row_ptr,
                           const float* cutoff_factor, int64_t n_atoms, int64_t n_edges,

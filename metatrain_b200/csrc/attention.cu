@@ -356,7 +356,7 @@ extern "C" PETB200_API int petb200_attention_bwd(const float* qkv, const float* 
                                      cudaStream_t stream) {
   if (precision != PETB200_PREC_FP32 && n_atoms > 0 && attention_tc_supports(num_heads, head_dim, max_row))
     return launch_attention_bwd_tc(qkv, out, lse, d_out, row_ptr, cutoff_factor, n_atoms, n_edges, scale,
-                                   max_row, d_qkv, d_fc, stream);
+                                   max_row, d_qkv, d_fc, dsum, stream);
   const size_t smem_a = fwd_smem_bytes(max_row + 1, 8), smem_b = dkv_smem_bytes(max_row + 1, 8);
   if (int rc = check_shape("attention_bwd", num_heads, head_dim, smem_b > smem_a ? smem_b : smem_a, max_row))
     return rc;

@@ -33,7 +33,6 @@ namespace {
 constexpr int H = 8, HD = 16, D = H * HD;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int kPrefetchDistance = 2 * kNumSMs;  // ~ CTAs resident at a time
 
 __device__ __forceinline__ int64_t token_row(int p, int row_lo, int64_t n_edges, int64_t atom) {
   return p == 0 ? n_edges + atom : (int64_t)row_lo + (p - 1);
@@ -54,7 +53,8 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                                          uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
+  // (not volatile: independent accumulator chains may be interleaved by the scheduler)
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
       "{%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -70,7 +70,7 @@ __device__ __forceinline__ void mma_x3(float (&c)[4], const uint32_t (&ah)[4], c
 // transpose of an 8x8 b16 matrix held one 32-bit register per lane (row g, cols 2t..2t+1)
 __device__ __forceinline__ uint32_t movm(uint32_t x) {
   uint32_t y;
-  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
@@ -106,13 +106,6 @@ __device__ __forceinline__ float key_bias(int k, int T, int lo, const float* __r
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void prefetch_atom_rows(const float* base, int ld, int64_t atom,
-                                                   const int32_t* __restrict__ row_ptr, int64_t n_edges) {
-  const int lo = __ldg(row_ptr + atom), hi = __ldg(row_ptr + atom + 1);
-  if (hi > lo) prefetch_l2(base + (int64_t)lo * ld, (uint32_t)(hi - lo) * ld * 4u);
-  prefetch_l2(base + (n_edges + atom) * ld, (uint32_t)ld * 4u);
-}
-
 // ------------------------------------------------------------------------- forward
 // Per warp (= head) shared memory: K fragments [2*NKB][32] uint4 (hi0, hi1, lo0, lo1 per
 // 8-key tile), V^T fragments [2*NKB][32] uint4, key bias [16*NKB] floats.  These are the
@@ -120,47 +113,69 @@ __device__ __forceinline__ void prefetch_atom_rows(const float* base, int ld, in
 template <int NKB>
 __global__ void __launch_bounds__(256, 3) attention_fwd_tc_kernel(
     const float* __restrict__ qkv, const int32_t* __restrict__ row_ptr,
-    const float* __restrict__ fc, int64_t n_edges, float scale, float* __restrict__ out,
+    const float* __restrict__ fc, int64_t n_atoms, int64_t n_edges, float scale, float* __restrict__ out,
     float* __restrict__ lse) {
   extern __shared__ uint4 smem4[];
   constexpr int WARP_U4 = 2 * (2 * NKB * 32) + 4 * NKB;  // uint4 units per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int64_t atom = blockIdx.x;
-  const int lo = __ldg(row_ptr + atom);
-  const int T = __ldg(row_ptr + atom + 1) - lo + 1;
-  const int nkb = (T + 15) >> 4;
   const int h = warp;
-  if (threadIdx.x == 0 && atom + kPrefetchDistance < (int64_t)gridDim.x)
-    prefetch_atom_rows(qkv, 3 * D, atom + kPrefetchDistance, row_ptr, n_edges);
   uint4* kfrag = smem4 + (size_t)warp * WARP_U4;
   uint4* vfrag = kfrag + 2 * NKB * 32;
   float* lbias = reinterpret_cast<float*>(vfrag + 2 * NKB * 32);
+  // Persistent CTAs: warp h of CTA b walks the atoms b, b + grid, ... (the eight heads of an atom run
+  // side by side and share its rows in L1 / L2, but never synchronise).  The CSR bounds of the next
+  // atom are loaded, and its rows pulled into L2, one atom ahead.
+  int64_t atom = blockIdx.x;
+  int lo_next = atom < n_atoms ? __ldg(row_ptr + atom) : 0;
+  int hi_next = atom < n_atoms ? __ldg(row_ptr + atom + 1) : 0;
+  for (; atom < n_atoms; atom += gridDim.x) {
+  const int lo = lo_next;
+  const int T = hi_next - lo + 1;
+  const int nkb = (T + 15) >> 4;
+  {
+    const int64_t nxt = atom + gridDim.x;
+    if (nxt < n_atoms) {
+      lo_next = __ldg(row_ptr + nxt);
+      hi_next = __ldg(row_ptr + nxt + 1);
+      if (threadIdx.x == 0) {
+        if (hi_next > lo_next) prefetch_l2(qkv + (int64_t)lo_next * (3 * D), (uint32_t)(hi_next - lo_next) * 3 * D * 4u);
+        prefetch_l2(qkv + (n_edges + nxt) * (3 * D), 3 * D * 4u);
+      }
+    }
+  }
 
-  // two 8-key tiles per iteration: all four global loads are issued before the conversions
-  for (int jb = 0; jb < nkb; ++jb) {
-    float4 k4[2], v4[2];
+  // all K / V rows of the atom are requested before the first conversion (one exposed memory
+  // latency per atom instead of one per 16-key tile)
+  float4 k4[NKB][2], v4[NKB][2];
+#pragma unroll
+  for (int jb = 0; jb < NKB; ++jb) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int key = 16 * jb + 8 * u + g;
-      const bool ok = key < T;
+      const bool ok = jb < nkb && key < T;
       const float* row = qkv + token_row(ok ? key : 0, lo, n_edges, atom) * (3 * D) + h * HD + 4 * t;
-      k4[u] = ok ? ldg4(row + D) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v4[u] = ok ? ldg4(row + 2 * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+      k4[jb][u] = ok ? ldg4(row + D) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v4[jb][u] = ok ? ldg4(row + 2 * D) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = 2 * jb + u;
-      uint4 kf, vf;
-      split2(k4[u].x, k4[u].y, kf.x, kf.z);
-      split2(k4[u].z, k4[u].w, kf.y, kf.w);
-      split2(v4[u].x, v4[u].y, vf.x, vf.z);
-      split2(v4[u].z, v4[u].w, vf.y, vf.w);
-      vf.x = movm(vf.x);
-      vf.y = movm(vf.y);
-      vf.z = movm(vf.z);
-      vf.w = movm(vf.w);
-      kfrag[j * 32 + lane] = kf;
-      vfrag[j * 32 + lane] = vf;
+  for (int jb = 0; jb < NKB; ++jb) {
+    if (jb < nkb) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = 2 * jb + u;
+        uint4 kf, vf;
+        split2(k4[jb][u].x, k4[jb][u].y, kf.x, kf.z);
+        split2(k4[jb][u].z, k4[jb][u].w, kf.y, kf.w);
+        split2(v4[jb][u].x, v4[jb][u].y, vf.x, vf.z);
+        split2(v4[jb][u].z, v4[jb][u].w, vf.y, vf.w);
+        vf.x = movm(vf.x);
+        vf.y = movm(vf.y);
+        vf.z = movm(vf.z);
+        vf.w = movm(vf.w);
+        kfrag[j * 32 + lane] = kf;
+        vfrag[j * 32 + lane] = vf;
+      }
     }
   }
   for (int k = lane; k < 16 * nkb; k += 32) lbias[k] = key_bias(k, T, lo, fc);
@@ -243,6 +258,8 @@ __global__ void __launch_bounds__(256, 3) attention_fwd_tc_kernel(
       if (t == 0) lse[r1 * H + h] = m1 + log2f(l1);
     }
   }
+    __syncwarp();   // the warp's fragments are rewritten by its next atom
+  }
 }
 
 // ------------------------------------------------------------------------ backward
@@ -260,68 +277,99 @@ template <int NKB>
 __global__ void __launch_bounds__(256, 2) attention_bwd_tc_kernel(
     const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ lse,
     const float* __restrict__ d_out, const int32_t* __restrict__ row_ptr,
-    const float* __restrict__ fc, int64_t n_edges, float scale, float* __restrict__ d_qkv,
-    float* __restrict__ d_fc) {
+    const float* __restrict__ fc, int64_t n_atoms, int64_t n_edges, float scale, float* __restrict__ d_qkv,
+    float* __restrict__ d_bias_part) {
   constexpr int Tp = 16 * NKB;
   constexpr int ARR = 2 * Tp * 16;                   // bytes of one staged array
-  constexpr int WARP_BYTES = 4 * ARR + 2 * Tp * 4;   // + L, Dq
+  constexpr int WARP_BYTES = 4 * ARR + 3 * Tp * 4;   // + L, Dq, key bias
   extern __shared__ uint4 smem4[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int64_t atom = blockIdx.x;
-  const int lo = __ldg(row_ptr + atom);
-  const int T = __ldg(row_ptr + atom + 1) - lo + 1;
-  const int nkb = (T + 15) >> 4;
   const int h = warp;
-  if (threadIdx.x < 3 && atom + kPrefetchDistance < (int64_t)gridDim.x) {
-    const float* base = threadIdx.x == 0 ? qkv : (threadIdx.x == 1 ? d_out : out);
-    prefetch_atom_rows(base, threadIdx.x == 0 ? 3 * D : D, atom + kPrefetchDistance, row_ptr, n_edges);
-  }
   uint8_t* wbase = smem + (size_t)warp * WARP_BYTES;
   const uint32_t w_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(wbase));
   float* Ls = reinterpret_cast<float*>(wbase + 4 * ARR);
   float* Dq = Ls + Tp;
-  float* dlb = reinterpret_cast<float*>(smem + (size_t)H * WARP_BYTES);  // [H][Tp]
+  float* Kb = Dq + Tp;
   const float qs = scale * kLog2e;
-
-  // ---- stage Q (scaled) and dO, L and D for every token of this (atom, head)
-  for (int ib = 0; ib < nkb; ++ib) {
-    float4 q4[2], g4[2], o4[2];
-    int64_t rows[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int p = 16 * ib + 8 * u + g;
-      const bool ok = p < T;
-      rows[u] = token_row(ok ? p : 0, lo, n_edges, atom);
-      q4[u] = g4[u] = o4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) {
-        q4[u] = ldg4(qkv + rows[u] * (3 * D) + h * HD + 4 * t);
-        g4[u] = ldg4(d_out + rows[u] * D + h * HD + 4 * t);
-        o4[u] = ldg4(out + rows[u] * D + h * HD + 4 * t);
+  const int64_t n_tokens = n_edges + n_atoms;
+  // Persistent CTAs, warp-independent items (see the forward kernel).  The key-bias gradient is
+  // written per head ([H][tokens] scratch) and reduced over the heads by attention_dfc_kernel, so
+  // the heads of an atom never synchronise.
+  int64_t atom = blockIdx.x;
+  int lo_next = atom < n_atoms ? __ldg(row_ptr + atom) : 0;
+  int hi_next = atom < n_atoms ? __ldg(row_ptr + atom + 1) : 0;
+  for (; atom < n_atoms; atom += gridDim.x) {
+  const int lo = lo_next;
+  const int T = hi_next - lo + 1;
+  const int nkb = (T + 15) >> 4;
+  {
+    const int64_t nxt = atom + gridDim.x;
+    if (nxt < n_atoms) {
+      lo_next = __ldg(row_ptr + nxt);
+      hi_next = __ldg(row_ptr + nxt + 1);
+      if (threadIdx.x < 3) {
+        const float* base = threadIdx.x == 0 ? qkv : (threadIdx.x == 1 ? d_out : out);
+        const int ld = threadIdx.x == 0 ? 3 * D : D;
+        if (hi_next > lo_next) prefetch_l2(base + (int64_t)lo_next * ld, (uint32_t)(hi_next - lo_next) * ld * 4u);
+        prefetch_l2(base + (n_edges + nxt) * ld, (uint32_t)ld * 4u);
       }
     }
+  }
+
+  // ---- stage Q (scaled) and dO, L and D for every token of this (atom, head).  All global rows of
+  // the atom are requested before the first conversion: one exposed memory latency per atom instead
+  // of one per 16-token block (nothing else is live in registers yet).
+  {
+    float4 q4[NKB][2], g4[NKB][2], o4[NKB][2];
+    float lq[NKB][2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int p = 16 * ib + 8 * u + g;
-      uint32_t h0, l0, h1, l1;
-      split2(q4[u].x * qs, q4[u].y * qs, h0, l0);
-      split2(q4[u].z * qs, q4[u].w * qs, h1, l1);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(wbase) + p * 4 + t;  // 16 B rows, word t
-      dst[0] = h0;
-      dst[Tp * 4] = h1;                      // half 1
-      dst[ARR / 4] = l0;
-      dst[ARR / 4 + Tp * 4] = l1;
-      split2(g4[u].x, g4[u].y, h0, l0);
-      split2(g4[u].z, g4[u].w, h1, l1);
-      dst[2 * (ARR / 4)] = h0;
-      dst[2 * (ARR / 4) + Tp * 4] = h1;
-      dst[3 * (ARR / 4)] = l0;
-      dst[3 * (ARR / 4) + Tp * 4] = l1;
-      const float dsum = quad_sum(g4[u].x * o4[u].x + g4[u].y * o4[u].y + g4[u].z * o4[u].z +
-                                  g4[u].w * o4[u].w);
-      if (t == 0) {
-        Dq[p] = dsum;
-        Ls[p] = p < T ? __ldg(lse + rows[u] * H + h) : INFINITY;
+    for (int ib = 0; ib < NKB; ++ib) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int p = 16 * ib + 8 * u + g;
+        const bool ok = ib < nkb && p < T;
+        const int64_t row = token_row(ok ? p : 0, lo, n_edges, atom);
+        q4[ib][u] = g4[ib][u] = o4[ib][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        lq[ib][u] = INFINITY;
+        if (ok) {
+          q4[ib][u] = ldg4(qkv + row * (3 * D) + h * HD + 4 * t);
+          g4[ib][u] = ldg4(d_out + row * D + h * HD + 4 * t);
+          o4[ib][u] = ldg4(out + row * D + h * HD + 4 * t);
+          if (t == 0) lq[ib][u] = __ldg(lse + row * H + h);
+        }
+      }
+    }
+    // key bias of every key of the atom (the cutoff factors are shared by the heads; each warp keeps
+    // its own copy so that no block-level barrier is needed)
+    for (int k = lane; k < 16 * nkb; k += 32) Kb[k] = key_bias(k, T, lo, fc);
+#pragma unroll
+    for (int ib = 0; ib < NKB; ++ib) {
+      if (ib < nkb) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int p = 16 * ib + 8 * u + g;
+          uint32_t h0, l0, h1, l1;
+          split2(q4[ib][u].x * qs, q4[ib][u].y * qs, h0, l0);
+          split2(q4[ib][u].z * qs, q4[ib][u].w * qs, h1, l1);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(wbase) + p * 4 + t;  // 16 B rows, word t
+          dst[0] = h0;
+          dst[Tp * 4] = h1;                      // half 1
+          dst[ARR / 4] = l0;
+          dst[ARR / 4 + Tp * 4] = l1;
+          split2(g4[ib][u].x, g4[ib][u].y, h0, l0);
+          split2(g4[ib][u].z, g4[ib][u].w, h1, l1);
+          dst[2 * (ARR / 4)] = h0;
+          dst[2 * (ARR / 4) + Tp * 4] = h1;
+          dst[3 * (ARR / 4)] = l0;
+          dst[3 * (ARR / 4) + Tp * 4] = l1;
+          const float dsum = quad_sum(g4[ib][u].x * o4[ib][u].x + g4[ib][u].y * o4[ib][u].y +
+                                      g4[ib][u].z * o4[ib][u].z + g4[ib][u].w * o4[ib][u].w);
+          if (t == 0) {
+            Dq[p] = dsum;
+            Ls[p] = lq[ib][u];
+          }
+        }
       }
     }
   }
@@ -378,7 +426,7 @@ __global__ void __launch_bounds__(256, 2) attention_bwd_tc_kernel(
       ktl[c] = movm(kl[c]);
     }
     if (kt + 1 < nkb) fetch_kv(kt + 1);
-    const float lb0 = key_bias(k0, T, lo, fc), lb1 = key_bias(k1, T, lo, fc);
+    const float lb0 = Kb[k0], lb1 = Kb[k1];
     float dk[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float dv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float db0 = 0.f, db1 = 0.f;
@@ -450,9 +498,9 @@ __global__ void __launch_bounds__(256, 2) attention_bwd_tc_kernel(
     }
     db0 = quad_sum(db0);
     db1 = quad_sum(db1);
-    if (t == 0) {
-      dlb[h * Tp + 16 * kt + g] = db0;
-      dlb[h * Tp + 16 * kt + g + 8] = db1;
+    if (t == 0) {   // key k >= 1 is edge row lo + k - 1 (the centre token, k = 0, has no cutoff factor)
+      if (ok0 && k0 > 0) d_bias_part[h * n_tokens + r0] = db0;
+      if (ok1 && k1 > 0) d_bias_part[h * n_tokens + r1] = db1;
     }
   }
 #pragma unroll
@@ -471,16 +519,21 @@ __global__ void __launch_bounds__(256, 2) attention_bwd_tc_kernel(
       }
     }
   }
-  __syncthreads();
-  if (d_fc) {
-    for (int k = 1 + threadIdx.x; k < T; k += blockDim.x) {
-      float acc = 0.f;
-#pragma unroll
-      for (int hh = 0; hh < H; ++hh) acc += dlb[hh * Tp + k];
-      const float f = __ldg(fc + lo + k - 1);
-      if (f >= 1e-15f) d_fc[lo + k - 1] += acc / f;
-    }
+  __syncwarp();   // the warp's staged rows are rewritten by its next atom
   }
+}
+
+// d_fc[e] += (sum over heads of the key-bias gradient of edge e) / f_e   (f_e > 1e-15: the clamp of
+// transformer.py:109-110 has zero slope below)
+__global__ void attention_dfc_kernel(const float* __restrict__ d_bias_part, const float* __restrict__ fc,
+                                     int64_t n_edges, int64_t n_tokens, float* __restrict__ d_fc) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int hh = 0; hh < H; ++hh) acc += d_bias_part[hh * n_tokens + e];
+  const float f = __ldg(fc + e);
+  if (f >= 1e-15f) d_fc[e] += acc / f;
 }
 
 template <int NKB>
@@ -488,7 +541,7 @@ size_t fwd_smem() { return (size_t)H * (2 * (2 * NKB * 32) + 4 * NKB) * 16; }
 template <int NKB>
 size_t bwd_smem() {
   constexpr int Tp = 16 * NKB;
-  return (size_t)H * (4 * 2 * Tp * 16 + 2 * Tp * 4) + (size_t)H * Tp * 4;
+  return (size_t)H * (4 * 2 * Tp * 16 + 3 * Tp * 4);
 }
 
 template <int NKB>
@@ -496,17 +549,22 @@ int launch_fwd(const float* qkv, const int32_t* row_ptr, const float* fc, int64_
                int64_t n_edges, float scale, float* out, float* lse, cudaStream_t stream) {
   auto kern = attention_fwd_tc_kernel<NKB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<NKB>());
-  kern<<<(unsigned)n_atoms, 256, fwd_smem<NKB>(), stream>>>(qkv, row_ptr, fc, n_edges, scale, out, lse);
+  const int64_t grid = n_atoms < 3 * kNumSMs ? n_atoms : 3 * kNumSMs;   // 3 resident CTAs per SM
+  kern<<<(unsigned)grid, 256, fwd_smem<NKB>(), stream>>>(qkv, row_ptr, fc, n_atoms, n_edges, scale, out, lse);
   return check_launch("attention_fwd_tc");
 }
 template <int NKB>
 int launch_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
                const int32_t* row_ptr, const float* fc, int64_t n_atoms, int64_t n_edges,
-               float scale, float* d_qkv, float* d_fc, cudaStream_t stream) {
+               float scale, float* d_qkv, float* d_fc, float* scratch, cudaStream_t stream) {
   auto kern = attention_bwd_tc_kernel<NKB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<NKB>());
-  kern<<<(unsigned)n_atoms, 256, bwd_smem<NKB>(), stream>>>(qkv, out, lse, d_out, row_ptr, fc, n_edges,
-                                                           scale, d_qkv, d_fc);
+  const int64_t grid = n_atoms < 2 * kNumSMs ? n_atoms : 2 * kNumSMs;   // 2 resident CTAs per SM
+  kern<<<(unsigned)grid, 256, bwd_smem<NKB>(), stream>>>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges,
+                                                        scale, d_qkv, scratch);
+  if (d_fc && n_edges > 0)
+    attention_dfc_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(scratch, fc, n_edges,
+                                                                              n_edges + n_atoms, d_fc);
   return check_launch("attention_bwd_tc");
 }
 
@@ -530,12 +588,12 @@ int launch_attention_fwd_tc(const float* qkv, const int32_t* row_ptr, const floa
 int launch_attention_bwd_tc(const float* qkv, const float* out, const float* lse, const float* d_out,
                             const int32_t* row_ptr, const float* fc, int64_t n_atoms,
                             int64_t n_edges, float scale, int max_row, float* d_qkv, float* d_fc,
-                            cudaStream_t stream) {
+                            float* scratch, cudaStream_t stream) {
   switch ((max_row + 1 + 15) / 16) {
-    case 1: return launch_bwd<1>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, stream);
-    case 2: return launch_bwd<2>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, stream);
-    case 3: return launch_bwd<3>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, stream);
-    default: return launch_bwd<4>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, stream);
+    case 1: return launch_bwd<1>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, scratch, stream);
+    case 2: return launch_bwd<2>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, scratch, stream);
+    case 3: return launch_bwd<3>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, scratch, stream);
+    default: return launch_bwd<4>(qkv, out, lse, d_out, row_ptr, fc, n_atoms, n_edges, scale, d_qkv, d_fc, scratch, stream);
   }
 }
 

@@ -45,6 +45,6 @@ int launch_attention_fwd_tc(const float* qkv, const int32_t* row_ptr, const floa
 int launch_attention_bwd_tc(const float* qkv, const float* out, const float* lse, const float* d_out,
                             const int32_t* row_ptr, const float* fc, int64_t n_atoms,
                             int64_t n_edges, float scale, int max_row, float* d_qkv, float* d_fc,
-                            cudaStream_t stream);
+                            float* scratch /* [num_heads, E + N] */, cudaStream_t stream);
 
 }  // namespace petb200
