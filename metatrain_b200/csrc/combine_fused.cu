@@ -22,9 +22,11 @@
 //
 // Both kernels reuse the structure of mlp_fused.cu: A operands in tensor memory (lane = row),
 // weights streamed from L2 as 16 KB stages of a pre-swizzled image (petb200_combine_pack), hidden
-// dimension walked in chunks of 32 units, 19 warps: 0-7 activation epilogues (two groups on
-// alternate chunks), 8 GEMM1 issue, 9-12 row producers, 13 weight stages, 14-17 output store,
-// 18 GEMM2 issue.  All products use the bf16 hi/lo 2-term split (fp32 accumulation in TMEM).
+// dimension walked in chunks of 32 units.  15 warps: 0-7 activation epilogues (two groups on
+// alternate chunks; they also run the output store of the tile, which falls into the row-producer
+// phase of the next tile, when they would idle — 480 threads leave them 126 registers, no spills),
+// 8 GEMM1 issue, 9-12 row producers, 13 weight stages, 14 GEMM2 issue.  All products use the bf16
+// hi/lo 2-term split (fp32 accumulation in TMEM).
 #include "fused_common.cuh"
 
 namespace petb200 {
@@ -35,8 +37,6 @@ using namespace fused;
 
 constexpr int HID = 256;            // hidden width of the combine MLP (= 2 d_pet) and LayerNorm width
 constexpr int NCH = HID / CH;       // 8 chunks of 32 hidden units
-constexpr int CB_NUM_THREADS = 32 * 19;
-constexpr int CB_STORE_WARP0 = 14, CB_MMA2_WARP = 18;
 constexpr int XPITCH = D + 4;                                // floats per staged row
 constexpr int CB_STAGING_BYTES = BM * XPITCH * 4;            // 67 584
 constexpr float kLnEps = 1e-5f;                              // torch.nn.LayerNorm default
@@ -129,21 +129,27 @@ __device__ __forceinline__ void split_part(const float* row, uint32_t (&hi)[16],
 }
 
 // ======================================================================== forward
-constexpr int CF_RING_A = 5, CF_RING_B = 4;
+// 15 warps: 0-7 epilogue groups (LayerNorm fold + SiLU per chunk, then the output store of the tile:
+// the store falls into the row-producer phase of the NEXT tile, when these warps would idle), 8 GEMM1
+// issue, 9-12 row producers, 13 weight stages, 14 GEMM2 issue
+constexpr int CF_NUM_THREADS = 32 * 15;
+constexpr int CF_PROD_WARPS = 4, CF_TMA_WARP = FIRST_PROD_WARP + CF_PROD_WARPS, CF_MMA2_WARP = CF_TMA_WARP + 1;
+constexpr int CF_RING_A = 5, CF_RING_B = 3;
 constexpr int CF_RING = CF_RING_A + CF_RING_B;
 constexpr int CF_XS_OFF = 0;
 constexpr int CF_RING_OFF = ((CF_XS_OFF + CB_STAGING_BYTES + 1023) / 1024) * 1024;
-constexpr int CF_EPI_OFF = CF_RING_OFF + CF_RING * STAGE;            // 4 store warps x 32 x STAGE_LD floats
-constexpr int CF_CONST_OFF = CF_EPI_OFF + 4 * 32 * STAGE_LD * 4;     // s [256], b' [256], b_b [128]
+constexpr int CF_EPI_OFF = CF_RING_OFF + CF_RING * STAGE;            // 8 epilogue warps x 32 x STAGE_LD floats
+constexpr int CF_CONST_OFF = CF_EPI_OFF + EPI_STAGE_BYTES;           // s [256], b' [256], b_b [128]
 constexpr int CF_STAT_OFF = CF_CONST_OFF + (2 * HID + D) * 4;        // (mu, r) [2 tile parities][128]
-constexpr int CF_BAR_OFF = CF_STAT_OFF + 2 * BM * 8;
+constexpr int CF_PART_OFF = CF_STAT_OFF + 2 * BM * 8;                // partial row sums exchanged by producer pairs
+constexpr int CF_BAR_OFF = CF_PART_OFF + BM * 8;
 constexpr int CF_SMEM = CF_BAR_OFF + 8 * (16 + 2 * CF_RING) + 16 + 1024;
 static_assert(CF_SMEM <= 232448, "combine_fwd: shared memory budget");
 // TMEM columns: c hi 0..127 (own half 0..63, reversed half 64..127), c lo 128..255 ; acc1[b] at
 // 256 + 32 b ; A2[b] at 320 + 32 b (hi 16 | lo 16) ; acc2 at 384 (single buffer)
 constexpr int CF_XLO_COL = 128, CF_ACC1_COL = 256, CF_A2_COL = 320, CF_ACC2_COL = 384;
 
-__global__ void __launch_bounds__(CB_NUM_THREADS, 1)
+__global__ void __launch_bounds__(CF_NUM_THREADS, 1)
 combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __restrict__ rev,
                    const uint8_t* __restrict__ image, const float* __restrict__ s_vec,
                    const float* __restrict__ b_fold, const float* __restrict__ b_out, int64_t M,
@@ -162,8 +168,9 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
   const TileSchedule sched(M);
 
   if (threadIdx.x == 0) {
-    bar.init_all();
-    mbar_init(bar.acc2_empty(0), 4 * 32);   // drained by the four store warps
+    bar.init_all();   // acc2_empty: drained by all eight epilogue warps
+    mbar_init(bar.x_full(0), CF_PROD_WARPS * 32);
+    mbar_init(bar.x_full(1), CF_PROD_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -171,20 +178,23 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
         smem_u32(const_cast<uint32_t*>(tmem_slot))));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < HID; i += CB_NUM_THREADS) {
+  for (int i = threadIdx.x; i < HID; i += CF_NUM_THREADS) {
     const_s[i] = s_vec[i];
     const_s[HID + i] = b_fold[i];
   }
-  for (int i = threadIdx.x; i < D; i += CB_NUM_THREADS) const_s[2 * HID + i] = b_out[i];
+  for (int i = threadIdx.x; i < D; i += CF_NUM_THREADS) const_s[2 * HID + i] = b_out[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
+  if (warp >= FIRST_PROD_WARP && warp < CF_TMA_WARP) {
     // ============================================================ row producers
     // warp -> rows 32 quarter .. + 31 (the TMEM lanes it may write); lane -> one row.  Two phases
     // per tile through one staging buffer: own rows, then the rows of the reversed edges.
+    // (Eight producer warps — two per lane quarter, half a row each — were tried: the register cap
+    // of a 608-thread CTA made the epilogue warps spill and the chunk loop lost more than the
+    // conversion gained, profiles/r2_combine_fwd_timeline.txt.)
     const uint32_t dst = smem_base + CF_XS_OFF;
     auto issue_own = [&](int i) {
       const int64_t m0 = sched.m0(i);
@@ -271,7 +281,7 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
       mbar_arrive(bar.x_full(1));
       if (lane == 0 && quarter == 0) ctrace(3, i, 0, 4);
     }
-  } else if (warp == TMA_WARP) {
+  } else if (warp == CF_TMA_WARP) {
     // ============================================================ weight-stage producer
     if (elect_one()) {
       Ring ra, rb;
@@ -329,7 +339,7 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
         }
       }
     }
-  } else if (warp == CB_MMA2_WARP) {
+  } else if (warp == CF_MMA2_WARP) {
     // ============================================================ GEMM2 issuer (one thread)
     if (elect_one()) {
       constexpr uint32_t idesc2 = make_idesc(BM, D);
@@ -378,7 +388,20 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
     const int half = warp >> 2;
     const float* s_s = const_s;
     const float* bf_s = const_s + HID;
+    const float* bo_s = const_s + 2 * HID;
+    const EpiStage es{reinterpret_cast<float*>(smem + CF_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
     for (int i = 0; i < sched.count; ++i) {
+      const int64_t m_base = sched.m0(i) + quarter * 32;
+      // the tile's rows of m are first touched by the store below: pull them into L2 now
+      if (half == 0) {
+        if (ld_m == D) {
+          if (lane == 0 && m_base < M)
+            prefetch_l2_bulk(m_io + m_base * ld_m, (uint32_t)((M - m_base < 32 ? M - m_base : 32) * D * 4));
+        } else if (m_base + lane < M) {
+          prefetch_l2_bulk(m_io + (m_base + lane) * ld_m, D * 4);
+        }
+      }
       mbar_wait(bar.x_full(1), i & 1);          // the tile's (mu, r) are in shared memory
       const float2 st = stat_s[(i & 1) * BM + quarter * 32 + lane];
       const float mu = st.x, rs = st.y;
@@ -422,60 +445,48 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
         mbar_arrive(bar.a2_full(b));
         if (lane == 0 && quarter == 0) ctrace(1 + half, i, c, 5);
       }
-    }
-  } else if (warp >= CB_STORE_WARP0 && warp < CB_STORE_WARP0 + 4) {
-    // ============================================================ output store warps
-    // m' = acc2 + b_b + t + m, in place on m.  Warp -> 32 rows x 128 columns in 8 slices of 16.
-    const int sw = warp - CB_STORE_WARP0;
-    const EpiStage es{reinterpret_cast<float*>(smem + CF_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
-    const float* bo_s = const_s + 2 * HID;
-    for (int i = 0; i < sched.count; ++i) {
-      const int64_t m_base = sched.m0(i) + quarter * 32;
-      // the tile's rows of m are first touched here: pull them into L2 while the chunk loop runs
-      if (ld_m == D) {
-        if (lane == 0 && m_base < M)
-          prefetch_l2_bulk(m_io + m_base * ld_m, (uint32_t)((M - m_base < 32 ? M - m_base : 32) * D * 4));
-      } else if (m_base + lane < M) {
-        prefetch_l2_bulk(m_io + (m_base + lane) * ld_m, D * 4);
+      // ---- output store: m' = acc2 + b_b + t + m, in place on m.  Warp -> its 32 rows x the 64
+      // columns of its group, in 4 slices of 16; overlaps the row-producer phase of the next tile.
+      {
+        float4 rt[2][4], rm[2][4];
+        auto fetch = [&](int sl) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int64_t mm = m_base + it * 8 + es.rsel;
+            const bool ok = mm < M;
+            rt[sl & 1][it] = ok ? ld4(t + mm * ld_t + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rm[sl & 1][it] = ok ? *reinterpret_cast<const float4*>(m_io + mm * ld_m + 16 * sl + 4 * es.c4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        fetch(4 * half);
+        if (lane == 0 && quarter == 0) ctrace(5, i, half, 0);
+        mbar_wait(bar.acc2_full(0), i & 1);
+        tc_fence_after();
+        if (lane == 0 && quarter == 0) ctrace(5, i, half, 1);
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int sl = 4 * half + s4;
+          if (s4 + 1 < 4) fetch(sl + 1);
+          const int c0 = 16 * sl + 4 * es.c4;
+          const float4 b4 = *reinterpret_cast<const float4*>(bo_s + c0);
+          es.fill(tmem_base + lane_base + CF_ACC2_COL + 16 * sl);
+          if (s4 == 3) {   // the accumulator is in registers / smem now: release it early
+            tc_fence_before();
+            mbar_arrive(bar.acc2_empty(0));
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int64_t mm = m_base + it * 8 + es.rsel;
+            if (mm >= M) continue;
+            const float4 a = es.get(it), x = rt[sl & 1][it], y = rm[sl & 1][it];
+            *reinterpret_cast<float4*>(m_io + mm * ld_m + c0) =
+                make_float4(a.x + b4.x + x.x + y.x, a.y + b4.y + x.y + y.y, a.z + b4.z + x.z + y.z,
+                            a.w + b4.w + x.w + y.w);
+          }
+        }
+        if (lane == 0 && quarter == 0) ctrace(5, i, half, 2);
       }
-      float4 rt[2][4], rm[2][4];
-      auto fetch = [&](int sl) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          const bool ok = m < M;
-          rt[sl & 1][it] = ok ? ld4(t + m * ld_t + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          rm[sl & 1][it] = ok ? *reinterpret_cast<const float4*>(m_io + m * ld_m + 16 * sl + 4 * es.c4)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      fetch(0);
-      if (lane == 0 && sw == 0) ctrace(5, i, 0, 0);
-      mbar_wait(bar.acc2_full(0), i & 1);
-      tc_fence_after();
-      if (lane == 0 && sw == 0) ctrace(5, i, 0, 1);
-#pragma unroll
-      for (int sl = 0; sl < 8; ++sl) {
-        if (sl + 1 < 8) fetch(sl + 1);
-        const int c0 = 16 * sl + 4 * es.c4;
-        const float4 b4 = *reinterpret_cast<const float4*>(bo_s + c0);
-        es.fill(tmem_base + lane_base + CF_ACC2_COL + 16 * sl);
-        if (sl == 7) {   // the accumulator is in registers / smem now: release it early
-          tc_fence_before();
-          mbar_arrive(bar.acc2_empty(0));
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          if (m >= M) continue;
-          const float4 a = es.get(it), x = rt[sl & 1][it], y = rm[sl & 1][it];
-          *reinterpret_cast<float4*>(m_io + m * ld_m + c0) =
-              make_float4(a.x + b4.x + x.x + y.x, a.y + b4.y + x.y + y.y, a.z + b4.z + x.z + y.z,
-                          a.w + b4.w + x.w + y.w);
-        }
-      }
-      if (lane == 0 && sw == 0) ctrace(5, i, 0, 2);
     }
   }
 
@@ -488,12 +499,16 @@ combine_fwd_kernel(const float* __restrict__ t, int64_t ld_t, const int32_t* __r
 }
 
 // ======================================================================= backward
-constexpr int CBW_RING_A = 3, CBW_RING_B = 6;                 // G1 stages / WT stages
+// 15 warps, as in the forward kernel: the eight epilogue warps also run the LayerNorm-backward store of
+// the tile (while the row producers convert the next tile), no dedicated store warps
+constexpr int CBW_NUM_THREADS = 32 * 15;
+constexpr int CBW_MMA2_WARP = 14;
+constexpr int CBW_RING_A = 3, CBW_RING_B = 5;                 // G1 stages / WT stages
 constexpr int CBW_RING = CBW_RING_A + CBW_RING_B;
 constexpr int CBW_XS_OFF = 0;
 constexpr int CBW_RING_OFF = ((CBW_XS_OFF + CB_STAGING_BYTES + 1023) / 1024) * 1024;
 constexpr int CBW_EPI_OFF = CBW_RING_OFF + CBW_RING * STAGE;
-constexpr int CBW_CONST_OFF = CBW_EPI_OFF + 4 * 32 * STAGE_LD * 4;   // s [256], b' [256]
+constexpr int CBW_CONST_OFF = CBW_EPI_OFF + EPI_STAGE_BYTES;         // s [256], b' [256]
 constexpr int CBW_ROWSTAT_OFF = CBW_CONST_OFF + 2 * HID * 4;         // partial (S1, S2) [2 groups][128]
 constexpr int CBW_BAR_OFF = CBW_ROWSTAT_OFF + 2 * BM * 8;
 constexpr int CBW_SMEM = CBW_BAR_OFF + 8 * (16 + 2 * CBW_RING) + 8 + 16 + 1024;
@@ -502,7 +517,7 @@ static_assert(CBW_SMEM <= 232448, "combine_bwd: shared memory budget");
 // acc2 at 256 (256 columns: z for the own half, then for the reversed half)
 constexpr int CBW_GLO_COL = 64, CBW_ACC1_COL = 128, CBW_A2_COL = 192, CBW_ACC2_COL = 256;
 
-__global__ void __launch_bounds__(CB_NUM_THREADS, 1)
+__global__ void __launch_bounds__(CBW_NUM_THREADS, 1)
 combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __restrict__ p,
                    const float* __restrict__ t, int64_t ld_t, const int32_t* __restrict__ rev,
                    const float2* __restrict__ stats, const uint8_t* __restrict__ image,
@@ -523,8 +538,7 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
   const TileSchedule sched(M);
 
   if (threadIdx.x == 0) {
-    bar.init_all();
-    mbar_init(bar.acc2_empty(0), 4 * 32);
+    bar.init_all();   // acc2_empty: drained by all eight epilogue warps
     mbar_init(rowstat_bar, NUM_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -533,7 +547,7 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
         smem_u32(const_cast<uint32_t*>(tmem_slot))));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < HID; i += CB_NUM_THREADS) {
+  for (int i = threadIdx.x; i < HID; i += CBW_NUM_THREADS) {
     const_s[i] = s_vec[i];
     const_s[HID + i] = b_fold[i];
   }
@@ -624,7 +638,7 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
         }
       }
     }
-  } else if (warp == CB_MMA2_WARP) {
+  } else if (warp == CBW_MMA2_WARP) {
     // ============================================================ GEMM2 issuer: z += d_p[chunk] . W'[chunk, :]
     if (elect_one()) {
       constexpr uint32_t idesc2 = make_idesc(BM, D);
@@ -676,7 +690,15 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
                          HID * BM * 4 / 8);
     };
     if (sched.count > 0) prefetch_p(0);
+    const EpiStage es{reinterpret_cast<float*>(smem + CBW_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
     for (int i = 0; i < sched.count; ++i) {
+      const int64_t m_base = sched.m0(i) + quarter * 32;
+      {   // rows of t this warp needs at the END of the tile (group 0: own rows, group 1: the rows of
+          // the reversed edges): into L2 now, one row per lane
+        const int64_t mp = m_base + lane;
+        if (mp < M) prefetch_l2_bulk(t + (half == 0 ? mp : (int64_t)__ldg(rev + mp)) * ld_t, D * 4);
+      }
       const int64_t m = sched.m0(i) + quarter * 32 + lane;
       const bool ok = m < M;
       if (i + 1 < sched.count) prefetch_p(i + 1);
@@ -726,77 +748,65 @@ combine_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __res
         tc_fence_before();
         mbar_arrive(bar.a2_full(b));
       }
-      // this group's share of mean(z) and mean(z x_hat) of the row; the store warps add the two groups
+      // this group's share of mean(z) and mean(z x_hat) of the row; both groups' shares are added below
       rowstat_s[half * BM + quarter * 32 + lane] = make_float2(s1 * (1.0f / HID), s2 * (1.0f / HID));
       mbar_arrive(rowstat_bar);
-    }
-  } else if (warp >= CB_STORE_WARP0 && warp < CB_STORE_WARP0 + 4) {
-    // ============================================================ output store: LayerNorm backward
-    // d_cat = r (z - S1 - x_hat S2), x_hat = (c - mu) r, c = [t_e | t_rev(e)].  Warp -> 32 rows x 256
-    // columns in 16 slices of 16; the rows of t of the next slice are in flight while the current one
-    // is transposed.
-    const int sw = warp - CB_STORE_WARP0;
-    const EpiStage es{reinterpret_cast<float*>(smem + CBW_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
-    for (int i = 0; i < sched.count; ++i) {
-      const int64_t m_base = sched.m0(i) + quarter * 32;
-      {   // rows of t this warp will need at the END of the tile: into L2 now (one row pair per lane)
-        const int64_t mp = m_base + lane;
-        if (mp < M) {
-          prefetch_l2_bulk(t + mp * ld_t, D * 4);
-          prefetch_l2_bulk(t + (int64_t)__ldg(rev + mp) * ld_t, D * 4);
-        }
-      }
-      int64_t own[4], other[4];
-      float mu[4], rs[4];
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int64_t m = m_base + it * 8 + es.rsel;
-        const bool ok = m < M;
-        own[it] = ok ? m : -1;
-        other[it] = ok ? (int64_t)__ldg(rev + m) : -1;
-        const float2 st = ok ? __ldg(stats + m) : make_float2(0.f, 0.f);
-        mu[it] = st.x;
-        rs[it] = st.y;
-      }
-      float4 xr[2][4];
-      auto fetch = [&](int sl) {
-        const int col = (16 * sl + 4 * es.c4) & (D - 1);
+      // ---- output store: LayerNorm backward, d_cat = r (z - S1 - x_hat S2), x_hat = (c - mu) r,
+      // c = [t_e | t_rev(e)].  Warp -> its 32 rows x the 128 columns of its group (group 0: the own
+      // half, group 1: the reversed half) in 8 slices of 16; the rows of t of the next slice are in
+      // flight while the current one is transposed.  Overlaps the row-producer phase of the next tile.
+      {
+        int64_t own[4], src[4];
+        float mu[4], rs[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int64_t src = sl < 8 ? own[it] : other[it];
-          xr[sl & 1][it] = src >= 0 ? ld4(t + src * ld_t + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int64_t mm = m_base + it * 8 + es.rsel;
+          const bool okr = mm < M;
+          own[it] = okr ? mm : -1;
+          src[it] = okr ? (half == 0 ? mm : (int64_t)__ldg(rev + mm)) : -1;
+          const float2 st = okr ? __ldg(stats + mm) : make_float2(0.f, 0.f);
+          mu[it] = st.x;
+          rs[it] = st.y;
         }
-      };
-      fetch(0);
-      mbar_wait(rowstat_bar, i & 1);
-      float s1[4], s2[4];
+        float4 xr[4][4];   // three slices of t in flight ahead of the one being processed
+        auto fetch = [&](int s8) {
+          const int col = 16 * s8 + 4 * es.c4;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int r = quarter * 32 + it * 8 + es.rsel;
-        const float2 a = rowstat_s[r], b = rowstat_s[BM + r];
-        s1[it] = a.x + b.x;
-        s2[it] = a.y + b.y;
-      }
-      mbar_wait(bar.acc2_full(0), i & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int sl = 0; sl < 16; ++sl) {
-        if (sl + 1 < 16) fetch(sl + 1);
-        const int c0 = 16 * sl + 4 * es.c4;
-        es.fill(tmem_base + lane_base + CBW_ACC2_COL + 16 * sl);
-        if (sl == 15) {
-          tc_fence_before();
-          mbar_arrive(bar.acc2_empty(0));
-        }
+          for (int it = 0; it < 4; ++it)
+            xr[s8 & 3][it] = src[it] >= 0 ? ld4(t + src[it] * ld_t + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        fetch(0);
+        fetch(1);
+        fetch(2);
+        mbar_wait(rowstat_bar, i & 1);
+        float a1[4], a2[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          if (own[it] < 0) continue;
-          const float4 z = es.get(it), x = xr[sl & 1][it];
-          const float r = rs[it], a = s1[it], k2 = s2[it] * r, mo = mu[it];
-          *reinterpret_cast<float4*>(d_cat + own[it] * HID + c0) =
-              make_float4(r * (z.x - a - (x.x - mo) * k2), r * (z.y - a - (x.y - mo) * k2),
-                          r * (z.z - a - (x.z - mo) * k2), r * (z.w - a - (x.w - mo) * k2));
+          const int r = quarter * 32 + it * 8 + es.rsel;
+          const float2 a = rowstat_s[r], b = rowstat_s[BM + r];
+          a1[it] = a.x + b.x;
+          a2[it] = a.y + b.y;
+        }
+        mbar_wait(bar.acc2_full(0), i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) {
+          if (s8 + 3 < 8) fetch(s8 + 3);
+          const int c0 = D * half + 16 * s8 + 4 * es.c4;
+          es.fill(tmem_base + lane_base + CBW_ACC2_COL + D * half + 16 * s8);
+          if (s8 == 7) {
+            tc_fence_before();
+            mbar_arrive(bar.acc2_empty(0));
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (own[it] < 0) continue;
+            const float4 z = es.get(it), x = xr[s8 & 3][it];
+            const float r = rs[it], a = a1[it], k2 = a2[it] * r, mo = mu[it];
+            *reinterpret_cast<float4*>(d_cat + own[it] * HID + c0) =
+                make_float4(r * (z.x - a - (x.x - mo) * k2), r * (z.y - a - (x.y - mo) * k2),
+                            r * (z.z - a - (x.z - mo) * k2), r * (z.w - a - (x.w - mo) * k2));
+          }
         }
       }
     }
@@ -863,7 +873,7 @@ extern "C" PETB200_API int petb200_combine_fwd(const float* t, int64_t ld_t, con
   if (n_edges == 0) return PETB200_OK;
   const int tiles = (int)ceil_div(n_edges, BM);
   cudaFuncSetAttribute(combine_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
-  combine_fwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, CB_NUM_THREADS, CF_SMEM, stream>>>(
+  combine_fwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, CF_NUM_THREADS, CF_SMEM, stream>>>(
       t, ld_t, rev, reinterpret_cast<const uint8_t*>(image_fwd), s_vec, b_fold, b_out, n_edges, m_io, ld_m, p_out,
       reinterpret_cast<float2*>(stats_out));
   return check_launch("combine_fwd");
@@ -878,7 +888,7 @@ extern "C" PETB200_API int petb200_combine_bwd(const float* g, int64_t ld_g, con
   if (n_edges == 0) return PETB200_OK;
   const int tiles = (int)ceil_div(n_edges, BM);
   cudaFuncSetAttribute(combine_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CBW_SMEM);
-  combine_bwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, CB_NUM_THREADS, CBW_SMEM, stream>>>(
+  combine_bwd_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, CBW_NUM_THREADS, CBW_SMEM, stream>>>(
       g, ld_g, p, t, ld_t, rev, reinterpret_cast<const float2*>(stats), reinterpret_cast<const uint8_t*>(image_bwd),
       s_vec, b_fold, n_edges, d_cat);
   return check_launch("combine_bwd");

@@ -63,6 +63,7 @@ names = {0: ["G1 wait acc1_empty", "acc1_empty ok", "W stage 0 ready", "W stage 
          4: ["G2 wait a2_full", "a2_full ok", "acc2_empty ok", "G2 issued"],
          5: ["wait acc2_full", "acc2_full ok", "store done"]}
 names[2] = names[1]
+names[5] = ["store: wait acc2_full", "store: acc2_full ok", "store done"]
 events = []
 for role in range(6):
     for tile in range(4):
