@@ -265,10 +265,16 @@ class B200PETBackend(PETParameters):
                 and hypers.get("adaptive_cutoff_method", "solver").lower() not in ("solver", "grid")):
             raise ValueError("adaptive_cutoff_method must be 'grid' or 'solver', got "
                              + hypers["adaptive_cutoff_method"])  # structures.py:244-248
-        if (hypers["d_pet"], hypers["d_node"], hypers["d_head"], hypers["num_heads"]) != (128, 256, 128, 8):
-            unsupported.append("d_pet/d_node/d_head/num_heads other than 128/256/128/8")
-        if hypers["d_feedforward"] % 128 != 0:
-            unsupported.append("d_feedforward not a multiple of 128")
+        # widths: the token width / head geometry is what the attention and row-wise kernels are built
+        # for; the node width and the feed-forward width only enter dense contractions
+        if (hypers["d_pet"], hypers["d_head"], hypers["num_heads"]) != (128, 128, 8):
+            unsupported.append("d_pet/d_head/num_heads other than 128/128/8")
+        if hypers["d_node"] != 256:
+            # (d_node == d_pet is a different layer in the reference: no centre contraction / expansion
+            # / centre feed-forward at all, transformer.py:189-201)
+            unsupported.append("d_node other than 256")
+        if hypers["d_feedforward"] % 64 != 0:
+            unsupported.append("d_feedforward not a multiple of 64")
         if unsupported:
             raise NotImplementedError(
                 "B200PETBackend: not built yet (SURVEY.md 8(f).4): " + ", ".join(unsupported))

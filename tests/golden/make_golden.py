@@ -271,6 +271,10 @@ def main():
                                                      "center_contraction", "center_expansion"])))
 
     make_case("carbon_5", carbon, [6], with_strain=False)
+    # other layer widths: feed-forward width a multiple of 64 inside (192) and outside (640) the fused
+    # kernel's range
+    make_case("qm9_5_dff192", qm9, [1, 6, 7, 8], target="mtt::U0", hypers=dict(d_feedforward=192), fp64=False)
+    make_case("water_384_dff640", [water], [1, 8], hypers=dict(d_feedforward=640), fp64=False)
 
     # adaptive cutoff, solver method (adaptive_cutoff.py:110-229, structures.py:222-262)
     make_case("water_384_adaptive", [water], [1, 8], hypers=dict(num_neighbors_adaptive=16))

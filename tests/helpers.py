@@ -26,7 +26,9 @@ GOLDEN_CASES = ["qm9_5", "water_384", "water_384_nonstrict", "carbon_5", "si_64"
                 # direct stress head (backend.py:780-813)
                 "stress_head_mix",
                 # all variants combined in one model / one ragged batch
-                "kitchen_sink"]
+                "kitchen_sink",
+                # layer widths other than the defaults
+                "qm9_5_dff192", "water_384_dff640"]
 
 # pet/documentation.py:159-259 defaults
 DEFAULT_HYPERS = dict(
