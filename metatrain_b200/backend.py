@@ -273,8 +273,12 @@ class B200PETBackend(PETParameters):
             # (d_node == d_pet is a different layer in the reference: no centre contraction / expansion
             # / centre feed-forward at all, transformer.py:189-201)
             unsupported.append("d_node other than 256")
-        if hypers["d_feedforward"] % 64 != 0:
-            unsupported.append("d_feedforward not a multiple of 64")
+        dff = hypers["d_feedforward"]
+        if dff % 128 != 0 and not (precision != "fp32" and dff % 64 == 0 and dff <= 512):
+            # multiples of 128 run on every path; other multiples of 64 only exist inside the fused
+            # feed-forward kernels (tensor-core precisions, width <= 512)
+            unsupported.append("d_feedforward that is neither a multiple of 128 nor a multiple of 64 <= 512 "
+                               "on a tensor-core precision")
         if unsupported:
             raise NotImplementedError(
                 "B200PETBackend: not built yet (SURVEY.md 8(f).4): " + ", ".join(unsupported))
@@ -301,6 +305,8 @@ class B200PETBackend(PETParameters):
 
     # ------------------------------------------------------------------ internals
     def set_precision(self, precision: str) -> None:
+        if precision == "fp32" and self.hypers["d_feedforward"] % 128 != 0:
+            raise NotImplementedError("B200PETBackend: the fp32 path needs d_feedforward to be a multiple of 128")
         self._precision = _PRECISIONS[precision]
 
     def _invalidate_packed(self) -> None:

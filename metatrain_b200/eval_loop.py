@@ -48,6 +48,55 @@ class _Accumulator:
         return out
 
 
+class PipelinedEvaluator:
+    """Throughput form of the loop: the host->device copy of batch ``i + 1`` runs on a copy stream
+    while batch ``i`` computes, and results come back asynchronously into pinned buffers — the job the
+    reference leaves to its ``DataLoader`` (pinned batches prepared ahead by worker processes,
+    ``src/metatrain/cli/eval.py:199-214``) plus ``batch_to`` (``:240-244``).
+
+        ev = PipelinedEvaluator(backend, target)
+        ticket = ev.submit(host_batch)          # enqueue H2D (pinned host tensors)
+        for nxt in more_batches:
+            upcoming = ev.submit(nxt)           # next copy overlaps ...
+            out = ev.run(ticket)                # ... this evaluation; out = pinned host tensors
+            ticket = upcoming
+    """
+
+    def __init__(self, backend, target: str = "energy", gradients: bool = True, device: str = "cuda:0"):
+        self.backend, self.target, self.gradients = backend, target, gradients
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._out: Dict[str, torch.Tensor] = {}
+
+    def submit(self, host: Dict[str, torch.Tensor]):
+        """Start the host->device copy of one batch on the copy stream; returns a ticket."""
+        with torch.cuda.stream(self.copy_stream):
+            dev = {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        return dev, done
+
+    def run(self, ticket) -> Dict[str, torch.Tensor]:
+        """Evaluate a submitted batch; returns energies (and dE_dpos) as pinned HOST tensors that are
+        valid when the call returns (one event wait, no device-wide synchronisation)."""
+        dev, done = ticket
+        compute = torch.cuda.current_stream(self.device)
+        compute.wait_event(done)
+        for v in dev.values():
+            v.record_stream(compute)
+        out = evaluate(self.backend, **dev, target=self.target, gradients=self.gradients)
+        keys = ["energies"] + (["dE_dpos"] if self.gradients else [])
+        for k in keys:
+            buf = self._out.get(k)
+            if buf is None or buf.shape != out[k].shape:
+                buf = self._out[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+            buf.copy_(out[k], non_blocking=True)
+        back = torch.cuda.Event()
+        back.record(compute)
+        back.synchronize()
+        return {k: self._out[k] for k in keys}
+
+
 def eval_targets(
     backend,
     structures: Sequence[dict],

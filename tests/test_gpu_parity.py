@@ -87,6 +87,20 @@ def test_elongated_boxes_match_reference(case, precision):
     assert abs(float(out["energies"]) - e_ref) <= 2e-6 * abs(e_ref)
 
 
+def test_feed_forward_width_inside_the_fused_kernel_only():
+    """d_feedforward = 192 (a multiple of 64, not of 128) exists only inside the fused feed-forward
+    kernels: served on the tensor-core precisions, rejected loudly on the fp32 path."""
+    g = load_golden("qm9_5_dff192")
+    be = make_backend(g, precision="bf16x3")
+    out = evaluate(be, **golden_inputs(g, DEV), target=g["target"])
+    assert np.abs(out["energies"].cpu().numpy() - g["ref32_energies"]).max() <= 1e-4
+    assert np.abs(out["dE_dpos"].cpu().numpy() - g["ref32_dE_dpos"]).max() <= FORCE_TOL
+    with pytest.raises(NotImplementedError):
+        make_backend(g, precision="fp32")
+    with pytest.raises(NotImplementedError):
+        be.set_precision("fp32")
+
+
 def test_lora_adapters_are_merged_and_repacked_on_update():
     """LoRA adapters (finetuning.py:357-378) are merged into the packed weights; zeroing every
     lora_B in place must fall back to the base model's golden (the packed weights follow the
@@ -455,6 +469,28 @@ def test_evaluator_loop_matches_reference_semantics():
     assert res["metrics"][g["target"] + " forces RMSE"] <= 2e-5
     assert res["metrics"][g["target"] + " (per atom) MAE"] <= 1e-5
     assert res["ms_per_atom"][0] > 0
+
+
+def test_pipelined_evaluator_overlaps_copies_without_changing_results():
+    """PipelinedEvaluator: the H2D copy of the next batch runs on a copy stream while this one is
+    evaluated; results (pinned host tensors) equal a plain evaluate() of the same batch."""
+    from metatrain_b200.eval_loop import PipelinedEvaluator
+    cases = [load_golden(c) for c in ("water_384", "si_64", "water_384")]
+    be = {c["target"]: None for c in cases}
+    g0 = cases[0]
+    backend = make_backend(g0, "bf16x3")
+    hosts = [{k: v.pin_memory() for k, v in golden_inputs(g0).items()} for _ in range(3)]
+    hosts[1]["positions"] = (hosts[1]["positions"] + 0.01).pin_memory()
+    ev = PipelinedEvaluator(backend, g0["target"], device=DEV)
+    ticket = ev.submit(hosts[0])
+    for k in range(3):
+        upcoming = ev.submit(hosts[(k + 1) % 3])
+        got = {n: t.clone() for n, t in ev.run(ticket).items()}
+        ticket = upcoming
+        ref = evaluate(backend, **{n: t.to(DEV) for n, t in hosts[k].items()}, target=g0["target"])
+        assert torch.equal(got["energies"], ref["energies"].cpu())
+        assert torch.equal(got["dE_dpos"], ref["dE_dpos"].cpu())
+    assert be is not None
 
 
 @pytest.mark.parametrize("case", ["water_384", "carbon_5", "si_64", "qm9_5", "co_periodic", "ragged_mix"])

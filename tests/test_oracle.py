@@ -30,7 +30,7 @@ def seeded_state_dict(g):
     return sd
 
 
-@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES + ["qm9_5_dff192"])
 def test_seeded_weights_equal_reference(case):
     g = load_golden(case)
     sd = seeded_state_dict(g)
@@ -50,7 +50,7 @@ def test_oracle_reproduces_reference_hard_coded_energies():
                                torch.tensor(REFERENCE_HARD_CODED, dtype=torch.float32))
 
 
-@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES + ["qm9_5_dff192"])
 def test_oracle_matches_golden(case):
     g = load_golden(case)
     strain = "ref32_dE_dstrain" in g
