@@ -425,6 +425,7 @@ PETB200_API int petb200_avg_reverse_bwd(const float* d_next, const int32_t* rev,
 /* ------------------------------------------------------------------- readout (a12)
  * backend.py:195-217, 762-772: atomic[i,p] = w_n[p].n2[i] + b_n[p] +
  * sum_{e in row i} f_e * (w_e[p].e2[e] + b_e[p]);  edge_pred[e,p] is kept for backward. */
+/* (edge_feat may be NULL: edge_pred then holds precomputed edge predictions, petb200_edge_head_fwd) */
 PETB200_API int petb200_readout_fwd(const float* node_feat, const float* edge_feat, const float* w_node,
                         const float* b_node, const float* w_edge, const float* b_edge,
                         const float* cutoff_factor, const int32_t* row_ptr, int64_t n_atoms,
@@ -438,6 +439,45 @@ PETB200_API int petb200_readout_bwd(const float* d_atomic, const float* edge_pre
                         const float* node_pre, const float* edge_pre,
                         int64_t n_atoms, int64_t n_edges, int d, int n_out, float* d_node_feat,
                         float* d_edge_feat, float* d_fc, petb200_stream_t stream);
+
+/* ------------------------------------------- fused 128 -> 128 -> 128 chains (chain_fused.cu)
+ * Two Linears with a SiLU between them as ONE persistent tcgen05 kernel per direction, for the two
+ * places PET has that shape on its edge rows.  petb200_chain_pack builds the operand-tile images
+ * (petb200_chain_image_bytes bytes each) from w1 [128, 128] and w2 [128, 128]; d = 128 only.
+ * `e1p` / `c1` (pre-activation of the first Linear) is an opaque buffer of ceil(E / 128) * 128 * 128
+ * floats in the kernels' private tile layout (see petb200_combine_fwd).
+ *
+ * Edge head (backend.py:171-217, 762-772; single-property targets):
+ *   fwd:  e2p = W_2 silu(W_1 m + b_1) + b_2  [E, 128],  edge_pred[e] = w_e . silu(e2p[e]) + b_e
+ *         (finish with petb200_readout_fwd, edge_feat = NULL: atomic = node part + sum_j f_ij pe_ij)
+ *   bwd:  d_m = W_1^T silu'(e1p) W_2^T g,  g[e] = d_atomic[ctr e] f_e w_e silu'(e2p[e]) (formed on the
+ *         fly), d_fc[e] += d_atomic[ctr e] edge_pred[e]
+ * replacing 2 x petb200_gemm + readout (forward) and readout_bwd + 2 x petb200_gemm (backward).
+ *
+ * Token builder of a CartesianTransformer (transformer.py:500-521; arguments as petb200_compress_gemm):
+ *   fwd:  c_1 = W_1m m + G (r, d) + Tbl[z_j] + b' ;  t = W_2 silu(c_1) + b_2
+ *   bwd:  d_c1 = silu'(c_1) W_2^T d_t ;  d_m (+)= W_1m^T d_c1 (skipped when d_m is NULL) ;
+ *         d_vec / d_dist += G^T d_c1
+ * replacing petb200_compress_gemm + petb200_gemm (forward) and 2 x petb200_gemm +
+ * petb200_geom_embed_bwd (backward).                                                              */
+PETB200_API size_t petb200_chain_image_bytes(int d);
+PETB200_API int petb200_chain_pack(const float* w1, const float* w2, int d, void* image_fwd, void* image_bwd,
+                       petb200_stream_t stream);
+PETB200_API int petb200_edge_head_fwd(const float* m, int64_t ld_m, const void* image_fwd, const float* b1,
+                          const float* b2, const float* w_e, float b_e, int64_t n_edges, int d,
+                          float* e1p, float* e2p, float* edge_pred, petb200_stream_t stream);
+PETB200_API int petb200_edge_head_bwd(const float* d_atomic, const int32_t* ctr, const float* cutoff_factor,
+                          const float* e1p, const float* e2p, const float* edge_pred,
+                          const void* image_bwd, const float* w_e, int64_t n_edges, int d, float* d_m,
+                          int64_t ld_dm, float* d_fc, petb200_stream_t stream);
+PETB200_API int petb200_compress_fwd(const float* messages, int64_t ld_m, const void* image_fwd,
+                         const float* b_fold, const float* geo_w, const float* nbr_table,
+                         const int32_t* z_neighbor, const float* edge_vec, const float* edge_dist,
+                         const float* b2, int64_t n_edges, int d, float* c1, float* t_out, int64_t ld_t,
+                         petb200_stream_t stream);
+PETB200_API int petb200_compress_bwd(const float* d_t, int64_t ld_dt, const float* c1, const void* image_bwd,
+                         const float* geo_w, int64_t n_edges, int d, float* d_m, int64_t ld_dm,
+                         int accumulate, float* d_vec, float* d_dist, petb200_stream_t stream);
 
 /* ------------------------------------------------------ stage-level schedule (schedule.cu)
  * One call enqueues the whole kernel sequence of a stage on the stream, from C++, with caller-owned
@@ -484,6 +524,8 @@ typedef struct petb200_gnn_weights {  /* one CartesianTransformer */
   const float* nbr_fold;              /* NbrEmb W_1nbr^T [S, d] or NULL (first GNN layer) */
   petb200_mat w2, w2_t;               /* compress[2] [d, d] */
   const float* b2;
+  const void* compress_image_fwd;     /* petb200_chain_pack(w1m, w2) images (NULL: unfused token builder) */
+  const void* compress_image_bwd;
   int n_tl;
   const petb200_tl_weights* tl;       /* HOST array of n_tl entries */
 } petb200_gnn_weights;

@@ -159,7 +159,12 @@ class _Predict(torch.autograd.Function):
         atomic, saved = engine.predict_forward(pw, topo, name, h.contiguous(), m.contiguous(),
                                                fc.contiguous(), prec, layer)
         if sink is not None:  # last-layer features (outputs of the node / edge heads), no gradient
-            sink.append((saved["n2"], saved["e2"]))
+            # (the fused edge head keeps only the pre-activation of its second Linear: the features are
+            # silu of it, formed only when the padded NEF view is produced anyway)
+            e2 = saved["e2"]
+            if e2 is None and backend.emit_nef:
+                e2 = torch.nn.functional.silu(saved["e2p"])
+            sink.append((saved["n2"], e2))
         ctx.topo, ctx.pw, ctx.saved, ctx.fc, ctx.name, ctx.prec, ctx.layer = topo, pw, saved, fc, name, prec, layer
         return atomic
 
@@ -543,5 +548,6 @@ class B200PETBackend(PETParameters):
                                                              blocks[0].shape[1] // 9)
             atomic_predictions[name] = blocks
             node_ll[name] = [n for n, _ in sink]
-            edge_ll[name] = [_CsrToNef.apply(e, topo) if self.emit_nef else e for _, e in sink]
+            # (CSR-only mode with the fused edge head: the edge features are not materialised)
+            edge_ll[name] = [_CsrToNef.apply(e, topo) if self.emit_nef else e for _, e in sink if e is not None]
         return atomic_predictions, node_ll, edge_ll

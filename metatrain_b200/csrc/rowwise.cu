@@ -448,11 +448,16 @@ __global__ void readout_fwd_kernel(const float* __restrict__ node_feat,
     const float4 we = __ldg(reinterpret_cast<const float4*>(w_edge) + p * 32 + lane);
     float acc = warp_sum(nf.x * wn.x + nf.y * wn.y + nf.z * wn.z + nf.w * wn.w) + b_node[p];
     const float be = b_edge[p];
-    for (int e = lo; e < hi; ++e) {
-      const float4 ef = __ldg(reinterpret_cast<const float4*>(edge_feat) + (int64_t)e * 32 + lane);
-      float pe = warp_sum(ef.x * we.x + ef.y * we.y + ef.z * we.z + ef.w * we.w) + be;
-      if (lane == 0) edge_pred[(int64_t)e * n_out + p] = pe;
-      acc = fmaf(fc[e], pe, acc);
+    if (edge_feat == nullptr) {
+      // precomputed edge predictions (petb200_edge_head_fwd): a plain segmented sum, same order
+      for (int e = lo; e < hi; ++e) acc = fmaf(fc[e], edge_pred[(int64_t)e * n_out + p], acc);
+    } else {
+      for (int e = lo; e < hi; ++e) {
+        const float4 ef = __ldg(reinterpret_cast<const float4*>(edge_feat) + (int64_t)e * 32 + lane);
+        float pe = warp_sum(ef.x * we.x + ef.y * we.y + ef.z * we.z + ef.w * we.w) + be;
+        if (lane == 0) edge_pred[(int64_t)e * n_out + p] = pe;
+        acc = fmaf(fc[e], pe, acc);
+      }
     }
     if (lane == 0) atomic[i * n_out + p] = acc;
   }

@@ -38,7 +38,7 @@ struct Saved {
 Saved carve_saved(Arena& a, const petb200_gnn_weights& w, const petb200_dims& g) {
   Saved s{};
   const int64_t E = g.n_edges, N = g.n_atoms, T = E + N;
-  s.c1 = a.f32(E, g.d);
+  s.c1 = a.f32((E + 127) / 128 * 128, g.d);   // (whole 128-edge tiles: private layout of the fused token builder)
   for (int k = 0; k < w.n_tl; ++k) {
     SavedLayer& L = s.tl[k];
     L.x = a.f32(T, g.d);
@@ -136,10 +136,16 @@ extern "C" PETB200_API int petb200_gnn_fwd(const petb200_gnn_weights* w, const p
 
   // token builder: t = W_2 silu(W_1 cat[geo, nbr, m] + b_1) + b_2, concatenation folded (compress_gemm)
   float* x = w->n_tl > 0 ? S.tl[0].x : x_out;
-  CHECK(petb200_compress_gemm(m_in, ld_m, w->w1m.w, w->b_fold, w->geo_fold, w->nbr_fold, z_neighbors, edge_vec,
-                              edge_dist, E, d, S.c1, a1, prec, stream));
-  CHECK(gemm(a1, d, w->w2, x, d, E, d, d, w->b2, nullptr, nullptr, 0, nullptr, nullptr, 0, PETB200_EPI_NONE, 0, prec,
-             stream));
+  if (w->compress_image_fwd != nullptr) {
+    // both Linears and the SiLU between them in one kernel (chain_fused.cu)
+    CHECK(petb200_compress_fwd(m_in, ld_m, w->compress_image_fwd, w->b_fold, w->geo_fold, w->nbr_fold, z_neighbors,
+                               edge_vec, edge_dist, w->b2, E, d, S.c1, x, d, stream));
+  } else {
+    CHECK(petb200_compress_gemm(m_in, ld_m, w->w1m.w, w->b_fold, w->geo_fold, w->nbr_fold, z_neighbors, edge_vec,
+                                edge_dist, E, d, S.c1, a1, prec, stream));
+    CHECK(gemm(a1, d, w->w2, x, d, E, d, d, w->b2, nullptr, nullptr, 0, nullptr, nullptr, 0, PETB200_EPI_NONE, 0, prec,
+               stream));
+  }
   const float* h = h_in;
   for (int k = 0; k < w->n_tl; ++k) {
     const petb200_tl_weights& t = w->tl[k];
@@ -230,6 +236,11 @@ extern "C" PETB200_API int petb200_gnn_bwd(const petb200_gnn_weights* w, const p
     d_t = d_t_new;
   }
   // token builder: t = W_2 silu(c_1) + b_2 ; c_1 = W_1m m + G (r, d) + Tbl[z_j] + b'
+  if (w->compress_image_bwd != nullptr) {
+    CHECK(petb200_compress_bwd(d_t, d, S.c1, w->compress_image_bwd, w->geo_fold, E, d, d_m, ld_dm, 1, d_vec, d_dist,
+                               stream));
+    return PETB200_OK;
+  }
   CHECK(gemm(d_t, d, w->w2_t, d_c1, d, E, d, d, nullptr, nullptr, nullptr, 0, S.c1, nullptr, d, PETB200_EPI_MUL_DSILU, 0,
              prec, stream));
   CHECK(petb200_geom_embed_bwd(d_c1, d, w->geo_fold, E, d, 1, d_vec, d_dist, stream));

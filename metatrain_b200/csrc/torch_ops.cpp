@@ -52,8 +52,8 @@ Tensor bytes(size_t n, const Tensor& like) {
 
 // meta ints / floats (metatrain_b200/export.py)
 enum { M_NGNN, M_NTL, M_D, M_DN, M_NH, M_DFF, M_DH, M_NOUT, M_PREC, M_CUTFN, M_COUNT };
-enum { F_CUTOFF, F_WIDTH, F_TEMP, F_COUNT };
-constexpr int GNN_T = 8, TL_T = 22, COMB_T = 5, HEAD_T = 16;
+enum { F_CUTOFF, F_WIDTH, F_TEMP, F_BE, F_COUNT };   // F_BE: bias of the edge last layer (fused edge head)
+constexpr int GNN_T = 10, TL_T = 22, COMB_T = 5, HEAD_T = 18;
 
 // views into the flat weight list
 struct Weights {
@@ -70,6 +70,8 @@ struct Weights {
     const int o = gnn0(l);
     g.w1m = M(w[o]); g.w1m_t = M(w[o + 1]); g.b_fold = F(w[o + 2]); g.geo_fold = F(w[o + 3]);
     g.nbr_fold = F(w[o + 4]); g.w2 = M(w[o + 5]); g.w2_t = M(w[o + 6]); g.b2 = F(w[o + 7]);
+    g.compress_image_fwd = w[o + 8].numel() > 0 ? B(w[o + 8]) : nullptr;
+    g.compress_image_bwd = w[o + 9].numel() > 0 ? B(w[o + 9]) : nullptr;
     tls.resize(n_tl);
     for (int k = 0; k < n_tl; ++k) {
       const int q = tl0(l, k);
@@ -200,15 +202,26 @@ struct PetAtomic : public torch::autograd::Function<PetAtomic> {
     }
     // a12: heads, last layers, sum_j f_ij e_ij
     Tensor n1 = f32({N, dh}, pos), n1p = f32({N, dh}, pos), n2 = f32({N, dh}, pos), n2p = f32({N, dh}, pos);
-    Tensor e1 = f32({E, dh}, pos), e1p = f32({E, dh}, pos), e2 = f32({E, dh}, pos), e2p = f32({E, dh}, pos);
+    const bool fused_head = W.head(16).numel() > 0 && n_out == 1;   // petb200_edge_head_fwd / _bwd
+    Tensor e1p = f32({fused_head ? (E + 127) / 128 * 128 : E, dh}, pos), e2p = f32({E, dh}, pos);
     gemm(h, W.head(0), n1, &W.head(1), PETB200_EPI_SILU, nullptr, &n1p, prec);
     gemm(n1, W.head(2), n2, &W.head(3), PETB200_EPI_SILU, nullptr, &n2p, prec);
-    gemm(m, W.head(4), e1, &W.head(5), PETB200_EPI_SILU, nullptr, &e1p, prec);
-    gemm(e1, W.head(6), e2, &W.head(7), PETB200_EPI_SILU, nullptr, &e2p, prec);
     Tensor atomic = f32({N, n_out}, pos), pe = f32({E, n_out}, pos);
-    ok(petb200_readout_fwd(F(n2), F(e2), F(W.head(12)), F(W.head(13)), F(W.head(14)), F(W.head(15)), F(fc), I(row_ptr),
-                           N, E, dh, n_out, Fm(atomic), Fm(pe), S()),
-       "readout_fwd");
+    if (fused_head) {
+      ok(petb200_edge_head_fwd(F(m), d, B(W.head(16)), F(W.head(5)), F(W.head(7)), F(W.head(14)), (float)fmeta[F_BE], E,
+                               dh, Fm(e1p), Fm(e2p), Fm(pe), S()),
+         "edge_head_fwd");
+      ok(petb200_readout_fwd(F(n2), nullptr, F(W.head(12)), F(W.head(13)), F(W.head(14)), F(W.head(15)), F(fc),
+                             I(row_ptr), N, E, dh, n_out, Fm(atomic), Fm(pe), S()),
+         "readout_fwd");
+    } else {
+      Tensor e1 = f32({E, dh}, pos), e2 = f32({E, dh}, pos);
+      gemm(m, W.head(4), e1, &W.head(5), PETB200_EPI_SILU, nullptr, &e1p, prec);
+      gemm(e1, W.head(6), e2, &W.head(7), PETB200_EPI_SILU, nullptr, &e2p, prec);
+      ok(petb200_readout_fwd(F(n2), F(e2), F(W.head(12)), F(W.head(13)), F(W.head(14)), F(W.head(15)), F(fc),
+                             I(row_ptr), N, E, dh, n_out, Fm(atomic), Fm(pe), S()),
+         "readout_fwd");
+    }
 
     std::vector<Tensor> to_save = {vec, dist, fc, n1p, n2p, e1p, e2p, pe};
     to_save.insert(to_save.end(), keep.begin(), keep.end());
@@ -243,15 +256,28 @@ struct PetAtomic : public torch::autograd::Function<PetAtomic> {
     Tensor d_atomic = grads[0].to(torch::kFloat32).contiguous();
 
     // readout and heads
-    Tensor d_n2p = f32({N, dh}, vec), d_e2p = f32({E, dh}, vec), d_fc = torch::zeros({E}, vec.options());
-    ok(petb200_readout_bwd(F(d_atomic), F(pe), F(W.head(12)), F(W.head(14)), F(fc), I(ctr), F(n2p), F(e2p), N, E, dh,
-                           n_out, Fm(d_n2p), Fm(d_e2p), Fm(d_fc), S()),
-       "readout_bwd");
-    Tensor d_n1p = f32({N, dh}, vec), d_h = f32({N, dn}, vec), d_e1p = f32({E, dh}, vec), d_m = f32({E, d}, vec);
-    gemm(d_n2p, W.head(9), d_n1p, nullptr, PETB200_EPI_MUL_DSILU, &n1p, nullptr, prec);
-    gemm(d_n1p, W.head(8), d_h, nullptr, PETB200_EPI_NONE, nullptr, nullptr, prec);
-    gemm(d_e2p, W.head(11), d_e1p, nullptr, PETB200_EPI_MUL_DSILU, &e1p, nullptr, prec);
-    gemm(d_e1p, W.head(10), d_m, nullptr, PETB200_EPI_NONE, nullptr, nullptr, prec);
+    const bool fused_head = W.head(16).numel() > 0 && n_out == 1;
+    Tensor d_n2p = f32({N, dh}, vec), d_fc = torch::zeros({E}, vec.options());
+    Tensor d_n1p = f32({N, dh}, vec), d_h = f32({N, dn}, vec), d_m = f32({E, d}, vec);
+    if (fused_head) {
+      ok(petb200_readout_bwd(F(d_atomic), nullptr, F(W.head(12)), F(W.head(14)), F(fc), I(ctr), F(n2p), nullptr, N, 0, dh,
+                             n_out, Fm(d_n2p), nullptr, nullptr, S()),
+         "readout_bwd");
+      gemm(d_n2p, W.head(9), d_n1p, nullptr, PETB200_EPI_MUL_DSILU, &n1p, nullptr, prec);
+      gemm(d_n1p, W.head(8), d_h, nullptr, PETB200_EPI_NONE, nullptr, nullptr, prec);
+      ok(petb200_edge_head_bwd(F(d_atomic), I(ctr), F(fc), F(e1p), F(e2p), F(pe), B(W.head(17)), F(W.head(14)), E, dh,
+                               Fm(d_m), d, Fm(d_fc), S()),
+         "edge_head_bwd");
+    } else {
+      Tensor d_e2p = f32({E, dh}, vec), d_e1p = f32({E, dh}, vec);
+      ok(petb200_readout_bwd(F(d_atomic), F(pe), F(W.head(12)), F(W.head(14)), F(fc), I(ctr), F(n2p), F(e2p), N, E, dh,
+                             n_out, Fm(d_n2p), Fm(d_e2p), Fm(d_fc), S()),
+         "readout_bwd");
+      gemm(d_n2p, W.head(9), d_n1p, nullptr, PETB200_EPI_MUL_DSILU, &n1p, nullptr, prec);
+      gemm(d_n1p, W.head(8), d_h, nullptr, PETB200_EPI_NONE, nullptr, nullptr, prec);
+      gemm(d_e2p, W.head(11), d_e1p, nullptr, PETB200_EPI_MUL_DSILU, &e1p, nullptr, prec);
+      gemm(d_e1p, W.head(10), d_m, nullptr, PETB200_EPI_NONE, nullptr, nullptr, prec);
+    }
 
     // GNN layers in reverse
     Tensor d_vec = torch::zeros({E, 3}, vec.options()), d_dist = torch::zeros({E}, vec.options());

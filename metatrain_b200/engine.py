@@ -187,6 +187,17 @@ def _mlp_images(w_in_folded: Tensor, w_out: Tensor):
     return imgs
 
 
+def _chain_images(w1: Tensor, w2: Tensor):
+    """(forward image, backward image) of a 128 -> 128 -> 128 chain for the fused kernels of
+    chain_fused.cu, or None for other widths."""
+    if tuple(w1.shape) != (128, 128) or tuple(w2.shape) != (128, 128):
+        return None
+    nbytes = lib.load().petb200_chain_image_bytes(128)
+    imgs = [torch.empty(nbytes, device=w1.device, dtype=torch.uint8) for _ in range(2)]
+    call("chain_pack", ptr(w1.contiguous()), ptr(w2.contiguous()), 128, ptr(imgs[0]), ptr(imgs[1]))
+    return imgs
+
+
 def _linear_image(w_folded: Tensor):
     """Operand-tile image for petb200_norm_linear, or None outside its shape range."""
     n_out, d = w_folded.shape
@@ -262,6 +273,8 @@ class PackedWeights:
             L["nbr_fold"] = ((L["nbr"].double() @ w1_64[:, dp:2 * dp].T).float().contiguous()
                              if L["nbr"] is not None else None)
             L["w1m"] = L["w1"][:, -dp:].contiguous()
+            # fused token builder (petb200_compress_fwd / _bwd): operand-tile images of (W_1m, W_2)
+            L["c_img"] = _chain_images(L["w1m"], L["w2"])
             L["tl"] = []
             for tl in layer.trans.layers:
                 T: dict = {}
@@ -350,6 +363,8 @@ class PackedWeights:
                 keys = list(module.node_last_layers[name][r].keys())
                 H["block_keys"] = keys
                 H["block_sizes"] = [module.node_last_layers[name][r][k].weight.shape[0] for k in keys]
+                # fused edge head (petb200_edge_head_fwd / _bwd), single-property targets
+                H["e_img"] = _chain_images(H["e1"], H["e2"])
                 H["wn"] = torch.cat([_w(module.node_last_layers[name][r][k]) for k in keys]).contiguous()
                 H["bn"] = torch.cat([_b(module.node_last_layers[name][r][k]) for k in keys]).contiguous()
                 H["we"] = torch.cat([_w(module.edge_last_layers[name][r][k]) for k in keys]).contiguous()
@@ -742,6 +757,8 @@ def _stage_structs(pw: PackedWeights, L: dict):
     g.w1m, g.w1m_t = _mat(L["w1m"], pw), _mat(L["w1_t"][width - d:], pw)
     g.b_fold, g.geo_fold, g.nbr_fold = ptr(L["b_fold"]), ptr(L["geo_fold"]), ptr(L["nbr_fold"])
     g.w2, g.w2_t, g.b2 = _mat(L["w2"], pw), _mat(L["w2_t"], pw), ptr(L["b2"])
+    if L["c_img"] is not None and USE_FUSED_CHAINS:
+        g.compress_image_fwd, g.compress_image_bwd = ptr(L["c_img"][0]), ptr(L["c_img"][1])
     g.n_tl, g.tl = len(L["tl"]), tls
     L["_stage"] = (g, tls)
     return L["_stage"]
@@ -756,6 +773,9 @@ def _dims(topo: Topology, hyp, H: int, prec: int) -> "lib.Dims":
 def _bytes(n: int, like: Tensor) -> Tensor:
     return torch.empty(max(int(n), 16), device=like.device, dtype=torch.uint8)
 
+
+#: use the fused 128 -> 128 -> 128 chain kernels (token builder, edge head) where they apply
+USE_FUSED_CHAINS = True
 
 #: use the C++ stage-level schedule (petb200_gnn_fwd / _bwd) where it applies; the per-op schedule
 #: below is the same sequence issued from Python (kept for the layer variants and as a cross-check)
@@ -787,8 +807,17 @@ def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc,
              saved.numel(), ptr(scratch), scratch.numel())
         return h_out, Xf[:E + N], Xf, {"stage": (gw, dims, saved), "tl": []}
     S: dict = {"tl": []}
-    c1, a1 = _empty((E, d), vec), _empty((E, d), vec)
-    if prec != PREC_FP32 and d == 128:
+    Xf = _empty((E + N + H, d), vec)
+    X = Xf[:E + N]
+    fused_tb = prec != PREC_FP32 and d == 128 and L["c_img"] is not None and USE_FUSED_CHAINS
+    c1 = _empty((-(-E // 128) * 128 if fused_tb else E, d), vec)
+    a1 = None if fused_tb else _empty((E, d), vec)
+    if fused_tb:
+        # token builder: both Linears and the SiLU between them in one kernel (c1 in its private layout)
+        call("compress_fwd", ptr(m), m.stride(0), ptr(L["c_img"][0]), ptr(L["b_fold"]), ptr(L["geo_fold"]),
+             ptr(L["nbr_fold"]), ptr(topo.z_neighbors), ptr(vec), ptr(dist), ptr(L["b2"]), E, d, ptr(c1), ptr(X), d)
+        S["c1_private"] = True
+    elif prec != PREC_FP32 and d == 128:
         # one K = d GEMM; geometry embedding and neighbour-species embedding enter as a
         # per-row term of the epilogue (no [E, 2d / 3d] concatenation in HBM)
         call("compress_gemm", ptr(m), m.stride(0), ptr(split_weight(L["w1m"], pw)), ptr(L["b_fold"]),
@@ -801,9 +830,8 @@ def _gnn_forward(pw: PackedWeights, L: dict, hyp, topo: Topology, vec, dist, fc,
              ptr(L["nbr"]), ptr(topo.z_neighbors), ptr(m), E, d, ptr(cat))
         gemm(cat, L["w1"], a1, bias=L["b1"], epilogue=EPI_SILU, aux_out=c1, precision=prec, pack=pw)
         del cat
-    Xf = _empty((E + N + H, d), vec)
-    X = Xf[:E + N]
-    gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec, pack=pw)
+    if not fused_tb:
+        gemm(a1, L["w2"], X[:E], bias=L["b2"], precision=prec, pack=pw)
     del a1
     S["c1"] = c1
     for T in L["tl"]:
@@ -1048,6 +1076,10 @@ def _gnn_backward(pw: PackedWeights, L: dict, S: dict, hyp, topo: Topology, fc, 
             d_h = d_h_new
         d_t = d_t_new
     # ---- token builder: t = W_2 silu(W_1 cat[geo, nbr, m] + b_1) + b_2
+    if S.get("c1_private"):
+        call("compress_bwd", ptr(d_t), d_t.stride(0), ptr(S["c1"]), ptr(L["c_img"][1]), ptr(L["geo_fold"]), E, d,
+             ptr(d_m), d_m.stride(0) if d_m is not None else 0, 1, ptr(d_vec), ptr(d_dist))
+        return d_h if h_grad_wanted else None
     d_c1 = _empty((E, d), ref)
     gemm(d_t, L["w2_t"], d_c1, epilogue=EPI_MUL_DSILU, aux_in=S["c1"], precision=prec, pack=pw)
     if prec != PREC_FP32 and d == 128:
@@ -1149,13 +1181,25 @@ def predict_forward(pw: PackedWeights, topo: Topology, name: str, h, m, fc, prec
     gemm(h, H["n1"], n1, bias=H["n1_b"], epilogue=EPI_SILU, aux_out=n1p, precision=prec, pack=pw)
     n2, n2p = _empty((N, dh), h), _empty((N, dh), h)
     gemm(n1, H["n2"], n2, bias=H["n2_b"], epilogue=EPI_SILU, aux_out=n2p, precision=prec, pack=pw)
+    n_out = H["wn"].shape[0]
+    atomic = _empty((N, n_out), h)
+    pe = _empty((E, n_out), h)
+    if (prec != PREC_FP32 and USE_FUSED_CHAINS and n_out == 1 and H["e_img"] is not None
+            and m.shape[1] == 128 and dh == 128):
+        # edge head, last layer and (in the backward) the readout gradient seed in one kernel per direction
+        if "be_host" not in H:
+            H["be_host"] = float(H["be"][0])   # one device -> host read per weight packing
+        e1p, e2p = _empty((-(-E // 128) * 128, dh), h), _empty((E, dh), h)
+        call("edge_head_fwd", ptr(m), m.stride(0), ptr(H["e_img"][0]), ptr(H["e1_b"]), ptr(H["e2_b"]),
+             ptr(H["we"]), H["be_host"], E, dh, ptr(e1p), ptr(e2p), ptr(pe))
+        call("readout_fwd", ptr(n2), None, ptr(H["wn"]), ptr(H["bn"]), ptr(H["we"]), ptr(H["be"]),
+             ptr(fc), ptr(topo.row_ptr), N, E, dh, n_out, ptr(atomic), ptr(pe))
+        saved = dict(n1p=n1p, n2p=n2p, e1p=e1p, e2p=e2p, pe=pe, n2=n2, e2=None, fused_head=True)
+        return atomic, saved
     e1, e1p = _empty((E, dh), h), _empty((E, dh), h)
     gemm(m, H["e1"], e1, bias=H["e1_b"], epilogue=EPI_SILU, aux_out=e1p, precision=prec, pack=pw)
     e2, e2p = _empty((E, dh), h), _empty((E, dh), h)
     gemm(e1, H["e2"], e2, bias=H["e2_b"], epilogue=EPI_SILU, aux_out=e2p, precision=prec, pack=pw)
-    n_out = H["wn"].shape[0]
-    atomic = _empty((N, n_out), h)
-    pe = _empty((E, n_out), h)
     call("readout_fwd", ptr(n2), ptr(e2), ptr(H["wn"]), ptr(H["bn"]), ptr(H["we"]), ptr(H["be"]),
          ptr(fc), ptr(topo.row_ptr), N, E, dh, n_out, ptr(atomic), ptr(pe))
     saved = dict(n1p=n1p, n2p=n2p, e1p=e1p, e2p=e2p, pe=pe, n2=n2, e2=e2)
@@ -1169,8 +1213,20 @@ def predict_backward(pw: PackedWeights, topo: Topology, name: str, fc, saved, d_
     dh = H["n2"].shape[0]
     n_out = H["wn"].shape[0]
     d_atomic = d_atomic.contiguous()
-    d_n2p, d_e2p = _empty((N, dh), fc), _empty((E, dh), fc)
     d_fc = torch.zeros((E,), device=fc.device, dtype=torch.float32)
+    if saved.get("fused_head"):
+        d_n2p = _empty((N, dh), fc)
+        call("readout_bwd", ptr(d_atomic), None, ptr(H["wn"]), ptr(H["we"]), ptr(fc), ptr(topo.ctr),
+             ptr(saved["n2p"]), None, N, 0, dh, n_out, ptr(d_n2p), None, None)
+        d_n1p = _empty((N, dh), fc)
+        gemm(d_n2p, H["n2_t"], d_n1p, epilogue=EPI_MUL_DSILU, aux_in=saved["n1p"], precision=prec, pack=pw)
+        d_h = _empty((N, H["n1"].shape[1]), fc)
+        gemm(d_n1p, H["n1_t"], d_h, precision=prec, pack=pw)
+        d_m = _empty((E, H["e1"].shape[1]), fc)
+        call("edge_head_bwd", ptr(d_atomic), ptr(topo.ctr), ptr(fc), ptr(saved["e1p"]), ptr(saved["e2p"]),
+             ptr(saved["pe"]), ptr(H["e_img"][1]), ptr(H["we"]), E, dh, ptr(d_m), d_m.stride(0), ptr(d_fc))
+        return d_h, d_m, d_fc
+    d_n2p, d_e2p = _empty((N, dh), fc), _empty((E, dh), fc)
     call("readout_bwd", ptr(d_atomic), ptr(saved["pe"]), ptr(H["wn"]), ptr(H["we"]), ptr(fc),
          ptr(topo.ctr), ptr(saved["n2p"]), ptr(saved["e2p"]), N, E, dh, n_out, ptr(d_n2p),
          ptr(d_e2p), ptr(d_fc))

@@ -82,8 +82,8 @@ def extension_libraries() -> List[str]:
 
 def export_weights(backend, target: str) -> Tuple[List[Tensor], List[int], List[float]]:
     """Flat weight list + metadata of ``torch.ops.petb200.pet_atomic`` (order mirrored by
-    ``Weights`` in csrc/torch_ops.cpp): per GNN layer 8 token-builder tensors, 22 tensors per
-    attention layer, 5 combine tensors; then the node / edge embeddings and 16 head tensors.
+    ``Weights`` in csrc/torch_ops.cpp): per GNN layer 10 token-builder tensors, 22 tensors per
+    attention layer, 5 combine tensors; then the node / edge embeddings and 18 head tensors.
     Matrices are in the bf16 hi/lo split format of ``petb200_split_bf16``."""
     hyp = backend.hypers
     if backend._precision == PREC_FP32:
@@ -101,8 +101,10 @@ def export_weights(backend, target: str) -> Tuple[List[Tensor], List[int], List[
             raise NotImplementedError("export: layer shape outside the fused kernels (d_pet = 128 needed)")
         d = L["w_geo"].shape[0]
         width = L["w1_t"].shape[0]
+        c_img = L["c_img"] if (L["c_img"] is not None and engine.USE_FUSED_CHAINS) else [empty.to(torch.uint8)] * 2
         out += [sp(L["w1m"]), sp(L["w1_t"][width - d:].contiguous()), L["b_fold"], L["geo_fold"],
-                L["nbr_fold"] if L["nbr_fold"] is not None else empty, sp(L["w2"]), sp(L["w2_t"]), L["b2"]]
+                L["nbr_fold"] if L["nbr_fold"] is not None else empty, sp(L["w2"]), sp(L["w2_t"]), L["b2"],
+                c_img[0], c_img[1]]
         for T in L["tl"]:
             out += [T["qkv_img"], T["b_qkv"], sp(T["w_qkv_t"]), sp(T["w_o"]), sp(T["w_o_t"]), T["b_o"],
                     T["mlp_img"][0], T["mlp_img"][1], T["b_in"], T["b_out"],
@@ -115,11 +117,14 @@ def export_weights(backend, target: str) -> Tuple[List[Tensor], List[int], List[
     out += [pw.node_emb[0], pw.edge_emb]
     out += [sp(H["n1"]), H["n1_b"], sp(H["n2"]), H["n2_b"], sp(H["e1"]), H["e1_b"], sp(H["e2"]), H["e2_b"],
             sp(H["n1_t"]), sp(H["n2_t"]), sp(H["e1_t"]), sp(H["e2_t"]), H["wn"], H["bn"], H["we"], H["be"]]
+    fused_head = H["e_img"] is not None and engine.USE_FUSED_CHAINS and H["wn"].shape[0] == 1
+    out += [H["e_img"][0], H["e_img"][1]] if fused_head else [empty.to(torch.uint8)] * 2
     out = [t.detach().contiguous() for t in out]
     dff = pw.gnn[0]["tl"][0]["w_out"].shape[1]
     meta = [len(pw.gnn), len(pw.gnn[0]["tl"]), hyp["d_pet"], hyp["d_node"], hyp["num_heads"], dff,
             H["n2"].shape[0], H["wn"].shape[0], backend._precision, backend._cutoff_id]
-    fmeta = [float(backend.cutoff), float(backend.cutoff_width), float(hyp["attention_temperature"])]
+    fmeta = [float(backend.cutoff), float(backend.cutoff_width), float(hyp["attention_temperature"]),
+             float(H["be"][0])]
     return out, [int(v) for v in meta], fmeta
 
 

@@ -88,6 +88,12 @@ _SIGNATURES = {
     "petb200_combine_bwd": [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I, _P, _P],
     "petb200_readout_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P],
     "petb200_readout_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P, _P, _P, _P],
+    "petb200_chain_image_bytes": [_I],
+    "petb200_chain_pack": [_P, _P, _I, _P, _P, _P],
+    "petb200_edge_head_fwd": [_P, _I64, _P, _P, _P, _P, _F, _I64, _I, _P, _P, _P, _P],
+    "petb200_edge_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _I64, _P, _P],
+    "petb200_compress_fwd": [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P, _I64, _P],
+    "petb200_compress_bwd": [_P, _I64, _P, _P, _P, _I64, _I, _P, _I64, _I, _P, _P, _P],
     "petb200_gnn_saved_bytes": [_P, _P],
     "petb200_gnn_scratch_bytes": [_P, _P],
     "petb200_gnn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _SZ, _P, _SZ, _P],
@@ -96,7 +102,7 @@ _SIGNATURES = {
     "petb200_last_error": [],
     "petb200_version": [],
 }
-_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_combine_image_bytes": _SZ, "petb200_gnn_saved_bytes": _SZ, "petb200_gnn_scratch_bytes": _SZ, "petb200_norm_linear_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
+_RESTYPE = {"petb200_csr_build_workspace": _SZ, "petb200_mlp_image_bytes": _SZ, "petb200_combine_image_bytes": _SZ, "petb200_chain_image_bytes": _SZ, "petb200_gnn_saved_bytes": _SZ, "petb200_gnn_scratch_bytes": _SZ, "petb200_norm_linear_image_bytes": _SZ, "petb200_last_error": ctypes.c_char_p,
             "petb200_nl_num_bins": _I64, "petb200_nl_workspace": _SZ}
 
 
@@ -114,7 +120,8 @@ class TLWeights(ctypes.Structure):
 
 class GNNWeights(ctypes.Structure):
     _fields_ = [("w1m", Mat), ("w1m_t", Mat), ("b_fold", _P), ("geo_fold", _P), ("nbr_fold", _P), ("w2", Mat),
-                ("w2_t", Mat), ("b2", _P), ("n_tl", _I), ("tl", ctypes.POINTER(TLWeights))]
+                ("w2_t", Mat), ("b2", _P), ("compress_image_fwd", _P), ("compress_image_bwd", _P),
+                ("n_tl", _I), ("tl", ctypes.POINTER(TLWeights))]
 
 
 class Dims(ctypes.Structure):
@@ -176,7 +183,7 @@ _KERNELS_PER_CALL = {"nl_count": 6, "attention_bwd": 2, "edges_bwd": 3, "edges_b
                      "force_scatter": 2, "mlp_pack": 2}
 launch_count = 0
 #: kernels enqueued by one petb200_gnn_fwd / _bwd call: (fixed part, per attention layer)
-GNN_KERNELS = {"gnn_fwd": (2, 9), "gnn_bwd": (3, 9)}
+GNN_KERNELS = {"gnn_fwd": (1, 9), "gnn_bwd": (1, 9)}
 #: optional profiler hook: ``hook(name, args) -> context manager`` wrapped around a call
 profile_hook = None
 

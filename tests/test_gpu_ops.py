@@ -291,6 +291,93 @@ def test_combine_fused_fwd_bwd(E, ghosts):
     assert_close(d_cat, cat.grad, 3e-4, 3e-5, "combine_bwd")
 
 
+def _chain_images(w1, w2):
+    handle = lib.load()
+    imgs = [torch.empty(handle.petb200_chain_image_bytes(128), device=DEV, dtype=torch.uint8) for _ in range(2)]
+    call("chain_pack", ptr(w1), ptr(w2), 128, ptr(imgs[0]), ptr(imgs[1]))
+    return imgs
+
+
+def _private_rows(p1, E, width):
+    """[tile][chunk of 32 units][unit][edge of the tile] -> [E, width]."""
+    tiles = p1.shape[0] // 128
+    return p1.view(tiles, width // 32, 32, 128).permute(0, 3, 1, 2).reshape(tiles * 128, width)[:E]
+
+
+@pytest.mark.parametrize("E", [999, 128, 3, 40000, 0])
+def test_edge_head_fused_fwd_bwd(E):
+    """petb200_edge_head_fwd / _bwd against fp64 autograd of backend.py:171-217, 762-772: edge head (two
+    Linears with SiLU), last layer, cutoff-weighted sum; the backward starts from d_atomic."""
+    d, N = 128, max(E // 30, 1)
+    m = rnd(E, d, seed=1)
+    w1, b1 = rnd(d, d, seed=2, scale=d ** -0.5), rnd(d, seed=3, scale=0.1)
+    w2, b2 = rnd(d, d, seed=4, scale=d ** -0.5), rnd(d, seed=5, scale=0.1)
+    w_e, b_e = rnd(1, d, seed=6, scale=d ** -0.5), 0.37
+    fc = torch.rand(E, device=DEV)
+    ctr = torch.sort(torch.randint(0, N, (E,), generator=torch.Generator().manual_seed(7))).values.to(torch.int32).to(DEV)
+    d_atomic = rnd(N, 1, seed=8)
+    imgs = _chain_images(w1, w2)
+    tiles = -(-E // 128)
+    e1p, e2p, pe = torch.empty(tiles * 128, d, device=DEV), torch.empty(E, d, device=DEV), torch.empty(E, device=DEV)
+    call("edge_head_fwd", ptr(m), d, ptr(imgs[0]), ptr(b1), ptr(b2), ptr(w_e), b_e, E, d, ptr(e1p), ptr(e2p), ptr(pe))
+    if E == 0:
+        return
+    mm = m.double().cpu().requires_grad_(True)
+    fcc = fc.double().cpu().requires_grad_(True)
+    p1 = mm @ w1.double().cpu().T + b1.double().cpu()
+    p2 = F.silu(p1) @ w2.double().cpu().T + b2.double().cpu()
+    pred = F.silu(p2) @ w_e.double().cpu().T + b_e                     # [E, 1]
+    assert_close(_private_rows(e1p, E, d), p1.detach(), 2e-4, 2e-5, "edge head: first pre-activation")
+    assert_close(e2p, p2.detach(), 2e-4, 2e-5, "edge head: second pre-activation")
+    assert_close(pe, pred.detach()[:, 0], 2e-4, 2e-5, "edge head: edge predictions")
+    loss = (d_atomic.double().cpu()[ctr.long().cpu()] * fcc[:, None] * pred).sum()
+    loss.backward()
+    d_m, d_fc = torch.empty(E, d, device=DEV), torch.zeros(E, device=DEV)
+    call("edge_head_bwd", ptr(d_atomic), ptr(ctr), ptr(fc), ptr(e1p), ptr(e2p), ptr(pe), ptr(imgs[1]), ptr(w_e), E, d,
+         ptr(d_m), d, ptr(d_fc))
+    assert_close(d_m, mm.grad, 3e-4, 3e-5, "edge head: d_m")
+    assert_close(d_fc, fcc.grad, 3e-4, 3e-5, "edge head: d_fc")
+
+
+@pytest.mark.parametrize("E,with_table,need_dm", [(999, True, True), (130, False, True), (40000, True, False), (0, True, True)])
+def test_compress_fused_fwd_bwd(E, with_table, need_dm):
+    """petb200_compress_fwd / _bwd (token builder, transformer.py:500-521 with the concatenation folded)
+    against fp64 autograd."""
+    d, S = 128, 5
+    m = rnd(E, d, seed=1)
+    vec, dist = rnd(E, 3, seed=2), rnd(E, seed=3).abs() + 0.5
+    w1m, b_fold = rnd(d, d, seed=4, scale=d ** -0.5), rnd(d, seed=5, scale=0.1)
+    geo_w = rnd(d, 4, seed=6, scale=0.3)
+    table = rnd(S, d, seed=7, scale=0.3) if with_table else None
+    z = torch.randint(0, S, (E,), generator=torch.Generator().manual_seed(8)).to(torch.int32).to(DEV)
+    w2, b2 = rnd(d, d, seed=9, scale=d ** -0.5), rnd(d, seed=10, scale=0.1)
+    imgs = _chain_images(w1m, w2)
+    tiles = -(-E // 128)
+    c1, t_out = torch.empty(tiles * 128, d, device=DEV), torch.empty(E, d, device=DEV)
+    call("compress_fwd", ptr(m), d, ptr(imgs[0]), ptr(b_fold), ptr(geo_w), ptr(table), ptr(z), ptr(vec), ptr(dist),
+         ptr(b2), E, d, ptr(c1), ptr(t_out), d)
+    if E == 0:
+        return
+    mm = m.double().cpu().requires_grad_(True)
+    geo = torch.cat([vec, dist[:, None]], dim=1).double().cpu().requires_grad_(True)
+    pre = mm @ w1m.double().cpu().T + geo @ geo_w.double().cpu().T + b_fold.double().cpu()
+    if with_table:
+        pre = pre + table.double().cpu()[z.long().cpu()]
+    tt = F.silu(pre) @ w2.double().cpu().T + b2.double().cpu()
+    assert_close(_private_rows(c1, E, d), pre.detach(), 2e-4, 2e-5, "compress: pre-activation")
+    assert_close(t_out, tt.detach(), 2e-4, 2e-5, "compress: tokens")
+    d_t = rnd(E, d, seed=11)
+    tt.backward(d_t.double().cpu())
+    base_m, base_v, base_d = rnd(E, d, seed=12), rnd(E, 3, seed=13), rnd(E, seed=14)
+    d_m, d_vec, d_dist = base_m.clone(), base_v.clone(), base_d.clone()
+    call("compress_bwd", ptr(d_t), d, ptr(c1), ptr(imgs[1]), ptr(geo_w), E, d, ptr(d_m) if need_dm else None, d, 1,
+         ptr(d_vec), ptr(d_dist))
+    if need_dm:
+        assert_close(d_m, base_m.double().cpu() + mm.grad, 3e-4, 3e-5, "compress: d_m (accumulated)")
+    assert_close(d_vec, base_v.double().cpu() + geo.grad[:, :3], 3e-4, 3e-5, "compress: d_vec")
+    assert_close(d_dist, base_d.double().cpu() + geo.grad[:, 3], 3e-4, 3e-5, "compress: d_dist")
+
+
 def test_embedding_transpose_compress_geom():
     E, d = 777, 128
     table = rnd(5, d)
