@@ -155,7 +155,7 @@ def build_shard(positions: np.ndarray, cell: np.ndarray, nl, rank: int, world: i
                  halo_recv, halo_send)
 
 
-def attach_halo(topo, shard: Shard, device, group=None) -> None:
+def attach_halo(topo, shard: Shard, device, group=None, device_lists=None) -> None:
     """Translate the shard's halo lists to CSR edge ids and patch ``topo.rev`` so that the
     reverse of a halo edge points at its ghost slot.  Two ghost bases are used: the forward
     token buffer is laid out [E edge rows | N centre rows | H ghost rows], backward edge
@@ -164,10 +164,15 @@ def attach_halo(topo, shard: Shard, device, group=None) -> None:
     # CSR edge k came from input edge perm[k]  ->  inverse map input edge -> CSR edge
     inv = torch.empty(len(shard.centers), dtype=torch.int64, device=device)
     inv[topo.perm.long()] = torch.arange(E, device=device)
-    recv_in = np.concatenate(shard.halo_recv) if shard.world > 1 else np.zeros(0, dtype=np.int64)
-    send_in = np.concatenate(shard.halo_send) if shard.world > 1 else np.zeros(0, dtype=np.int64)
-    halo_edges = inv[torch.from_numpy(recv_in).to(device)]
-    send_idx = inv[torch.from_numpy(send_in).to(device)]
+    if device_lists is not None and "halo_recv" in device_lists:
+        # (the halo lists only depend on the shard: uploaded once, or with the step's other inputs)
+        recv_d, send_d = device_lists["halo_recv"], device_lists["halo_send"]
+    else:
+        recv_in = np.concatenate(shard.halo_recv) if shard.world > 1 else np.zeros(0, dtype=np.int64)
+        send_in = np.concatenate(shard.halo_send) if shard.world > 1 else np.zeros(0, dtype=np.int64)
+        recv_d, send_d = torch.from_numpy(recv_in).to(device), torch.from_numpy(send_in).to(device)
+    halo_edges = inv[recv_d]
+    send_idx = inv[send_d]
     H = int(halo_edges.numel())
     slots = torch.arange(H, device=device, dtype=torch.int32)
     rev_fwd = topo.rev.clone()
@@ -182,10 +187,13 @@ def attach_halo(topo, shard: Shard, device, group=None) -> None:
 
 def shard_to_host_tensors(shard: Shard, pin_memory: bool = False) -> Dict[str, Tensor]:
     """The rank's index lists as (optionally pinned) host tensors."""
+    cat = lambda parts: (np.concatenate(parts) if shard.world > 1 else np.zeros(0, dtype=np.int64))  # noqa: E731
     out = dict(ids=torch.from_numpy(np.ascontiguousarray(shard.local_ids)),
                centers=torch.from_numpy(shard.centers.astype(np.int32)),
                neighbors=torch.from_numpy(shard.neighbors.astype(np.int32)),
-               shifts=torch.from_numpy(np.ascontiguousarray(shard.cell_shifts.astype(np.int32))))
+               shifts=torch.from_numpy(np.ascontiguousarray(shard.cell_shifts.astype(np.int32))),
+               halo_recv=torch.from_numpy(np.ascontiguousarray(cat(shard.halo_recv)).astype(np.int64)),
+               halo_send=torch.from_numpy(np.ascontiguousarray(cat(shard.halo_send)).astype(np.int64)))
     return {k: v.pin_memory() for k, v in out.items()} if pin_memory else out
 
 
@@ -219,17 +227,24 @@ def evaluate_sharded(backend, shard: Shard, positions: Tensor, species: Tensor, 
     topo = engine.build_topology(pos_local, centers, neighbors, shifts, cells, sysidx, z_nodes,
                                  backend.cutoff, check_symmetric=False,
                                  n_rows=len(shard.own_ids))
-    attach_halo(topo, shard, dev, group)
+    attach_halo(topo, shard, dev, group, lists)
     vec, dist_, fc = _EdgeGeometry.apply(pos_local, cells, topo, backend.cutoff,
                                          backend.cutoff_width, backend._cutoff_id)
     h, m = _Features.apply(vec, dist_, fc, backend, topo, None, None)
     atomic = _Predict.apply(h, m, fc, backend, topo, target, 0, None)    # [n_own, P]
     energy = atomic.sum(dim=0, keepdim=True)
-    total = energy.detach().clone()
-    dist.all_reduce(total, group=group)
-    out = {"energies": total, "atomic_local": atomic.detach()}
+    out = {"atomic_local": atomic.detach()}
     if gradients:
+        # one all-reduce for the position gradient (every row is non-zero on exactly one rank: the
+        # force scatter already pulled the halo contributions in) and the per-structure energy
         (grad,) = torch.autograd.grad(energy.sum(), pos)
-        dist.all_reduce(grad, group=group)
-        out["dE_dpos"] = grad
+        packed = torch.cat([grad.reshape(-1), energy.detach().reshape(-1)])
+        dist.all_reduce(packed, group=group)
+        n3 = grad.numel()
+        out["dE_dpos"] = packed[:n3].view_as(grad)
+        out["energies"] = packed[n3:].view_as(energy)
+    else:
+        total = energy.detach().clone()
+        dist.all_reduce(total, group=group)
+        out["energies"] = total
     return out
