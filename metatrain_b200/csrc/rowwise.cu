@@ -512,19 +512,36 @@ __global__ void readout_bwd_edge_kernel(const float* __restrict__ d_atomic,
   if (lane == 0 && d_fc) d_fc[e] += dfc;
 }
 
-// sum_over_atoms.py:31 — atoms of one structure are contiguous: one warp per structure.
-__global__ void sum_over_atoms_kernel(const float* __restrict__ atomic,
-                                      const int32_t* __restrict__ struct_ptr, int64_t n_structures,
-                                      int n_out, float* __restrict__ energies) {
-  int64_t b = global_warp();
-  if (b >= n_structures) return;
-  const int lane = threadIdx.x & 31;
+// sum_over_atoms.py:31 — atoms of one structure are contiguous: one CTA per structure, a fixed
+// (thread-strided, then warp-tree, then warp-ordered) summation order, so the result is deterministic.
+constexpr int kSumThreads = 256;
+__global__ void __launch_bounds__(kSumThreads) sum_over_atoms_kernel(const float* __restrict__ atomic,
+                                                                     const int32_t* __restrict__ struct_ptr,
+                                                                     int n_out, float* __restrict__ energies) {
+  __shared__ float part[kSumThreads / 32];
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lo = struct_ptr[b], hi = struct_ptr[b + 1];
   for (int p = 0; p < n_out; ++p) {
-    float acc = 0.f;
-    for (int i = lo + lane; i < hi; i += 32) acc += atomic[(int64_t)i * n_out + p];
-    acc = warp_sum(acc);
-    if (lane == 0) energies[b * n_out + p] = acc;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four loads in flight per thread
+    int i = lo + threadIdx.x;
+    for (; i + 3 * kSumThreads < hi; i += 4 * kSumThreads) {
+      a0 += atomic[(int64_t)i * n_out + p];
+      a1 += atomic[(int64_t)(i + kSumThreads) * n_out + p];
+      a2 += atomic[(int64_t)(i + 2 * kSumThreads) * n_out + p];
+      a3 += atomic[(int64_t)(i + 3 * kSumThreads) * n_out + p];
+    }
+    for (; i < hi; i += kSumThreads) a0 += atomic[(int64_t)i * n_out + p];
+    const float acc = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSumThreads / 32; ++w) tot += part[w];
+      energies[b * n_out + p] = tot;
+    }
+    __syncthreads();
   }
 }
 
@@ -761,7 +778,7 @@ extern "C" PETB200_API int petb200_readout_bwd(const float* d_atomic, const floa
 extern "C" PETB200_API int petb200_sum_over_atoms(const float* atomic, const int32_t* struct_ptr,
                                       int64_t n_structures, int n_out, float* energies,
                                       cudaStream_t stream) {
-  LAUNCH_ROWS(sum_over_atoms_kernel, n_structures, atomic, struct_ptr, n_structures, n_out,
-              energies);
+  if (n_structures > 0)
+    sum_over_atoms_kernel<<<(unsigned)n_structures, kSumThreads, 0, stream>>>(atomic, struct_ptr, n_out, energies);
   return check_launch("sum_over_atoms");
 }
