@@ -1021,7 +1021,10 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
       tc_fence_after();
       if (lane == 0 && sw == 0) trace(1, i, 15, 1);
-      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+      // The row's RMS statistic is re-derived here from the x values this pass reads anyway: the
+      // producers' rstd_s buffer of this parity is rewritten for tile i + 2 as soon as GEMM1 of tile
+      // i + 1 is done, and nothing orders that against this (overlapped, possibly late) store phase.
+      float dot[4] = {0.f, 0.f, 0.f, 0.f}, ssx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl) {
         if (sl + 1 < 8) fetch_x(sl + 1);
@@ -1030,17 +1033,19 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int it = 0; it < 4; ++it) {
           const float4 a = es.get(it), xv = xr[sl & 1][it];
           dot[it] += a.x * xv.x + a.y * xv.y + a.z * xv.z + a.w * xv.w;
+          ssx[it] += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
         }
       }
       fetch_x(0);
       fetch_g(0);
       float rr[4], kap[4];
-      const float* rstd_t = rstd_s + t * BM;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 1);
         dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 2);
-        rr[it] = rstd_t[quarter * 32 + it * 8 + es.rsel];
+        ssx[it] += __shfl_xor_sync(0xffffffffu, ssx[it], 1);
+        ssx[it] += __shfl_xor_sync(0xffffffffu, ssx[it], 2);
+        rr[it] = rsqrtf(ssx[it] * (1.0f / D) + kRmsEps);
         kap[it] = rr[it] * rr[it] * rr[it] * dot[it] * (1.0f / D);
       }
 #pragma unroll
