@@ -16,7 +16,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// -DPETB200_CHAOS (test builds only, tools/race_ops.py): pseudo-random sleeps of up to ~4 us around every
+// mbarrier wait and arrive, different per warp, CTA and time.  Results of the deterministic kernels must not
+// change: whatever ordering the roles of a persistent kernel rely on has to come from a barrier, not from
+// their usual relative speed.
+#ifdef PETB200_CHAOS
+__device__ __forceinline__ void chaos_delay() {
+  unsigned t = (unsigned)clock64() * 2654435761u + (threadIdx.x >> 5) * 40503u + blockIdx.x * 9176u;
+  t ^= t >> 13;
+  t *= 2246822519u;
+  t ^= t >> 16;
+  t = __shfl_sync(__activemask(), t, __ffs(__activemask()) - 1);
+  if ((t & 3) == 0) __nanosleep((t >> 8) & 4095);
+}
+#else
+__device__ __forceinline__ void chaos_delay() {}
+#endif
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  chaos_delay();
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -33,8 +50,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  chaos_delay();
   while (!mbar_try_wait(bar, parity)) {
   }
+  chaos_delay();
 }
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {

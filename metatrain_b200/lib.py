@@ -12,7 +12,9 @@ import threading
 import torch
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-_LIB_PATH = os.path.join(_CSRC, "libpetb200.so")
+#: PETB200_LIB selects another build of the same library (e.g. the `make chaos` stress build)
+_LIB_PATH = os.path.abspath(os.environ["PETB200_LIB"]) if os.environ.get("PETB200_LIB") else os.path.join(
+    _CSRC, "libpetb200.so")
 _lock = threading.Lock()
 _lib = None
 

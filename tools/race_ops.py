@@ -16,6 +16,7 @@ import torch  # noqa: E402
 from metatrain_b200 import engine, lib  # noqa: E402
 from metatrain_b200.lib import (EPI_NONE, EPI_SILU, EPI_SWIGLU, PREC_BF16X3, call, ptr)  # noqa: E402
 
+# PETB200_LIB=build_tmp/chaos/libpetb200.so (`make chaos` in csrc/) selects the stress build (lib.py reads it)
 dev = "cuda:0"
 mode, path = sys.argv[1], sys.argv[2]
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 120000
@@ -87,6 +88,66 @@ def attention_case():
     results.update({"attention_fwd": out, "attention_fwd/lse": lse, "attention_bwd": d_qkv, "attention_bwd/d_fc": d_fc})
 
 
+def combine_case():
+    d, E = 128, M
+    t_all, m, g = rnd(E, d, seed=1), rnd(E, d, seed=2), rnd(E, d, seed=3)
+    w_a, w_b = rnd(2 * d, 2 * d, seed=6, scale=(2 * d) ** -0.5), rnd(d, 2 * d, seed=8, scale=(2 * d) ** -0.5)
+    s_vec, b_fold, b_b = w_a.sum(1).contiguous(), rnd(2 * d, seed=7, scale=0.1), rnd(d, seed=9, scale=0.1)
+    gen = torch.Generator().manual_seed(11)
+    perm = torch.randperm(E, generator=gen)
+    rev = torch.empty(E, dtype=torch.int32)
+    half = E // 2
+    rev[perm[:half]] = perm[half:2 * half].int()
+    rev[perm[half:2 * half]] = perm[:half].int()
+    if E % 2:
+        rev[perm[-1]] = perm[-1].int()
+    rev = rev.to(dev)
+    imgs = [torch.empty(h.petb200_combine_image_bytes(d, b), device=dev, dtype=torch.uint8) for b in (0, 1)]
+    call("combine_pack", ptr(w_a), ptr(w_b), d, ptr(imgs[0]), ptr(imgs[1]))
+    tiles = -(-E // 128)
+    p1, stats = torch.zeros(tiles * 128, 2 * d, device=dev), torch.zeros(E, 2, device=dev)
+    call("combine_fwd", ptr(t_all), d, ptr(rev), ptr(imgs[0]), ptr(s_vec), ptr(b_fold), ptr(b_b), E, d, ptr(m), d,
+         ptr(p1), ptr(stats))
+    d_cat = torch.zeros(E, 2 * d, device=dev)
+    call("combine_bwd", ptr(g), d, ptr(p1), ptr(t_all), d, ptr(rev), ptr(stats), ptr(imgs[1]), ptr(s_vec),
+         ptr(b_fold), E, d, ptr(d_cat))
+    out = torch.zeros(E, d, device=dev)
+    call("combine_scatter_bwd", ptr(d_cat), ptr(g), ptr(rev), E, d, ptr(out))
+    results.update({"combine_fwd/m": m, "combine_fwd/p1": p1, "combine_fwd/stats": stats, "combine_bwd": d_cat,
+                    "combine_scatter_bwd": out})
+
+
+def chain_case():
+    d, E, N = 128, M, M // 40
+    m = rnd(E, d, seed=1)
+    w1, w2 = rnd(d, d, seed=2, scale=d ** -0.5), rnd(d, d, seed=3, scale=d ** -0.5)
+    b1, b2, w_e = rnd(d, seed=4, scale=0.1), rnd(d, seed=5, scale=0.1), rnd(d, seed=6, scale=d ** -0.5)
+    gen = torch.Generator().manual_seed(7)
+    fc = torch.rand(E, generator=gen).to(dev)
+    ctr = torch.sort(torch.randint(0, N, (E,), generator=gen)).values.int().to(dev)
+    d_atomic = rnd(N, 1, seed=8)
+    img = [torch.empty(h.petb200_chain_image_bytes(d), device=dev, dtype=torch.uint8) for _ in range(2)]
+    call("chain_pack", ptr(w1), ptr(w2), d, ptr(img[0]), ptr(img[1]))
+    tiles = -(-E // 128)
+    e1p, e2p, pe = torch.zeros(tiles * 128, d, device=dev), torch.zeros(E, d, device=dev), torch.zeros(E, device=dev)
+    call("edge_head_fwd", ptr(m), d, ptr(img[0]), ptr(b1), ptr(b2), ptr(w_e), 0.1, E, d, ptr(e1p), ptr(e2p), ptr(pe))
+    d_m, d_fc = torch.zeros(E, d, device=dev), torch.zeros(E, device=dev)
+    call("edge_head_bwd", ptr(d_atomic), ptr(ctr), ptr(fc), ptr(e1p), ptr(e2p), ptr(pe), ptr(img[1]), ptr(w_e), E, d,
+         ptr(d_m), d, ptr(d_fc))
+    results.update({"edge_head_fwd/e1": e1p, "edge_head_fwd/e2": e2p, "edge_head_fwd/pe": pe,
+                    "edge_head_bwd/d_m": d_m, "edge_head_bwd/d_fc": d_fc})
+    vec, dist = rnd(E, 3, seed=9), torch.rand(E, generator=gen).to(dev) + 0.5
+    geo_w, table = rnd(d, 4, seed=10, scale=0.3), rnd(2, d, seed=11, scale=0.3)
+    z = torch.randint(0, 2, (E,), generator=gen).int().to(dev)
+    c1, t_out = torch.zeros(tiles * 128, d, device=dev), torch.zeros(E, d, device=dev)
+    call("compress_fwd", ptr(m), d, ptr(img[0]), ptr(b1), ptr(geo_w), ptr(table), ptr(z), ptr(vec), ptr(dist), ptr(b2),
+         E, d, ptr(c1), ptr(t_out), d)
+    d_m2, d_vec, d_dist = torch.zeros(E, d, device=dev), torch.zeros(E, 3, device=dev), torch.zeros(E, device=dev)
+    call("compress_bwd", ptr(m), d, ptr(c1), ptr(img[1]), ptr(geo_w), E, d, ptr(d_m2), d, 1, ptr(d_vec), ptr(d_dist))
+    results.update({"compress_fwd/c1": c1, "compress_fwd/t": t_out, "compress_bwd/d_m": d_m2,
+                    "compress_bwd/d_vec": d_vec, "compress_bwd/d_dist": d_dist})
+
+
 cases = [
     ("gemm 128x128 +residual (stationary)", lambda: gemm_case("gemm_none_res", 128, 128, EPI_NONE, True)),
     ("gemm 128x384 (streaming)", lambda: gemm_case("gemm_k384", 128, 384, EPI_NONE, True)),
@@ -95,6 +156,8 @@ cases = [
     ("norm_linear", norm_linear_case),
     ("mlp fwd / bwd", mlp_case),
     ("attention fwd / bwd", attention_case),
+    ("combine fwd / bwd / scatter", combine_case),
+    ("edge head and token builder chains", chain_case),
 ]
 for label, fn in cases:
     fn()
