@@ -601,6 +601,36 @@ def run_petb200(args):
     _engine.USE_STAGE_SCHEDULE = True
     lib.profile_hook = None
     tot = timer.totals()
+    # communication share of the sharded step: every collective of 3 more steps (stage schedule on, as in
+    # the timed region) bracketed by events on the compute stream, so a collective's time includes the wait
+    # for the slowest peer.  Max over ranks.
+    comm = None
+    if sharded:
+        from metatrain_b200 import sharded as _sh
+        _sh.comm_timer = []
+        for _ in range(3):
+            step_resident()
+        torch.cuda.synchronize()
+        rec, _sh.comm_timer = _sh.comm_timer, None
+        agg = {}
+        for label, a, b, nb in rec:
+            t, n, by = agg.get(label, (0.0, 0, 0))
+            agg[label] = (t + a.elapsed_time(b), n + 1, by + nb)
+        local = torch.tensor([agg.get(k, (0.0, 0, 0))[0] / 3 for k in ("halo_all_to_all", "all_reduce")],
+                             device="cuda", dtype=torch.float64)
+        hi, lo = local.clone(), local.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        comm = {"what": "collectives of the sharded step bracketed by CUDA events on the compute stream.  A rank "
+                        "that reaches a collective early waits there for its peers, so max over ranks = transfer "
+                        "+ load skew between ranks, min over ranks (the rank the others wait for) = the transfer "
+                        "and launch cost itself",
+                "halo_all_to_all": {"ms_per_step_min_over_ranks": float(lo[0]), "ms_per_step_max_over_ranks": float(hi[0]),
+                                    "calls_per_step": agg.get("halo_all_to_all", (0, 0, 0))[1] // 3,
+                                    "bytes_sent_per_step_this_rank": agg.get("halo_all_to_all", (0, 0, 0))[2] // 3},
+                "all_reduce": {"ms_per_step_min_over_ranks": float(lo[1]), "ms_per_step_max_over_ranks": float(hi[1]),
+                               "calls_per_step": agg.get("all_reduce", (0, 0, 0))[1] // 3,
+                               "bytes_per_step": agg.get("all_reduce", (0, 0, 0))[2] // 3}}
     if os.environ.get("PETB200_GEMM_SHAPES") and rank == 0:
         shapes = {}
         for name, a, b, work, byt in timer.records:
@@ -711,7 +741,7 @@ def run_petb200(args):
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec / args.steps * 1e3},
         "e2e_device_neighbor_list": md,
-        "strong_scaling": strong, "config4": config4,
+        "strong_scaling": strong, "config4": config4, "comm": comm,
         "gpu_launches": launches, "clocks": clocks,
         "roofline": roofline, "whole_step": whole, "edge_scatter": edge_scatter, "kernels": kernels,
     }

@@ -31,6 +31,28 @@ import torch.distributed as dist
 Tensor = torch.Tensor
 
 
+#: optional profiler: a list that receives ``(label, start_event, end_event, bytes_sent)`` per collective
+#: (bench.py's instrumented steps); None = no events recorded
+comm_timer: Optional[list] = None
+
+
+def _timed(label: str, nbytes: int):
+    """Context manager bracketing one collective with CUDA events when ``comm_timer`` is set."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def ctx():
+        if comm_timer is None:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        comm_timer.append((label, a, b, nbytes))
+    return ctx()
+
+
 @dataclass
 class Halo:
     """Index lists of one rank's halo edges (all tensors on the compute device)."""
@@ -49,7 +71,8 @@ class Halo:
         if self.n_ghost == 0 and sum(self.send_splits) == 0:
             # still a collective: every rank must take part
             pass
-        dist.all_to_all_single(out, rows, self.recv_splits, self.send_splits, group=self.group)
+        with _timed("halo_all_to_all", rows.numel() * rows.element_size()):
+            dist.all_to_all_single(out, rows, self.recv_splits, self.send_splits, group=self.group)
         return out
 
 
@@ -239,7 +262,8 @@ def evaluate_sharded(backend, shard: Shard, positions: Tensor, species: Tensor, 
         # force scatter already pulled the halo contributions in) and the per-structure energy
         (grad,) = torch.autograd.grad(energy.sum(), pos)
         packed = torch.cat([grad.reshape(-1), energy.detach().reshape(-1)])
-        dist.all_reduce(packed, group=group)
+        with _timed("all_reduce", packed.numel() * packed.element_size()):
+            dist.all_reduce(packed, group=group)
         n3 = grad.numel()
         out["dE_dpos"] = packed[:n3].view_as(grad)
         out["energies"] = packed[n3:].view_as(energy)
