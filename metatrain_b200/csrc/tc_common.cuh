@@ -37,6 +37,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  // (a suspend-time hint of 2 us on this instruction was measured: no effect on any fused kernel, +-1 %)
   uint32_t done;
   asm volatile(
       "{\n\t"
