@@ -537,13 +537,17 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
 // tile produces all N output columns in chunks of 64 — the generic GEMM (gemm_tc.cu) lets a
 // CTA own one 128-column chunk, so a 384-column projection re-reads and re-converts every
 // activation tile three times and needs a separate RMS-statistics kernel in front.
-// 14 warps: 0-7 epilogue (two groups on alternate chunks, TMEM -> smem transpose -> coalesced
-// stores), 8 MMA issue, 9-12 activation producers, 13 weight stages.
-constexpr int NL_RING = 8;
+// 14 warps: 0-7 epilogue (two groups on alternate chunks; TMEM -> registers (+ bias) -> a swizzled
+// [32 rows x 32 columns] box in shared memory -> ONE TMA tile store per box: per 32 columns a warp issues
+// 1 tcgen05.ld + 8 STS.128 + 1 bulk tensor store instead of 2 tcgen05.ld + 8 STS.128 + 8 LDS.128 +
+// 8 STG.128 — the memory-instruction queue (MIO) of the SM was what this kernel waited for), 8 MMA
+// issue, 9-12 activation producers, 13 weight stages.
+constexpr int NL_RING = 5;
+constexpr int NL_BOX_BYTES = 32 * 128;                        // [32 rows x 32 floats], SWIZZLE_128B
 constexpr int NL_XS_OFF = 0;
 constexpr int NL_RING_OFF = ((NL_XS_OFF + FWD_STAGING_BYTES + 1023) / 1024) * 1024;
-constexpr int NL_EPI_OFF = NL_RING_OFF + NL_RING * STAGE;
-constexpr int NL_BIAS_OFF = NL_EPI_OFF + EPI_STAGE_BYTES;    // bias [NL_MAX_N]
+constexpr int NL_EPI_OFF = NL_RING_OFF + NL_RING * STAGE;    // 8 warps x 2 boxes
+constexpr int NL_BIAS_OFF = NL_EPI_OFF + NUM_EPI_WARPS * 2 * NL_BOX_BYTES;    // bias [NL_MAX_N]
 constexpr int NL_MAX_N = 1024;
 constexpr int NL_BAR_OFF = NL_BIAS_OFF + NL_MAX_N * 4;
 constexpr int NL_SMEM = NL_BAR_OFF + 8 * (16 + 2 * NL_RING) + 16 + 1024;
@@ -551,8 +555,8 @@ constexpr int NL_SMEM = NL_BAR_OFF + 8 * (16 + 2 * NL_RING) + 16 + 1024;
 constexpr int NL_ACC_COL = 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ image,
-                   const float* __restrict__ bias, int64_t M, int N, float* __restrict__ out, int64_t ldo,
+norm_linear_kernel(const __grid_constant__ CUtensorMap map_out, const float* __restrict__ x, int64_t ldx,
+                   const uint8_t* __restrict__ image, const float* __restrict__ bias, int64_t M, int N,
                    float* __restrict__ rstd_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -670,10 +674,11 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
   } else {
     // ============================================================ epilogue: out = acc + bias
     const int grp = warp >> 2;
-    const EpiStage es{reinterpret_cast<float*>(smem + NL_EPI_OFF) + warp * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    const uint32_t box_u32 = smem_base + NL_EPI_OFF + (uint32_t)warp * 2 * NL_BOX_BYTES;
+    uint8_t* box = smem + NL_EPI_OFF + warp * 2 * NL_BOX_BYTES;
+    uint32_t nbox = 0;
     for (int i = 0; i < sched.count; ++i) {
-      const int64_t m_base = sched.m0(i) + quarter * 32;
+      const int m_row = (int)(sched.m0(i) + quarter * 32);
       for (int c = 0; c < nch; ++c) {
         const uint32_t n = (uint32_t)(i * nch + c);
         const int b = n & 1;
@@ -681,25 +686,34 @@ norm_linear_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __re
         mbar_wait(bar.acc1_full(b), (n >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          const int c0 = c * 64 + 16 * sl + 4 * es.c4;
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0);
-          es.fill(tmem_base + lane_base + NL_ACC_COL + b * 64 + 16 * sl);
-          if (sl == 3) {
+        for (int sl = 0; sl < 2; ++sl, ++nbox) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_base + NL_ACC_COL + b * 64 + 32 * sl, v);
+          if (sl == 1) {
             tc_fence_before();
             mbar_arrive(bar.acc1_empty(b));
           }
+          // the tile store that used this box two slices ago has read it
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+          const float* bs = bias_s + c * 64 + 32 * sl;
+          uint8_t* dst = box + (nbox & 1) * NL_BOX_BYTES + lane * 128;
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int64_t m = m_base + it * 8 + es.rsel;
-            if (m >= M) continue;
-            const float4 a = es.get(it);
-            *reinterpret_cast<float4*>(out + m * ldo + c0) =
-                make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
+          for (int j = 0; j < 8; ++j) {   // row `lane`, 16-byte chunk j at its SWIZZLE_128B position
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j);
+            *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_out, c * 64 + 32 * sl, m_row, box_u32 + (nbox & 1) * NL_BOX_BYTES);
+            bulk_commit_group();
           }
         }
       }
     }
+    if (lane == 0) bulk_wait_group<0>();
   }
 
   tc_fence_before();
@@ -1181,8 +1195,13 @@ extern "C" PETB200_API int petb200_norm_linear(const float* x, int64_t ldx, cons
   PETB200_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "norm_linear: leading dimensions must be multiples of 4");
   if (n_rows == 0) return PETB200_OK;
   const int tiles = (int)ceil_div(n_rows, BM);
+  CUtensorMap map_out;
+  if (make_tma_map_f32(&map_out, out, n_rows, n_out, ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
+    set_error("norm_linear: cuTensorMapEncodeTiled failed (output pointer must be 16-byte aligned)");
+    return PETB200_ERR_CUDA;
+  }
   cudaFuncSetAttribute(norm_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NL_SMEM);
   norm_linear_kernel<<<tiles < kNumSMs ? tiles : kNumSMs, NUM_THREADS, NL_SMEM, stream>>>(
-      x, ldx, reinterpret_cast<const uint8_t*>(image), bias, n_rows, n_out, out, ldo, rstd_out);
+      map_out, x, ldx, reinterpret_cast<const uint8_t*>(image), bias, n_rows, n_out, rstd_out);
   return check_launch("norm_linear");
 }

@@ -53,6 +53,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   chaos_delay();
   while (!mbar_try_wait(bar, parity)) {
+#ifdef PETB200_SPIN_SLEEP_NS
+    __nanosleep(PETB200_SPIN_SLEEP_NS);
+#endif
   }
   chaos_delay();
 }
@@ -182,6 +185,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
           "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// 2-D tiled TMA store (SASS UTMASTG): dense (or swizzled, as the map says) [box rows][box cols] block at `src`
+// -> box (c0.., c1..) of the tensor map; rows / columns outside the tensor are not written.  Completion is
+// tracked by bulk async-groups of the issuing thread.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// wait until at most N of this thread's bulk groups are incomplete (writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 // L2 prefetch of the same box (no shared-memory destination, no completion signal)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
@@ -205,7 +227,7 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 inline int make_tma_map_f32(CUtensorMap* map, const float* base, int64_t rows, int cols, int64_t ld,
-                            int box_cols, int box_rows) {
+                            int box_cols, int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
   const EncodeTiledFn encode = encode_tiled_fn();
   if (encode == nullptr) return -1;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -214,7 +236,7 @@ inline int make_tma_map_f32(CUtensorMap* map, const float* base, int64_t rows, i
   const cuuint32_t elem[2] = {1, 1};
   const CUresult rc = encode(
       map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, elem,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS ? 0 : (int)rc;
 }
