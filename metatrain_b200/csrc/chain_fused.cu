@@ -35,12 +35,13 @@ constexpr int CN_NUM_THREADS = 32 * 19;
 constexpr int CN_STORE_WARP0 = 14, CN_MMA2_WARP = 18;
 constexpr int XPITCH = D + 4;
 constexpr int CN_STAGING_BYTES = BM * XPITCH * 4;
-constexpr int CN_RING_A = 4, CN_RING_B = 4;
+constexpr int CN_RING_A = 3, CN_RING_B = 4;
+constexpr int CN_BOX_BYTES = 32 * 128;   // [32 rows x 32 floats] output box, SWIZZLE_128B (TMA tile store)
 constexpr int CN_RING = CN_RING_A + CN_RING_B;
 constexpr int CN_XS_OFF = 0;
 constexpr int CN_RING_OFF = ((CN_XS_OFF + CN_STAGING_BYTES + 1023) / 1024) * 1024;
-constexpr int CN_EPI_OFF = CN_RING_OFF + CN_RING * STAGE;           // 4 store warps x 32 x STAGE_LD floats
-constexpr int CN_CONST_OFF = CN_EPI_OFF + 4 * 32 * STAGE_LD * 4;    // b1 [128], b2 [128], w_e [128], G [128 x 4]
+constexpr int CN_EPI_OFF = CN_RING_OFF + CN_RING * STAGE;           // 4 store warps x 2 output boxes
+constexpr int CN_CONST_OFF = CN_EPI_OFF + 4 * 2 * CN_BOX_BYTES;     // b1 [128], b2 [128], w_e [128], G [128 x 4]
 constexpr int CN_CONST_FLOATS = 3 * HID + 4 * HID;
 constexpr int CN_PART_OFF = CN_CONST_OFF + CN_CONST_FLOATS * 4;     // geometry partials [2 groups][128] float4
 constexpr int CN_BAR_OFF = CN_PART_OFF + 2 * BM * 16;
@@ -125,7 +126,7 @@ struct ChainArgs {
 
 // ======================================================================== forward
 template <int MODE>
-__global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_fwd_kernel(const ChainArgs g) {
+__global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_fwd_kernel(const __grid_constant__ CUtensorMap map_out, const ChainArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -348,50 +349,55 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_fwd_kernel(const Chai
   } else if (warp >= CN_STORE_WARP0 && warp < CN_STORE_WARP0 + 4) {
     // ============================================================ output store warps
     // out = acc2 + b_2 ; HEADS: also pe = w_e . silu(out) + b_e (a store warp holds all 128 columns of
-    // its 32 rows, so the row dot is complete after a 4-lane shuffle).
+    // its 32 rows: the row dot is complete inside the thread).
+    // A thread owns one row (its TMEM lane): per 32-column slice it adds the bias, writes the row's 128 bytes
+    // into a SWIZZLE_128B box in shared memory and one lane hands the box to the TMA (tile store; rows beyond
+    // M are clipped by the tensor map) — 1 tcgen05.ld + 8 STS.128 + 1 bulk store per slice and warp.
     const int sw = warp - CN_STORE_WARP0;
-    const EpiStage es{reinterpret_cast<float*>(smem + CN_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    const uint32_t box_u32 = smem_base + CN_EPI_OFF + (uint32_t)sw * 2 * CN_BOX_BYTES;
+    uint8_t* box = smem + CN_EPI_OFF + sw * 2 * CN_BOX_BYTES;
     const float* b2_s = const_s + HID;
     const float* we_s = const_s + 2 * HID;
+    uint32_t nbox = 0;
     for (int i = 0; i < sched.count; ++i) {
-      const int64_t m_base = sched.m0(i) + quarter * 32;
+      const int64_t m = sched.m0(i) + quarter * 32 + lane;
+      const int m_row = (int)(sched.m0(i) + quarter * 32);
       const int t = i & 1;
       mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
       tc_fence_after();
-      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+      float dot = 0.f;
 #pragma unroll
-      for (int sl = 0; sl < 8; ++sl) {
-        const int c0 = 16 * sl + 4 * es.c4;
-        const float4 b4 = *reinterpret_cast<const float4*>(b2_s + c0);
-        const float4 w4 = *reinterpret_cast<const float4*>(we_s + c0);
-        es.fill(tmem_base + lane_base + CN_ACC2_COL + t * D + 16 * sl);
-        if (sl == 7) {
+      for (int sl = 0; sl < 4; ++sl, ++nbox) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + CN_ACC2_COL + t * D + 32 * sl, v);
+        if (sl == 3) {   // the accumulator is in registers now: release it early
           tc_fence_before();
           mbar_arrive(bar.acc2_empty(t));
         }
+        if (lane == 0) bulk_wait_group_read<1>();   // the store that used this box two slices ago has read it
+        __syncwarp();
+        uint8_t* dst = box + (nbox & 1) * CN_BOX_BYTES + lane * 128;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          if (m >= M) continue;
-          const float4 a = es.get(it);
-          const float4 o = make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
-          *reinterpret_cast<float4*>(g.out + m * g.ld_out + c0) = o;
-          if (MODE == MODE_HEADS)
-            dot[it] += w4.x * o.x * fsigmoid(o.x) + w4.y * o.y * fsigmoid(o.y) + w4.z * o.z * fsigmoid(o.z) +
-                       w4.w * o.w * fsigmoid(o.w);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(b2_s + 32 * sl + 4 * j);
+          const float4 o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+          *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = o;
+          if (MODE == MODE_HEADS) {
+            const float4 w4 = *reinterpret_cast<const float4*>(we_s + 32 * sl + 4 * j);
+            dot += w4.x * o.x * fsigmoid(o.x) + w4.y * o.y * fsigmoid(o.y) + w4.z * o.z * fsigmoid(o.z) +
+                   w4.w * o.w * fsigmoid(o.w);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
+          bulk_commit_group();
         }
       }
-      if (MODE == MODE_HEADS) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 1);
-          dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 2);
-          const int64_t m = m_base + it * 8 + es.rsel;
-          if (es.c4 == 0 && m < M) g.pe[m] = dot[it] + g.b_e;
-        }
-      }
+      if (MODE == MODE_HEADS && m < M) g.pe[m] = dot + g.b_e;
     }
+    if (lane == 0) bulk_wait_group<0>();
   }
 
   tc_fence_before();
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_fwd_kernel(const Chai
 
 // ======================================================================= backward
 template <int MODE>
-__global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_bwd_kernel(const ChainArgs g) {
+__global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_bwd_kernel(const __grid_constant__ CUtensorMap map_out, const ChainArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -651,43 +657,43 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_bwd_kernel(const Chai
   } else if (warp >= CN_STORE_WARP0 && warp < CN_STORE_WARP0 + 4) {
     // ============================================================ output store: d_m (+)= acc2
     if (!need_dm) goto done;
+    // as in the forward kernel: rows go through SWIZZLE_128B boxes and the TMA; with `accumulate` the tile
+    // operation is a reduction (d_m += box, added at the L2 — one contribution per element and launch), so
+    // the old values are never loaded by the SM
     const int sw = warp - CN_STORE_WARP0;
-    const EpiStage es{reinterpret_cast<float*>(smem + CN_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+    const uint32_t box_u32 = smem_base + CN_EPI_OFF + (uint32_t)sw * 2 * CN_BOX_BYTES;
+    uint8_t* box = smem + CN_EPI_OFF + sw * 2 * CN_BOX_BYTES;
+    uint32_t nbox = 0;
     for (int i = 0; i < sched.count; ++i) {
-      const int64_t m_base = sched.m0(i) + quarter * 32;
+      const int m_row = (int)(sched.m0(i) + quarter * 32);
       const int t = i & 1;
-      float4 old[2][4];
-      auto fetch = [&](int sl) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          old[sl & 1][it] = (g.accumulate && m < M)
-                                ? *reinterpret_cast<const float4*>(g.out + m * g.ld_out + 16 * sl + 4 * es.c4)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      fetch(0);
       mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int sl = 0; sl < 8; ++sl) {
-        if (sl + 1 < 8) fetch(sl + 1);
-        const int c0 = 16 * sl + 4 * es.c4;
-        es.fill(tmem_base + lane_base + CN_ACC2_COL + t * D + 16 * sl);
-        if (sl == 7) {
+      for (int sl = 0; sl < 4; ++sl, ++nbox) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + CN_ACC2_COL + t * D + 32 * sl, v);
+        if (sl == 3) {
           tc_fence_before();
           mbar_arrive(bar.acc2_empty(t));
         }
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+        uint8_t* dst = box + (nbox & 1) * CN_BOX_BYTES + lane * 128;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          if (m >= M) continue;
-          const float4 a = es.get(it), o = old[sl & 1][it];
-          *reinterpret_cast<float4*>(g.out + m * g.ld_out + c0) = make_float4(a.x + o.x, a.y + o.y, a.z + o.z, a.w + o.w);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (g.accumulate) tma_reduce_add_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
+          else tma_store_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
+          bulk_commit_group();
         }
       }
     }
+    if (lane == 0) bulk_wait_group<0>();
   }
 
 done:
@@ -702,18 +708,31 @@ done:
 template <int MODE>
 int launch_fwd(const ChainArgs& g, cudaStream_t stream) {
   const int tiles = (int)ceil_div(g.M, BM);
+  CUtensorMap map_out;
+  if (make_tma_map_f32(&map_out, g.out, g.M, D, g.ld_out, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
+    set_error("chain_fwd: cuTensorMapEncodeTiled failed (output must be 16-byte aligned, ld a multiple of 4)");
+    return PETB200_ERR_CUDA;
+  }
   cudaFuncSetAttribute(chain_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_SMEM);
-  chain_fwd_kernel<MODE><<<tiles < kNumSMs ? tiles : kNumSMs, CN_NUM_THREADS, CN_SMEM, stream>>>(g);
+  chain_fwd_kernel<MODE><<<tiles < kNumSMs ? tiles : kNumSMs, CN_NUM_THREADS, CN_SMEM, stream>>>(map_out, g);
   return check_launch("chain_fwd");
 }
 template <int MODE>
 int launch_bwd(const ChainArgs& g, cudaStream_t stream) {
   const int tiles = (int)ceil_div(g.M, BM);
+  CUtensorMap map_out;
+  if (g.out != nullptr) {
+    if (make_tma_map_f32(&map_out, g.out, g.M, D, g.ld_out, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
+      set_error("chain_bwd: cuTensorMapEncodeTiled failed (output must be 16-byte aligned, ld a multiple of 4)");
+      return PETB200_ERR_CUDA;
+    }
+  } else {
+    memset(&map_out, 0, sizeof(map_out));   // no d_m requested: the store warps exit without touching it
+  }
   cudaFuncSetAttribute(chain_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_SMEM);
-  chain_bwd_kernel<MODE><<<tiles < kNumSMs ? tiles : kNumSMs, CN_NUM_THREADS, CN_SMEM, stream>>>(g);
+  chain_bwd_kernel<MODE><<<tiles < kNumSMs ? tiles : kNumSMs, CN_NUM_THREADS, CN_SMEM, stream>>>(map_out, g);
   return check_launch("chain_bwd");
 }
-
 }  // namespace
 }  // namespace petb200
 

@@ -193,6 +193,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
                "r"(c1), "r"(src)
                : "memory");
 }
+// the same with a reduction: global[box] += shared[box] (fp32 add performed at the L2; every element
+// receives exactly one contribution per launch here, so the result is deterministic)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+               "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared-memory source
 template <int N>
