@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "metatrain_b200", "csrc", "libpetb200.so")
-WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMAPF", "UBLKCP", "UTCATOMSWS", "HMMA",
+WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP", "UTCATOMSWS", "HMMA",
          "LDGSTS", "SYNCS", "ELECT", "FFMA", "MUFU", "LDG", "STG", "ATOMG", "RED"]
 
 
@@ -54,7 +54,7 @@ def main():
         pass
     print("# SASS instruction counts per kernel (`cuobjdump -sass metatrain_b200/csrc/libpetb200.so`, sm_100a)\n")
     print("UTCHMMA = tcgen05.mma (kind::f16), UTCBAR = tcgen05.commit, LDTM / STTM = tcgen05.ld / st (tensor memory), "
-          "UTMALDG = cp.async.bulk.tensor (TMA tile load), UTMAPF = TMA L2 prefetch, UBLKCP = cp.async.bulk, "
+          "UTMALDG / UTMASTG / UTMAREDG = cp.async.bulk.tensor (TMA tile load / store / reduce-add), UTMAPF = TMA L2 prefetch, UBLKCP = cp.async.bulk, "
           "HMMA = warp-level mma.sync, LDGSTS = cp.async, SYNCS = mbarrier ops.\n")
     cols = [w for w in WATCH if any(c[w] for c in counts.values())]
     print("| kernel | total | " + " | ".join(cols) + " |")
