@@ -269,7 +269,9 @@ PETB200_API int petb200_mlp_bwd(const float* x, int64_t ldx, const float* d_y, i
  * [n_out, d] with the norm weight folded into its columns; petb200_norm_linear_pack builds the
  * operand-tile image (petb200_norm_linear_image_bytes bytes).  rstd_out (nullable, [n_rows])
  * receives rsqrt(mean(x^2) + eps) for the backward.  One persistent tcgen05 kernel: every
- * activation tile is normalised and converted once and produces all n_out columns.        */
+ * activation tile is normalised and converted once and produces all n_out columns.  The output leaves
+ * through TMA tile stores: `out` must be 16-byte aligned and ldo a multiple of 4 floats
+ * (PETB200_ERR_CUDA if the tensor map cannot be encoded).                                   */
 PETB200_API size_t petb200_norm_linear_image_bytes(int n_out);
 PETB200_API int petb200_norm_linear_pack(const float* w, int d, int n_out, void* image,
                              petb200_stream_t stream);
@@ -460,6 +462,9 @@ PETB200_API int petb200_readout_bwd(const float* d_atomic, const float* edge_pre
  *         d_vec / d_dist += G^T d_c1
  * replacing petb200_compress_gemm + petb200_gemm (forward) and 2 x petb200_gemm +
  * petb200_geom_embed_bwd (backward).                                                              */
+/* (the row-major outputs e2p / t_out / d_m of the four chain kernels are written by TMA tile stores —
+ *  d_m by a TMA reduce-add when it accumulates: they must be 16-byte aligned with leading dimensions
+ *  that are multiples of 4 floats) */
 PETB200_API size_t petb200_chain_image_bytes(int d);
 PETB200_API int petb200_chain_pack(const float* w1, const float* w2, int d, void* image_fwd, void* image_bwd,
                        petb200_stream_t stream);
