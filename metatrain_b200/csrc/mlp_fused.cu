@@ -123,26 +123,10 @@ __global__ void mlp_pack_kernel(const float* __restrict__ w_in, const float* __r
 
 // ------------------------------------------------------------------ shared pieces
 
-// Producer: bring the 128 x 128 fp32 tile `src` (rows m0.., leading dimension ld) into the four
-// bf16 operand tiles at `dst` ([k-chunk][hi|lo], 16 KB each).  Warp `pw` owns rows 32 pw .. 32 pw + 31:
-// cp.async lands floats 0..31 of a k-chunk in the bytes of the hi row and floats 32..63 in the lo
-// row, then the warp converts the rows in place (same scheme as gemm_tc.cu).  Returns, in
-// ss[b][jj], this lane's partial sum of squares of row 32 pw + 16 b + 2 jj + (lane >> 4).
-__device__ __forceinline__ void issue_tile_copies(uint32_t dst_u32, const float* __restrict__ src,
-                                                  int64_t ld, int64_t m0, int64_t M, int pw, int lane) {
-#pragma unroll
-  for (int kc = 0; kc < 2; ++kc) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int row = pw * 32 + 2 * i + (lane >> 4), piece = lane & 15;
-      const int64_t m = m0 + row;
-      const bool ok = m < M;
-      const float* s = src + (ok ? m : 0) * ld + kc * 64 + 4 * piece;
-      cp_async16(dst_u32 + (uint32_t)((kc * 2 + (piece >> 3)) * TILE + row * 128 + (piece & 7) * 16), s,
-                 ok ? 16u : 0u);
-    }
-  }
-}
+// Producer side of the backward kernel: a 128 x 128 fp32 tile lands (TMA boxes) as the four bf16 operand
+// tiles' bytes ([k-chunk][hi|lo], 16 KB each): floats 0..31 of a k-chunk in the bytes of the hi row and
+// floats 32..63 in the lo row; warp `pw` then converts its rows 32 pw .. 32 pw + 31 in place (same scheme
+// as gemm_tc.cu).
 // In-place conversion of 16 rows (row_base ..) of one k-chunk: fp32 landed as [hi tile row | lo
 // tile row] -> bf16 hi / lo swizzled rows.  Lane l works on row 2 jj + (l >> 4) of the batch and
 // owns k = 4 (l & 15) .. + 3.  ss[jj] accumulates this lane's partial sum of squares.

@@ -21,6 +21,7 @@ and, in the force path, the scatter of edge gradients onto the neighbour atom
   the per-structure energy and one of the [N, 3] position gradient;
 * everything else (geometry, GEMMs, attention, readout) runs unchanged on the local rows.
 """
+import contextlib
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -36,21 +37,17 @@ Tensor = torch.Tensor
 comm_timer: Optional[list] = None
 
 
+@contextlib.contextmanager
 def _timed(label: str, nbytes: int):
-    """Context manager bracketing one collective with CUDA events when ``comm_timer`` is set."""
-    import contextlib
-
-    @contextlib.contextmanager
-    def ctx():
-        if comm_timer is None:
-            yield
-            return
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+    """Brackets one collective with CUDA events when ``comm_timer`` is set."""
+    if comm_timer is None:
         yield
-        b.record()
-        comm_timer.append((label, a, b, nbytes))
-    return ctx()
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    yield
+    b.record()
+    comm_timer.append((label, a, b, nbytes))
 
 
 @dataclass
