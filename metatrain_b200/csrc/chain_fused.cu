@@ -31,8 +31,11 @@ using namespace fused;
 constexpr int MODE_HEADS = 0, MODE_COMPRESS = 1;
 constexpr int HID = 128;            // hidden width (= d_pet = d_head)
 constexpr int NCH = HID / CH;       // 4 chunks of 32 hidden units
-constexpr int CN_NUM_THREADS = 32 * 19;
-constexpr int CN_STORE_WARP0 = 14, CN_MMA2_WARP = 18;
+// 15 warps: 0-7 epilogue groups, 8 GEMM1 issue, 9-12 row producers (which also run the output store of the
+// previous tile once their tile is converted: no dedicated store warps, 480 threads, 128 registers), 13
+// weight stages, 14 GEMM2 issue
+constexpr int CN_NUM_THREADS = 32 * 15;
+constexpr int CN_MMA2_WARP = 14;
 constexpr int XPITCH = D + 4;
 constexpr int CN_STAGING_BYTES = BM * XPITCH * 4;
 constexpr int CN_RING_A = 3, CN_RING_B = 4;
@@ -162,6 +165,60 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_fwd_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+    // ============================================================ output store (run by the row-producer warps)
+    // out = acc2 + b_2 ; HEADS: also pe = w_e . silu(out) + b_e (a store warp holds all 128 columns of
+    // its 32 rows: the row dot is complete inside the thread).
+    // A thread owns one row (its TMEM lane): per 32-column slice it adds the bias, writes the row's 128 bytes
+    // into a SWIZZLE_128B box in shared memory and one lane hands the box to the TMA (tile store; rows beyond
+    // M are clipped by the tensor map) — 1 tcgen05.ld + 8 STS.128 + 1 bulk store per slice and warp.
+    const int sw = (warp - FIRST_PROD_WARP) & 3;
+    const uint32_t box_u32 = smem_base + CN_EPI_OFF + (uint32_t)sw * 2 * CN_BOX_BYTES;
+    uint8_t* box = smem + CN_EPI_OFF + sw * 2 * CN_BOX_BYTES;
+    const float* b2_s = const_s + HID;
+    const float* we_s = const_s + 2 * HID;
+    uint32_t nbox = 0;
+    auto store_tile = [&](int i) {
+      const int64_t m = sched.m0(i) + quarter * 32 + lane;
+      const int m_row = (int)(sched.m0(i) + quarter * 32);
+      const int t = i & 1;
+      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
+      tc_fence_after();
+      float dot = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl, ++nbox) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + CN_ACC2_COL + t * D + 32 * sl, v);
+        if (sl == 3) {   // the accumulator is in registers now: release it early
+          tc_fence_before();
+          mbar_arrive(bar.acc2_empty(t));
+        }
+        if (lane == 0) bulk_wait_group_read<1>();   // the store that used this box two slices ago has read it
+        __syncwarp();
+        uint8_t* dst = box + (nbox & 1) * CN_BOX_BYTES + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(b2_s + 32 * sl + 4 * j);
+          const float4 o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+          *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = o;
+          if (MODE == MODE_HEADS) {
+            const float4 w4 = *reinterpret_cast<const float4*>(we_s + 32 * sl + 4 * j);
+            dot += w4.x * o.x * fsigmoid(o.x) + w4.y * o.y * fsigmoid(o.y) + w4.z * o.z * fsigmoid(o.z) +
+                   w4.w * o.w * fsigmoid(o.w);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
+          bulk_commit_group();
+        }
+      }
+      if (MODE == MODE_HEADS && m < M) g.pe[m] = dot + g.b_e;
+    };
+    auto store_drain = [&]() {
+      if (lane == 0) bulk_wait_group<0>();
+    };
+
   if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
     // ============================================================ row producers: m -> TMEM (raw rows)
     const uint32_t dst = smem_base + CN_XS_OFF;
@@ -202,7 +259,10 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_fwd_kernel(const __gr
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar.x_full(0));
+      if (i > 0) store_tile(i - 1);   // overlaps the chunk loop of tile i
     }
+    if (sched.count > 0) store_tile(sched.count - 1);
+    store_drain();
   } else if (warp == TMA_WARP) {
     // ============================================================ weight-stage producer
     if (elect_one()) {
@@ -346,58 +406,6 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_fwd_kernel(const __gr
         mbar_arrive(bar.a2_full(b));
       }
     }
-  } else if (warp >= CN_STORE_WARP0 && warp < CN_STORE_WARP0 + 4) {
-    // ============================================================ output store warps
-    // out = acc2 + b_2 ; HEADS: also pe = w_e . silu(out) + b_e (a store warp holds all 128 columns of
-    // its 32 rows: the row dot is complete inside the thread).
-    // A thread owns one row (its TMEM lane): per 32-column slice it adds the bias, writes the row's 128 bytes
-    // into a SWIZZLE_128B box in shared memory and one lane hands the box to the TMA (tile store; rows beyond
-    // M are clipped by the tensor map) — 1 tcgen05.ld + 8 STS.128 + 1 bulk store per slice and warp.
-    const int sw = warp - CN_STORE_WARP0;
-    const uint32_t box_u32 = smem_base + CN_EPI_OFF + (uint32_t)sw * 2 * CN_BOX_BYTES;
-    uint8_t* box = smem + CN_EPI_OFF + sw * 2 * CN_BOX_BYTES;
-    const float* b2_s = const_s + HID;
-    const float* we_s = const_s + 2 * HID;
-    uint32_t nbox = 0;
-    for (int i = 0; i < sched.count; ++i) {
-      const int64_t m = sched.m0(i) + quarter * 32 + lane;
-      const int m_row = (int)(sched.m0(i) + quarter * 32);
-      const int t = i & 1;
-      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
-      tc_fence_after();
-      float dot = 0.f;
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl, ++nbox) {
-        float v[32];
-        tmem_ld32(tmem_base + lane_base + CN_ACC2_COL + t * D + 32 * sl, v);
-        if (sl == 3) {   // the accumulator is in registers now: release it early
-          tc_fence_before();
-          mbar_arrive(bar.acc2_empty(t));
-        }
-        if (lane == 0) bulk_wait_group_read<1>();   // the store that used this box two slices ago has read it
-        __syncwarp();
-        uint8_t* dst = box + (nbox & 1) * CN_BOX_BYTES + lane * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(b2_s + 32 * sl + 4 * j);
-          const float4 o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
-          *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = o;
-          if (MODE == MODE_HEADS) {
-            const float4 w4 = *reinterpret_cast<const float4*>(we_s + 32 * sl + 4 * j);
-            dot += w4.x * o.x * fsigmoid(o.x) + w4.y * o.y * fsigmoid(o.y) + w4.z * o.z * fsigmoid(o.z) +
-                   w4.w * o.w * fsigmoid(o.w);
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
-          bulk_commit_group();
-        }
-      }
-      if (MODE == MODE_HEADS && m < M) g.pe[m] = dot + g.b_e;
-    }
-    if (lane == 0) bulk_wait_group<0>();
   }
 
   tc_fence_before();
@@ -448,6 +456,48 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_bwd_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+    // ============================================================ output store: d_m (+)= acc2
+    // as in the forward kernel: rows go through SWIZZLE_128B boxes and the TMA; with `accumulate` the tile
+    // operation is a reduction (d_m += box, added at the L2 — one contribution per element and launch), so
+    // the old values are never loaded by the SM
+    const int sw = (warp - FIRST_PROD_WARP) & 3;
+    const uint32_t box_u32 = smem_base + CN_EPI_OFF + (uint32_t)sw * 2 * CN_BOX_BYTES;
+    uint8_t* box = smem + CN_EPI_OFF + sw * 2 * CN_BOX_BYTES;
+    uint32_t nbox = 0;
+    auto store_tile = [&](int i) {
+      if (!need_dm) return;
+      const int m_row = (int)(sched.m0(i) + quarter * 32);
+      const int t = i & 1;
+      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl, ++nbox) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + CN_ACC2_COL + t * D + 32 * sl, v);
+        if (sl == 3) {
+          tc_fence_before();
+          mbar_arrive(bar.acc2_empty(t));
+        }
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+        uint8_t* dst = box + (nbox & 1) * CN_BOX_BYTES + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (g.accumulate) tma_reduce_add_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
+          else tma_store_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
+          bulk_commit_group();
+        }
+      }
+    };
+    auto store_drain = [&]() {
+      if (lane == 0) bulk_wait_group<0>();
+    };
 
   if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
     // ============================================================ row producers
@@ -505,7 +555,10 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_bwd_kernel(const __gr
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar.x_full(0));
+      if (i > 0) store_tile(i - 1);   // overlaps the chunk loop of tile i
     }
+    if (sched.count > 0) store_tile(sched.count - 1);
+    store_drain();
   } else if (warp == TMA_WARP) {
     if (elect_one()) {
       Ring ra, rb;
@@ -654,49 +707,8 @@ __global__ void __launch_bounds__(CN_NUM_THREADS, 1) chain_bwd_kernel(const __gr
         }
       }
     }
-  } else if (warp >= CN_STORE_WARP0 && warp < CN_STORE_WARP0 + 4) {
-    // ============================================================ output store: d_m (+)= acc2
-    if (!need_dm) goto done;
-    // as in the forward kernel: rows go through SWIZZLE_128B boxes and the TMA; with `accumulate` the tile
-    // operation is a reduction (d_m += box, added at the L2 — one contribution per element and launch), so
-    // the old values are never loaded by the SM
-    const int sw = warp - CN_STORE_WARP0;
-    const uint32_t box_u32 = smem_base + CN_EPI_OFF + (uint32_t)sw * 2 * CN_BOX_BYTES;
-    uint8_t* box = smem + CN_EPI_OFF + sw * 2 * CN_BOX_BYTES;
-    uint32_t nbox = 0;
-    for (int i = 0; i < sched.count; ++i) {
-      const int m_row = (int)(sched.m0(i) + quarter * 32);
-      const int t = i & 1;
-      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl, ++nbox) {
-        float v[32];
-        tmem_ld32(tmem_base + lane_base + CN_ACC2_COL + t * D + 32 * sl, v);
-        if (sl == 3) {
-          tc_fence_before();
-          mbar_arrive(bar.acc2_empty(t));
-        }
-        if (lane == 0) bulk_wait_group_read<1>();
-        __syncwarp();
-        uint8_t* dst = box + (nbox & 1) * CN_BOX_BYTES + lane * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (g.accumulate) tma_reduce_add_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
-          else tma_store_2d(&map_out, 32 * sl, m_row, box_u32 + (nbox & 1) * CN_BOX_BYTES);
-          bulk_commit_group();
-        }
-      }
-    }
-    if (lane == 0) bulk_wait_group<0>();
   }
 
-done:
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {

@@ -201,8 +201,8 @@ __device__ __forceinline__ void weight_producer(const uint8_t* __restrict__ imag
 // where GEMM1 reads its A operand at full rate.  19 warps: 0-7 SwiGLU epilogue groups,
 // 8 GEMM1 issue, 9-12 activation producers, 13 weight stages, 14-17 output store, 18 GEMM2
 // issue (two issuing threads: the per-chunk barrier hops of one GEMM no longer delay the other).
-constexpr int FWD_NUM_THREADS = 32 * 19;
-constexpr int FWD_STORE_WARP0 = 14, FWD_MMA2_WARP = 18;
+constexpr int FWD_NUM_THREADS = 32 * 15;   // the four producer warps also run the output store (see below)
+constexpr int FWD_MMA2_WARP = 14;
 constexpr int FWD_RING_A = 5, FWD_RING_B = 4;   // W1 stages / W2 stages
 constexpr int FWD_RING = FWD_RING_A + FWD_RING_B;
 constexpr int XPITCH = D + 4;                                // floats per staged row
@@ -254,6 +254,56 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // ============================================================ output store (run by the producer warps:
+  // they are idle once their tile is converted, and without four dedicated store warps the CTA has 480
+  // threads = 128 registers per thread)
+    // y = acc2 + b_out + x, overlapped with the chunk loop of the next tile.  Warp -> 32 rows
+    // (its TMEM lane quarter) x 128 columns in 8 slices of 16; the residual of the next slice is
+    // in flight while the current one is transposed and stored.
+    const int sw = warp - FIRST_PROD_WARP;
+    const EpiStage es{reinterpret_cast<float*>(smem + FWD_EPI_OFF) + (sw & 3) * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+  auto store_tile = [&](int i) {
+    {
+      const int64_t m_base = sched.m0(i) + quarter * 32;
+      const int t = i & 1;
+      float4 res[3][4];
+      auto fetch = [&](int sl) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          res[sl % 3][it] = m < M ? ld4(x + m * ldx + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      fetch(0);
+      fetch(1);
+      if (lane == 0 && sw == 0) trace(1, i, 15, 0);
+      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0 && sw == 0) trace(1, i, 15, 1);
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) {
+        if (sl + 2 < 8) fetch(sl + 2);
+        const int c0 = 16 * sl + 4 * es.c4;
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * MAX_F + c0);
+        es.fill(tmem_base + lane_base + FWD_ACC2_COL + t * D + 16 * sl);
+        if (sl == 7) {   // the accumulator is in registers / smem now: release it early
+          tc_fence_before();
+          mbar_arrive(bar.acc2_empty(t));
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          if (m >= M) continue;
+          const float4 a = es.get(it), r = res[sl % 3][it];
+          *reinterpret_cast<float4*>(y + m * ldy + c0) =
+              make_float4(a.x + b4.x + r.x, a.y + b4.y + r.y, a.z + b4.z + r.z, a.w + b4.w + r.w);
+        }
+      }
+      if (lane == 0 && sw == 0) trace(1, i, 15, 2);
+    }
+  };
 
   if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
     // ============================================================ activation producers
@@ -313,7 +363,9 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
       tc_fence_before();
       mbar_arrive(bar.x_full(0));
       if (lane == 0 && quarter == 1) trace(3, i, 0, 3);
+      if (i > 0) store_tile(i - 1);   // overlaps the chunk loop of tile i
     }
+    if (sched.count > 0) store_tile(sched.count - 1);
   } else if (warp == TMA_WARP) {
     // ============================================================ weight-stage producer
     // one thread walks the image in order and routes W1 stages to ring A (slots 0..RA-1) and
@@ -456,52 +508,6 @@ mlp_fwd_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
         mbar_arrive(bar.a2_full(b));
         if (lane == 0 && quarter == 0) trace(1 + half, i, c, 4);
       }
-    }
-  } else if (warp >= FWD_STORE_WARP0 && warp < FWD_STORE_WARP0 + 4) {
-    // ============================================================ output store warps
-    // y = acc2 + b_out + x, overlapped with the chunk loop of the next tile.  Warp -> 32 rows
-    // (its TMEM lane quarter) x 128 columns in 8 slices of 16; the residual of the next slice is
-    // in flight while the current one is transposed and stored.
-    const int sw = warp - FWD_STORE_WARP0;
-    const EpiStage es{reinterpret_cast<float*>(smem + FWD_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
-    for (int i = 0; i < sched.count; ++i) {
-      const int64_t m_base = sched.m0(i) + quarter * 32;
-      const int t = i & 1;
-      float4 res[3][4];
-      auto fetch = [&](int sl) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          res[sl % 3][it] = m < M ? ld4(x + m * ldx + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      fetch(0);
-      fetch(1);
-      if (lane == 0 && sw == 0) trace(1, i, 15, 0);
-      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0 && sw == 0) trace(1, i, 15, 1);
-#pragma unroll
-      for (int sl = 0; sl < 8; ++sl) {
-        if (sl + 2 < 8) fetch(sl + 2);
-        const int c0 = 16 * sl + 4 * es.c4;
-        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * MAX_F + c0);
-        es.fill(tmem_base + lane_base + FWD_ACC2_COL + t * D + 16 * sl);
-        if (sl == 7) {   // the accumulator is in registers / smem now: release it early
-          tc_fence_before();
-          mbar_arrive(bar.acc2_empty(t));
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          if (m >= M) continue;
-          const float4 a = es.get(it), r = res[sl % 3][it];
-          *reinterpret_cast<float4*>(y + m * ldy + c0) =
-              make_float4(a.x + b4.x + r.x, a.y + b4.y + r.y, a.z + b4.z + r.z, a.w + b4.w + r.w);
-        }
-      }
-      if (lane == 0 && sw == 0) trace(1, i, 15, 2);
     }
   }
 
@@ -725,12 +731,13 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, int N, uint4* __
 }
 
 // ======================================================================= backward
-// 19 warps, as in the forward kernel: 0-7 swiglu' epilogue groups, 8 GEMM1 issue (ug and ds),
-// 9-12 activation producers (X and dY tiles as bf16 hi / lo operand tiles in shared memory),
-// 13 weight stages, 14-17 output store (RMSNorm backward, overlapped with the next tile),
-// 18 GEMM2 issue.
-constexpr int BWD_NUM_THREADS = 32 * 19;
-constexpr int BWD_STORE_WARP0 = 14, BWD_MMA2_WARP = 18;
+// 15 warps: 0-7 swiglu' epilogue groups, 8 GEMM1 issue (ug and ds), 9-12 activation producers (X and
+// dY tiles as bf16 hi / lo operand tiles in shared memory) which ALSO run the output store of the
+// previous tile (RMSNorm backward) once their tile is converted — they are idle for the rest of the
+// chunk loop, and without four dedicated store warps the CTA has 480 threads: 128 registers per
+// thread instead of 96, no spills in the epilogue —, 13 weight stages, 14 GEMM2 issue.
+constexpr int BWD_NUM_THREADS = 32 * 15;
+constexpr int BWD_MMA2_WARP = 14;
 constexpr int BWD_RING_A = 3, BWD_RING_B = 2;                 // G1 stages / WT stages
 constexpr int BWD_RING = BWD_RING_A + BWD_RING_B;
 constexpr int BWD_X_OFF = 0;                                  // X tiles (4), then dY tiles (4)
@@ -788,6 +795,91 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ============================================================ output store (run by the producer warps)
+    // dx = dy + rs * d - x * rs^3 * (d . x) / D   (d = acc2 = gradient w.r.t. x_hat), overlapped
+    // with the chunk loop of the next tile.  Warp -> 32 rows x 128 columns in 8 slices of 16:
+    // pass 1 accumulates d . x per row, pass 2 forms the output; x (and dy) of the next slice
+    // are in flight while the current one is transposed.
+    const int sw = warp - FIRST_PROD_WARP;
+    const EpiStage es{reinterpret_cast<float*>(smem + BWD_EPI_OFF) + (sw & 3) * (32 * STAGE_LD), lane, lane & 3,
+                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
+  auto store_tile = [&](int i) {
+    {
+      const int t = i & 1;
+      const int64_t m_base = sched.m0(i) + quarter * 32;
+      float4 xr[2][4], gr[2][4];
+      auto fetch_x = [&](int sl) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          xr[sl & 1][it] = m < M ? ld4(x + m * ldx + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto fetch_g = [&](int sl) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          gr[sl & 1][it] = m < M ? ld4(dy + m * ld_dy + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      fetch_x(0);
+      if (lane == 0 && sw == 0) trace(1, i, 15, 0);
+      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0 && sw == 0) trace(1, i, 15, 1);
+      // The row's RMS statistic is re-derived here from the x values this pass reads anyway: the
+      // producers' rstd_s buffer of this parity is rewritten for tile i + 2 as soon as GEMM1 of tile
+      // i + 1 is done, and nothing orders that against this (overlapped, possibly late) store phase.
+      float dot[4] = {0.f, 0.f, 0.f, 0.f}, ssx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) {
+        if (sl + 1 < 8) fetch_x(sl + 1);
+        es.fill(tmem_base + lane_base + BWD_ACC2_COL + t * D + 16 * sl);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 a = es.get(it), xv = xr[sl & 1][it];
+          dot[it] += a.x * xv.x + a.y * xv.y + a.z * xv.z + a.w * xv.w;
+          ssx[it] += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
+        }
+      }
+      fetch_x(0);
+      fetch_g(0);
+      float rr[4], kap[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 1);
+        dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 2);
+        ssx[it] += __shfl_xor_sync(0xffffffffu, ssx[it], 1);
+        ssx[it] += __shfl_xor_sync(0xffffffffu, ssx[it], 2);
+        rr[it] = rsqrtf(ssx[it] * (1.0f / D) + kRmsEps);
+        kap[it] = rr[it] * rr[it] * rr[it] * dot[it] * (1.0f / D);
+      }
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) {
+        if (sl + 1 < 8) {
+          fetch_x(sl + 1);
+          fetch_g(sl + 1);
+        }
+        const int c0 = 16 * sl + 4 * es.c4;
+        es.fill(tmem_base + lane_base + BWD_ACC2_COL + t * D + 16 * sl);
+        if (sl == 7) {
+          tc_fence_before();
+          mbar_arrive(bar.acc2_empty(t));
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t m = m_base + it * 8 + es.rsel;
+          if (m >= M) continue;
+          const float4 a = es.get(it), xv = xr[sl & 1][it], g = gr[sl & 1][it];
+          *reinterpret_cast<float4*>(dx + m * ld_dx + c0) =
+              make_float4(g.x + rr[it] * a.x - xv.x * kap[it], g.y + rr[it] * a.y - xv.y * kap[it],
+                          g.z + rr[it] * a.z - xv.z * kap[it], g.w + rr[it] * a.w - xv.w * kap[it]);
+        }
+      }
+      if (lane == 0 && sw == 0) trace(1, i, 15, 2);
+    }
+  };
+
   if (warp >= FIRST_PROD_WARP && warp < TMA_WARP) {
     // ============================================================ activation producers
     const int pw = warp - FIRST_PROD_WARP;
@@ -825,7 +917,9 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       fence_proxy_async();
       mbar_arrive(bar.x_full(0));
       if (lane == 0 && pw == 0) trace(3, i, 0, 3);
+      if (i > 0) store_tile(i - 1);   // overlaps the chunk loop of tile i
     }
+    if (sched.count > 0) store_tile(sched.count - 1);
   } else if (warp == TMA_WARP) {
     // ============================================================ weight-stage producer
     // image order: G1 stages of chunk 0; for c >= 1: G1 stages of c, then WT(c-1); WT(last).
@@ -986,89 +1080,6 @@ mlp_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         mbar_arrive(bar.a2_full(b));
         if (lane == 0 && quarter == 0) trace(1 + half, i, c, 4);
       }
-    }
-  } else if (warp >= BWD_STORE_WARP0 && warp < BWD_STORE_WARP0 + 4) {
-    // ============================================================ output store warps
-    // dx = dy + rs * d - x * rs^3 * (d . x) / D   (d = acc2 = gradient w.r.t. x_hat), overlapped
-    // with the chunk loop of the next tile.  Warp -> 32 rows x 128 columns in 8 slices of 16:
-    // pass 1 accumulates d . x per row, pass 2 forms the output; x (and dy) of the next slice
-    // are in flight while the current one is transposed.
-    const int sw = warp - BWD_STORE_WARP0;
-    const EpiStage es{reinterpret_cast<float*>(smem + BWD_EPI_OFF) + sw * (32 * STAGE_LD), lane, lane & 3,
-                      (lane >> 3) + 4 * ((lane >> 2) & 1)};
-    for (int i = 0; i < sched.count; ++i) {
-      const int t = i & 1;
-      const int64_t m_base = sched.m0(i) + quarter * 32;
-      float4 xr[2][4], gr[2][4];
-      auto fetch_x = [&](int sl) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          xr[sl & 1][it] = m < M ? ld4(x + m * ldx + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      auto fetch_g = [&](int sl) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          gr[sl & 1][it] = m < M ? ld4(dy + m * ld_dy + 16 * sl + 4 * es.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      fetch_x(0);
-      if (lane == 0 && sw == 0) trace(1, i, 15, 0);
-      mbar_wait(bar.acc2_full(t), (i >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0 && sw == 0) trace(1, i, 15, 1);
-      // The row's RMS statistic is re-derived here from the x values this pass reads anyway: the
-      // producers' rstd_s buffer of this parity is rewritten for tile i + 2 as soon as GEMM1 of tile
-      // i + 1 is done, and nothing orders that against this (overlapped, possibly late) store phase.
-      float dot[4] = {0.f, 0.f, 0.f, 0.f}, ssx[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int sl = 0; sl < 8; ++sl) {
-        if (sl + 1 < 8) fetch_x(sl + 1);
-        es.fill(tmem_base + lane_base + BWD_ACC2_COL + t * D + 16 * sl);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const float4 a = es.get(it), xv = xr[sl & 1][it];
-          dot[it] += a.x * xv.x + a.y * xv.y + a.z * xv.z + a.w * xv.w;
-          ssx[it] += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
-        }
-      }
-      fetch_x(0);
-      fetch_g(0);
-      float rr[4], kap[4];
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 1);
-        dot[it] += __shfl_xor_sync(0xffffffffu, dot[it], 2);
-        ssx[it] += __shfl_xor_sync(0xffffffffu, ssx[it], 1);
-        ssx[it] += __shfl_xor_sync(0xffffffffu, ssx[it], 2);
-        rr[it] = rsqrtf(ssx[it] * (1.0f / D) + kRmsEps);
-        kap[it] = rr[it] * rr[it] * rr[it] * dot[it] * (1.0f / D);
-      }
-#pragma unroll
-      for (int sl = 0; sl < 8; ++sl) {
-        if (sl + 1 < 8) {
-          fetch_x(sl + 1);
-          fetch_g(sl + 1);
-        }
-        const int c0 = 16 * sl + 4 * es.c4;
-        es.fill(tmem_base + lane_base + BWD_ACC2_COL + t * D + 16 * sl);
-        if (sl == 7) {
-          tc_fence_before();
-          mbar_arrive(bar.acc2_empty(t));
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t m = m_base + it * 8 + es.rsel;
-          if (m >= M) continue;
-          const float4 a = es.get(it), xv = xr[sl & 1][it], g = gr[sl & 1][it];
-          *reinterpret_cast<float4*>(dx + m * ld_dx + c0) =
-              make_float4(g.x + rr[it] * a.x - xv.x * kap[it], g.y + rr[it] * a.y - xv.y * kap[it],
-                          g.z + rr[it] * a.z - xv.z * kap[it], g.w + rr[it] * a.w - xv.w * kap[it]);
-        }
-      }
-      if (lane == 0 && sw == 0) trace(1, i, 15, 2);
     }
   }
 
